@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — SVGD pairwise interactions/s (n^2 * d per step) at n=65536, d=128 (BASELINE.json configs[3]).
+
+A "step" is one pass of the hot path over synthetic particles:
+    [all-gather X,S when row-sharded] -> median-heuristic bandwidth (exact select, kernels.py:160-172)
+    -> phi* + KSD/l2 statistics (stein.py:180-203, 99-106) -> scaled sgd update (models.py:143-167, 677-689)
+i.e. what models.Particles.step does for KernelGradient(bandwidth=None, scaled=True).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (torchrun for N > 1)
+    python bench.py --impl reference ...                      # CPU arm (the oracle port: JAX is not installable)
+
+Prints ONE JSON line on rank 0.  Timing: CUDA events on the launching stream, barrier +
+synchronize on both sides, max over ranks; particles move every step and an L2-sized buffer is
+rewritten between steps (config.l2_flush).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "projects-2020-neural-svgd_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "svgd_pairwise_interactions_per_s"
+UNIT = "n^2*d/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=65536)
+    ap.add_argument("--d", type=int, default=128)
+    ap.add_argument("--path", default="auto")
+    ap.add_argument("--median-mode", default="literal", choices=["literal", "offdiag", "full"])
+    ap.add_argument("--bandwidth", type=float, default=0.0, help="> 0: fixed bandwidth (skip the median heuristic)")
+    ap.add_argument("--cpu-rows", type=int, default=2048, help="query rows of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(n, d, seed=0):
+    """X ~ N(0, I) + 0.5, S = -X / diag(logspace(-2, 0, d)) scaled to O(1).
+    Generated with NumPy on the host (identical on every rank / arm), then copied."""
+    from oracle.svgd_oracle import gaussian_diag_workload
+    X, S = gaussian_diag_workload(n, d, seed=seed, shift=0.5)
+    return X, (S * np.float32(0.02)).astype(np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.lines, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"bf16_tflops": p.get("bf16_tflops_sustained", p.get("bf16_tflops")), "hbm_gbs": p.get("hbm_gbs"),
+                "source": "MEASURED_PEAKS.json (sustained bf16: kernel timed inside a long step)"}
+    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def cpu_port_rate(X, S, h, rows, repeats=1):
+    """The oracle's fp32 blocked port (sgemm Gram -> exp -> sgemm) on all host cores for `rows` query
+    rows against all n particles.  Returns (n^2*d-units per second, seconds, cores)."""
+    from oracle.svgd_oracle import phistar_f32_blocked
+    n, d = X.shape
+    rows = min(rows, n)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        phistar_f32_blocked(X[:rows], X, S, h, block=1024)
+        best = min(best, time.perf_counter() - t0)
+    return rows * n * d / best, best, os.cpu_count()
+
+
+def run_reference(args):
+    """--impl reference: the reference's own implementation cannot be installed (JAX/jaxlib/haiku/optax
+    absent, no network), so this arm times the CPU restatement (oracle port) on the host cores, each
+    step a bounded sample (cpu-rows query rows x all n particles) of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    X, S = workload(args.n, args.d)
+    h = 6.0 if args.bandwidth <= 0 else args.bandwidth     # the exact CPU median at n=65536 is out of reach; phi-only sample
+    for _ in range(max(args.warmup, 1)):
+        cpu_port_rate(X, S, h, min(args.cpu_rows, 512))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_rate(X, S, h, args.cpu_rows)
+    dt = time.perf_counter() - t0
+    rows = min(args.cpu_rows, args.n)
+    value = args.steps * rows * args.n * args.d / dt
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"svgd_step n={args.n} d={args.d} (BASELINE configs[3])", "n": args.n, "d": args.d,
+                   "note": "reference JAX unavailable in image; CPU restatement (oracle port), phi* only, bounded sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{rows} query rows x {args.n} particles per step (phi* only, fixed h={h}), numpy/BLAS fp32"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from nsvgd import _lib, engine
+    from nsvgd.parallel import ShardedSVGD, row_partition
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs CUDA; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, d, K, W = args.n, args.d, args.steps, args.warmup
+    lr, lam = 1e-3, 0.5
+    fixed_h = args.bandwidth if args.bandwidth > 0 else None
+
+    Xh, Sh = workload(n, d)
+    r0, r1 = row_partition(n, world, rank)
+    X0 = torch.tensor(Xh[r0:r1], device=dev)
+    S_loc = torch.tensor(Sh[r0:r1], device=dev)
+    X_loc = X0.clone()
+    sharded = ShardedSVGD(n, d, median_mode=args.median_mode) if world > 1 else None
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def one_step():
+        if world > 1:
+            h, aux, _ = sharded.step(X_loc, S_loc, lr, scaled=True, lambda_reg=lam, bandwidth=fixed_h)
+        else:
+            h = fixed_h if fixed_h else engine.median_heuristic(X_loc, args.median_mode)
+            aux, _ = engine.svgd_step_sgd(X_loc, S_loc, h, lr, scaled=True, lambda_reg=lam, path=args.path)
+        return h, aux
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        flush.fill_(1)
+        one_step()
+    barrier()
+
+    # ---- timed region: K steps, device events, L2 flushed between steps (flush excluded by events) ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.profile_enable(True)
+    launches0 = _lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.fill_(i & 1)
+        ev[i][0].record()
+        h, aux = one_step()
+        ev[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = sum(a.elapsed_time(b) for a, b in ev)
+    phi_main_ms, phi_main_cnt = _lib.profile_read(0)
+    hist_ms, hist_cnt = _lib.profile_read(1)
+    phi_op_ms, _ = _lib.profile_read(2)
+    med_op_ms, _ = _lib.profile_read(3)
+    _lib.profile_enable(False)
+    t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = K * float(n) * n * d / (total_ms * 1e-3)
+    h_val = float(h) if not isinstance(h, torch.Tensor) else float(h.item())
+    aux_host = aux.cpu().numpy()
+
+    # ---- e2e: the reference-facing call with HOST buffers, copies inside the timed region -------------
+    e2e = None
+    if not args.no_e2e:
+        Xp = torch.tensor(Xh[r0:r1]).pin_memory(); Sp = torch.tensor(Sh[r0:r1]).pin_memory()
+        out_host = torch.empty_like(Xp).pin_memory()
+        aux_hostbuf = torch.empty(8, dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            X_loc.copy_(Xp, non_blocking=True)
+            S_loc.copy_(Sp, non_blocking=True)
+            _, a = one_step()
+            out_host.copy_(X_loc, non_blocking=True)        # reference logs the particle array every step (models.py:187-197)
+            aux_hostbuf.copy_(a, non_blocking=True)
+        e2e_step()
+        barrier()
+        KE = max(2, min(K, 5))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(KE):
+            e2e_step()
+        e1.record()
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": KE * float(n) * n * d / (float(te.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(2 * (r1 - r0) * d * 4), "d2h_bytes_per_step": int((r1 - r0) * d * 4 + 64),
+               "steps": KE, "api": "nsvgd.engine.median_heuristic + svgd_step_sgd (C ABI nsvgd_median_h_f32 / nsvgd_step_sgd_f32), pinned host buffers"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (phi* main kernel) --------------------------------------------
+    pk = peaks()
+    m_local = r1 - r0
+    roofline = None
+    if phi_main_cnt:
+        avg_ms = phi_main_ms / phi_main_cnt
+        flop = 6.0 * m_local * n * d            # algorithmic: Gram 2 m n d + K [S|X] 4 m n d   
+        achieved = flop / (avg_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "phi_tc_kernel" if d > 32 else "phi_smalld_kernel",
+                    "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
+                    "traffic": None, "avg_kernel_ms": avg_ms, "launches": phi_main_cnt,
+                    "executed_mma_frac": 3 * achieved / pk["bf16_tflops"],
+                    "note": "achieved = algorithmic 6*m*n*d flop / CUDA-event time of the kernel; the bf16 2-piece split "
+                            "executes 3 MMA passes per algorithmic flop (executed_mma_frac); peak = " + pk["source"]}
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, secs, cores = cpu_port_rate(Xh, Sh, h_val if np.isfinite(h_val) and h_val > 0 else 6.0, args.cpu_rows)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{min(args.cpu_rows, n)} query rows x {n} particles, phi* only (no median), numpy/BLAS fp32, {secs:.2f} s; "
+                                  "reference JAX not installable in this image"}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 (bf16x2-split tensor-core MMAs, fp32 accumulate)" if d > 32 else "f32",
+        "data": "synthetic",
+        "config": {"workload": f"svgd_step n={n} d={d} (BASELINE configs[3])", "n": n, "d": d, "rows_per_gpu": m_local,
+                   "bandwidth": "median heuristic (%s) every step" % args.median_mode if not fixed_h else f"fixed {fixed_h}",
+                   "scaled": True, "optimizer": "sgd", "parallelism": f"row-sharded x{world}", "l2_flush": "192 MiB fill between steps",
+                   "path": args.path},
+        "breakdown_ms_per_step": {"median_op": med_op_ms / K, "median_hist_kernels": hist_ms / K, "phi_op": phi_op_ms / K,
+                                  "phi_main_kernel": phi_main_ms / K},
+        "phi_only_value": (K * float(m_local) * n * d / (phi_op_ms * 1e-3)) if phi_op_ms else None,
+        "result": {"h": h_val, "ksd": float(aux_host[0]), "l2": float(aux_host[1]), "alpha": float(aux_host[2])},
+        "wall_s": t_wall, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "cpu_baseline": cpu_baseline, "e2e": e2e,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,174 @@
+/* nsvgd.h — C ABI of the B200-native SVGD particle-interaction engine (libnsvgd.so).
+ *
+ * Drop-in boundary for the SVGD hot path of ratschlab/projects-2020-Neural-SVGD
+ * (reference paths below are relative to that repository).  The reference is pure
+ * Python/JAX; what a `jax.ffi` custom call (or the ctypes/torch host mirror in
+ * projects-2020-neural-svgd_b200/nsvgd/) binds for this path is exactly the entry
+ * points declared here: plain pointers and sizes, no torch / XLA types.
+ *
+ * Conventions
+ *   - All matrices are row-major fp32 DEVICE pointers with an explicit leading
+ *     dimension (ld*, in elements).  X (n x d) particles, S (n x d) scores
+ *     grad log p(x_j), Q (m x d) query points (Q = X in an SVGD step).
+ *   - `stream` is a cudaStream_t passed as void*.  Every call is ENQUEUE-ONLY:
+ *     no host synchronisation, no allocation; scratch comes from the caller
+ *     (`ws`, size from nsvgd_workspace_bytes).  Safe to capture in a CUDA graph.
+ *   - The bandwidth h lives in device memory (h_dev, 1 float) so the median
+ *     heuristic can feed phi* without a host round trip.
+ *   - Return value: 0 = NSVGD_OK, otherwise an nsvgd_status; the message is
+ *     available from nsvgd_last_error() (thread-local).  Nothing throws/aborts.
+ *   - NaN in -> NaN out (h = NaN if any particle is NaN, like jnp.median).
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns NSVGD_ERR_CUDA.
+ */
+#ifndef NSVGD_H_
+#define NSVGD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  NSVGD_OK = 0,
+  NSVGD_ERR_INVALID = 1,     /* bad shape / null pointer / bad enum (reference: ValueError, kernels.py:13-28, stein.py:29-31) */
+  NSVGD_ERR_CUDA = 2,        /* CUDA runtime / driver error, or no device */
+  NSVGD_ERR_UNSUPPORTED = 3, /* e.g. forced tensor-core path with d > 128 (reference: NotImplementedError) */
+  NSVGD_ERR_WORKSPACE = 4    /* ws too small */
+} nsvgd_status;
+
+/* kernels.median_heuristic semantics (kernels.py:160-172); see SURVEY.md App. B */
+typedef enum {
+  NSVGD_MEDIAN_LITERAL = 0,  /* what kernels.py:169 executes: remove_diagonal on the PARTICLES + clamped gather */
+  NSVGD_MEDIAN_OFFDIAG = 1,  /* docstring intent: median of the n(n-1) off-diagonal squared distances */
+  NSVGD_MEDIAN_FULL = 2      /* full n x n matrix including the zero diagonal (original SVGD code) */
+} nsvgd_median_mode;
+
+typedef enum {
+  NSVGD_PATH_AUTO = 0,
+  NSVGD_PATH_SIMT = 1,       /* small-d direct-difference FP32/MUFU kernel (d <= 32) */
+  NSVGD_PATH_TC = 2,         /* fused tcgen05/TMEM kernel, bf16 hi/lo split, 3 MMA passes (d <= 128) */
+  NSVGD_PATH_GENERIC = 3     /* any d: K row-chunks materialised in ws + SIMT GEMM */
+} nsvgd_path;
+
+typedef enum {
+  NSVGD_OP_MEDIAN = 0,
+  NSVGD_OP_PHI = 1,
+  NSVGD_OP_KSD = 2,
+  NSVGD_OP_MMD = 3,
+  NSVGD_OP_STEP = 4
+} nsvgd_op;
+
+typedef enum {
+  NSVGD_KSD_RECT = 0,        /* stein.ksd_squared   (stein.py:273-295): mean over n x m */
+  NSVGD_KSD_U = 1,           /* stein.ksd_squared_u (stein.py:299-323): sum_{i!=j} / (n(n-1)) */
+  NSVGD_KSD_V = 2            /* stein.ksd_squared_v (stein.py:327-349): sum / n^2 */
+} nsvgd_ksd_variant;
+
+/* ---- introspection ------------------------------------------------------- */
+int nsvgd_version(void);
+const char* nsvgd_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+uint64_t nsvgd_launch_count(void);
+
+/* Optional device-side timing (bench.py's roofline leg): when enabled, the library brackets its
+ * dominant kernels with CUDA events on the launching stream.  tag 0 = phi* main kernel,
+ * 1 = median histogram passes, 2 = whole phi* op, 3 = whole median op.  read() synchronises on the
+ * recorded events, returns the summed milliseconds and launch count, and clears the tag. */
+int nsvgd_profile_enable(int on);
+int nsvgd_profile_read(int tag, double* total_ms, int* count);
+
+/* Scratch size for one call of `op` (upper bound over paths unless `path` forces one). */
+int nsvgd_workspace_bytes(int op, int64_t n, int64_t m, int64_t d, int path, size_t* out_bytes);
+
+/* ---- A2: median-heuristic bandwidth  (kernels.py:160-172, utils.py:178-197, 653-658)
+ * h = sqrt(0.5 * median(D) / log(n+1)) in fp32, exact order statistics of the
+ * defined-order fp32 pair distances (bit-exact vs oracle/svgd_oracle.py). */
+int nsvgd_median_h_f32(void* stream, const float* X, int64_t n, int64_t d, int64_t ldx,
+                       int mode, float* h_dev, void* ws, size_t ws_bytes);
+
+/* Building blocks of the same select for row-sharded multi-GPU runs: every rank
+ * histograms the tile rows  tile_row_start, +tile_row_stride, ...  of the upper
+ * triangle, the host all-reduces `hist` (NCCL sum over uint64[2*2048]) between
+ * passes, and advance/finish then take identical decisions on every rank. */
+#define NSVGD_SELECT_BINS 2048
+#define NSVGD_SELECT_PASSES 3
+#define NSVGD_SELECT_STATE_BYTES 256
+int nsvgd_median_prepare(void* stream, const float* X, int64_t n, int64_t d, int64_t ldx, int mode,
+                         float* Z /* n x dz out (literal mode) or NULL */, int64_t* dz_out, float* w_last_out,
+                         void* state_dev);
+int nsvgd_median_hist_pass(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last,
+                           int64_t tile_row_start, int64_t tile_row_stride,
+                           const void* state_dev, int pass, uint64_t* hist_dev /* 2*NSVGD_SELECT_BINS, zeroed by the call */);
+int nsvgd_median_advance(void* stream, void* state_dev, const uint64_t* hist_dev, int pass);
+int nsvgd_median_finish(void* stream, const void* state_dev, int64_t n, float* h_dev);
+
+/* ---- A1/A3/A4: phi*  (stein.py:71-96, 180-222; kernels.py:52-65)
+ * phi[i,:] = (1/n) sum_j k_ij s_j + k_ij (q_i - x_j)/h^2,  k_ij = exp(-|q_i-x_j|^2/(2h^2)).
+ * Optional outputs (NULL to skip):
+ *   aux   (m x 2 x d): [drift, repulsion] split of stein.phistar (stein.py:206-222)
+ *   stats (double[4], device): {sum_i (s_i.phi_i + div phi(q_i)), sum_i |phi_i|^2, m, 0}
+ *          — needs Sq (scores at the queries, = S when Q = X); feeds
+ *          stein.stein_discrepancy(f=phi*) (stein.py:99-106) and utils.l2_norm_squared (utils.py:483-487).
+ */
+int nsvgd_phi_f32(void* stream,
+                  const float* Q, const float* Sq, int64_t m, int64_t ldq,
+                  const float* X, const float* S, int64_t n, int64_t ldx,
+                  int64_t d, const float* h_dev,
+                  float* phi, int64_t ldphi, float* aux, double* stats_dev,
+                  int path, void* ws, size_t ws_bytes);
+
+/* ---- A5/A7/A8: one SVGD step, sgd particle optimizer  (models.py:143-167, 654-689)
+ * grads = -phi (scaled == 0) or -alpha*phi with alpha = ksd/(2*lambda_reg*l2);
+ * X <- X - lr*grads.  h_dev must already hold the bandwidth (fixed, or from
+ * nsvgd_median_h_f32).  Rows [row_begin,row_end) of X are the queries this call
+ * updates (whole range on one GPU; the local block when row-sharded — then
+ * pass stats_allreduced = 0 and use the two-phase entry points below).
+ * step_aux_dev (double[8]): {ksd, l2, alpha, sum grads^2, sum updates^2, 0,0,0}. */
+int nsvgd_step_sgd_f32(void* stream, float* X, const float* S, int64_t n, int64_t d, int64_t ldx,
+                       const float* h_dev, float lr, int scaled, float lambda_reg,
+                       float* grads /* n x d out, may be NULL */, double* step_aux_dev,
+                       int path, void* ws, size_t ws_bytes);
+
+/* two-phase form for row-sharded runs: (1) nsvgd_phi_f32 on the local rows with
+ * stats, (2) host all-reduces stats (double[4]), (3) apply: */
+int nsvgd_apply_update_f32(void* stream, float* Xrows, const float* phi, int64_t m, int64_t d, int64_t ldx, int64_t ldphi,
+                           const double* stats_dev /* global sums, or NULL when !scaled */,
+                           float lr, int scaled, float lambda_reg,
+                           float* grads, double* step_aux_dev);
+
+/* ---- A6: KSD^2  (stein.py:273-349), closed form
+ * u_p(x,y) = k [ s_x.s_y + (s_x-s_y).(x-y)/h^2 + d/h^2 - r^2/h^4 ].  out_dev: 1 double. */
+int nsvgd_ksd_f32(void* stream, const float* X, const float* Sx, int64_t n, int64_t ldx,
+                  const float* Y, const float* Sy, int64_t m, int64_t ldy,
+                  int64_t d, const float* h_dev, int variant, double* out_dev, void* ws, size_t ws_bytes);
+
+/* ---- A9: MMD^2  (metrics.py:88-127; funnel != 0 applies kernels.defunnelize, kernels.py:112-123)
+ * out_dev: 1 double = mean offdiag Kxx + mean offdiag Kyy - 2 mean Kxy. */
+int nsvgd_mmd_f32(void* stream, const float* X, int64_t n, int64_t ldx,
+                  const float* Y, int64_t m, int64_t ldy, int64_t d,
+                  float h, int funnel, double* out_dev, void* ws, size_t ws_bytes);
+
+/* sum of the RBF kernel matrix between two point sets (building block of MMD; symmetric != 0
+ * requires A == B and returns sum_{i != j} = 2 sum_{i<j}, the diagonal excluded).  out_dev: 1 double. */
+int nsvgd_ksum_f32(void* stream, const float* A, int64_t na, int64_t lda,
+                   const float* B, int64_t nb, int64_t ldb, int64_t d,
+                   float h, int symmetric, double* out_dev, void* ws, size_t ws_bytes);
+
+/* adam particle optimizer used by models.Particles(optimizer="adam") (utils.py:711-715):
+ * standard optax.adam(lr) on `grads`; m1/m2 are caller-owned state, t the 1-based step. */
+int nsvgd_adam_update_f32(void* stream, float* X, const float* grads, float* m1, float* m2,
+                          int64_t count, float lr, float b1, float b2, float eps, int64_t t);
+
+/* ---- tcgen05 bring-up probes (used by tests/test_tc_probe.py; not part of the drop-in API) */
+int nsvgd_tc_probe_gram(void* stream, const float* A /*128 x 128*/, const float* B /*64 x 128*/,
+                        float* G /*128 x 64*/, void* ws, size_t ws_bytes);
+int nsvgd_tc_probe_pv(void* stream, const float* P /*128 x 64*/, const float* V /*64 x 256*/,
+                      float* O /*128 x 256*/, void* ws, size_t ws_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSVGD_H_ */

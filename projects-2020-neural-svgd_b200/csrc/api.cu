@@ -1,0 +1,206 @@
+// api.cu — extern "C" entry points of libnsvgd.so: error plumbing, path dispatch, the composite
+// SVGD step.  Reference boundary: models.KernelGradient.gradient (models.py:662-675) and
+// models.Particles._step (models.py:143-167).
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace nsvgd {
+
+static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launch_count{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int device_sm_count() {
+  static int cached = 0;
+  if (cached) return cached;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
+  cached = sms;
+  return cached;
+}
+
+// ---- optional event timing of the dominant kernels (off by default; not graph-capturable when on)
+struct ProfSlot { cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfSlot> g_prof[4];
+static std::mutex g_prof_mu;
+
+void prof_begin(int tag, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfSlot s{};
+  if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return;
+  cudaEventRecord(s.a, st);
+  g_prof[tag].push_back(s);
+}
+void prof_end(int tag, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof[tag].empty()) cudaEventRecord(g_prof[tag].back().b, st);
+}
+
+static int have_device() {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    (void)cudaGetLastError();
+    set_error("no CUDA device available (%s); libnsvgd has no CPU fallback", cudaGetErrorString(e));
+    return NSVGD_ERR_CUDA;
+  }
+  return NSVGD_OK;
+}
+
+// path choice (SURVEY 7.1 / north_star): SIMT FP32+MUFU for small d, tcgen05 where the
+// contraction is a real GEMM, generic otherwise.  NSVGD_FORCE_PATH={simt,tc,generic} overrides AUTO.
+static int choose_path(int path, int64_t n, int64_t m, int64_t d) {
+  if (path == NSVGD_PATH_AUTO) {
+    const char* env = getenv("NSVGD_FORCE_PATH");
+    if (env && *env) {
+      if (!strcmp(env, "simt")) path = NSVGD_PATH_SIMT;
+      else if (!strcmp(env, "tc")) path = NSVGD_PATH_TC;
+      else if (!strcmp(env, "generic")) path = NSVGD_PATH_GENERIC;
+    }
+  }
+  if (path != NSVGD_PATH_AUTO) return path;
+  if (d <= 32) return NSVGD_PATH_SIMT;
+  if (d <= 128 && n >= 1024 && m >= 256) return NSVGD_PATH_TC;
+  return NSVGD_PATH_GENERIC;
+}
+
+static int phi_dispatch(cudaStream_t st, const PhiArgs& a, int path, void* ws, size_t ws_bytes, bool dry, size_t* need) {
+  const int p = choose_path(path, a.n, a.m, a.d);
+  switch (p) {
+    case NSVGD_PATH_SIMT: return phi_simt(st, a, ws, ws_bytes, dry, need);
+    case NSVGD_PATH_TC: return phi_tc(st, a, ws, ws_bytes, dry, need);
+    case NSVGD_PATH_GENERIC: return phi_generic(st, a, ws, ws_bytes, dry, need);
+    default: set_error("phi: bad path %d", path); return NSVGD_ERR_INVALID;
+  }
+}
+
+}  // namespace nsvgd
+
+using namespace nsvgd;
+
+extern "C" int nsvgd_version(void) { return 100; }
+
+extern "C" int nsvgd_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  for (auto& v : g_prof) {
+    for (auto& s : v) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    v.clear();
+  }
+  return NSVGD_OK;
+}
+
+extern "C" int nsvgd_profile_read(int tag, double* total_ms, int* count) {
+  NSVGD_REQUIRE(tag >= 0 && tag < 4 && total_ms && count, NSVGD_ERR_INVALID, "profile_read: bad arguments");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double tot = 0.0; int c = 0;
+  for (auto& s : g_prof[tag]) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) { tot += ms; ++c; }
+    cudaEventDestroy(s.a); cudaEventDestroy(s.b);
+  }
+  (void)cudaGetLastError();
+  g_prof[tag].clear();
+  *total_ms = tot; *count = c;
+  return NSVGD_OK;
+}
+extern "C" const char* nsvgd_last_error(void) { return g_err; }
+extern "C" uint64_t nsvgd_launch_count(void) { return g_launch_count.load(); }
+
+static int check_phi_shapes(const char* who, const void* Q, int64_t m, int64_t ldq, const void* X, const void* S,
+                            int64_t n, int64_t ldx, int64_t d) {
+  NSVGD_REQUIRE(Q && X && S, NSVGD_ERR_INVALID, "%s: null pointer", who);
+  NSVGD_REQUIRE(n >= 1 && m >= 1 && d >= 1, NSVGD_ERR_INVALID, "%s: need n, m, d >= 1 (n=%lld m=%lld d=%lld)", who,
+                (long long)n, (long long)m, (long long)d);
+  NSVGD_REQUIRE(ldq >= d && ldx >= d, NSVGD_ERR_INVALID, "%s: leading dimension smaller than d", who);
+  return NSVGD_OK;
+}
+
+extern "C" int nsvgd_phi_f32(void* stream, const float* Q, const float* Sq, int64_t m, int64_t ldq, const float* X,
+                             const float* S, int64_t n, int64_t ldx, int64_t d, const float* h_dev, float* phi,
+                             int64_t ldphi, float* aux, double* stats_dev, int path, void* ws, size_t ws_bytes) {
+  NSVGD_PROPAGATE(check_phi_shapes("phi", Q, m, ldq, X, S, n, ldx, d));
+  NSVGD_REQUIRE(h_dev && phi && ldphi >= d, NSVGD_ERR_INVALID, "phi: null h_dev/phi or ldphi < d");
+  NSVGD_REQUIRE(!stats_dev || Sq, NSVGD_ERR_INVALID, "phi: stats need the scores at the queries (Sq)");
+  NSVGD_REQUIRE(path >= 0 && path <= 3, NSVGD_ERR_INVALID, "phi: bad path %d", path);
+  NSVGD_REQUIRE(ws, NSVGD_ERR_WORKSPACE, "phi: null workspace");
+  NSVGD_PROPAGATE(have_device());
+  PhiArgs a{Q, Sq, m, ldq, X, S, n, ldx, d, h_dev, phi, ldphi, aux, stats_dev};
+  prof_begin(2, (cudaStream_t)stream);
+  const int rc = phi_dispatch((cudaStream_t)stream, a, path, ws, ws_bytes, false, nullptr);
+  prof_end(2, (cudaStream_t)stream);
+  return rc;
+}
+
+extern "C" int nsvgd_step_sgd_f32(void* stream, float* X, const float* S, int64_t n, int64_t d, int64_t ldx,
+                                  const float* h_dev, float lr, int scaled, float lambda_reg, float* grads,
+                                  double* step_aux_dev, int path, void* ws, size_t ws_bytes) {
+  NSVGD_PROPAGATE(check_phi_shapes("step", X, n, ldx, X, S, n, ldx, d));
+  NSVGD_REQUIRE(h_dev && step_aux_dev && ws, NSVGD_ERR_INVALID, "step: null pointer");
+  NSVGD_REQUIRE(path >= 0 && path <= 3, NSVGD_ERR_INVALID, "step: bad path %d", path);
+  NSVGD_PROPAGATE(have_device());
+  WsCarver w(ws, ws_bytes);
+  float* phi = w.take<float>((size_t)(n * d));
+  double* stats = w.take<double>(4);
+  w.off = (w.off + 255) / 256 * 256;
+  NSVGD_REQUIRE(w.off <= ws_bytes, NSVGD_ERR_WORKSPACE, "step: workspace too small");
+  PhiArgs a{X, S, n, ldx, X, S, n, ldx, d, h_dev, phi, d, nullptr, stats};
+  prof_begin(2, (cudaStream_t)stream);
+  const int rc = phi_dispatch((cudaStream_t)stream, a, path, (char*)ws + w.off, ws_bytes - w.off, false, nullptr);
+  prof_end(2, (cudaStream_t)stream);
+  NSVGD_PROPAGATE(rc);
+  return nsvgd_apply_update_f32(stream, X, phi, n, d, ldx, d, stats, lr, scaled, lambda_reg, grads, step_aux_dev);
+}
+
+extern "C" int nsvgd_workspace_bytes(int op, int64_t n, int64_t m, int64_t d, int path, size_t* out_bytes) {
+  NSVGD_REQUIRE(out_bytes, NSVGD_ERR_INVALID, "workspace_bytes: null out pointer");
+  NSVGD_REQUIRE(n >= 1 && d >= 1, NSVGD_ERR_INVALID, "workspace_bytes: bad shape");
+  if (m < 1) m = n;
+  size_t need = 0;
+  auto phi_need = [&](int64_t mm) -> size_t {
+    PhiArgs a{};
+    a.m = mm; a.n = n; a.d = d; a.ldq = d; a.ldx = d; a.ldphi = d;
+    size_t best = 0;
+    const int p0 = path == NSVGD_PATH_AUTO ? NSVGD_PATH_SIMT : path;
+    const int p1 = path == NSVGD_PATH_AUTO ? NSVGD_PATH_GENERIC : path;
+    for (int p = p0; p <= p1; ++p) {
+      if (p == NSVGD_PATH_SIMT && d > 32) continue;
+      if (p == NSVGD_PATH_TC && d > 128) continue;
+      size_t s = 0;
+      if (phi_dispatch(nullptr, a, p, nullptr, 0, true, &s) == NSVGD_OK) best = std::max(best, s);
+    }
+    return best;
+  };
+  const int64_t tiles_n = ceil_div(n, 64), tiles_m = ceil_div(m, 64);
+  switch (op) {
+    case NSVGD_OP_MEDIAN: need = median_workspace(n, d); break;
+    case NSVGD_OP_PHI: need = phi_need(m); break;
+    case NSVGD_OP_STEP: need = phi_need(n) + (size_t)(n * d) * sizeof(float) + 1024; break;
+    case NSVGD_OP_KSD: need = (size_t)(tiles_n * std::max(tiles_n, tiles_m)) * sizeof(double) + 256; break;
+    case NSVGD_OP_MMD: {
+      const int64_t t = std::max(tiles_n, tiles_m);
+      need = (size_t)(t * t) * sizeof(double) + (size_t)((n + m) * d) * sizeof(float) + 1024;
+      break;
+    }
+    default: set_error("workspace_bytes: bad op %d", op); return NSVGD_ERR_INVALID;
+  }
+  *out_bytes = need + 512;
+  return NSVGD_OK;
+}

@@ -1,0 +1,598 @@
+// pair_engine.cu — SIMT tiled pairwise engine (any d), direct differences.
+//
+// One 64x64 tile of pairs per CTA (256 threads, 4x4 pairs per thread), the coordinate
+// axis streamed through shared memory in chunks of 16.  Four epilogues share the tile loop:
+//   HIST : radix-select histogram of the fp32 bit patterns of the squared distances, with
+//          the DEFINED summation order of oracle/svgd_oracle.py::pair_sqdist_f32
+//          (sequential over coordinates, separate mul and add, weighted last coordinate)
+//          -> bit-exact median bandwidth   [kernels.py:160-172, utils.py:178-197, 653-658]
+//   KSUM : sum of RBF kernel values (MMD building block)        [metrics.py:96-104]
+//   KMAT : materialise a row-chunk of K for the generic phi path [stein.py:180-203]
+//   KSD  : sum of u_p(x_i, y_j)                                  [stein.py:273-349]
+#include <algorithm>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace nsvgd {
+
+constexpr int TILE = 64;
+constexpr int DK = 16;
+constexpr int LDS_ = TILE + 4;  // padded row of the transposed smem tiles (floats)
+
+enum PairMode { MODE_HIST = 0, MODE_KSUM = 1, MODE_KMAT = 2, MODE_KSD = 3 };
+
+struct SelectState {
+  uint32_t prefix[2];
+  uint32_t mask;
+  uint32_t nan_flag;
+  unsigned long long rank[2];
+  int32_t is_zero[2];
+  float value[2];
+  float log_np1;
+  int32_t done;
+};
+static_assert(sizeof(SelectState) <= NSVGD_SELECT_STATE_BYTES, "state too large");
+
+struct PairArgs {
+  const float* A; int64_t na, lda;       // "row" points (tile index blockIdx.y)
+  const float* B; int64_t nb, ldb;       // "column" points (tile index blockIdx.x)
+  const float* SA; const float* SB;      // scores (KSD only)
+  int64_t d;
+  float w_last;                          // HIST: weight of the last coordinate
+  int symmetric;                         // only tiles J >= I, pairs i < j
+  int64_t tile_row_start, tile_row_stride;
+  const float* h_dev; float h_host;      // bandwidth (device pointer wins)
+  // HIST
+  const SelectState* state; int pass; unsigned long long* hist;
+  // KSUM / KSD
+  double* partials; float diag_weight;
+  // KMAT
+  float* K; int64_t ldk;
+};
+
+__device__ __forceinline__ int pass_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
+__device__ __forceinline__ int pass_bins(int pass) { return pass == 2 ? 1024 : 2048; }
+
+template <int MODE>
+__global__ void __launch_bounds__(256) pair_tile_kernel(const PairArgs a) {
+  constexpr bool EXACT = (MODE == MODE_HIST);
+  const int64_t I = a.tile_row_start + a.tile_row_stride * (int64_t)blockIdx.y;
+  const int64_t J = blockIdx.x;
+  if (a.symmetric && J < I) return;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t i0 = I * TILE, j0 = J * TILE;
+
+  __shared__ __align__(16) float As[DK][LDS_];
+  __shared__ __align__(16) float Bs[DK][LDS_];
+  __shared__ __align__(16) float SAs[MODE == MODE_KSD ? DK : 1][LDS_];
+  __shared__ __align__(16) float SBs[MODE == MODE_KSD ? DK : 1][LDS_];
+  __shared__ unsigned int hist_s[MODE == MODE_HIST ? 2 * NSVGD_SELECT_BINS : 1];
+  __shared__ double red_s[32];
+
+  if (MODE == MODE_HIST) {
+    for (int t = threadIdx.x; t < 2 * NSVGD_SELECT_BINS; t += 256) hist_s[t] = 0u;
+  }
+
+  float acc[4][4];
+  float acc_ss[MODE == MODE_KSD ? 4 : 1][MODE == MODE_KSD ? 4 : 1];
+  float acc_sd[MODE == MODE_KSD ? 4 : 1][MODE == MODE_KSD ? 4 : 1];
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      acc[ii][jj] = 0.f;
+      if (MODE == MODE_KSD) { acc_ss[ii][jj] = 0.f; acc_sd[ii][jj] = 0.f; }
+    }
+
+  // EXACT: the last coordinate is handled separately (weighted), main loop covers [0, d-1)
+  const int64_t dmain = EXACT ? a.d - 1 : a.d;
+  const int lr = threadIdx.x >> 4;   // 0..15: row within a 16-row load pass
+  const int lc = threadIdx.x & 15;   // coordinate within the chunk
+  for (int64_t c0 = 0; c0 < dmain; c0 += DK) {
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int r = lr + 16 * p;
+      const int64_t c = c0 + lc;
+      const bool cv = c < dmain;
+      const int64_t gi = i0 + r, gj = j0 + r;
+      As[lc][r] = (cv && gi < a.na) ? a.A[gi * a.lda + c] : 0.f;
+      Bs[lc][r] = (cv && gj < a.nb) ? a.B[gj * a.ldb + c] : 0.f;
+      if (MODE == MODE_KSD) {
+        SAs[lc][r] = (cv && gi < a.na) ? a.SA[gi * a.lda + c] : 0.f;
+        SBs[lc][r] = (cv && gj < a.nb) ? a.SB[gj * a.ldb + c] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < DK; ++c) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[c][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[c][tx * 4]);
+      const float ar[4] = {av.x, av.y, av.z, av.w};
+      const float br[4] = {bv.x, bv.y, bv.z, bv.w};
+      float sar[4], sbr[4];
+      if (MODE == MODE_KSD) {
+        const float4 sa = *reinterpret_cast<const float4*>(&SAs[c][ty * 4]);
+        const float4 sb = *reinterpret_cast<const float4*>(&SBs[c][tx * 4]);
+        sar[0] = sa.x; sar[1] = sa.y; sar[2] = sa.z; sar[3] = sa.w;
+        sbr[0] = sb.x; sbr[1] = sb.y; sbr[2] = sb.z; sbr[3] = sb.w;
+      }
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const float diff = ar[ii] - br[jj];
+          if (EXACT) {
+            acc[ii][jj] = __fadd_rn(acc[ii][jj], __fmul_rn(diff, diff));
+          } else {
+            acc[ii][jj] = fmaf(diff, diff, acc[ii][jj]);
+          }
+          if (MODE == MODE_KSD) {
+            acc_ss[ii][jj] = fmaf(sar[ii], sbr[jj], acc_ss[ii][jj]);
+            acc_sd[ii][jj] = fmaf(sar[ii] - sbr[jj], diff, acc_sd[ii][jj]);
+          }
+        }
+    }
+  }
+
+  if (EXACT) {
+    // weighted last coordinate: t = fl(diff*diff); t = fl(w*t); acc = fl(acc + t)
+    float al[4], bl[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t gi = i0 + ty * 4 + q, gj = j0 + tx * 4 + q;
+      al[q] = gi < a.na ? a.A[gi * a.lda + (a.d - 1)] : 0.f;
+      bl[q] = gj < a.nb ? a.B[gj * a.ldb + (a.d - 1)] : 0.f;
+    }
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const float diff = al[ii] - bl[jj];
+        float t = __fmul_rn(diff, diff);
+        t = __fmul_rn(a.w_last, t);
+        acc[ii][jj] = __fadd_rn(acc[ii][jj], t);
+      }
+  }
+
+  // ------------------------------------------------------------------ epilogues
+  if (MODE == MODE_HIST) {
+    __syncthreads();
+    const SelectState stt = *a.state;
+    const int shift = pass_shift(a.pass);
+    const unsigned int binmask = (unsigned int)pass_bins(a.pass) - 1u;
+    bool any_nan = false;
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int64_t gi = i0 + ty * 4 + ii, gj = j0 + tx * 4 + jj;
+        if (gi < a.na && gj < a.nb && gi < gj) {
+          const float v = acc[ii][jj];
+          if (v != v) { any_nan = true; continue; }
+          const unsigned int bits = __float_as_uint(v);
+          const unsigned int bin = (bits >> shift) & binmask;
+          if ((bits & stt.mask) == stt.prefix[0]) atomicAdd(&hist_s[bin], 1u);
+          if ((bits & stt.mask) == stt.prefix[1]) atomicAdd(&hist_s[NSVGD_SELECT_BINS + bin], 1u);
+        }
+      }
+    if (any_nan) atomicOr(const_cast<uint32_t*>(&a.state->nan_flag), 1u);
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * NSVGD_SELECT_BINS; t += 256) {
+      const unsigned int v = hist_s[t];
+      if (v) atomicAdd(&a.hist[t], (unsigned long long)v);
+    }
+    return;
+  }
+
+  const float h = a.h_dev ? *a.h_dev : a.h_host;
+  const float inv_h2 = 1.f / (h * h);
+  const float nc = -NSVGD_HALF_LOG2E * inv_h2;
+
+  if (MODE == MODE_KMAT) {
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const int64_t gi = i0 + ty * 4 + ii;
+      if (gi >= a.na) continue;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int64_t gj = j0 + tx * 4 + jj;
+        if (gj < a.nb) a.K[gi * a.ldk + gj] = ex2_approx(acc[ii][jj] * nc);
+      }
+    }
+    return;
+  }
+
+  // KSUM / KSD: weighted block sum -> partials[block]
+  double local = 0.0;
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int64_t gi = i0 + ty * 4 + ii, gj = j0 + tx * 4 + jj;
+      if (gi >= a.na || gj >= a.nb) continue;
+      float wgt = 1.f;
+      if (a.symmetric) wgt = gi < gj ? 2.f : (gi == gj ? a.diag_weight : 0.f);
+      if (wgt == 0.f) continue;
+      const float k = ex2_approx(acc[ii][jj] * nc);
+      float v = k;
+      if (MODE == MODE_KSD) {
+        const float r2 = acc[ii][jj];
+        v = k * (acc_ss[ii][jj] + acc_sd[ii][jj] * inv_h2 + (float)a.d * inv_h2 - r2 * inv_h2 * inv_h2);
+      }
+      local += (double)(wgt * v);
+    }
+  const double tot = block_sum(local, red_s);
+  if (threadIdx.x == 0) a.partials[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
+}
+
+// deterministic single-block reduction of the per-CTA partials: out = [out +] scale * sum
+__global__ void __launch_bounds__(1024) reduce_partials_kernel(const double* __restrict__ p, int64_t count,
+                                                               double scale, int accumulate, double* out) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int64_t t = threadIdx.x; t < count; t += 1024) s += p[t];
+  const double tot = block_sum(s, sh);
+  if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.0) + scale * tot;
+}
+
+__global__ void zero_partials_kernel(double* p, int64_t count) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x)
+    p[t] = 0.0;
+}
+
+static dim3 tile_grid(int64_t na, int64_t nb, int64_t start, int64_t stride) {
+  const int64_t ti = ceil_div(na, TILE), tj = ceil_div(nb, TILE);
+  const int64_t rows = start < ti ? ceil_div(ti - start, stride) : 0;
+  return dim3((unsigned)tj, (unsigned)rows, 1);
+}
+
+int launch_kmat(cudaStream_t st, const float* Q, int64_t m, int64_t ldq, const float* X, int64_t n, int64_t ldx,
+                int64_t d, const float* h_dev, float* K, int64_t ldk) {
+  PairArgs a{};
+  a.A = Q; a.na = m; a.lda = ldq; a.B = X; a.nb = n; a.ldb = ldx; a.d = d;
+  a.tile_row_start = 0; a.tile_row_stride = 1; a.h_dev = h_dev; a.K = K; a.ldk = ldk;
+  dim3 g = tile_grid(m, n, 0, 1);
+  NSVGD_REQUIRE(g.y <= 65535, NSVGD_ERR_INVALID, "kmat: too many row tiles (%u)", g.y);
+  pair_tile_kernel<MODE_KMAT><<<g, 256, 0, st>>>(a);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
+int launch_ksum(cudaStream_t st, const float* A, int64_t na, int64_t lda, const float* B, int64_t nb, int64_t ldb,
+                int64_t d, const float* h_dev, float h_host, int symmetric, double* out_dev, double scale,
+                int accumulate, void* ws, size_t ws_bytes, bool dry, size_t* need) {
+  dim3 g = tile_grid(na, nb, 0, 1);
+  const int64_t nblocks = (int64_t)g.x * g.y;
+  WsCarver w(ws, ws_bytes, dry);
+  double* partials = w.take<double>((size_t)nblocks);
+  if (need) *need = w.off;
+  if (dry) return NSVGD_OK;
+  NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "ksum: workspace too small (%zu < %zu)", ws_bytes, w.off);
+  NSVGD_REQUIRE(g.y <= 65535, NSVGD_ERR_INVALID, "ksum: too many row tiles (%u)", g.y);
+  PairArgs a{};
+  a.A = A; a.na = na; a.lda = lda; a.B = B; a.nb = nb; a.ldb = ldb; a.d = d;
+  a.symmetric = symmetric; a.tile_row_start = 0; a.tile_row_stride = 1;
+  a.h_dev = h_dev; a.h_host = h_host; a.partials = partials; a.diag_weight = 0.f;
+  if (symmetric) {  // skipped (J < I) tiles never write their partial
+    zero_partials_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nblocks, 256), 1024), 256, 0, st>>>(partials, nblocks);
+    NSVGD_LAUNCH_CHECK();
+  }
+  pair_tile_kernel<MODE_KSUM><<<g, 256, 0, st>>>(a);
+  NSVGD_LAUNCH_CHECK();
+  reduce_partials_kernel<<<1, 1024, 0, st>>>(partials, nblocks, scale, accumulate, out_dev);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
+// ------------------------------------------------------------------ median select
+__global__ void select_init_kernel(SelectState* s, long long r_lo, long long r_hi, float log_np1) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    s->prefix[0] = s->prefix[1] = 0u;
+    s->mask = 0u;
+    s->nan_flag = 0u;
+    s->is_zero[0] = r_lo < 0; s->is_zero[1] = r_hi < 0;
+    s->rank[0] = r_lo < 0 ? 0ull : (unsigned long long)r_lo;
+    s->rank[1] = r_hi < 0 ? 0ull : (unsigned long long)r_hi;
+    s->value[0] = s->value[1] = 0.f;
+    s->log_np1 = log_np1;
+    s->done = 0;
+  }
+}
+
+// literal mode: Z[a] = [x_a without column a (a < d-1) | x_a[:d-1], x_a[d-1]]   (n > d)
+//               Z[a] = x_a[:n] without column a                                 (n <= d)
+__global__ void literal_z_kernel(const float* __restrict__ X, int64_t n, int64_t d, int64_t ldx,
+                                 float* __restrict__ Z, int64_t dz) {
+  const int64_t total = n * dz;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t a = t / dz, c = t % dz;
+    int64_t src;
+    if (n > d) {
+      if (c == d - 1) src = d - 1;
+      else src = (a < d - 1 && c >= a) ? c + 1 : c;
+    } else {
+      src = c >= a ? c + 1 : c;
+    }
+    Z[t] = X[a * ldx + src];
+  }
+}
+
+__global__ void __launch_bounds__(1024) select_advance_kernel(SelectState* s, const unsigned long long* hist, int pass) {
+  // warp t (t = 0,1) resolves target t: find the bin whose cumulative count exceeds rank[t]
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ uint32_t new_prefix[2];
+  __shared__ unsigned long long new_rank[2];
+  const int nb = pass == 2 ? 1024 : 2048;
+  const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+  if (w < 2) {
+    const unsigned long long* hh = hist + (size_t)w * NSVGD_SELECT_BINS;
+    const unsigned long long target = s->rank[w];
+    const int per = nb / 32;
+    unsigned long long lsum = 0;
+    for (int b = 0; b < per; ++b) lsum += hh[lane * per + b];
+    unsigned long long incl = lsum;   // inclusive scan over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned long long excl = incl - lsum;
+    const bool mine = target >= excl && target < incl;
+    const unsigned int ball = __ballot_sync(0xffffffffu, mine);
+    if (ball == 0u) {  // rank beyond the population (cannot happen for valid ranks)
+      if (lane == 0) { new_prefix[w] = s->prefix[w]; new_rank[w] = target; }
+    } else if (lane == (__ffs(ball) - 1)) {
+      unsigned long long cum = excl;
+      int b = 0;
+      for (; b < per; ++b) {
+        const unsigned long long c = hh[lane * per + b];
+        if (target < cum + c) break;
+        cum += c;
+      }
+      new_prefix[w] = s->prefix[w] | ((uint32_t)(lane * per + b) << shift);
+      new_rank[w] = target - cum;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s->prefix[0] = new_prefix[0]; s->prefix[1] = new_prefix[1];
+    s->rank[0] = new_rank[0]; s->rank[1] = new_rank[1];
+    s->mask |= ((uint32_t)(nb - 1)) << shift;
+    if (pass == NSVGD_SELECT_PASSES - 1) {
+      s->value[0] = s->is_zero[0] ? 0.f : __uint_as_float(s->prefix[0]);
+      s->value[1] = s->is_zero[1] ? 0.f : __uint_as_float(s->prefix[1]);
+      s->done = 1;
+    }
+  }
+}
+
+__global__ void select_finish_kernel(const SelectState* s, float* h_dev) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float h;
+    if (s->nan_flag) {
+      h = __uint_as_float(0x7fc00000u);
+    } else {
+      const float med = __fmul_rn(__fadd_rn(s->value[0], s->value[1]), 0.5f);   // np.median midpoint rule
+      h = __fsqrt_rn(__fdiv_rn(__fmul_rn(0.5f, med), s->log_np1));             // kernels.py:171
+    }
+    h_dev[0] = h;
+  }
+}
+
+}  // namespace nsvgd
+
+using namespace nsvgd;
+
+static void median_ranks(int64_t n, int mode, long long* r_lo, long long* r_hi) {
+  // SURVEY.md Appendix B; mirrors oracle/svgd_oracle.py::median_ranks
+  const long long P = (long long)n * (n - 1) / 2;
+  if (mode == NSVGD_MEDIAN_OFFDIAG) {
+    *r_lo = (P - 1) / 2; *r_hi = P / 2;
+    return;
+  }
+  const long long N = (long long)n * n;
+  auto f = [&](long long r) -> long long { return r < n ? -1 : (r - n) / 2; };
+  if (N % 2 == 0) { *r_lo = f(N / 2 - 1); *r_hi = f(N / 2); }
+  else { *r_lo = *r_hi = f((N - 1) / 2); }
+}
+
+extern "C" int nsvgd_median_prepare(void* stream, const float* X, int64_t n, int64_t d, int64_t ldx, int mode,
+                                    float* Z, int64_t* dz_out, float* w_last_out, void* state_dev) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NSVGD_REQUIRE(X && state_dev && dz_out && w_last_out, NSVGD_ERR_INVALID, "median_prepare: null pointer");
+  NSVGD_REQUIRE(n >= 2 && d >= 1 && ldx >= d, NSVGD_ERR_INVALID, "median_prepare: need n >= 2, d >= 1, ldx >= d (n=%lld d=%lld)", (long long)n, (long long)d);
+  NSVGD_REQUIRE(mode >= 0 && mode <= 2, NSVGD_ERR_INVALID, "median_prepare: bad mode %d", mode);
+  long long r_lo, r_hi;
+  median_ranks(n, mode, &r_lo, &r_hi);
+  const float log_np1 = (float)log((double)(n + 1));
+  select_init_kernel<<<1, 32, 0, st>>>((SelectState*)state_dev, r_lo, r_hi, log_np1);
+  NSVGD_LAUNCH_CHECK();
+  if (mode == NSVGD_MEDIAN_LITERAL) {
+    NSVGD_REQUIRE(Z, NSVGD_ERR_INVALID, "median_prepare: literal mode needs a Z buffer");
+    const int64_t dz = n > d ? d : n - 1;
+    *dz_out = dz;
+    *w_last_out = n > d ? (float)(n - d) : 1.f;
+    const int64_t total = n * dz;
+    literal_z_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256), 4096), 256, 0, st>>>(X, n, d, ldx, Z, dz);
+    NSVGD_LAUNCH_CHECK();
+  } else {
+    *dz_out = d;
+    *w_last_out = 1.f;
+  }
+  return NSVGD_OK;
+}
+
+extern "C" int nsvgd_median_hist_pass(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last,
+                                      int64_t tile_row_start, int64_t tile_row_stride, const void* state_dev, int pass,
+                                      uint64_t* hist_dev) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NSVGD_REQUIRE(Z && state_dev && hist_dev, NSVGD_ERR_INVALID, "median_hist_pass: null pointer");
+  NSVGD_REQUIRE(pass >= 0 && pass < NSVGD_SELECT_PASSES, NSVGD_ERR_INVALID, "median_hist_pass: bad pass %d", pass);
+  NSVGD_REQUIRE(tile_row_stride >= 1 && tile_row_start >= 0, NSVGD_ERR_INVALID, "median_hist_pass: bad tile row partition");
+  NSVGD_CUDA(cudaMemsetAsync(hist_dev, 0, sizeof(uint64_t) * 2 * NSVGD_SELECT_BINS, st));
+  PairArgs a{};
+  a.A = Z; a.na = n; a.lda = ldz; a.B = Z; a.nb = n; a.ldb = ldz; a.d = dz; a.w_last = w_last;
+  a.symmetric = 1; a.tile_row_start = tile_row_start; a.tile_row_stride = tile_row_stride;
+  a.state = (const SelectState*)state_dev; a.pass = pass; a.hist = (unsigned long long*)hist_dev;
+  dim3 g = tile_grid(n, n, tile_row_start, tile_row_stride);
+  NSVGD_REQUIRE(g.y <= 65535, NSVGD_ERR_INVALID, "median_hist_pass: too many row tiles (%u)", g.y);
+  if (g.y > 0) {
+    prof_begin(1, st);
+    pair_tile_kernel<MODE_HIST><<<g, 256, 0, st>>>(a);
+    prof_end(1, st);
+    NSVGD_LAUNCH_CHECK();
+  }
+  return NSVGD_OK;
+}
+
+extern "C" int nsvgd_median_advance(void* stream, void* state_dev, const uint64_t* hist_dev, int pass) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NSVGD_REQUIRE(state_dev && hist_dev, NSVGD_ERR_INVALID, "median_advance: null pointer");
+  NSVGD_REQUIRE(pass >= 0 && pass < NSVGD_SELECT_PASSES, NSVGD_ERR_INVALID, "median_advance: bad pass %d", pass);
+  select_advance_kernel<<<1, 64, 0, st>>>((SelectState*)state_dev, (const unsigned long long*)hist_dev, pass);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
+extern "C" int nsvgd_median_finish(void* stream, const void* state_dev, int64_t n, float* h_dev) {
+  (void)n;
+  cudaStream_t st = (cudaStream_t)stream;
+  NSVGD_REQUIRE(state_dev && h_dev, NSVGD_ERR_INVALID, "median_finish: null pointer");
+  select_finish_kernel<<<1, 32, 0, st>>>((const SelectState*)state_dev, h_dev);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
+static size_t median_ws_layout(int64_t n, int64_t d, int mode, WsCarver& w, void** state, uint64_t** hist, float** Z) {
+  *state = w.take<char>(NSVGD_SELECT_STATE_BYTES);
+  *hist = w.take<uint64_t>(2 * NSVGD_SELECT_BINS);
+  *Z = nullptr;
+  if (mode == NSVGD_MEDIAN_LITERAL) {
+    const int64_t dz = n > d ? d : n - 1;
+    *Z = w.take<float>((size_t)(n * dz));
+  }
+  return w.off;
+}
+
+namespace nsvgd {
+size_t median_workspace(int64_t n, int64_t d) {
+  WsCarver w(nullptr, 0, true);
+  void* s; uint64_t* h; float* Z;
+  return median_ws_layout(n, d, NSVGD_MEDIAN_LITERAL, w, &s, &h, &Z) + 256;
+}
+}  // namespace nsvgd
+
+extern "C" int nsvgd_median_h_f32(void* stream, const float* X, int64_t n, int64_t d, int64_t ldx, int mode,
+                                  float* h_dev, void* ws, size_t ws_bytes) {
+  NSVGD_REQUIRE(X && h_dev && ws, NSVGD_ERR_INVALID, "median_h: null pointer");
+  NSVGD_REQUIRE(n >= 2 && d >= 1 && ldx >= d, NSVGD_ERR_INVALID, "median_h: need n >= 2, d >= 1, ldx >= d (n=%lld d=%lld)", (long long)n, (long long)d);
+  NSVGD_REQUIRE(mode >= 0 && mode <= 2, NSVGD_ERR_INVALID, "median_h: bad mode %d", mode);
+  WsCarver w(ws, ws_bytes);
+  void* state; uint64_t* hist; float* Z;
+  median_ws_layout(n, d, mode, w, &state, &hist, &Z);
+  NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "median_h: workspace too small (%zu < %zu)", ws_bytes, w.off);
+  int64_t dz; float w_last;
+  prof_begin(3, (cudaStream_t)stream);
+  NSVGD_PROPAGATE(nsvgd_median_prepare(stream, X, n, d, ldx, mode, Z, &dz, &w_last, state));
+  const float* P = mode == NSVGD_MEDIAN_LITERAL ? Z : X;
+  const int64_t ldp = mode == NSVGD_MEDIAN_LITERAL ? dz : ldx;
+  for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
+    NSVGD_PROPAGATE(nsvgd_median_hist_pass(stream, P, n, dz, ldp, w_last, 0, 1, state, pass, hist));
+    NSVGD_PROPAGATE(nsvgd_median_advance(stream, state, hist, pass));
+  }
+  const int rc = nsvgd_median_finish(stream, state, n, h_dev);
+  prof_end(3, (cudaStream_t)stream);
+  return rc;
+}
+
+extern "C" int nsvgd_ksum_f32(void* stream, const float* A, int64_t na, int64_t lda, const float* B, int64_t nb,
+                              int64_t ldb, int64_t d, float h, int symmetric, double* out_dev, void* ws, size_t ws_bytes) {
+  NSVGD_REQUIRE(A && B && out_dev, NSVGD_ERR_INVALID, "ksum: null pointer");
+  NSVGD_REQUIRE(na >= 1 && nb >= 1 && d >= 1 && lda >= d && ldb >= d, NSVGD_ERR_INVALID, "ksum: bad shape");
+  NSVGD_REQUIRE(!symmetric || (A == B && na == nb), NSVGD_ERR_INVALID, "ksum: symmetric needs A == B");
+  return launch_ksum((cudaStream_t)stream, A, na, lda, B, nb, ldb, d, nullptr, h, symmetric, out_dev,
+                     symmetric ? 1.0 : 1.0, 0, ws, ws_bytes, false, nullptr);
+}
+
+// ------------------------------------------------------------------ KSD (stein.py:273-349)
+extern "C" int nsvgd_ksd_f32(void* stream, const float* X, const float* Sx, int64_t n, int64_t ldx, const float* Y,
+                             const float* Sy, int64_t m, int64_t ldy, int64_t d, const float* h_dev, int variant,
+                             double* out_dev, void* ws, size_t ws_bytes) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NSVGD_REQUIRE(X && Sx && h_dev && out_dev, NSVGD_ERR_INVALID, "ksd: null pointer");
+  NSVGD_REQUIRE(variant >= 0 && variant <= 2, NSVGD_ERR_INVALID, "ksd: bad variant %d", variant);
+  NSVGD_REQUIRE(n >= 1 && d >= 1 && ldx >= d, NSVGD_ERR_INVALID, "ksd: bad shape");
+  const bool rect = variant == NSVGD_KSD_RECT;
+  if (rect) {
+    NSVGD_REQUIRE(Y && Sy && m >= 1 && ldy >= d, NSVGD_ERR_INVALID, "ksd: rectangular variant needs Y, Sy");
+  } else {
+    NSVGD_REQUIRE(n >= 2 || variant == NSVGD_KSD_V, NSVGD_ERR_INVALID, "ksd: U-statistic needs n >= 2");
+    Y = X; Sy = Sx; m = n; ldy = ldx;
+  }
+  dim3 g = tile_grid(n, m, 0, 1);
+  const int64_t nblocks = (int64_t)g.x * g.y;
+  WsCarver w(ws, ws_bytes);
+  double* partials = w.take<double>((size_t)nblocks);
+  NSVGD_REQUIRE(ws && w.ok(), NSVGD_ERR_WORKSPACE, "ksd: workspace too small (%zu < %zu)", ws_bytes, w.off);
+  NSVGD_REQUIRE(g.y <= 65535, NSVGD_ERR_INVALID, "ksd: too many row tiles");
+  PairArgs a{};
+  a.A = X; a.na = n; a.lda = ldx; a.B = Y; a.nb = m; a.ldb = ldy; a.SA = Sx; a.SB = Sy; a.d = d;
+  a.symmetric = rect ? 0 : 1; a.tile_row_start = 0; a.tile_row_stride = 1; a.h_dev = h_dev;
+  a.partials = partials; a.diag_weight = variant == NSVGD_KSD_V ? 1.f : 0.f;
+  if (!rect) {
+    zero_partials_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nblocks, 256), 1024), 256, 0, st>>>(partials, nblocks);
+    NSVGD_LAUNCH_CHECK();
+  }
+  pair_tile_kernel<MODE_KSD><<<g, 256, 0, st>>>(a);
+  NSVGD_LAUNCH_CHECK();
+  double scale;
+  if (variant == NSVGD_KSD_RECT) scale = 1.0 / ((double)n * (double)m);
+  else if (variant == NSVGD_KSD_U) scale = 1.0 / ((double)n * (double)(n - 1));
+  else scale = 1.0 / ((double)n * (double)n);
+  reduce_partials_kernel<<<1, 1024, 0, st>>>(partials, nblocks, scale, 0, out_dev);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
+// ------------------------------------------------------------------ MMD (metrics.py:88-127)
+namespace nsvgd {
+__global__ void defunnelize_kernel(const float* __restrict__ Z, int64_t n, int64_t d, int64_t ldz, float* __restrict__ out) {
+  // kernels.py:112-116: [x * exp(-y/2), y/3]
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * d; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / d, c = t % d;
+    const float y = Z[i * ldz + d - 1];
+    out[t] = c == d - 1 ? y / 3.f : Z[i * ldz + c] * expf(-0.5f * y);
+  }
+}
+}  // namespace nsvgd
+
+extern "C" int nsvgd_mmd_f32(void* stream, const float* X, int64_t n, int64_t ldx, const float* Y, int64_t m,
+                             int64_t ldy, int64_t d, float h, int funnel, double* out_dev, void* ws, size_t ws_bytes) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NSVGD_REQUIRE(X && Y && out_dev && ws, NSVGD_ERR_INVALID, "mmd: null pointer");
+  NSVGD_REQUIRE(n >= 2 && m >= 2 && d >= 1 && ldx >= d && ldy >= d, NSVGD_ERR_INVALID, "mmd: need n, m >= 2");
+  NSVGD_REQUIRE(h > 0.f, NSVGD_ERR_INVALID, "mmd: bandwidth must be positive");
+  WsCarver w(ws, ws_bytes);
+  const float* A = X; const float* B = Y; int64_t lda = ldx, ldb = ldy;
+  if (funnel) {
+    float* Xf = w.take<float>((size_t)(n * d));
+    float* Yf = w.take<float>((size_t)(m * d));
+    NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "mmd: workspace too small");
+    defunnelize_kernel<<<(unsigned)std::min<int64_t>(ceil_div(n * d, 256), 2048), 256, 0, st>>>(X, n, d, ldx, Xf);
+    NSVGD_LAUNCH_CHECK();
+    defunnelize_kernel<<<(unsigned)std::min<int64_t>(ceil_div(m * d, 256), 2048), 256, 0, st>>>(Y, m, d, ldy, Yf);
+    NSVGD_LAUNCH_CHECK();
+    A = Xf; B = Yf; lda = d; ldb = d;
+  }
+  w.off = (w.off + 255) / 256 * 256;
+  char* sub = (char*)ws + w.off;
+  NSVGD_REQUIRE(w.off <= ws_bytes, NSVGD_ERR_WORKSPACE, "mmd: workspace too small");
+  const size_t sub_bytes = ws_bytes - w.off;
+  // mean offdiag Kxx = 2 sum_{i<j} k / (n(n-1))   (k(x,x) = 1 is excluded analytically)
+  NSVGD_PROPAGATE(launch_ksum(st, A, n, lda, A, n, lda, d, nullptr, h, 1, out_dev, 1.0 / ((double)n * (n - 1)), 0, sub, sub_bytes, false, nullptr));
+  NSVGD_PROPAGATE(launch_ksum(st, B, m, ldb, B, m, ldb, d, nullptr, h, 1, out_dev, 1.0 / ((double)m * (m - 1)), 1, sub, sub_bytes, false, nullptr));
+  NSVGD_PROPAGATE(launch_ksum(st, A, n, lda, B, m, ldb, d, nullptr, h, 0, out_dev, -2.0 / ((double)n * m), 1, sub, sub_bytes, false, nullptr));
+  return NSVGD_OK;
+}

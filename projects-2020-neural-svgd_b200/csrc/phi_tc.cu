@@ -1,0 +1,690 @@
+// phi_tc.cu — fused flash-style phi* on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), d <= 128.
+// [stein.py:180-222 + kernels.py:52-65; closed forms in SURVEY.md 8a]
+//
+// Per CTA: 128 query rows x a range of 64-wide tiles of inducing particles j.  For every tile
+//   (1) Gram   G = Qc Xc^T                 tcgen05.mma SS, M=128 N=64, operands TMA-staged (SWIZZLE_128B)
+//   (2) k_ij = exp2(2c g - c|q_i|^2 - c|x_j|^2), c = log2(e)/(2h^2), in registers: one thread per
+//       row (tcgen05.ld 32x32b), MUFU.EX2; rowsum, sum k c_j, sum k r2 ride along in registers
+//   (3) O += P [S | Xc]                     tcgen05.mma TS (P from TMEM), M=128 N=2*DP, accumulators in TMEM
+// The n x n kernel matrix is never materialised.  fp32 accuracy on bf16 tensor cores comes from a
+// 2-piece split of every operand (x = b0 + b1, |x - b0 - b1| <= 2^-18 |x|) and 3 MMA passes
+// (b0*b0' + b0*b1' + b1*b0'), the same error-compensation scheme as 3xTF32 at half the shared-memory
+// and TMEM footprint and twice the MMA rate (DESIGN.md "why bf16 pieces").
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
+// warps 2-5 = pair-function / epilogue warps (TMEM lane quarter = warp_idx % 4).
+// TMEM map (512 cols): O [0,256) | G0 [256,320) | G1 [320,384) | P(0) [384,448) | P(1) [448,512)
+#include <algorithm>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace nsvgd {
+
+using namespace tc;
+
+// ---------------------------------------------------------------------------- host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !p) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                      uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  NSVGD_REQUIRE(fn, NSVGD_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NSVGD_REQUIRE(r == CUDA_SUCCESS, NSVGD_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return NSVGD_OK;
+}
+
+// ---------------------------------------------------------------------------- prep (K0)
+// Per 64-row block: centre, split into bf16 pieces, row norms, c_j = s_j . xc_j, and the
+// transposed [S | Xc] pieces (K-major B operand of the second GEMM) via a shared-memory transpose.
+//   Xb0/Xb1 : [rows_pad x DP] bf16        Vt0/Vt1 : [2*DP x rows_pad] bf16 (rows 0..DP-1 = S^T, DP.. = Xc^T)
+//   xn      : |xc_j|^2 (1e30 for padded rows, which zeroes k)      cv : s_j . xc_j
+__global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ X, const float* __restrict__ S,
+                                                      int64_t n, int64_t d, int64_t ldx, int64_t rows_pad, int dp,
+                                                      const float* __restrict__ mu,
+                                                      __nv_bfloat16* __restrict__ Xb0, __nv_bfloat16* __restrict__ Xb1,
+                                                      __nv_bfloat16* __restrict__ Vt0, __nv_bfloat16* __restrict__ Vt1,
+                                                      float* __restrict__ xn, float* __restrict__ cv) {
+  __shared__ float T[64][129];   // one half (S or Xc) of the block, fp32
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * 64;
+  for (int half = 0; half < 2; ++half) {      // 0: Xc (also writes Xb, xn, cv), 1: S
+    if (half == 1 && !Vt0) break;
+    __syncthreads();
+    for (int rr = w; rr < 64; rr += 8) {
+      const int64_t row = r0 + rr;
+      const bool rv = row < n;
+      float acc_n = 0.f, acc_c = 0.f;
+      for (int c = lane; c < dp; c += 32) {
+        float v = 0.f;
+        if (rv && c < d) {
+          if (half == 0) {
+            v = X[row * ldx + c] - mu[c];
+            acc_n = fmaf(v, v, acc_n);
+            if (S) acc_c = fmaf(S[row * ldx + c], v, acc_c);
+          } else {
+            v = S[row * ldx + c];
+          }
+        }
+        T[rr][c] = v;
+        if (half == 0) {
+          const __nv_bfloat16 b0 = __float2bfloat16_rn(v);
+          const __nv_bfloat16 b1 = __float2bfloat16_rn(v - __bfloat162float(b0));
+          Xb0[row * dp + c] = b0;
+          Xb1[row * dp + c] = b1;
+        }
+      }
+      if (half == 0) {
+        acc_n = warp_sum(acc_n); acc_c = warp_sum(acc_c);
+        if (lane == 0) {
+          xn[row] = rv ? acc_n : 1e30f;   // padded row: k underflows to 0, and 0 * finite stays 0
+          if (cv) cv[row] = rv ? acc_c : 0.f;
+        }
+      }
+    }
+    __syncthreads();
+    if (Vt0) {
+      // transposed write: warp handles one coordinate c at a time, lane -> rows (2 lane, 2 lane + 1)
+      const int64_t vrow0 = half == 0 ? dp : 0;   // Xc^T goes to rows [dp, 2dp), S^T to [0, dp)
+      for (int c = w; c < dp; c += 8) {
+        const float a = T[2 * lane][c], b = T[2 * lane + 1][c];
+        const uint32_t p0 = pack_bf16x2(a, b);
+        const uint32_t p1 = pack_bf16x2(a - bf16lo_to_float(p0), b - bf16hi_to_float(p0));
+        const int64_t off = (vrow0 + c) * rows_pad + r0 + 2 * lane;
+        *reinterpret_cast<uint32_t*>(&Vt0[off]) = p0;
+        *reinterpret_cast<uint32_t*>(&Vt1[off]) = p1;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- main kernel
+struct TcParams {
+  const float* xn; const float* cv; const float* qn;
+  const float* h_dev;
+  float* O; float* scal;          // [nsplit][m_pad][2*DP], [nsplit][m_pad][4]
+  int64_t m_pad;
+  int tiles_total, tiles_per_split;
+  uint32_t* err_flag;
+};
+
+constexpr int TC_BM = 128, TC_BN = 64;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TM_O = 0, TM_G = 256, TM_P = 384;
+
+template <int DP>
+struct TcSmem {
+  static constexpr int KH = DP / 64;                    // 64-column (128-byte) K slabs of the Gram operands
+  static constexpr int QSLAB = TC_BM * 128;             // 16 KB: 128 rows x 128 B
+  static constexpr int XSLAB = TC_BN * 128;             // 8 KB
+  static constexpr int VSLOT = 2 * DP * 128;            // [2DP rows x 64 j] bf16 = 32 KB (DP=128)
+  static constexpr int XSTAGES = 2;
+  static constexpr int VSLOTS = (DP == 128) ? 3 : 4;
+  static constexpr int Q_BYTES = 2 * KH * QSLAB;
+  static constexpr int X_STAGE_BYTES = 2 * KH * XSLAB;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_X = OFF_Q + Q_BYTES;
+  static constexpr int OFF_V = OFF_X + XSTAGES * X_STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_V + VSLOTS * VSLOT;
+  static constexpr int NBARS = 1 + 2 * XSTAGES + 2 * VSLOTS + 8 + 1;
+  static constexpr int TOTAL = OFF_BAR + NBARS * 8 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;         // slack for manual 1024-B alignment
+};
+
+template <int DP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ CUtensorMap tmQ1,
+              const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
+              const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmV1,
+              const TcParams p) {
+  using L = TcSmem<DP>;
+  constexpr int KH = L::KH;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem + L::OFF_Q;
+  uint8_t* sX = smem + L::OFF_X;
+  uint8_t* sV = smem + L::OFF_V;
+  uint64_t* bars = (uint64_t*)(smem + L::OFF_BAR);
+  uint64_t* q_full = bars;
+  uint64_t* x_full = q_full + 1;
+  uint64_t* x_empty = x_full + L::XSTAGES;
+  uint64_t* v_full = x_empty + L::XSTAGES;
+  uint64_t* v_empty = v_full + L::VSLOTS;
+  uint64_t* g_full = v_empty + L::VSLOTS;
+  uint64_t* g_empty = g_full + 2;
+  uint64_t* p_full = g_empty + 2;
+  uint64_t* p_empty = p_full + 2;
+  uint64_t* o_full = p_empty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(o_full + 1);
+  volatile uint32_t* abort_s = tmem_slot + 1;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM;
+  const int split = blockIdx.y;
+  const int t_begin = split * p.tiles_per_split;
+  const int t_end = min(t_begin + p.tiles_per_split, p.tiles_total);
+  const int T = t_end - t_begin;
+  Watch watch{abort_s, p.err_flag};
+
+  if (threadIdx.x == 0) {
+    *abort_s = (*(volatile uint32_t*)p.err_flag) ? 1u : 0u;
+    mbar_init(q_full, 1);
+    for (int i = 0; i < L::XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < L::VSLOTS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 128);
+      mbar_init(&p_full[i], 128); mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ0); tma_prefetch_desc(&tmQ1); tma_prefetch_desc(&tmX0);
+    tma_prefetch_desc(&tmX1); tma_prefetch_desc(&tmV0); tma_prefetch_desc(&tmV1);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0 && T > 0) {
+      mbar_arrive_expect_tx(q_full, L::Q_BYTES);
+      for (int kh = 0; kh < KH; ++kh) {
+        tma_load_2d(sQ + (0 * KH + kh) * L::QSLAB, &tmQ0, q_full, kh * 64, m0);
+        tma_load_2d(sQ + (1 * KH + kh) * L::QSLAB, &tmQ1, q_full, kh * 64, m0);
+      }
+      int vcount = 0;
+      auto load_x = [&](int t) {
+        const int st = t % L::XSTAGES, u = t / L::XSTAGES;
+        mbar_wait(&x_empty[st], (u & 1) ^ 1, watch, 0x100 + st);
+        mbar_arrive_expect_tx(&x_full[st], L::X_STAGE_BYTES);
+        uint8_t* dst = sX + st * L::X_STAGE_BYTES;
+        const int j0 = (t_begin + t) * TC_BN;
+        for (int kh = 0; kh < KH; ++kh) {
+          tma_load_2d(dst + (0 * KH + kh) * L::XSLAB, &tmX0, &x_full[st], kh * 64, j0);
+          tma_load_2d(dst + (1 * KH + kh) * L::XSLAB, &tmX1, &x_full[st], kh * 64, j0);
+        }
+      };
+      auto load_v = [&](int t) {
+        const int j0 = (t_begin + t) * TC_BN;
+        for (int piece = 0; piece < 2; ++piece) {
+          const int sl = vcount % L::VSLOTS, u = vcount / L::VSLOTS;
+          ++vcount;
+          mbar_wait(&v_empty[sl], (u & 1) ^ 1, watch, 0x200 + sl);
+          mbar_arrive_expect_tx(&v_full[sl], L::VSLOT);
+          tma_load_2d(sV + sl * L::VSLOT, piece == 0 ? &tmV0 : &tmV1, &v_full[sl], j0, 0);
+        }
+      };
+      // same order as the MMA warp consumes: X(0), X(1), V(0), X(2), V(1), ...
+      load_x(0);
+      for (int t = 1; t < T; ++t) { load_x(t); load_v(t - 1); }
+      load_v(T - 1);
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0 && T > 0) {
+      constexpr uint32_t idesc_g = umma_idesc_bf16(TC_BM, TC_BN);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(TC_BM, 2 * DP);
+      const uint32_t sQ_a = smem_u32(sQ), sX_a = smem_u32(sX), sV_a = smem_u32(sV);
+      int vcount = 0;
+      mbar_wait(q_full, 0, watch, 0x300);
+      tc_fence_after();
+      auto issue_gram = [&](int t) {
+        const int b = t & 1, ub = t >> 1;
+        const int st = t % L::XSTAGES, us = t / L::XSTAGES;
+        mbar_wait(&g_empty[b], (ub & 1) ^ 1, watch, 0x310 + b);
+        mbar_wait(&x_full[st], us & 1, watch, 0x320 + st);
+        tc_fence_after();
+        const uint32_t d_tm = tmem + TM_G + b * TC_BN;
+        const uint32_t xs = sX_a + st * L::X_STAGE_BYTES;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const int pa = pass == 2 ? 1 : 0;     // Q piece: b0, b0, b1
+          const int pb = pass == 1 ? 1 : 0;     // X piece: b0, b1, b0
+#pragma unroll
+          for (int kh = 0; kh < KH; ++kh) {
+            const uint64_t ad = umma_desc_sw128(sQ_a + (pa * KH + kh) * L::QSLAB);
+            const uint64_t bd = umma_desc_sw128(xs + (pb * KH + kh) * L::XSLAB);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_ss(d_tm, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 32), idesc_g, acc);
+              acc = 1;
+            }
+          }
+        }
+        umma_commit(&x_empty[st]);
+        umma_commit(&g_full[b]);
+      };
+      auto issue_pv = [&](int u) {
+        const int pb = u & 1, up = u >> 1;
+        mbar_wait(&p_full[pb], up & 1, watch, 0x330 + pb);
+        tc_fence_after();
+        const uint32_t p0 = tmem + TM_P + pb * 64, p1 = p0 + 32;
+        {
+          const int sl = vcount % L::VSLOTS, uv = vcount / L::VSLOTS; ++vcount;
+          mbar_wait(&v_full[sl], uv & 1, watch, 0x340 + sl);
+          tc_fence_after();
+          const uint64_t bd = umma_desc_sw128(sV_a + sl * L::VSLOT);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ts(tmem + TM_O, p0 + ks * 8, umma_desc_advance(bd, ks * 32), idesc_pv, (u > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ts(tmem + TM_O, p1 + ks * 8, umma_desc_advance(bd, ks * 32), idesc_pv, 1u);
+          umma_commit(&v_empty[sl]);
+        }
+        {
+          const int sl = vcount % L::VSLOTS, uv = vcount / L::VSLOTS; ++vcount;
+          mbar_wait(&v_full[sl], uv & 1, watch, 0x350 + sl);
+          tc_fence_after();
+          const uint64_t bd = umma_desc_sw128(sV_a + sl * L::VSLOT);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ts(tmem + TM_O, p0 + ks * 8, umma_desc_advance(bd, ks * 32), idesc_pv, 1u);
+          umma_commit(&v_empty[sl]);
+        }
+        umma_commit(&p_empty[pb]);
+      };
+      issue_gram(0);
+      for (int t = 1; t < T; ++t) { issue_gram(t); issue_pv(t - 1); }
+      issue_pv(T - 1);
+      umma_commit(o_full);
+    }
+  } else {
+    // =============================== pair-function warps (one thread per query row) ===============
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const float h = *p.h_dev;
+    const float cs = NSVGD_HALF_LOG2E / (h * h);          // k = exp2(-cs r2)
+    const float two_cs = 2.f * cs, neg_cs = -cs;
+    const float ai = neg_cs * p.qn[m0 + row_in_tile];
+    float rowsum = 0.f, kc = 0.f, ke = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1, ub = t >> 1;
+      const int j0 = (t_begin + t) * TC_BN;
+      const float4* xn4 = reinterpret_cast<const float4*>(p.xn + j0);
+      const float4* cv4 = reinterpret_cast<const float4*>(p.cv + j0);
+      mbar_wait(&g_full[b], ub & 1, watch, 0x400 + b);
+      __syncwarp();
+      tc_fence_after();
+      uint32_t g[64];
+      tmem_ld32(tmem + lane_addr + TM_G + b * TC_BN, g);
+      tmem_ld32(tmem + lane_addr + TM_G + b * TC_BN + 32, g + 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&g_empty[b]);
+      uint32_t pk0[32], pk1[32];
+#pragma unroll
+      for (int q4 = 0; q4 < 16; ++q4) {
+        const float4 xv = __ldg(&xn4[q4]);
+        const float4 cvv = __ldg(&cv4[q4]);
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+        const float cc[4] = {cvv.x, cvv.y, cvv.z, cvv.w};
+        float k[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float ex = fmaf(__uint_as_float(g[q4 * 4 + e]), two_cs, ai);
+          ex = fmaf(xs[e], neg_cs, ex);
+          k[e] = ex2_approx(ex);
+          rowsum += k[e];
+          kc = fmaf(k[e], cc[e], kc);
+          ke = fmaf(k[e], ex, ke);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e += 2) {
+          const uint32_t a0 = pack_bf16x2(k[e], k[e + 1]);
+          const uint32_t a1 = pack_bf16x2(k[e] - bf16lo_to_float(a0), k[e + 1] - bf16hi_to_float(a0));
+          pk0[q4 * 2 + (e >> 1)] = a0;
+          pk1[q4 * 2 + (e >> 1)] = a1;
+        }
+      }
+      mbar_wait(&p_empty[b], (ub & 1) ^ 1, watch, 0x410 + b);
+      __syncwarp();
+      tc_fence_after();
+      tmem_st32(tmem + lane_addr + TM_P + b * 64, pk0);
+      tmem_st32(tmem + lane_addr + TM_P + b * 64 + 32, pk1);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[b]);
+    }
+    // ---- epilogue: O (TMEM) -> workspace, one row per thread
+    if (T > 0) {
+      mbar_wait(o_full, 0, watch, 0x500);
+      __syncwarp();
+      tc_fence_after();
+      const int64_t row = (int64_t)m0 + row_in_tile;
+      float* orow = p.O + ((int64_t)split * p.m_pad + row) * (2 * DP);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 2 * DP; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_addr + TM_O + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(orow + c0 + q * 4) =
+              make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
+                          __uint_as_float(v[q * 4 + 3]));
+      }
+      // b = sum k r2 = -sum k e / cs
+      *reinterpret_cast<float4*>(p.scal + ((int64_t)split * p.m_pad + row) * 4) =
+          make_float4(rowsum, kc, -ke / cs, 0.f);
+      tc_fence_before();
+    } else {
+      // empty j-range (tail split): contribute zeros
+      const int64_t row = (int64_t)m0 + row_in_tile;
+      float* orow = p.O + ((int64_t)split * p.m_pad + row) * (2 * DP);
+      for (int c = 0; c < 2 * DP; c += 4) *reinterpret_cast<float4*>(orow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(p.scal + ((int64_t)split * p.m_pad + row) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------- host driver
+struct TcPlan {
+  int dp; int64_t n_pad, m_pad; int nsplit, tiles_total, tiles_per_split; bool q_is_x;
+};
+
+static TcPlan make_plan(const PhiArgs& a) {
+  TcPlan pl{};
+  pl.dp = a.d <= 64 ? 64 : 128;
+  pl.n_pad = round_up(a.n, 128);
+  pl.m_pad = round_up(a.m, 128);
+  pl.q_is_x = (a.Q == a.X && a.m == a.n && a.ldq == a.ldx);
+  pl.tiles_total = (int)(pl.n_pad / TC_BN);
+  // split the j range so the grid covers the SMs in whole waves (row blocks x splits CTAs, 1 CTA/SM)
+  const int sms = device_sm_count();
+  const int64_t row_blocks = pl.m_pad / TC_BM;
+  int best = 1; double best_eff = 0.0;
+  for (int s = 1; s <= 8; ++s) {
+    if (pl.tiles_total / s < 8 && s > 1) break;
+    const int64_t ctas = row_blocks * s;
+    const double eff = (double)ctas / (double)(ceil_div(ctas, sms) * sms);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+  }
+  pl.nsplit = best;
+  pl.tiles_per_split = (int)ceil_div(pl.tiles_total, pl.nsplit);
+  return pl;
+}
+
+template <int DP>
+static int launch_tc(cudaStream_t st, const TcPlan& pl, const CUtensorMap* maps, const TcParams& prm) {
+  using L = TcSmem<DP>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NSVGD_CUDA(cudaFuncSetAttribute(phi_tc_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(pl.m_pad / TC_BM), (unsigned)pl.nsplit);
+  prof_begin(0, st);
+  phi_tc_kernel<DP><<<grid, TC_THREADS, L::DYN_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], prm);
+  prof_end(0, st);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
+int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dry, size_t* need) {
+  if (!dry) NSVGD_REQUIRE(a.d <= 128, NSVGD_ERR_UNSUPPORTED, "phi_tc: tensor-core path supports d <= 128 (d=%lld)", (long long)a.d);
+  const TcPlan pl = make_plan(a);
+  const int dp = pl.dp;
+  WsCarver w(ws, ws_bytes, dry);
+  float* mu = w.take<float>((size_t)a.d);
+  double* mpart = w.take<double>((size_t)colmean_partials(a.n, a.d));
+  __nv_bfloat16* Xb0 = w.take<__nv_bfloat16>((size_t)(pl.n_pad * dp), 1024);
+  __nv_bfloat16* Xb1 = w.take<__nv_bfloat16>((size_t)(pl.n_pad * dp), 1024);
+  __nv_bfloat16* Vt0 = w.take<__nv_bfloat16>((size_t)(2 * dp * pl.n_pad), 1024);
+  __nv_bfloat16* Vt1 = w.take<__nv_bfloat16>((size_t)(2 * dp * pl.n_pad), 1024);
+  float* xn = w.take<float>((size_t)pl.n_pad);
+  float* cv = w.take<float>((size_t)pl.n_pad);
+  __nv_bfloat16 *Qb0 = Xb0, *Qb1 = Xb1;
+  float* qn = xn;
+  if (!pl.q_is_x || dry) {   // dry run sizes for the rectangular worst case
+    Qb0 = w.take<__nv_bfloat16>((size_t)(pl.m_pad * dp), 1024);
+    Qb1 = w.take<__nv_bfloat16>((size_t)(pl.m_pad * dp), 1024);
+    qn = w.take<float>((size_t)pl.m_pad);
+  }
+  float* O = w.take<float>((size_t)pl.nsplit * pl.m_pad * 2 * dp, 1024);
+  float* scal = w.take<float>((size_t)pl.nsplit * pl.m_pad * 4);
+  uint32_t* err_flag = w.take<uint32_t>(4);
+  double* partials = w.take<double>((size_t)(2 * epilogue_blocks(a.m)));
+  if (need) *need = w.off;
+  if (dry) return NSVGD_OK;
+  NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "phi_tc: workspace too small (%zu < %zu)", ws_bytes, w.off);
+
+  NSVGD_PROPAGATE(launch_colmean(st, a.X, a.n, a.d, a.ldx, mpart, mu));
+  NSVGD_CUDA(cudaMemsetAsync(err_flag, 0, 16, st));
+  tc_prep_kernel<<<(unsigned)(pl.n_pad / 64), 256, 0, st>>>(a.X, a.S, a.n, a.d, a.ldx, pl.n_pad, dp, mu, Xb0, Xb1, Vt0,
+                                                            Vt1, xn, cv);
+  NSVGD_LAUNCH_CHECK();
+  if (!pl.q_is_x) {
+    tc_prep_kernel<<<(unsigned)(pl.m_pad / 64), 256, 0, st>>>(a.Q, nullptr, a.m, a.d, a.ldq, pl.m_pad, dp, mu, Qb0, Qb1,
+                                                              nullptr, nullptr, qn, nullptr);
+    NSVGD_LAUNCH_CHECK();
+  }
+  CUtensorMap maps[6];
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[0], Qb0, dp, pl.m_pad, (uint64_t)dp * 2, 64, TC_BM));
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[1], Qb1, dp, pl.m_pad, (uint64_t)dp * 2, 64, TC_BM));
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[2], Xb0, dp, pl.n_pad, (uint64_t)dp * 2, 64, TC_BN));
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[3], Xb1, dp, pl.n_pad, (uint64_t)dp * 2, 64, TC_BN));
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[4], Vt0, pl.n_pad, 2 * dp, (uint64_t)pl.n_pad * 2, TC_BN, 2 * dp));
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[5], Vt1, pl.n_pad, 2 * dp, (uint64_t)pl.n_pad * 2, TC_BN, 2 * dp));
+  TcParams prm{};
+  prm.xn = xn; prm.cv = cv; prm.qn = qn; prm.h_dev = a.h_dev; prm.O = O; prm.scal = scal; prm.m_pad = pl.m_pad;
+  prm.tiles_total = pl.tiles_total; prm.tiles_per_split = pl.tiles_per_split; prm.err_flag = err_flag;
+  if (dp == 64) NSVGD_PROPAGATE(launch_tc<64>(st, pl, maps, prm));
+  else NSVGD_PROPAGATE(launch_tc<128>(st, pl, maps, prm));
+
+  EpilogueArgs e{};
+  e.form = 1; e.O = O; e.scal = scal; e.nsplit = pl.nsplit; e.m_pad = pl.m_pad; e.ldo = 2 * dp; e.dpad = dp; e.mu = mu;
+  e.Q = a.Q; e.ldq = a.ldq; e.Sq = a.Sq; e.m = a.m; e.n = a.n; e.d = a.d; e.h_dev = a.h_dev;
+  e.phi = a.phi; e.ldphi = a.ldphi; e.aux = a.aux; e.stats_dev = a.stats_dev; e.partials = partials;
+  return launch_epilogue(st, e);
+}
+
+// ---------------------------------------------------------------------------- bring-up probes
+// probe_gram: G[128 x 64] = bf16(A[128 x 128]) bf16(B[64 x 128])^T through TMA -> smem -> tcgen05.mma SS -> TMEM -> ld
+__global__ void __launch_bounds__(128) tc_probe_gram_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                            const __grid_constant__ CUtensorMap tmB, float* G,
+                                                            uint32_t* err_flag) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                 // 2 slabs x 16 KB
+  uint8_t* sB = smem + 32768;         // 2 slabs x 8 KB
+  uint64_t* bars = (uint64_t*)(smem + 49152);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2);
+  volatile uint32_t* abort_s = tmem_slot + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Watch watch{abort_s, err_flag};
+  if (threadIdx.x == 0) {
+    *abort_s = 0u;
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 64); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0 && lane == 0) {
+    mbar_arrive_expect_tx(&bars[0], 49152);
+    for (int kh = 0; kh < 2; ++kh) {
+      tma_load_2d(sA + kh * 16384, &tmA, &bars[0], kh * 64, 0);
+      tma_load_2d(sB + kh * 8192, &tmB, &bars[0], kh * 64, 0);
+    }
+    mbar_wait(&bars[0], 0, watch, 1);
+    tc_fence_after();
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+    uint32_t acc = 0;
+    for (int kh = 0; kh < 2; ++kh) {
+      const uint64_t ad = umma_desc_sw128(smem_u32(sA + kh * 16384));
+      const uint64_t bd = umma_desc_sw128(smem_u32(sB + kh * 8192));
+      for (int ks = 0; ks < 4; ++ks) {
+        umma_ss(tmem, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 32), idesc, acc);
+        acc = 1;
+      }
+    }
+    umma_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0, watch, 2);
+  __syncwarp();
+  tc_fence_after();
+  uint32_t v[64];
+  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  tmem_ld32(tmem + lane_addr, v);
+  tmem_ld32(tmem + lane_addr + 32, v + 32);
+  tmem_wait_ld();
+  const int row = warp * 32 + lane;
+  for (int c = 0; c < 64; ++c) G[row * 64 + c] = __uint_as_float(v[c]);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 64); }
+}
+
+// probe_pv: O[128 x 256] = bf16(P[128 x 64]) bf16(V[64 x 256]) with P stored to TMEM by the threads
+// (tcgen05.st, packed bf16 pairs) and consumed as the A operand of tcgen05.mma TS, N = 256.
+__global__ void __launch_bounds__(128) tc_probe_pv_kernel(const __grid_constant__ CUtensorMap tmV, const float* P,
+                                                          float* O, uint32_t* err_flag) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sV = smem;                 // 256 rows x 128 B = 32 KB
+  uint64_t* bars = (uint64_t*)(smem + 32768);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2);
+  volatile uint32_t* abort_s = tmem_slot + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Watch watch{abort_s, err_flag};
+  if (threadIdx.x == 0) {
+    *abort_s = 0u;
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  const int row = warp * 32 + lane;
+  if (warp == 0 && lane == 0) {
+    mbar_arrive_expect_tx(&bars[0], 32768);
+    tma_load_2d(sV, &tmV, &bars[0], 0, 0);
+  }
+  uint32_t pk[32];
+  for (int c = 0; c < 32; ++c) pk[c] = pack_bf16x2(P[row * 64 + 2 * c], P[row * 64 + 2 * c + 1]);
+  tmem_st32(tmem + lane_addr + 384, pk);
+  tmem_wait_st();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0 && lane == 0) {
+    mbar_wait(&bars[0], 0, watch, 1);
+    tc_fence_after();
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+    const uint64_t bd = umma_desc_sw128(smem_u32(sV));
+    for (int ks = 0; ks < 4; ++ks)
+      umma_ts(tmem, tmem + 384 + ks * 8, umma_desc_advance(bd, ks * 32), idesc, ks > 0 ? 1u : 0u);
+    umma_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0, watch, 2);
+  __syncwarp();
+  tc_fence_after();
+  for (int c0 = 0; c0 < 256; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem + lane_addr + c0, v);
+    tmem_wait_ld();
+    for (int c = 0; c < 32; ++c) O[row * 256 + c0 + c] = __uint_as_float(v[c]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int cols,
+                                   int transpose) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < rows * cols; t += gridDim.x * blockDim.x) {
+    const int r = t / cols, c = t % cols;
+    if (transpose) dst[c * rows + r] = __float2bfloat16_rn(src[t]);
+    else dst[t] = __float2bfloat16_rn(src[t]);
+  }
+}
+
+}  // namespace nsvgd
+
+using namespace nsvgd;
+
+extern "C" int nsvgd_tc_probe_gram(void* stream, const float* A, const float* B, float* G, void* ws, size_t ws_bytes) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NSVGD_REQUIRE(A && B && G && ws, NSVGD_ERR_INVALID, "tc_probe_gram: null pointer");
+  WsCarver w(ws, ws_bytes);
+  __nv_bfloat16* Ab = w.take<__nv_bfloat16>(128 * 128, 1024);
+  __nv_bfloat16* Bb = w.take<__nv_bfloat16>(64 * 128, 1024);
+  uint32_t* err = w.take<uint32_t>(4);
+  NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "tc_probe_gram: workspace too small");
+  NSVGD_CUDA(cudaMemsetAsync(err, 0, 16, st));
+  f32_to_bf16_kernel<<<64, 256, 0, st>>>(A, Ab, 128, 128, 0);
+  NSVGD_LAUNCH_CHECK();
+  f32_to_bf16_kernel<<<32, 256, 0, st>>>(B, Bb, 64, 128, 0);
+  NSVGD_LAUNCH_CHECK();
+  CUtensorMap ma, mb;
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&ma, Ab, 128, 128, 256, 64, 128));
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&mb, Bb, 128, 64, 256, 64, 64));
+  const int smem = 49152 + 64 + 1024;
+  NSVGD_CUDA(cudaFuncSetAttribute(tc_probe_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tc_probe_gram_kernel<<<1, 128, smem, st>>>(ma, mb, G, err);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
+extern "C" int nsvgd_tc_probe_pv(void* stream, const float* P, const float* V, float* O, void* ws, size_t ws_bytes) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NSVGD_REQUIRE(P && V && O && ws, NSVGD_ERR_INVALID, "tc_probe_pv: null pointer");
+  WsCarver w(ws, ws_bytes);
+  __nv_bfloat16* Vt = w.take<__nv_bfloat16>(256 * 64, 1024);
+  uint32_t* err = w.take<uint32_t>(4);
+  NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "tc_probe_pv: workspace too small");
+  NSVGD_CUDA(cudaMemsetAsync(err, 0, 16, st));
+  f32_to_bf16_kernel<<<64, 256, 0, st>>>(V, Vt, 64, 256, 1);   // Vt[256 x 64]
+  NSVGD_LAUNCH_CHECK();
+  CUtensorMap mv;
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&mv, Vt, 64, 256, 128, 64, 256));
+  const int smem = 32768 + 64 + 1024;
+  NSVGD_CUDA(cudaFuncSetAttribute(tc_probe_pv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tc_probe_pv_kernel<<<1, 128, smem, st>>>(mv, P, O, err);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}

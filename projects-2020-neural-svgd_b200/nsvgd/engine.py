@@ -1,0 +1,176 @@
+"""Array-facing operations of the SVGD particle-interaction engine (thin wrappers over the C ABI).
+
+Everything is enqueue-only on the current CUDA stream; the bandwidth stays on the device
+(a 1-element float32 tensor) so median -> phi* -> update never synchronises with the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+from ._lib import check, ld, load, ptr, require_cuda_f32, stream_ptr, workspace, workspace_bytes
+
+DEFAULT_MEDIAN_MODE = os.environ.get("NSVGD_MEDIAN_MODE", "literal")
+
+
+def as_h_dev(h, device) -> torch.Tensor:
+    """bandwidth as a 1-element float32 device tensor (no sync when it already is one)."""
+    if isinstance(h, torch.Tensor):
+        if h.numel() != 1:
+            raise ValueError(f"Bandwidth needs to be a scalar on the SVGD hot path. Instead it has shape {tuple(h.shape)}")
+        return h.to(device=device, dtype=torch.float32).reshape(1)
+    return torch.full((1,), float(h), dtype=torch.float32, device=device)
+
+
+def median_heuristic(x: torch.Tensor, mode: str | None = None) -> torch.Tensor:
+    """kernels.median_heuristic (kernels.py:160-172) -> 1-element float32 device tensor.
+
+    mode: "literal" (what kernels.py:169 executes), "offdiag" (docstring intent), "full"."""
+    mode = mode or DEFAULT_MEDIAN_MODE
+    if mode not in _lib.MEDIAN_MODES:
+        raise ValueError(f"unknown median mode {mode!r}")
+    if x.ndim == 1:
+        x = x[:, None]
+    x = require_cuda_f32(x, "x")
+    n, d = x.shape
+    h = torch.empty(1, dtype=torch.float32, device=x.device)
+    ws = workspace(workspace_bytes("median", n, n, d), x.device)
+    check(load().nsvgd_median_h_f32(stream_ptr(x.device), ptr(x), n, d, ld(x), _lib.MEDIAN_MODES[mode],
+                                    ptr(h), ptr(ws), ws.numel()))
+    return h
+
+
+def phistar(Q, X, S, h, Sq=None, aux=False, stats=False, path="auto"):
+    """phi*(q_i) for all rows of Q (stein.py:180-222).  Returns phi, or (phi, aux (m,2,d)), and
+    additionally a float64[4] device tensor {sum_i(s_i.phi_i + div phi_i), sum_i|phi_i|^2, m, 0}
+    when stats=True (requires Sq = scores at the queries)."""
+    X = require_cuda_f32(X, "X"); S = require_cuda_f32(S, "S"); Q = require_cuda_f32(Q, "Q")
+    if X.shape != S.shape:
+        raise ValueError(f"particles and scores must have the same shape, got {tuple(X.shape)} and {tuple(S.shape)}")
+    if Q.shape[1] != X.shape[1]:
+        raise ValueError(f"Shapes of particles x and y need to match. Received d={Q.shape[1]} and d={X.shape[1]}")
+    if ld(X) != ld(S):
+        S = S.contiguous(); X = X.contiguous()
+    m, d = Q.shape
+    n = X.shape[0]
+    if Sq is not None:
+        Sq = require_cuda_f32(Sq, "Sq")
+        if Sq.shape != Q.shape:
+            raise ValueError("Sq must have the shape of Q")
+        if ld(Sq) != ld(Q):
+            Sq = Sq.contiguous(); Q = Q.contiguous()
+    if stats and Sq is None:
+        raise ValueError("stats=True needs the scores at the query points (Sq)")
+    h_dev = as_h_dev(h, X.device)
+    phi = torch.empty((m, d), dtype=torch.float32, device=X.device)
+    aux_t = torch.empty((m, 2, d), dtype=torch.float32, device=X.device) if aux else None
+    stats_t = torch.empty(4, dtype=torch.float64, device=X.device) if stats else None
+    ws = workspace(workspace_bytes("phi", n, m, d, path), X.device)
+    check(load().nsvgd_phi_f32(stream_ptr(X.device), ptr(Q), ptr(Sq), m, ld(Q), ptr(X), ptr(S), n, ld(X), d,
+                               ptr(h_dev), ptr(phi), d, ptr(aux_t), ptr(stats_t), _lib.PATHS[path], ptr(ws), ws.numel()))
+    out = (phi,)
+    if aux:
+        out += (aux_t,)
+    if stats:
+        out += (stats_t,)
+    return out[0] if len(out) == 1 else out
+
+
+def svgd_step_sgd(X, S, h, lr, scaled=False, lambda_reg=0.5, want_grads=False, path="auto"):
+    """One fused SVGD step in place on X (models.py:143-167 with optax.sgd; 654-689):
+    grads = -phi or -alpha phi, X <- X - lr grads.  Returns (step_aux float64[8] device tensor
+    {ksd, l2, alpha, sum grads^2, sum updates^2, ...}, grads or None)."""
+    X = require_cuda_f32(X, "X"); S = require_cuda_f32(S, "S")
+    if not X.is_contiguous():
+        raise ValueError("X must be contiguous for the in-place step")
+    S = S.contiguous()
+    n, d = X.shape
+    h_dev = as_h_dev(h, X.device)
+    grads = torch.empty_like(X) if want_grads else None
+    step_aux = torch.empty(8, dtype=torch.float64, device=X.device)
+    ws = workspace(workspace_bytes("step", n, n, d, path), X.device)
+    check(load().nsvgd_step_sgd_f32(stream_ptr(X.device), ptr(X), ptr(S), n, d, d, ptr(h_dev), float(lr), int(bool(scaled)),
+                                    float(lambda_reg), ptr(grads), ptr(step_aux), _lib.PATHS[path], ptr(ws), ws.numel()))
+    return step_aux, grads
+
+
+def apply_update(Xrows, phi, stats, lr, scaled, lambda_reg, want_grads=False):
+    """second phase of a row-sharded step: stats are the (all-reduced) global sums."""
+    m, d = Xrows.shape
+    grads = torch.empty_like(phi) if want_grads else None
+    step_aux = torch.empty(8, dtype=torch.float64, device=Xrows.device)
+    check(load().nsvgd_apply_update_f32(stream_ptr(Xrows.device), ptr(Xrows), ptr(phi), m, d, ld(Xrows), ld(phi), ptr(stats),
+                                        float(lr), int(bool(scaled)), float(lambda_reg), ptr(grads), ptr(step_aux)))
+    return step_aux, grads
+
+
+def ksd(X, Sx, h, variant="v", Y=None, Sy=None) -> torch.Tensor:
+    """KSD^2 closed form (stein.py:273-349) -> 0-dim float64 device tensor."""
+    X = require_cuda_f32(X, "X").contiguous(); Sx = require_cuda_f32(Sx, "Sx").contiguous()
+    n, d = X.shape
+    m = n
+    if variant == "rect":
+        Y = require_cuda_f32(Y, "Y").contiguous(); Sy = require_cuda_f32(Sy, "Sy").contiguous()
+        m = Y.shape[0]
+    h_dev = as_h_dev(h, X.device)
+    out = torch.empty(1, dtype=torch.float64, device=X.device)
+    ws = workspace(workspace_bytes("ksd", n, m, d), X.device)
+    check(load().nsvgd_ksd_f32(stream_ptr(X.device), ptr(X), ptr(Sx), n, d, ptr(Y), ptr(Sy), m, d, d, ptr(h_dev),
+                               _lib.KSD_VARIANTS[variant], ptr(out), ptr(ws), ws.numel()))
+    return out[0]
+
+
+def mmd(X, Y, h=1.0, funnel=False) -> torch.Tensor:
+    """MMD^2 (metrics.py:88-105) -> 0-dim float64 device tensor."""
+    X = require_cuda_f32(X, "xs").contiguous(); Y = require_cuda_f32(Y, "ys").contiguous()
+    if X.shape[1] != Y.shape[1]:
+        raise ValueError(f"Shapes of particles x and y need to match. Received d={X.shape[1]} and d={Y.shape[1]}")
+    n, d = X.shape
+    m = Y.shape[0]
+    out = torch.empty(1, dtype=torch.float64, device=X.device)
+    ws = workspace(workspace_bytes("mmd", n, m, d), X.device)
+    check(load().nsvgd_mmd_f32(stream_ptr(X.device), ptr(X), n, d, ptr(Y), m, d, d, float(h), int(bool(funnel)),
+                               ptr(out), ptr(ws), ws.numel()))
+    return out[0]
+
+
+def adam_update(X, grads, m1, m2, lr, t, b1=0.9, b2=0.999, eps=1e-8):
+    """optax.adam(lr) applied to the particles in place (utils.py:711-715)."""
+    check(load().nsvgd_adam_update_f32(stream_ptr(X.device), ptr(X), ptr(grads), ptr(m1), ptr(m2), X.numel(),
+                                       float(lr), float(b1), float(b2), float(eps), int(t)))
+
+
+# ---- select building blocks for the row-sharded median (parallel.py) -------------------------------
+class MedianSelect:
+    """Stateful wrapper over nsvgd_median_{prepare,hist_pass,advance,finish}."""
+
+    def __init__(self, x: torch.Tensor, mode: str):
+        x = require_cuda_f32(x, "x")
+        self.x, self.mode = x, mode
+        n, d = x.shape
+        self.n = n
+        self.state = torch.zeros(_lib.SELECT_STATE_BYTES, dtype=torch.uint8, device=x.device)
+        self.hist = torch.zeros(2 * _lib.SELECT_BINS, dtype=torch.int64, device=x.device)
+        dz_max = d if n > d else n - 1
+        self.Z = torch.empty((n, dz_max), dtype=torch.float32, device=x.device) if mode == "literal" else None
+        dz, w = C.c_int64(0), C.c_float(0)
+        check(load().nsvgd_median_prepare(stream_ptr(x.device), ptr(x), n, d, ld(x), _lib.MEDIAN_MODES[mode], ptr(self.Z),
+                                          C.byref(dz), C.byref(w), ptr(self.state)))
+        self.dz, self.w_last = int(dz.value), float(w.value)
+        self.P = self.Z if mode == "literal" else x
+
+    def hist_pass(self, p: int, tile_row_start=0, tile_row_stride=1) -> torch.Tensor:
+        check(load().nsvgd_median_hist_pass(stream_ptr(self.x.device), ptr(self.P), self.n, self.dz, ld(self.P), self.w_last,
+                                            tile_row_start, tile_row_stride, ptr(self.state), p, ptr(self.hist)))
+        return self.hist
+
+    def advance(self, p: int):
+        check(load().nsvgd_median_advance(stream_ptr(self.x.device), ptr(self.state), ptr(self.hist), p))
+
+    def finish(self) -> torch.Tensor:
+        h = torch.empty(1, dtype=torch.float32, device=self.x.device)
+        check(load().nsvgd_median_finish(stream_ptr(self.x.device), ptr(self.state), self.n, ptr(h)))
+        return h

@@ -1,0 +1,247 @@
+"""Drop-in for the SVGD plug-in of nvgd/src/models.py: `KernelGradient` (models.py:622-689) and the
+`Particles` container (models.py:61-211).  Same constructor arguments and aux-dict contract; arrays
+are CUDA float32 tensors; `key` is an int seed or a torch.Generator (JAX PRNG keys do not exist here)."""
+from __future__ import annotations
+
+import torch
+
+from . import engine, kernels, metrics, stein, utils
+from .utils import vmap
+
+
+class KernelGradient:
+    """Computes the SVGD approximation to grad(KL), ie
+    phi*(y) = E[grad(log p)(y) k(x, y) + div(k)(x, y)]                    models.py:622-652"""
+
+    def __init__(self,
+                 target_logp: callable = None,
+                 get_target_logp: callable = None,
+                 kernel=kernels.get_rbf_kernel,
+                 bandwidth=None,
+                 scaled=False,
+                 lambda_reg=1 / 2,
+                 use_hutchinson: bool = False):
+        if target_logp:
+            assert not get_target_logp
+            self.get_target_logp = lambda *args: target_logp
+        elif get_target_logp:
+            self.get_target_logp = get_target_logp
+        else:
+            # the reference *returns* the ValueError here (models.py:645-646, a bug); we raise it
+            raise ValueError("One of target_logp and get_target_logp must be given.")
+        if use_hutchinson:
+            raise NotImplementedError("use_hutchinson (random estimator) is outside the hot path (SURVEY.md 2)")
+        self.bandwidth = bandwidth
+        self.kernel = kernel
+        self.lambda_reg = lambda_reg
+        self.rundata = {}
+        self.scaled = scaled
+        self.use_hutchinson = use_hutchinson
+
+    def _bandwidth(self, inducing_particles):
+        # truthiness test as in models.py:657/680: None or 0 -> median heuristic
+        if isinstance(self.bandwidth, torch.Tensor):
+            return self.bandwidth
+        return self.bandwidth if self.bandwidth else kernels.median_heuristic(inducing_particles)
+
+    def get_field(self, inducing_particles, batch=None):
+        """return -phistar                                                 models.py:654-660"""
+        target_logp = self.get_target_logp(batch)
+        bandwidth = self._bandwidth(inducing_particles)
+        kernel = self.kernel(bandwidth)
+        phi = stein.get_phistar(kernel, target_logp, inducing_particles)
+        return utils.negative(phi), bandwidth
+
+    def get_field_scaled(self, inducing_particles, batch=None):
+        """-alpha phi*, alpha = ksd / (2 lambda l2)                        models.py:677-689
+        One fused engine pass yields phi, sum_i(s_i.phi_i + div phi_i) and sum_i|phi_i|^2, replacing
+        the reference's n extra phi evaluations (l2_norm_squared) and its jacfwd (stein_discrepancy)."""
+        target_logp = self.get_target_logp(batch)
+        bandwidth = self._bandwidth(inducing_particles)
+        kernel = self.kernel(bandwidth)
+        phi = stein.get_phistar(kernel, target_logp, inducing_particles)
+        vals, stats = engine.phistar(inducing_particles, inducing_particles, phi.scores, phi.h,
+                                     Sq=phi.scores, stats=True)
+        ksd = stats[0] / stats[2]
+        l2_phi_squared = stats[1] / stats[2]
+        alpha = (ksd / (2 * self.lambda_reg * l2_phi_squared)).to(torch.float32)
+        field = utils.mul(phi, -alpha)
+        field._cached = (inducing_particles, vals)   # reuse when evaluated at the inducing particles
+        self._last_scaled = {"ksd": ksd, "l2": l2_phi_squared, "alpha": alpha}
+        return field, bandwidth
+
+    def gradient(self, batch, particles, aux=False):
+        """Compute approximate KL gradient.                                models.py:662-675
+        args:
+            batch: minibatch data used to estimate logp (can be None)
+            particles: array of shape (n, d)
+        """
+        target_logp = self.get_target_logp(batch)
+        v, h = self.get_field_scaled(particles, batch) if self.scaled \
+            else self.get_field(particles, batch)
+        cached = getattr(v, "_cached", None)
+        if cached is not None and cached[0] is particles:
+            grads = cached[1] * v.scale
+        else:
+            grads = vmap(v)(particles)
+        if aux:
+            h_out = h if isinstance(h, torch.Tensor) else torch.tensor(float(h), device=particles.device)
+            auxd = {"bandwidth": h_out}
+            if hasattr(target_logp, "batch_logp"):
+                auxd["logp"] = target_logp.batch_logp(particles)
+            else:
+                auxd["logp"] = torch.func.vmap(target_logp)(particles)
+            return grads, auxd
+        else:
+            return grads
+
+    # ---- fused fast path used by Particles when the optimizer is plain sgd ---------------------------
+    def step_sgd(self, particles, batch, lr):
+        """median (if needed) -> phi* (+ KSD, l2) -> x += lr alpha phi, all enqueued on the stream by
+        ONE composite C call (nsvgd_step_sgd_f32).  Mutates `particles`; returns (grads, aux)."""
+        target_logp = self.get_target_logp(batch)
+        h = self._bandwidth(particles)
+        _ = stein._require_rbf(self.kernel(h), "KernelGradient")
+        s = stein.score(target_logp, particles)
+        if hasattr(target_logp, "batch_logp"):
+            logp_vals = target_logp.batch_logp(particles)
+        else:
+            logp_vals = torch.func.vmap(target_logp)(particles)
+        step_aux, grads = engine.svgd_step_sgd(particles, s, h, lr, self.scaled, self.lambda_reg, want_grads=True)
+        h_out = h if isinstance(h, torch.Tensor) else torch.tensor(float(h), device=particles.device)
+        return grads, {"bandwidth": h_out, "logp": logp_vals,
+                       "global_grad_norm": torch.sqrt(step_aux[3]).to(torch.float32),
+                       "global_grad_norm_post_update": torch.sqrt(step_aux[4]).to(torch.float32)}
+
+
+class Particles:
+    """Container class for particles, particle optimizer, particle update step method, and
+    particle metrics.                                                       models.py:61-211"""
+
+    def __init__(self,
+                 key,
+                 gradient: callable,
+                 init_samples,
+                 learning_rate=1e-2,
+                 optimizer="sgd",
+                 custom_optimizer=None,
+                 n_particles: int = 50,
+                 compute_metrics=None,
+                 device="cuda"):
+        self.gradient = gradient
+        self.n_particles = n_particles
+        self.device = torch.device(device)
+        if isinstance(key, torch.Generator):
+            self.generator = key
+        else:
+            self.generator = torch.Generator(device="cpu")
+            self.generator.manual_seed(int(key))
+        self.init_samples = init_samples
+        self.particles = self.init_particles()
+
+        if custom_optimizer:
+            self.optimizer_str = "custom"
+            self.learning_rate = None
+            self.opt = custom_optimizer     # callable(grads, state, particles) -> (updates, state)
+            self.optimizer_state = None
+        else:
+            if optimizer not in ("sgd", "adam"):
+                raise KeyError(optimizer)   # utils.optimizer_mapping (utils.py:711-715)
+            self.optimizer_str = optimizer
+            self.learning_rate = learning_rate
+            self.opt = None
+            self.optimizer_state = None
+            if optimizer == "adam":
+                self.optimizer_state = (torch.zeros_like(self.particles), torch.zeros_like(self.particles), 0)
+        self.step_counter = 0
+        self.rundata = {}
+        self.donedone = False
+        self.compute_metrics = compute_metrics
+
+    def init_particles(self, key=None):
+        """Returns a tensor of shape (n, d) containing particles.          models.py:107-117"""
+        if callable(self.init_samples):
+            particles = self.init_samples(self.n_particles, self.generator if key is None else key)
+        else:
+            particles = self.init_samples
+            self.n_particles = len(particles)
+        particles = torch.as_tensor(particles, dtype=torch.float32).to(self.device).contiguous().clone()
+        self.d = particles.shape[1]
+        return particles
+
+    def get_params(self):
+        return self.particles
+
+    def _step(self, particles, optimizer_state, params):
+        """Updates particles in the direction given by self.gradient      models.py:143-167
+        Returns: particles (updated), optimizer_state (updated), grad_aux dict."""
+        owner = getattr(self.gradient, "__self__", None)
+        if isinstance(owner, KernelGradient) and self.optimizer_str == "sgd":
+            particles = particles.clone()
+            grads, grad_aux = owner.step_sgd(particles, params, self.learning_rate)
+            return particles, optimizer_state, grad_aux
+        grads, grad_aux = self.gradient(params, particles, aux=True)
+        particles = particles.clone()
+        if self.optimizer_str == "sgd":
+            updated_grads = -self.learning_rate * grads
+            particles += updated_grads
+        elif self.optimizer_str == "adam":
+            m1, m2, t = optimizer_state
+            before = particles.clone()
+            engine.adam_update(particles, grads.contiguous(), m1, m2, self.learning_rate, t + 1)
+            optimizer_state = (m1, m2, t + 1)
+            updated_grads = particles - before
+        else:
+            updated_grads, optimizer_state = self.opt(grads, optimizer_state, particles)
+            particles += updated_grads
+        grad_aux.update({
+            "global_grad_norm": torch.linalg.vector_norm(grads),
+            "global_grad_norm_post_update": torch.linalg.vector_norm(updated_grads),
+        })
+        return particles, optimizer_state, grad_aux
+
+    def step(self, params):
+        """Log rundata, take step. Mutates state                            models.py:169-176"""
+        updated_particles, self.optimizer_state, auxdata = self._step(
+            self.particles, self.optimizer_state, params)
+        self.log(auxdata)
+        self.particles = updated_particles
+        self.step_counter += 1
+        return None
+
+    def log(self, grad_aux=None):
+        """models.py:178-185 (tracer cadence: every 10 steps)"""
+        metrics.append_to_log(self.rundata, self._log(self.particles, self.step_counter))
+        if self.step_counter % 10 == 0 and self.compute_metrics:
+            aux_metrics = self.compute_metrics(self.particles)
+            metrics.append_to_log(self.rundata,
+                                  {k: (self.step_counter, v) for k, v in aux_metrics.items()})
+        if grad_aux is not None:
+            metrics.append_to_log(self.rundata, grad_aux)
+
+    def _log(self, particles, step):
+        """models.py:187-197.  Device tensors are logged as-is (no forced host copy per step)."""
+        auxdata = {}
+        if self.d < 400:
+            auxdata.update({
+                "step": step,
+                "particles": particles,
+                "mean": torch.mean(particles, dim=0),
+                "std": torch.std(particles, dim=0, unbiased=False),
+            })
+        return auxdata
+
+    def done(self):
+        """converts rundata into arrays                                     models.py:199-211"""
+        if self.donedone:
+            print("already done.")
+            return
+
+        def to_array(v):
+            if len(v) and isinstance(v[0], torch.Tensor):
+                return torch.stack([t.detach() for t in v]).cpu()
+            if len(v) and isinstance(v[0], tuple) and isinstance(v[0][1], torch.Tensor):
+                return torch.tensor([[float(s), float(t)] for s, t in v])
+            return torch.as_tensor(v)
+        self.rundata = {k: to_array(v) for k, v in self.rundata.items()}
+        self.donedone = True

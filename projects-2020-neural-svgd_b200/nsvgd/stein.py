@@ -1,0 +1,98 @@
+"""Drop-in for the hot-path functions of nvgd/src/stein.py.  The reference's nested
+vmap/grad/jacfwd closures are replaced by closed forms evaluated in CUDA;
+`kernel` must be a tagged RBF kernel (kernels.get_rbf_kernel), `logp` a callable on (d,)
+torch tensors (scores through torch.func.vmap(grad)) or an object with a batched `.score(X)`."""
+from __future__ import annotations
+
+import torch
+
+from . import engine
+from .utils import BatchedFunction
+
+
+def score(logp, xs):
+    """S = vmap(grad(logp))(xs), (n,d) float32.  The reference computes this inside its double
+    vmap (stein.py:50); it depends on x_j only, so it is hoisted."""
+    if hasattr(logp, "score"):
+        s = logp.score(xs)
+    else:
+        s = torch.func.vmap(torch.func.grad(logp))(xs)
+    return s.to(torch.float32).contiguous()
+
+
+def _require_rbf(kernel, who):
+    if not getattr(kernel, "is_rbf", False):
+        raise NotImplementedError(f"{who}: only kernels.get_rbf_kernel kernels dispatch to the CUDA engine "
+                                  "(north_star: no fallback path)")
+    if getattr(kernel, "funnel", False):
+        raise NotImplementedError(f"{who}: the funnel kernel is only supported by metrics.get_mmd")
+    return kernel.h()
+
+
+class PhiStar(BatchedFunction):
+    """phi* as a function of one point; carries what the closed forms need."""
+
+    def __init__(self, kernel, logp, samples, scores=None):
+        self.kernel, self.logp, self.samples = kernel, logp, samples
+        self.h = _require_rbf(kernel, "get_phistar")
+        self.scores = score(logp, samples) if scores is None else scores
+        super().__init__(self._phi_batch)
+
+    def _phi_batch(self, xs):
+        return engine.phistar(xs, self.samples, self.scores, self.h)
+
+
+def get_phistar(kernel, logp, samples):
+    """stein.py:200-203: returns x -> phi*(x) estimated from `samples`."""
+    return PhiStar(kernel, logp, samples)
+
+
+def phistar_i(xi, x, logp, kernel, aux=True):
+    """stein.py:180-197"""
+    if xi.ndim > 1:
+        raise ValueError(f"Shape of xi must be (d,). Instead, received shape {tuple(xi.shape)}")
+    h = _require_rbf(kernel, "phistar_i")
+    out = engine.phistar(xi[None, :], x, score(logp, x), h, aux=aux)
+    if aux:
+        return out[0][0], out[1][0]
+    return out[0]
+
+
+def phistar(particles, leaders, logp, kernel):
+    """stein.py:206-222: (n,d) updates and (n,2,d) [drift, repulsion] aux; rectangular n x l."""
+    h = _require_rbf(kernel, "phistar")
+    return engine.phistar(particles, leaders, score(logp, leaders), h, aux=True)
+
+
+def stein_discrepancy(xs, logp, f, aux=False):
+    """stein.py:99-106 for a witness f built from get_phistar (optionally through
+    utils.negative / utils.mul): mean_i[ s_i . f(x_i) + div f(x_i) ] in closed form.
+    Arbitrary callables f would need jacfwd through user code -> NotImplementedError."""
+    base = getattr(f, "base", None)
+    if not isinstance(base, PhiStar):
+        raise NotImplementedError("stein_discrepancy: f must come from stein.get_phistar")
+    if aux:
+        raise NotImplementedError("stein_discrepancy(aux=True) is not on the hot path")
+    s_q = score(logp, xs)
+    _, stats = engine.phistar(xs, base.samples, base.scores, base.h, Sq=s_q, stats=True)
+    val = stats[0] / stats[2]
+    scale = f.scale
+    return (val * scale).to(torch.float32) if isinstance(scale, torch.Tensor) else (val * scale).to(torch.float32)
+
+
+def ksd_squared(xs, ys, logp, k):
+    """stein.py:273-295"""
+    h = _require_rbf(k, "ksd_squared")
+    return engine.ksd(xs, score(logp, xs), h, "rect", ys, score(logp, ys)).to(torch.float32)
+
+
+def ksd_squared_u(xs, logp, k):
+    """stein.py:299-323"""
+    h = _require_rbf(k, "ksd_squared_u")
+    return engine.ksd(xs, score(logp, xs), h, "u").to(torch.float32)
+
+
+def ksd_squared_v(xs, logp, k, dummy_arg1=None, dummy_arg2=None):
+    """stein.py:327-349"""
+    h = _require_rbf(k, "ksd_squared_v")
+    return engine.ksd(xs, score(logp, xs), h, "v").to(torch.float32)

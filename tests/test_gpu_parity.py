@@ -1,0 +1,184 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden vectors and the oracle.
+Tolerances: bandwidth bit-exact; phi / KSD / MMD <= 1e-4 relative (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import svgd_oracle as so
+
+from conftest import GOLDEN_CASES
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).cuda()
+
+
+def rel_fro(got, ref):
+    got = np.asarray(got, np.float64); ref = np.asarray(ref, np.float64)
+    return np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-300)
+
+
+def max_row_rel(got, ref):
+    got = np.asarray(got, np.float64); ref = np.asarray(ref, np.float64)
+    num = np.linalg.norm(got - ref, axis=-1)
+    den = np.maximum(np.linalg.norm(ref, axis=-1), 1e-3 * np.linalg.norm(ref, axis=-1).max())
+    return float((num / den).max())
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_bandwidth_bit_exact_vs_golden(golden, name):
+    from nsvgd import engine
+    g = golden[name]
+    X = dev(g["X"])
+    for mode in so.MEDIAN_MODES:
+        h = engine.median_heuristic(X, mode).cpu().numpy()[0]
+        assert np.float32(h).tobytes() == np.float32(g[f"h_{mode}"]).tobytes(), (mode, h, g[f"h_{mode}"])
+
+
+@pytest.mark.parametrize("n,d,seed", [(2, 1, 0), (3, 5, 1), (65, 3, 2), (64, 64, 3), (129, 17, 4), (500, 7, 5),
+                                      (1000, 50, 6), (40, 100, 7), (777, 128, 8)])
+@pytest.mark.parametrize("mode", so.MEDIAN_MODES)
+def test_bandwidth_bit_exact_vs_oracle(n, d, seed, mode):
+    from nsvgd import engine
+    rng = np.random.default_rng(seed)
+    X = (rng.standard_normal((n, d)) * 1.7 + 0.3).astype(np.float32)
+    if n > 10:
+        X[5] = X[2]                      # duplicates (zero distance)
+    want = so.median_heuristic(X, mode)
+    got = engine.median_heuristic(dev(X), mode).cpu().numpy()[0]
+    assert np.float32(got).tobytes() == np.float32(want).tobytes(), (got, want)
+
+
+def test_bandwidth_nan_and_zero():
+    from nsvgd import engine
+    X = np.random.default_rng(0).standard_normal((70, 3)).astype(np.float32)
+    X[11, 2] = np.nan
+    assert np.isnan(engine.median_heuristic(dev(X), "offdiag").item())
+    same = np.ones((9, 4), dtype=np.float32)
+    assert engine.median_heuristic(dev(same), "offdiag").item() == 0.0
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("tag", ["hfix", "hmed"])
+def test_phi_ksd_against_golden(golden, name, tag):
+    from nsvgd import engine
+    g = golden[name]
+    X, Y, Sx, Sy = dev(g["X"]), dev(g["Y"]), dev(g["Sx"]), dev(g["Sy"])
+    h = float(g[f"h_{tag}"])
+    phi, aux, stats = engine.phistar(X, X, Sx, h, Sq=Sx, aux=True, stats=True)
+    assert rel_fro(phi.cpu(), g[f"phi_{tag}"]) < TOL
+    assert max_row_rel(phi.cpu(), g[f"phi_{tag}"]) < 10 * TOL
+    assert rel_fro(aux.cpu(), g[f"aux_{tag}"]) < TOL
+    assert rel_fro(engine.phistar(Y, X, Sx, h).cpu(), g[f"phi_rect_{tag}"]) < TOL
+    stats = stats.cpu().numpy()
+    n = X.shape[0]
+    assert stats[2] == n
+    assert stats[0] / n == pytest.approx(float(g[f"sd_phistar_{tag}"]), rel=TOL)
+    assert stats[1] / n == pytest.approx(float(g[f"l2_{tag}"]), rel=TOL)
+    # KSD U/V are differences of near-equal sums: tolerance relative to the V-statistic scale
+    scale = abs(float(g[f"ksd_v_{tag}"]))
+    assert engine.ksd(X, Sx, h, "v").item() == pytest.approx(float(g[f"ksd_v_{tag}"]), rel=TOL)
+    assert engine.ksd(X, Sx, h, "u").item() == pytest.approx(float(g[f"ksd_u_{tag}"]), abs=TOL * scale)
+    assert engine.ksd(X, Sx, h, "rect", Y, Sy).item() == pytest.approx(float(g[f"ksd_rect_{tag}"]), abs=TOL * scale)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_mmd_against_golden(golden, name):
+    from nsvgd import engine
+    g = golden[name]
+    X, Y = dev(g["X"]), dev(g["Y"])
+    # MMD^2 is a difference of O(1) kernel means: tolerance relative to mean(K) ~ O(1)
+    assert engine.mmd(X, Y, 1.0).item() == pytest.approx(float(g["mmd_rbf"]), abs=2e-6)
+    assert engine.mmd(X, Y, 1.0, funnel=True).item() == pytest.approx(float(g["mmd_funnel"]), abs=2e-6)
+
+
+PATH_CASES = [
+    ("simt", 1000, 3, 1.3), ("simt", 333, 1, 0.7), ("simt", 257, 8, 2.0), ("simt", 300, 16, 3.0), ("simt", 130, 31, 4.0),
+    ("generic", 700, 50, 5.0), ("generic", 300, 3, 1.3), ("generic", 129, 200, 12.0), ("generic", 64, 1030, 30.0),
+    ("tc", 2048, 128, 8.0), ("tc", 1500, 100, 7.0), ("tc", 1024, 64, 5.5), ("tc", 1111, 50, 5.0), ("tc", 4096, 128, 3.0),
+]
+
+
+@pytest.mark.parametrize("path,n,d,h", PATH_CASES)
+def test_phi_paths_vs_oracle(path, n, d, h):
+    """every phi path against the fp64 oracle on a cloud with non-zero mean (centring exercised),
+    square and rectangular, with the fused KSD/l2 statistics."""
+    from nsvgd import engine
+    X, S = so.gaussian_diag_workload(n, d, seed=n + d, shift=0.5)
+    S = (S * 0.1).astype(np.float32)
+    m = 77
+    Q = (np.random.default_rng(1).standard_normal((m, d)) * 0.9 + 0.4).astype(np.float32)
+    Xd, Sd, Qd = dev(X), dev(S), dev(Q)
+    phi, aux, stats = engine.phistar(Xd, Xd, Sd, h, Sq=Sd, aux=True, stats=True, path=path)
+    ref, ref_aux = so.phistar(X, X, S, h, aux=True)
+    assert rel_fro(phi.cpu(), ref) < TOL, rel_fro(phi.cpu(), ref)
+    assert max_row_rel(phi.cpu(), ref) < 10 * TOL
+    assert rel_fro(aux.cpu(), ref_aux) < TOL
+    st = stats.cpu().numpy()
+    sd_ref = so.stein_discrepancy_phistar(X, S, h)
+    assert st[0] / n == pytest.approx(sd_ref, rel=2 * TOL, abs=2 * TOL * abs(so.l2_norm_squared(ref)) ** 0.5)
+    assert st[1] / n == pytest.approx(so.l2_norm_squared(ref), rel=2 * TOL)
+    got_rect = engine.phistar(Qd, Xd, Sd, h, path=path)
+    assert rel_fro(got_rect.cpu(), so.phistar(Q, X, S, h)) < TOL
+
+
+def test_phi_far_from_origin_and_tight_cloud():
+    """cancellation guard: cloud far from the origin, Gram-trick paths must centre."""
+    from nsvgd import engine
+    rng = np.random.default_rng(3)
+    n, d = 1536, 128
+    X = (rng.standard_normal((n, d)) * 0.05 + 30.0).astype(np.float32)
+    S = rng.standard_normal((n, d)).astype(np.float32)
+    h = float(so.median_heuristic(X[:400], "offdiag"))
+    ref = so.phistar(X, X, S, h)
+    for path in ("generic", "tc"):
+        got = engine.phistar(dev(X), dev(X), dev(S), h, path=path)
+        assert rel_fro(got.cpu(), ref) < TOL, (path, rel_fro(got.cpu(), ref))
+
+
+def test_phi_nan_propagates():
+    from nsvgd import engine
+    X, S = so.gaussian_diag_workload(300, 4, seed=1)
+    X[7, 1] = np.nan
+    phi = engine.phistar(dev(X), dev(X), dev(S), 1.0)
+    assert torch.isnan(phi).any()
+
+
+def test_step_sgd_scaled_and_unscaled():
+    from nsvgd import engine
+    X, S = so.gaussian_diag_workload(400, 6, seed=9)
+    S = (S * 0.05).astype(np.float32)
+    for scaled in (False, True):
+        Xd = dev(X).clone()
+        aux, grads = engine.svgd_step_sgd(Xd, dev(S), 1.4, lr=0.05, scaled=scaled, lambda_reg=0.5, want_grads=True)
+        newX, g_ref, _, extras = so.svgd_step_sgd(X, S, 0.05, bandwidth=1.4, scaled=scaled, lambda_reg=0.5)
+        assert rel_fro(grads.cpu(), g_ref) < 2 * TOL
+        assert rel_fro(Xd.cpu(), newX) < 1e-6
+        a = aux.cpu().numpy()
+        if scaled:
+            assert a[2] == pytest.approx(extras["alpha"], rel=2 * TOL)
+            assert a[0] == pytest.approx(extras["ksd"], rel=2 * TOL)
+        assert a[3] == pytest.approx(float((g_ref ** 2).sum()), rel=4 * TOL)
+
+
+def test_full_size_rows_sampled_against_oracle():
+    """BASELINE size (n=65536, d=128): 48 sampled rows of phi against the fp64 oracle evaluated on
+    those rows only (rectangular form), plus permutation equivariance on the device."""
+    from nsvgd import engine
+    n, d = 65536, 128
+    X, S = so.gaussian_diag_workload(n, d, seed=0)
+    S = (S * 0.02).astype(np.float32)
+    Xd, Sd = dev(X), dev(S)
+    h = 6.0
+    phi = engine.phistar(Xd, Xd, Sd, h)
+    rows = np.random.default_rng(0).choice(n, 48, replace=False)
+    ref = so.phistar(X[rows], X, S, h)
+    assert rel_fro(phi[rows].cpu(), ref) < TOL
+    assert max_row_rel(phi[rows].cpu(), ref) < 10 * TOL
+    perm = torch.randperm(n, device="cuda")
+    phi_p = engine.phistar(Xd[perm].contiguous(), Xd[perm].contiguous(), Sd[perm].contiguous(), h)
+    assert rel_fro(phi_p.cpu(), phi[perm].cpu()) < 2e-5

@@ -1,0 +1,91 @@
+"""GPU: the reference-facing plug-in API (KernelGradient / Particles / svgd_flow / tracers)
+driven exactly like flows.svgd_flow and the experiment scripts drive it."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import svgd_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def test_kernel_gradient_matches_oracle_funnel():
+    from nsvgd import distributions, models, kernels
+    tgt = distributions.Funnel(2)
+    gen = torch.Generator().manual_seed(0)
+    X = (torch.randn(100, 2, generator=gen) * 1.5).cuda()
+    S = so.funnel_score(X.cpu().numpy())
+    for scaled in (False, True):
+        for bandwidth in (1.0, None):
+            kg = models.KernelGradient(target_logp=tgt.logpdf, kernel=kernels.get_rbf_kernel,
+                                       bandwidth=bandwidth, scaled=scaled, lambda_reg=0.5)
+            grads, aux = kg.gradient(None, X, aux=True)
+            ref, h, _ = so.kernel_gradient(X.cpu().numpy(), S, bandwidth=bandwidth, scaled=scaled, lambda_reg=0.5,
+                                           median_mode="literal")
+            assert float(aux["bandwidth"]) == pytest.approx(h, rel=1e-6)
+            assert np.linalg.norm(grads.cpu().numpy() - ref) / np.linalg.norm(ref) < 2e-4
+            assert aux["logp"].shape == (100,)
+
+
+def test_autograd_scores_equal_analytic_scores():
+    """logp given as a plain callable (the reference's contract): scores via torch.func.grad."""
+    from nsvgd import stein, kernels
+    X = torch.randn(64, 3, device="cuda")
+    prec = torch.tensor([1.0, 4.0, 0.25], device="cuda")
+    logp = lambda x: -0.5 * torch.sum(prec * x * x)
+    phi = stein.get_phistar(kernels.get_rbf_kernel(0.9), logp, X)
+    from nsvgd import vmap
+    got = vmap(phi)(X)
+    ref = so.phistar(X.cpu().numpy(), X.cpu().numpy(), (-X * prec).cpu().numpy(), 0.9)
+    assert np.linalg.norm(got.cpu().numpy() - ref) / np.linalg.norm(ref) < 1e-4
+    one = phi(X[3])
+    assert torch.allclose(one, got[3], rtol=1e-5, atol=1e-7)
+    u = stein.ksd_squared_u(X, logp, kernels.get_rbf_kernel(0.9)).item()
+    assert u == pytest.approx(so.ksd_squared_u(X.cpu().numpy(), (-X * prec).cpu().numpy(), 0.9), rel=1e-3, abs=1e-4)
+
+
+def test_particles_trajectory_matches_oracle_loop():
+    """cfg1-shaped run (funnel, n=100, median bandwidth, scaled, sgd): 30 steps vs the oracle loop."""
+    from nsvgd import distributions, models, kernels
+    tgt = distributions.Funnel(2)
+    gen = torch.Generator().manual_seed(3)
+    X0 = torch.randn(100, 2, generator=gen)
+    kg = models.KernelGradient(target_logp=tgt.logpdf, kernel=kernels.get_rbf_kernel, bandwidth=None,
+                               scaled=True, lambda_reg=0.5)
+    P = models.Particles(key=0, gradient=kg.gradient, init_samples=X0, learning_rate=5e-2, optimizer="sgd")
+    Xo = X0.numpy().astype(np.float64)
+    for _ in range(30):
+        P.step(None)
+        h = float(so.median_heuristic(Xo.astype(np.float32), "literal"))
+        Xo, _, _, _ = so.svgd_step_sgd(Xo, so.funnel_score(Xo), 5e-2, bandwidth=h, scaled=True, lambda_reg=0.5)
+    got = P.particles.cpu().numpy()
+    assert np.linalg.norm(got - Xo) / np.linalg.norm(Xo) < 5e-3
+    assert len(P.rundata["bandwidth"]) == 30 and "global_grad_norm" in P.rundata
+    P.done()
+
+
+def test_particles_generic_optimizers_and_unfused_path_agree():
+    from nsvgd import distributions, models, kernels
+    tgt = distributions.Gaussian([0.5, -0.5, 1.0], [1.0, 0.1, 2.0])
+    X0 = torch.randn(200, 3, generator=torch.Generator().manual_seed(1))
+    kg = models.KernelGradient(target_logp=tgt.logpdf, bandwidth=1.0, scaled=True)
+    fused = models.Particles(0, kg.gradient, X0, learning_rate=0.1, optimizer="sgd")
+    plain = models.Particles(0, lambda p, x, aux=False: kg.gradient(p, x, aux=aux), X0, learning_rate=0.1, optimizer="sgd")
+    adam = models.Particles(0, kg.gradient, X0, learning_rate=0.05, optimizer="adam")
+    for _ in range(5):
+        fused.step(None); plain.step(None); adam.step(None)
+    assert torch.allclose(fused.particles, plain.particles, rtol=1e-4, atol=1e-5)
+    assert torch.isfinite(adam.particles).all()
+    assert not torch.allclose(adam.particles, X0.cuda())
+
+
+def test_svgd_flow_runs_unchanged_and_improves_mmd():
+    from nsvgd import distributions, flows, metrics
+    setup = distributions.Setup(distributions.Gaussian([1.0, -1.0], [0.5, 2.0]), distributions.Gaussian([0.0, 0.0], [1.0, 1.0]))
+    kg, particles, err = flows.svgd_flow(0, setup, n_particles=200, n_steps=60, particle_lr=0.1, bandwidth=None,
+                                         catch_exceptions=False)
+    assert err is None
+    mm = particles.rundata["mmd"]
+    assert mm[-1, 1] < mm[0, 1]
+    tr = metrics.get_funnel_tracer(torch.randn(50, 2, device="cuda"))(particles.particles)
+    assert set(tr) == {"rbf_mmd", "funnel_mmd"}
