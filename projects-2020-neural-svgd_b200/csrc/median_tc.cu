@@ -1,0 +1,481 @@
+// median_tc.cu — exact median-heuristic order statistics with a tensor-core filter
+// [kernels.py:160-172, utils.py:178-197, 653-658].  Bit-exact with the 3-pass SIMT select and the
+// oracle: the tensor cores only DISCARD pairs that provably lie outside a bracket; every value that
+// can influence the result is recomputed with the defined-order fp32 arithmetic.
+//
+//   1. sample  : 2^22 pseudo-random pairs, exact distances, radix-select two sample quantiles
+//                L <= (target order statistics) <= U   (7 sigma + slack of the binomial rank error)
+//   2. filter  : ONE pass over all pairs on the tensor cores: Gram tile (bf16 2-piece split, 3 MMA
+//                passes, TMEM accumulator) -> dt = |z_i|^2 + |z_j|^2 - 2 g.  With the rigorous error
+//                radius eps_ij = kappa (|z_i|^2 + |z_j|^2):  dt + eps < L -> counted "below";
+//                dt - eps > U -> dropped; otherwise the pair (i,j) is appended to a list.
+//   3. exact   : listed pairs are recomputed in the defined order: < L counted, in [L,U] kept as
+//                candidates, > U dropped.
+//   4. resolve : rank' = rank - below must fall inside the candidates; radix-select among them.
+//                If the bracket missed or a list overflowed (massive ties), a device-side flag makes
+//                the conditional SIMT 3-pass kernels run instead — still enqueue-only, still exact.
+#include <math.h>
+
+#include <algorithm>
+
+#include "select.cuh"
+#include "tc_common.cuh"
+
+namespace nsvgd {
+
+using namespace tc;
+
+constexpr int MF_BM = 128, MF_BN = 64, MF_CHUNK = 64, MF_THREADS = 192, MF_XSTAGES = 4;
+constexpr uint32_t MF_SAMPLES = 1u << 22;
+// error radius of the filter relative to |z_i|^2 + |z_j|^2: bf16 2-piece products 2^-15, norms 2^-17,
+// defined-order rounding of the exact value 2^-16, centring 2^-22  =>  < 2^-14.2; kappa = 2^-13.
+constexpr float MF_KAPPA = 1.220703125e-4f;
+
+bool median_fast_supported(int64_t n, int64_t dz) { return n >= 8192 && n <= (1ll << 22) && dz > 32 && dz <= 128; }
+
+static uint32_t list_capacity(int64_t n) {
+  const double P = 0.5 * (double)n * (double)(n - 1);
+  return (uint32_t)std::min<double>(P / 48.0 + (double)(1 << 22), 4.0e9);
+}
+static uint32_t cand_capacity(int64_t n) {
+  const double P = 0.5 * (double)n * (double)(n - 1);
+  return (uint32_t)std::min<double>(P / 96.0 + (double)(1 << 22), 4.0e9);
+}
+
+struct FastWs {
+  FastMedState* fs; SelectState* bracket; SelectState* cand_state;
+  float* mu; double* mpart; __nv_bfloat16* Zb0; __nv_bfloat16* Zb1; float* zn; float* Ds;
+  unsigned long long* list; float* cand; uint32_t* err_flag;
+  uint32_t list_cap, cand_cap; int64_t n_pad; int dp;
+};
+
+static size_t fast_layout(int64_t n, int64_t dz, WsCarver& w, FastWs* o) {
+  const int dp = dz <= 64 ? 64 : 128;
+  const int64_t n_pad = round_up(n, 128);
+  FastWs f{};
+  f.dp = dp; f.n_pad = n_pad; f.list_cap = list_capacity(n); f.cand_cap = cand_capacity(n);
+  f.fs = w.take<FastMedState>(1);
+  f.bracket = (SelectState*)w.take<char>(NSVGD_SELECT_STATE_BYTES);
+  f.cand_state = (SelectState*)w.take<char>(NSVGD_SELECT_STATE_BYTES);
+  f.mu = w.take<float>((size_t)dz);
+  f.mpart = w.take<double>((size_t)colmean_partials(n, dz));
+  f.Zb0 = w.take<__nv_bfloat16>((size_t)(n_pad * dp), 1024);
+  f.Zb1 = w.take<__nv_bfloat16>((size_t)(n_pad * dp), 1024);
+  f.zn = w.take<float>((size_t)n_pad);
+  f.Ds = w.take<float>(MF_SAMPLES);
+  f.list = w.take<unsigned long long>(f.list_cap);
+  f.cand = w.take<float>(f.cand_cap);
+  f.err_flag = w.take<uint32_t>(4);
+  if (o) *o = f;
+  return w.off;
+}
+
+size_t median_fast_workspace(int64_t n, int64_t dz) {
+  WsCarver w(nullptr, 0, true);
+  return fast_layout(n, dz, w, nullptr) + 1024;
+}
+
+// ---------------------------------------------------------------------------- exact pair distance, vectorised loads
+__device__ __forceinline__ float exact_pair_sqdist_v4(const float* __restrict__ a, const float* __restrict__ b, int d,
+                                                      float w_last) {
+  float acc = 0.f;
+  const int dm = d - 1;            // coordinates [0, dm) unweighted, dm weighted
+  const int groups = d >> 2;
+  float last_diff = 0.f;
+  for (int g = 0; g < groups; ++g) {
+    const float4 av = __ldg(reinterpret_cast<const float4*>(a) + g);
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(b) + g);
+    const float da[4] = {av.x - bv.x, av.y - bv.y, av.z - bv.z, av.w - bv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = 4 * g + e;
+      if (c < dm) acc = __fadd_rn(acc, __fmul_rn(da[e], da[e]));
+      else last_diff = da[e];
+    }
+  }
+  for (int c = groups << 2; c < d; ++c) {
+    const float diff = a[c] - b[c];
+    if (c < dm) acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+    else last_diff = diff;
+  }
+  float t = __fmul_rn(last_diff, last_diff);
+  t = __fmul_rn(w_last, t);
+  return __fadd_rn(acc, t);
+}
+
+__device__ __forceinline__ float exact_pair(const float* P, int64_t ldp, int64_t i, int64_t j, int d, float w_last,
+                                            bool vec) {
+  return vec ? exact_pair_sqdist_v4(P + i * ldp, P + j * ldp, d, w_last)
+             : exact_pair_sqdist(P + i * ldp, P + j * ldp, d, w_last);
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256) sample_pairs_kernel(const float* __restrict__ P, int64_t n, int d, int64_t ldp,
+                                                           float w_last, int vec, uint32_t ns, float* __restrict__ Ds) {
+  for (uint32_t s = blockIdx.x * 256u + threadIdx.x; s < ns; s += gridDim.x * 256u) {
+    const uint64_t z = splitmix64(s);
+    const uint64_t i = ((z >> 32) * (uint64_t)n) >> 32;
+    uint64_t j = ((z & 0xFFFFFFFFull) * (uint64_t)(n - 1)) >> 32;
+    if (j >= i) ++j;
+    Ds[s] = exact_pair(P, ldp, (int64_t)min(i, j), (int64_t)max(i, j), d, w_last, vec != 0);
+  }
+}
+
+__global__ void bracket_set_kernel(FastMedState* fs, const SelectState* bracket, int l_is_zero, int u_is_inf) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    fs->below = 0ull; fs->list_count = 0u; fs->cand_count = 0u; fs->overflow = 0u; fs->fallback = 0u;
+    fs->L = l_is_zero ? 0.f : bracket->value[0];
+    fs->U = u_is_inf ? __uint_as_float(0x7f800000u) : bracket->value[1];
+    fs->u_is_inf = (uint32_t)u_is_inf; fs->pad = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------- the tensor-core filter
+struct MfParams {
+  const float* zn;
+  int64_t n;
+  int n_tiles;                 // n_pad / 64
+  int64_t rb_start, rb_stride; // 128-row blocks handled by this rank
+  FastMedState* fs;
+  unsigned long long* list;
+  uint32_t list_cap;
+  uint32_t* err_flag;
+};
+
+template <int DP>
+struct MfSmem {
+  static constexpr int KH = DP / 64;
+  static constexpr int QSLAB = MF_BM * 128;
+  static constexpr int XSLAB = MF_BN * 128;
+  static constexpr int Q_BYTES = 2 * KH * QSLAB;
+  static constexpr int X_STAGE_BYTES = 2 * KH * XSLAB;
+  static constexpr int OFF_X = Q_BYTES;
+  static constexpr int OFF_BAR = OFF_X + MF_XSTAGES * X_STAGE_BYTES;
+  static constexpr int NBARS = 1 + 2 * MF_XSTAGES + 4;
+  static constexpr int DYN_BYTES = OFF_BAR + NBARS * 8 + 16 + 1024;
+};
+
+template <int DP>
+__global__ void __launch_bounds__(MF_THREADS, 1)
+median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                        const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                        const MfParams p) {
+  using L = MfSmem<DP>;
+  constexpr int KH = L::KH;
+  const int64_t rb = p.rb_start + p.rb_stride * (int64_t)blockIdx.y;
+  const int t_begin = (int)(2 * rb) + (int)blockIdx.x * MF_CHUNK;
+  if (t_begin >= p.n_tiles) return;
+  const int t_end = min(t_begin + MF_CHUNK, p.n_tiles);
+  const int T = t_end - t_begin;
+  const int m0 = (int)(rb * MF_BM);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sX = smem + L::OFF_X;
+  uint64_t* bars = (uint64_t*)(smem + L::OFF_BAR);
+  uint64_t* q_full = bars;
+  uint64_t* x_full = q_full + 1;
+  uint64_t* x_empty = x_full + MF_XSTAGES;
+  uint64_t* g_full = x_empty + MF_XSTAGES;
+  uint64_t* g_empty = g_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(g_empty + 2);
+  volatile uint32_t* abort_s = tmem_slot + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Watch watch{abort_s, p.err_flag};
+
+  if (threadIdx.x == 0) {
+    *abort_s = (*(volatile uint32_t*)p.err_flag) ? 1u : 0u;
+    mbar_init(q_full, 1);
+    for (int i = 0; i < MF_XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 128); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, L::Q_BYTES);
+      for (int kh = 0; kh < KH; ++kh) {
+        tma_load_2d(sQ + (0 * KH + kh) * L::QSLAB, &tmA0, q_full, kh * 64, m0);
+        tma_load_2d(sQ + (1 * KH + kh) * L::QSLAB, &tmA1, q_full, kh * 64, m0);
+      }
+      for (int t = 0; t < T; ++t) {
+        const int st = t % MF_XSTAGES, u = t / MF_XSTAGES;
+        mbar_wait(&x_empty[st], (u & 1) ^ 1, watch, 0x100 + st);
+        mbar_arrive_expect_tx(&x_full[st], L::X_STAGE_BYTES);
+        uint8_t* dst = sX + st * L::X_STAGE_BYTES;
+        const int j0 = (t_begin + t) * MF_BN;
+        for (int kh = 0; kh < KH; ++kh) {
+          tma_load_2d(dst + (0 * KH + kh) * L::XSLAB, &tmB0, &x_full[st], kh * 64, j0);
+          tma_load_2d(dst + (1 * KH + kh) * L::XSLAB, &tmB1, &x_full[st], kh * 64, j0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(MF_BM, MF_BN);
+      const uint32_t sQ_a = smem_u32(sQ), sX_a = smem_u32(sX);
+      mbar_wait(q_full, 0, watch, 0x300);
+      tc_fence_after();
+      for (int t = 0; t < T; ++t) {
+        const int b = t & 1, ub = t >> 1;
+        const int st = t % MF_XSTAGES, us = t / MF_XSTAGES;
+        mbar_wait(&g_empty[b], (ub & 1) ^ 1, watch, 0x310 + b);
+        mbar_wait(&x_full[st], us & 1, watch, 0x320 + st);
+        tc_fence_after();
+        const uint32_t d_tm = tmem + b * MF_BN;
+        const uint32_t xs = sX_a + st * L::X_STAGE_BYTES;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const int pa = pass == 2 ? 1 : 0;
+          const int pb = pass == 1 ? 1 : 0;
+#pragma unroll
+          for (int kh = 0; kh < KH; ++kh) {
+            const uint64_t ad = umma_desc_sw128(sQ_a + (pa * KH + kh) * L::QSLAB);
+            const uint64_t bd = umma_desc_sw128(xs + (pb * KH + kh) * L::XSLAB);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              umma_ss(d_tm, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 32), idesc, acc);
+              acc = 1;
+            }
+          }
+        }
+        umma_commit(&x_empty[st]);
+        umma_commit(&g_full[b]);
+      }
+    }
+  } else {
+    // ---- classification warps: one thread per row i
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const int64_t gi = (int64_t)m0 + row_in_tile;
+    const float qn = p.zn[gi];
+    const float qe = MF_KAPPA * qn;
+    const float Lv = p.fs->L, Uv = p.fs->U;
+    uint32_t cnt = 0;
+    for (int t = 0; t < T; ++t) {
+      const int b = t & 1, ub = t >> 1;
+      const int tile = t_begin + t;
+      const int64_t j0 = (int64_t)tile * MF_BN;
+      const float4* zn4 = reinterpret_cast<const float4*>(p.zn + j0);
+      mbar_wait(&g_full[b], ub & 1, watch, 0x400 + b);
+      __syncwarp();
+      tc_fence_after();
+      uint32_t g[64];
+      tmem_ld32(tmem + lane_addr + b * MF_BN, g);
+      tmem_ld32(tmem + lane_addr + b * MF_BN + 32, g + 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&g_empty[b]);
+      // boundary tiles (diagonal or padded) need the i < j < n mask
+      const bool boundary = (tile <= 2 * (int)rb + 1) || (j0 + MF_BN > p.n) || ((int64_t)m0 + MF_BM > p.n);
+      uint32_t unc_lo = 0u, unc_hi = 0u;
+#pragma unroll
+      for (int q4 = 0; q4 < 16; ++q4) {
+        const float4 zv = __ldg(&zn4[q4]);
+        const float zs[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = q4 * 4 + e;
+          const float u = fmaf(__uint_as_float(g[col]), -2.f, qn) + zs[e];
+          const float er = fmaf(MF_KAPPA, zs[e], qe);
+          bool below = (u + er) < Lv;
+          const bool above = (u - er) > Uv;
+          bool unc = !(below || above);
+          if (boundary) {
+            const int64_t gj = j0 + col;
+            const bool valid = (gi < gj) && (gj < p.n) && (gi < p.n);
+            below = below && valid;
+            unc = unc && valid;
+          }
+          cnt += below ? 1u : 0u;
+          if (col < 32) unc_lo |= (unc ? 1u : 0u) << col;
+          else unc_hi |= (unc ? 1u : 0u) << (col - 32);
+        }
+      }
+      while (unc_lo) {
+        const int c = __ffs(unc_lo) - 1;
+        unc_lo &= unc_lo - 1;
+        const uint32_t pos = atomicAdd(&p.fs->list_count, 1u);
+        if (pos < p.list_cap) p.list[pos] = ((unsigned long long)gi << 32) | (unsigned long long)(j0 + c);
+      }
+      while (unc_hi) {
+        const int c = __ffs(unc_hi) - 1;
+        unc_hi &= unc_hi - 1;
+        const uint32_t pos = atomicAdd(&p.fs->list_count, 1u);
+        if (pos < p.list_cap) p.list[pos] = ((unsigned long long)gi << 32) | (unsigned long long)(j0 + 32 + c);
+      }
+    }
+    uint32_t tot = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0 && tot) atomicAdd(&p.fs->below, (unsigned long long)tot);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 128); }
+}
+
+// ---------------------------------------------------------------------------- exact evaluation of the uncertain list
+__global__ void __launch_bounds__(256) exact_list_kernel(const float* __restrict__ P, int d, int64_t ldp, float w_last,
+                                                         int vec, FastMedState* fs, const unsigned long long* __restrict__ list,
+                                                         uint32_t list_cap, float* __restrict__ cand, uint32_t cand_cap,
+                                                         SelectState* main_state) {
+  __shared__ unsigned int sh_below;
+  if (threadIdx.x == 0) sh_below = 0u;
+  __syncthreads();
+  const uint32_t count = min(fs->list_count, list_cap);
+  const float Lv = fs->L, Uv = fs->U;
+  uint32_t below = 0;
+  bool any_nan = false;
+  for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < count; t += gridDim.x * 256u) {
+    const unsigned long long e = list[t];
+    const int64_t i = (int64_t)(e >> 32), j = (int64_t)(e & 0xFFFFFFFFull);
+    const float dv = exact_pair(P, ldp, i, j, d, w_last, vec != 0);
+    if (dv != dv) { any_nan = true; continue; }
+    if (dv < Lv) ++below;
+    else if (dv <= Uv) {
+      const uint32_t pos = atomicAdd(&fs->cand_count, 1u);
+      if (pos < cand_cap) cand[pos] = dv;
+    }
+  }
+  if (any_nan) atomicOr(&main_state->nan_flag, 1u);
+  if (below) atomicAdd(&sh_below, below);
+  __syncthreads();
+  if (threadIdx.x == 0 && sh_below) atomicAdd(&fs->below, (unsigned long long)sh_below);
+}
+
+__global__ void fast_resolve_kernel(FastMedState* fs, const SelectState* main_state, SelectState* cs, uint32_t list_cap,
+                                    uint32_t cand_cap, const uint32_t* err_flag) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint32_t fb = (fs->list_count > list_cap || fs->cand_count > cand_cap || *err_flag != 0u) ? 1u : 0u;
+  cs->prefix[0] = cs->prefix[1] = 0u; cs->mask = 0u; cs->nan_flag = 0u;
+  cs->value[0] = cs->value[1] = 0.f; cs->log_np1 = main_state->log_np1; cs->done = 0;
+  for (int t = 0; t < 2; ++t) {
+    cs->is_zero[t] = main_state->is_zero[t];
+    cs->rank[t] = 0ull;
+    if (main_state->is_zero[t]) continue;
+    const unsigned long long r = main_state->rank[t];
+    if (r < fs->below || r - fs->below >= (unsigned long long)fs->cand_count) fb = 1u;   // bracket missed
+    else cs->rank[t] = r - fs->below;
+  }
+  fs->fallback = fb;
+  if (fs->cand_count > cand_cap) fs->cand_count = cand_cap;
+}
+
+__global__ void fast_commit_kernel(const FastMedState* fs, const SelectState* cs, SelectState* main_state) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (fs->fallback) return;     // the conditional SIMT passes will resolve main_state instead
+  for (int t = 0; t < 2; ++t) main_state->value[t] = main_state->is_zero[t] ? 0.f : cs->value[t];
+  main_state->done = 1;
+}
+
+template <int DP>
+static int launch_filter(cudaStream_t st, const CUtensorMap* maps, const MfParams& prm, int64_t row_blocks) {
+  using L = MfSmem<DP>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NSVGD_CUDA(cudaFuncSetAttribute(median_filter_tc_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    attr_set = true;
+  }
+  const int64_t my_blocks = prm.rb_start < row_blocks ? ceil_div(row_blocks - prm.rb_start, prm.rb_stride) : 0;
+  if (my_blocks == 0) return NSVGD_OK;
+  const unsigned chunks = (unsigned)ceil_div(prm.n_tiles, MF_CHUNK);
+  NSVGD_REQUIRE(my_blocks <= 65535, NSVGD_ERR_INVALID, "median filter: too many row blocks");
+  prof_begin(1, st);
+  median_filter_tc_kernel<DP><<<dim3(chunks, (unsigned)my_blocks), MF_THREADS, L::DYN_BYTES, st>>>(maps[0], maps[1], maps[2],
+                                                                                                  maps[3], prm);
+  prof_end(1, st);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
+int median_fast(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, long long r_lo,
+                long long r_hi, int64_t tile_row_start, int64_t tile_row_stride, SelectState* main_state, uint64_t* hist,
+                void* ws, size_t ws_bytes) {
+  NSVGD_REQUIRE(median_fast_supported(n, dz), NSVGD_ERR_UNSUPPORTED, "median_fast: unsupported shape");
+  NSVGD_REQUIRE(r_lo >= 0 && r_hi >= r_lo, NSVGD_ERR_UNSUPPORTED, "median_fast: needs genuine pair ranks");
+  WsCarver w(ws, ws_bytes);
+  FastWs f;
+  fast_layout(n, dz, w, &f);
+  NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "median_fast: workspace too small (%zu < %zu)", ws_bytes, w.off);
+  const int vec = (ldp % 4 == 0) && (((uintptr_t)P & 15) == 0);
+  const int sms = device_sm_count();
+
+  // --- 0. centred bf16 pieces + norms (weighted last coordinate scaled by sqrt(w) after centring)
+  NSVGD_PROPAGATE(launch_colmean(st, P, n, dz, ldp, f.mpart, f.mu));
+  NSVGD_CUDA(cudaMemsetAsync(f.err_flag, 0, 16, st));
+  NSVGD_PROPAGATE(launch_tc_prep(st, P, nullptr, n, dz, ldp, f.n_pad, f.dp, f.mu, sqrtf(w_last), f.Zb0, f.Zb1, nullptr,
+                                 nullptr, f.zn, nullptr));
+
+  // --- 1. bracket [L, U] from the sample quantiles: 7 sigma of the binomial rank error + slack
+  const double Ppairs = 0.5 * (double)n * (double)(n - 1);
+  const double ns = (double)MF_SAMPLES;
+  const double p_lo = ((double)r_lo + 0.5) / Ppairs, p_hi = ((double)r_hi + 0.5) / Ppairs;
+  const double sig_lo = sqrt(ns * p_lo * (1.0 - p_lo)), sig_hi = sqrt(ns * p_hi * (1.0 - p_hi));
+  long long a = (long long)floor(p_lo * ns - 7.0 * sig_lo - 16.0);
+  long long b = (long long)ceil(p_hi * ns + 7.0 * sig_hi + 16.0);
+  const int l_is_zero = a < 0, u_is_inf = b >= (long long)MF_SAMPLES;
+  if (a < 0) a = 0;
+  if (b >= (long long)MF_SAMPLES) b = (long long)MF_SAMPLES - 1;
+  sample_pairs_kernel<<<sms * 8, 256, 0, st>>>(P, n, (int)dz, ldp, w_last, vec, MF_SAMPLES, f.Ds);
+  NSVGD_LAUNCH_CHECK();
+  NSVGD_PROPAGATE(launch_select_init(st, f.bracket, a, b, 1.f));
+  for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
+    NSVGD_PROPAGATE(launch_buffer_hist(st, f.Ds, nullptr, MF_SAMPLES, f.bracket, pass, hist, nullptr));
+    NSVGD_PROPAGATE(launch_select_advance(st, f.bracket, hist, pass, nullptr));
+  }
+  bracket_set_kernel<<<1, 32, 0, st>>>(f.fs, f.bracket, l_is_zero, u_is_inf);
+  NSVGD_LAUNCH_CHECK();
+
+  // --- 2. tensor-core filter over the upper triangle (row blocks strided across ranks)
+  CUtensorMap maps[4];
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[0], f.Zb0, f.dp, f.n_pad, (uint64_t)f.dp * 2, 64, MF_BM));
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[1], f.Zb1, f.dp, f.n_pad, (uint64_t)f.dp * 2, 64, MF_BM));
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[2], f.Zb0, f.dp, f.n_pad, (uint64_t)f.dp * 2, 64, MF_BN));
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[3], f.Zb1, f.dp, f.n_pad, (uint64_t)f.dp * 2, 64, MF_BN));
+  MfParams prm{};
+  prm.zn = f.zn; prm.n = n; prm.n_tiles = (int)(f.n_pad / MF_BN); prm.rb_start = tile_row_start; prm.rb_stride = tile_row_stride;
+  prm.fs = f.fs; prm.list = f.list; prm.list_cap = f.list_cap; prm.err_flag = f.err_flag;
+  const int64_t row_blocks = f.n_pad / MF_BM;
+  if (f.dp == 64) NSVGD_PROPAGATE(launch_filter<64>(st, maps, prm, row_blocks));
+  else NSVGD_PROPAGATE(launch_filter<128>(st, maps, prm, row_blocks));
+
+  // --- 3. exact evaluation of the uncertain pairs
+  exact_list_kernel<<<sms * 8, 256, 0, st>>>(P, (int)dz, ldp, w_last, vec, f.fs, f.list, f.list_cap, f.cand, f.cand_cap,
+                                             main_state);
+  NSVGD_LAUNCH_CHECK();
+
+  // --- 4. resolve among the candidates, or flag the fallback
+  fast_resolve_kernel<<<1, 32, 0, st>>>(f.fs, main_state, f.cand_state, f.list_cap, f.cand_cap, f.err_flag);
+  NSVGD_LAUNCH_CHECK();
+  for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
+    NSVGD_PROPAGATE(launch_buffer_hist(st, f.cand, &f.fs->cand_count, 0, f.cand_state, pass, hist, nullptr));
+    NSVGD_PROPAGATE(launch_select_advance(st, f.cand_state, hist, pass, nullptr));
+  }
+  fast_commit_kernel<<<1, 32, 0, st>>>(f.fs, f.cand_state, main_state);
+  NSVGD_LAUNCH_CHECK();
+
+  // --- 5. conditional fallback: the SIMT 3-pass select, kernels return at once unless fs->fallback
+  for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
+    NSVGD_PROPAGATE(launch_pair_hist(st, P, n, dz, ldp, w_last, tile_row_start, tile_row_stride, main_state, pass, hist,
+                                     &f.fs->fallback));
+    NSVGD_PROPAGATE(launch_select_advance(st, main_state, hist, pass, &f.fs->fallback));
+  }
+  return NSVGD_OK;
+}
+
+}  // namespace nsvgd

@@ -11,8 +11,9 @@
 //   KSD  : sum of u_p(x_i, y_j)                                  [stein.py:273-349]
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 
-#include "common.cuh"
+#include "select.cuh"
 
 namespace nsvgd {
 
@@ -22,17 +23,6 @@ constexpr int LDS_ = TILE + 4;  // padded row of the transposed smem tiles (floa
 
 enum PairMode { MODE_HIST = 0, MODE_KSUM = 1, MODE_KMAT = 2, MODE_KSD = 3 };
 
-struct SelectState {
-  uint32_t prefix[2];
-  uint32_t mask;
-  uint32_t nan_flag;
-  unsigned long long rank[2];
-  int32_t is_zero[2];
-  float value[2];
-  float log_np1;
-  int32_t done;
-};
-static_assert(sizeof(SelectState) <= NSVGD_SELECT_STATE_BYTES, "state too large");
 
 struct PairArgs {
   const float* A; int64_t na, lda;       // "row" points (tile index blockIdx.y)
@@ -44,24 +34,19 @@ struct PairArgs {
   int64_t tile_row_start, tile_row_stride;
   const float* h_dev; float h_host;      // bandwidth (device pointer wins)
   // HIST
-  const SelectState* state; int pass; unsigned long long* hist;
+  const SelectState* state; int pass; unsigned long long* hist; const uint32_t* run_flag;
   // KSUM / KSD
   double* partials; float diag_weight;
   // KMAT
   float* K; int64_t ldk;
 };
 
-__device__ __forceinline__ int pass_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
-__device__ __forceinline__ int pass_bins(int pass) { return pass == 2 ? 1024 : 2048; }
 
 template <int MODE>
 __global__ void __launch_bounds__(256) pair_tile_kernel(const PairArgs a) {
   constexpr bool EXACT = (MODE == MODE_HIST);
-  const int64_t I = a.tile_row_start + a.tile_row_stride * (int64_t)blockIdx.y;
-  const int64_t J = blockIdx.x;
-  if (a.symmetric && J < I) return;
+  if (MODE == MODE_HIST && a.run_flag && *a.run_flag == 0u) return;   // conditional fallback pass
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int64_t i0 = I * TILE, j0 = J * TILE;
 
   __shared__ __align__(16) float As[DK][LDS_];
   __shared__ __align__(16) float Bs[DK][LDS_];
@@ -73,6 +58,19 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(const PairArgs a) {
   if (MODE == MODE_HIST) {
     for (int t = threadIdx.x; t < 2 * NSVGD_SELECT_BINS; t += 256) hist_s[t] = 0u;
   }
+  __syncthreads();
+  bool any_nan = false;
+  // HIST: persistent grid-stride walk over the upper-triangular tiles (rows strided across ranks),
+  // one shared-memory histogram per CTA flushed once.  Other modes: one tile per CTA.
+  const int64_t tiles_j = (a.nb + TILE - 1) / TILE;
+  const int64_t tiles_i = (a.na + TILE - 1) / TILE;
+  const int64_t n_rows = a.tile_row_start < tiles_i ? (tiles_i - a.tile_row_start + a.tile_row_stride - 1) / a.tile_row_stride : 0;
+  for (int64_t rr = blockIdx.y; rr < (MODE == MODE_HIST ? n_rows : (int64_t)blockIdx.y + 1); rr += gridDim.y) {
+  const int64_t I = a.tile_row_start + a.tile_row_stride * rr;
+  for (int64_t J = (MODE == MODE_HIST ? I + blockIdx.x : (int64_t)blockIdx.x);
+       J < (MODE == MODE_HIST ? tiles_j : (int64_t)blockIdx.x + 1); J += gridDim.x) {
+  if (MODE != MODE_HIST && a.symmetric && J < I) return;
+  const int64_t i0 = I * TILE, j0 = J * TILE;
 
   float acc[4][4];
   float acc_ss[MODE == MODE_KSD ? 4 : 1][MODE == MODE_KSD ? 4 : 1];
@@ -158,11 +156,9 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(const PairArgs a) {
 
   // ------------------------------------------------------------------ epilogues
   if (MODE == MODE_HIST) {
-    __syncthreads();
     const SelectState stt = *a.state;
     const int shift = pass_shift(a.pass);
     const unsigned int binmask = (unsigned int)pass_bins(a.pass) - 1u;
-    bool any_nan = false;
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
@@ -177,13 +173,7 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(const PairArgs a) {
           if ((bits & stt.mask) == stt.prefix[1]) atomicAdd(&hist_s[NSVGD_SELECT_BINS + bin], 1u);
         }
       }
-    if (any_nan) atomicOr(const_cast<uint32_t*>(&a.state->nan_flag), 1u);
-    __syncthreads();
-    for (int t = threadIdx.x; t < 2 * NSVGD_SELECT_BINS; t += 256) {
-      const unsigned int v = hist_s[t];
-      if (v) atomicAdd(&a.hist[t], (unsigned long long)v);
-    }
-    return;
+    continue;
   }
 
   const float h = a.h_dev ? *a.h_dev : a.h_host;
@@ -225,6 +215,16 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(const PairArgs a) {
     }
   const double tot = block_sum(local, red_s);
   if (threadIdx.x == 0) a.partials[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
+  }  // J
+  }  // rr
+  if (MODE == MODE_HIST) {
+    if (any_nan) atomicOr(const_cast<uint32_t*>(&a.state->nan_flag), 1u);
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * NSVGD_SELECT_BINS; t += 256) {
+      const unsigned int v = hist_s[t];
+      if (v) atomicAdd(&a.hist[t], (unsigned long long)v);
+    }
+  }
 }
 
 // deterministic single-block reduction of the per-CTA partials: out = [out +] scale * sum
@@ -319,7 +319,9 @@ __global__ void literal_z_kernel(const float* __restrict__ X, int64_t n, int64_t
   }
 }
 
-__global__ void __launch_bounds__(1024) select_advance_kernel(SelectState* s, const unsigned long long* hist, int pass) {
+__global__ void __launch_bounds__(1024) select_advance_kernel(SelectState* s, const unsigned long long* hist, int pass,
+                                                              const uint32_t* run_flag) {
+  if (run_flag && *run_flag == 0u) return;
   // warp t (t = 0,1) resolves target t: find the bin whose cumulative count exceeds rank[t]
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __shared__ uint32_t new_prefix[2];
@@ -381,11 +383,82 @@ __global__ void select_finish_kernel(const SelectState* s, float* h_dev) {
   }
 }
 
+// histogram of an in-memory value buffer (sampled distances / candidate distances) for the same select
+__global__ void __launch_bounds__(256) buffer_hist_kernel(const float* __restrict__ vals, const uint32_t* count_dev,
+                                                          uint32_t count_host, const SelectState* state, int pass,
+                                                          unsigned long long* hist, const uint32_t* run_flag) {
+  if (run_flag && *run_flag == 0u) return;
+  __shared__ unsigned int hist_s[2 * NSVGD_SELECT_BINS];
+  for (int t = threadIdx.x; t < 2 * NSVGD_SELECT_BINS; t += 256) hist_s[t] = 0u;
+  __syncthreads();
+  const uint32_t count = count_dev ? *count_dev : count_host;
+  const SelectState stt = *state;
+  const int shift = pass_shift(pass);
+  const unsigned int binmask = (unsigned int)pass_bins(pass) - 1u;
+  bool any_nan = false;
+  for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < count; t += gridDim.x * 256u) {
+    const float v = vals[t];
+    if (v != v) { any_nan = true; continue; }
+    const unsigned int bits = __float_as_uint(v);
+    const unsigned int bin = (bits >> shift) & binmask;
+    if ((bits & stt.mask) == stt.prefix[0]) atomicAdd(&hist_s[bin], 1u);
+    if ((bits & stt.mask) == stt.prefix[1]) atomicAdd(&hist_s[NSVGD_SELECT_BINS + bin], 1u);
+  }
+  if (any_nan) atomicOr(const_cast<uint32_t*>(&state->nan_flag), 1u);
+  __syncthreads();
+  for (int t = threadIdx.x; t < 2 * NSVGD_SELECT_BINS; t += 256) {
+    const unsigned int v = hist_s[t];
+    if (v) atomicAdd(&hist[t], (unsigned long long)v);
+  }
+}
+
+int launch_select_init(cudaStream_t st, SelectState* s, long long r_lo, long long r_hi, float log_np1) {
+  select_init_kernel<<<1, 32, 0, st>>>(s, r_lo, r_hi, log_np1);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
+int launch_buffer_hist(cudaStream_t st, const float* vals, const uint32_t* count_dev, uint32_t count_host,
+                       const SelectState* state, int pass, uint64_t* hist, const uint32_t* run_flag) {
+  NSVGD_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint64_t) * 2 * NSVGD_SELECT_BINS, st));
+  buffer_hist_kernel<<<device_sm_count() * 4, 256, 0, st>>>(vals, count_dev, count_host, state, pass,
+                                                            (unsigned long long*)hist, run_flag);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
+int launch_select_advance(cudaStream_t st, SelectState* s, const uint64_t* hist, int pass, const uint32_t* run_flag) {
+  select_advance_kernel<<<1, 64, 0, st>>>(s, (const unsigned long long*)hist, pass, run_flag);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
+int launch_pair_hist(cudaStream_t st, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last,
+                     int64_t tile_row_start, int64_t tile_row_stride, const SelectState* state, int pass,
+                     uint64_t* hist, const uint32_t* run_flag) {
+  NSVGD_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint64_t) * 2 * NSVGD_SELECT_BINS, st));
+  PairArgs a{};
+  a.A = Z; a.na = n; a.lda = ldz; a.B = Z; a.nb = n; a.ldb = ldz; a.d = dz; a.w_last = w_last;
+  a.symmetric = 1; a.tile_row_start = tile_row_start; a.tile_row_stride = tile_row_stride;
+  a.state = state; a.pass = pass; a.hist = (unsigned long long*)hist; a.run_flag = run_flag;
+  const int64_t tiles = ceil_div(n, TILE);
+  const int64_t rows = tile_row_start < tiles ? ceil_div(tiles - tile_row_start, tile_row_stride) : 0;
+  if (rows == 0) return NSVGD_OK;
+  // persistent 2-D grid-stride walk: ~8 CTAs per SM, never more CTAs than tiles
+  const int64_t target = (int64_t)device_sm_count() * 8;
+  const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(tiles, 32));
+  const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(rows, ceil_div(target, gx)));
+  prof_begin(1, st);
+  pair_tile_kernel<MODE_HIST><<<dim3(gx, gy), 256, 0, st>>>(a);
+  prof_end(1, st);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
 }  // namespace nsvgd
 
-using namespace nsvgd;
-
-static void median_ranks(int64_t n, int mode, long long* r_lo, long long* r_hi) {
+namespace nsvgd {
+void median_ranks_host(int64_t n, int mode, long long* r_lo, long long* r_hi) {
   // SURVEY.md Appendix B; mirrors oracle/svgd_oracle.py::median_ranks
   const long long P = (long long)n * (n - 1) / 2;
   if (mode == NSVGD_MEDIAN_OFFDIAG) {
@@ -397,6 +470,9 @@ static void median_ranks(int64_t n, int mode, long long* r_lo, long long* r_hi) 
   if (N % 2 == 0) { *r_lo = f(N / 2 - 1); *r_hi = f(N / 2); }
   else { *r_lo = *r_hi = f((N - 1) / 2); }
 }
+}  // namespace nsvgd
+
+using namespace nsvgd;
 
 extern "C" int nsvgd_median_prepare(void* stream, const float* X, int64_t n, int64_t d, int64_t ldx, int mode,
                                     float* Z, int64_t* dz_out, float* w_last_out, void* state_dev) {
@@ -405,10 +481,9 @@ extern "C" int nsvgd_median_prepare(void* stream, const float* X, int64_t n, int
   NSVGD_REQUIRE(n >= 2 && d >= 1 && ldx >= d, NSVGD_ERR_INVALID, "median_prepare: need n >= 2, d >= 1, ldx >= d (n=%lld d=%lld)", (long long)n, (long long)d);
   NSVGD_REQUIRE(mode >= 0 && mode <= 2, NSVGD_ERR_INVALID, "median_prepare: bad mode %d", mode);
   long long r_lo, r_hi;
-  median_ranks(n, mode, &r_lo, &r_hi);
+  median_ranks_host(n, mode, &r_lo, &r_hi);
   const float log_np1 = (float)log((double)(n + 1));
-  select_init_kernel<<<1, 32, 0, st>>>((SelectState*)state_dev, r_lo, r_hi, log_np1);
-  NSVGD_LAUNCH_CHECK();
+  NSVGD_PROPAGATE(launch_select_init(st, (SelectState*)state_dev, r_lo, r_hi, log_np1));
   if (mode == NSVGD_MEDIAN_LITERAL) {
     NSVGD_REQUIRE(Z, NSVGD_ERR_INVALID, "median_prepare: literal mode needs a Z buffer");
     const int64_t dz = n > d ? d : n - 1;
@@ -427,33 +502,17 @@ extern "C" int nsvgd_median_prepare(void* stream, const float* X, int64_t n, int
 extern "C" int nsvgd_median_hist_pass(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last,
                                       int64_t tile_row_start, int64_t tile_row_stride, const void* state_dev, int pass,
                                       uint64_t* hist_dev) {
-  cudaStream_t st = (cudaStream_t)stream;
   NSVGD_REQUIRE(Z && state_dev && hist_dev, NSVGD_ERR_INVALID, "median_hist_pass: null pointer");
   NSVGD_REQUIRE(pass >= 0 && pass < NSVGD_SELECT_PASSES, NSVGD_ERR_INVALID, "median_hist_pass: bad pass %d", pass);
   NSVGD_REQUIRE(tile_row_stride >= 1 && tile_row_start >= 0, NSVGD_ERR_INVALID, "median_hist_pass: bad tile row partition");
-  NSVGD_CUDA(cudaMemsetAsync(hist_dev, 0, sizeof(uint64_t) * 2 * NSVGD_SELECT_BINS, st));
-  PairArgs a{};
-  a.A = Z; a.na = n; a.lda = ldz; a.B = Z; a.nb = n; a.ldb = ldz; a.d = dz; a.w_last = w_last;
-  a.symmetric = 1; a.tile_row_start = tile_row_start; a.tile_row_stride = tile_row_stride;
-  a.state = (const SelectState*)state_dev; a.pass = pass; a.hist = (unsigned long long*)hist_dev;
-  dim3 g = tile_grid(n, n, tile_row_start, tile_row_stride);
-  NSVGD_REQUIRE(g.y <= 65535, NSVGD_ERR_INVALID, "median_hist_pass: too many row tiles (%u)", g.y);
-  if (g.y > 0) {
-    prof_begin(1, st);
-    pair_tile_kernel<MODE_HIST><<<g, 256, 0, st>>>(a);
-    prof_end(1, st);
-    NSVGD_LAUNCH_CHECK();
-  }
-  return NSVGD_OK;
+  return launch_pair_hist((cudaStream_t)stream, Z, n, dz, ldz, w_last, tile_row_start, tile_row_stride,
+                          (const SelectState*)state_dev, pass, hist_dev, nullptr);
 }
 
 extern "C" int nsvgd_median_advance(void* stream, void* state_dev, const uint64_t* hist_dev, int pass) {
-  cudaStream_t st = (cudaStream_t)stream;
   NSVGD_REQUIRE(state_dev && hist_dev, NSVGD_ERR_INVALID, "median_advance: null pointer");
   NSVGD_REQUIRE(pass >= 0 && pass < NSVGD_SELECT_PASSES, NSVGD_ERR_INVALID, "median_advance: bad pass %d", pass);
-  select_advance_kernel<<<1, 64, 0, st>>>((SelectState*)state_dev, (const unsigned long long*)hist_dev, pass);
-  NSVGD_LAUNCH_CHECK();
-  return NSVGD_OK;
+  return launch_select_advance((cudaStream_t)stream, (SelectState*)state_dev, hist_dev, pass, nullptr);
 }
 
 extern "C" int nsvgd_median_finish(void* stream, const void* state_dev, int64_t n, float* h_dev) {
@@ -465,22 +524,31 @@ extern "C" int nsvgd_median_finish(void* stream, const void* state_dev, int64_t 
   return NSVGD_OK;
 }
 
-static size_t median_ws_layout(int64_t n, int64_t d, int mode, WsCarver& w, void** state, uint64_t** hist, float** Z) {
+// workspace: [state | hist | Z (literal) | fast-path scratch]
+static void median_ws_layout(int64_t n, int64_t d, int mode, WsCarver& w, void** state, uint64_t** hist, float** Z,
+                             void** fast, size_t* fast_bytes) {
   *state = w.take<char>(NSVGD_SELECT_STATE_BYTES);
   *hist = w.take<uint64_t>(2 * NSVGD_SELECT_BINS);
   *Z = nullptr;
-  if (mode == NSVGD_MEDIAN_LITERAL) {
-    const int64_t dz = n > d ? d : n - 1;
-    *Z = w.take<float>((size_t)(n * dz));
+  const int64_t dz = mode == NSVGD_MEDIAN_LITERAL ? (n > d ? d : n - 1) : d;
+  if (mode == NSVGD_MEDIAN_LITERAL) *Z = w.take<float>((size_t)(n * dz));
+  *fast = nullptr; *fast_bytes = 0;
+  if (median_fast_supported(n, dz)) {
+    *fast_bytes = median_fast_workspace(n, dz);
+    *fast = w.take<char>(*fast_bytes, 1024);
   }
-  return w.off;
 }
 
 namespace nsvgd {
 size_t median_workspace(int64_t n, int64_t d) {
-  WsCarver w(nullptr, 0, true);
-  void* s; uint64_t* h; float* Z;
-  return median_ws_layout(n, d, NSVGD_MEDIAN_LITERAL, w, &s, &h, &Z) + 256;
+  size_t best = 0;
+  for (int mode = 0; mode < 3; ++mode) {
+    WsCarver w(nullptr, 0, true);
+    void* s; uint64_t* h; float* Z; void* f; size_t fb;
+    median_ws_layout(n, d, mode, w, &s, &h, &Z, &f, &fb);
+    best = std::max(best, w.off);
+  }
+  return best + 256;
 }
 }  // namespace nsvgd
 
@@ -489,21 +557,32 @@ extern "C" int nsvgd_median_h_f32(void* stream, const float* X, int64_t n, int64
   NSVGD_REQUIRE(X && h_dev && ws, NSVGD_ERR_INVALID, "median_h: null pointer");
   NSVGD_REQUIRE(n >= 2 && d >= 1 && ldx >= d, NSVGD_ERR_INVALID, "median_h: need n >= 2, d >= 1, ldx >= d (n=%lld d=%lld)", (long long)n, (long long)d);
   NSVGD_REQUIRE(mode >= 0 && mode <= 2, NSVGD_ERR_INVALID, "median_h: bad mode %d", mode);
+  cudaStream_t st = (cudaStream_t)stream;
   WsCarver w(ws, ws_bytes);
-  void* state; uint64_t* hist; float* Z;
-  median_ws_layout(n, d, mode, w, &state, &hist, &Z);
+  void* state; uint64_t* hist; float* Z; void* fast; size_t fast_bytes;
+  median_ws_layout(n, d, mode, w, &state, &hist, &Z, &fast, &fast_bytes);
   NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "median_h: workspace too small (%zu < %zu)", ws_bytes, w.off);
   int64_t dz; float w_last;
-  prof_begin(3, (cudaStream_t)stream);
+  prof_begin(3, st);
   NSVGD_PROPAGATE(nsvgd_median_prepare(stream, X, n, d, ldx, mode, Z, &dz, &w_last, state));
   const float* P = mode == NSVGD_MEDIAN_LITERAL ? Z : X;
   const int64_t ldp = mode == NSVGD_MEDIAN_LITERAL ? dz : ldx;
-  for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
-    NSVGD_PROPAGATE(nsvgd_median_hist_pass(stream, P, n, dz, ldp, w_last, 0, 1, state, pass, hist));
-    NSVGD_PROPAGATE(nsvgd_median_advance(stream, state, hist, pass));
+  const char* env = getenv("NSVGD_MEDIAN_FAST");
+  const bool want_fast = fast && !(env && env[0] == '0');
+  if (want_fast) {
+    // tensor-core filtered exact select; falls back on the device to the 3-pass SIMT select if its
+    // bracket misses (probability ~1e-9) or a candidate list overflows (massive ties)
+    long long r_lo, r_hi;
+    median_ranks_host(n, mode, &r_lo, &r_hi);
+    NSVGD_PROPAGATE(median_fast(st, P, n, dz, ldp, w_last, r_lo, r_hi, 0, 1, (SelectState*)state, hist, fast, fast_bytes));
+  } else {
+    for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
+      NSVGD_PROPAGATE(launch_pair_hist(st, P, n, dz, ldp, w_last, 0, 1, (const SelectState*)state, pass, hist, nullptr));
+      NSVGD_PROPAGATE(launch_select_advance(st, (SelectState*)state, hist, pass, nullptr));
+    }
   }
   const int rc = nsvgd_median_finish(stream, state, n, h_dev);
-  prof_end(3, (cudaStream_t)stream);
+  prof_end(3, st);
   return rc;
 }
 

@@ -14,9 +14,11 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
 // warps 2-5 = pair-function / epilogue warps (TMEM lane quarter = warp_idx % 4).
 // TMEM map (512 cols): O [0,256) | G0 [256,320) | G1 [320,384) | P(0) [384,448) | P(1) [448,512)
+#include <stdlib.h>
+
 #include <algorithm>
 
-#include "common.cuh"
+#include "select.cuh"
 #include "tc_common.cuh"
 
 namespace nsvgd {
@@ -64,7 +66,7 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
 //   xn      : |xc_j|^2 (1e30 for padded rows, which zeroes k)      cv : s_j . xc_j
 __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ X, const float* __restrict__ S,
                                                       int64_t n, int64_t d, int64_t ldx, int64_t rows_pad, int dp,
-                                                      const float* __restrict__ mu,
+                                                      const float* __restrict__ mu, float last_scale,
                                                       __nv_bfloat16* __restrict__ Xb0, __nv_bfloat16* __restrict__ Xb1,
                                                       __nv_bfloat16* __restrict__ Vt0, __nv_bfloat16* __restrict__ Vt1,
                                                       float* __restrict__ xn, float* __restrict__ cv) {
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
         if (rv && c < d) {
           if (half == 0) {
             v = X[row * ldx + c] - mu[c];
+            if (c == d - 1) v *= last_scale;
             acc_n = fmaf(v, v, acc_n);
             if (S) acc_c = fmaf(S[row * ldx + c], v, acc_c);
           } else {
@@ -121,6 +124,16 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
   }
 }
 
+int launch_tc_prep(cudaStream_t st, const float* X, const float* S, int64_t n, int64_t d, int64_t ldx, int64_t rows_pad,
+                   int dp, const float* mu, float last_scale, void* Xb0, void* Xb1, void* Vt0, void* Vt1, float* xn,
+                   float* cv) {
+  tc_prep_kernel<<<(unsigned)(rows_pad / 64), 256, 0, st>>>(X, S, n, d, ldx, rows_pad, dp, mu, last_scale,
+                                                            (__nv_bfloat16*)Xb0, (__nv_bfloat16*)Xb1, (__nv_bfloat16*)Vt0,
+                                                            (__nv_bfloat16*)Vt1, xn, cv);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
 // ---------------------------------------------------------------------------- main kernel
 struct TcParams {
   const float* xn; const float* cv; const float* qn;
@@ -133,6 +146,7 @@ struct TcParams {
 
 constexpr int TC_BM = 128, TC_BN = 64;
 constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_RUN_TILES = 64;   // <= 768 sequential TMEM accumulations per run
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_O = 0, TM_G = 256, TM_P = 384;
 
@@ -352,22 +366,26 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
         const float4 cvv = __ldg(&cv4[q4]);
         const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
         const float cc[4] = {cvv.x, cvv.y, cvv.z, cvv.w};
-        float k[4];
+        float k[4], ex[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          float ex = fmaf(__uint_as_float(g[q4 * 4 + e]), two_cs, ai);
-          ex = fmaf(xs[e], neg_cs, ex);
-          k[e] = ex2_approx(ex);
-          rowsum += k[e];
-          kc = fmaf(k[e], cc[e], kc);
-          ke = fmaf(k[e], ex, ke);
+          ex[e] = fmaf(__uint_as_float(g[q4 * 4 + e]), two_cs, ai);
+          ex[e] = fmaf(xs[e], neg_cs, ex[e]);
+          k[e] = ex2_approx(ex[e]);
         }
 #pragma unroll
         for (int e = 0; e < 4; e += 2) {
+          // k = p0 + p1 (+ <= 2^-18 k): the MMA consumes the pieces, so the row statistics use
+          // kq = p0 + p1 as well -> rowsum*q_i - K X cancels the self term exactly
           const uint32_t a0 = pack_bf16x2(k[e], k[e + 1]);
-          const uint32_t a1 = pack_bf16x2(k[e] - bf16lo_to_float(a0), k[e + 1] - bf16hi_to_float(a0));
+          const float h0 = bf16lo_to_float(a0), h1 = bf16hi_to_float(a0);
+          const uint32_t a1 = pack_bf16x2(k[e] - h0, k[e + 1] - h1);
           pk0[q4 * 2 + (e >> 1)] = a0;
           pk1[q4 * 2 + (e >> 1)] = a1;
+          const float kq0 = h0 + bf16lo_to_float(a1), kq1 = h1 + bf16hi_to_float(a1);
+          rowsum += kq0; rowsum += kq1;
+          kc = fmaf(kq0, cc[e], kc); kc = fmaf(kq1, cc[e + 1], kc);
+          ke = fmaf(kq0, ex[e], ke); ke = fmaf(kq1, ex[e + 1], ke);
         }
       }
       mbar_wait(&p_empty[b], (ub & 1) ^ 1, watch, 0x410 + b);
@@ -428,17 +446,26 @@ static TcPlan make_plan(const PhiArgs& a) {
   pl.m_pad = round_up(a.m, 128);
   pl.q_is_x = (a.Q == a.X && a.m == a.n && a.ldq == a.ldx);
   pl.tiles_total = (int)(pl.n_pad / TC_BN);
-  // split the j range so the grid covers the SMs in whole waves (row blocks x splits CTAs, 1 CTA/SM)
+  // Split the j range.  (1) Accuracy: the TMEM accumulator truncates (measured bias ~2^-25 per
+  // accumulating MMA, profiles/r01_accuracy_vs_nsplit.txt), so one CTA accumulates at most
+  // TC_MAX_RUN_TILES tiles (12 MMAs each) and the partial sums are added in fp32 RN by the epilogue.
+  // (2) Occupancy: row blocks x splits CTAs should cover the SMs in whole waves (1 CTA/SM).
   const int sms = device_sm_count();
   const int64_t row_blocks = pl.m_pad / TC_BM;
-  int best = 1; double best_eff = 0.0;
-  for (int s = 1; s <= 8; ++s) {
-    if (pl.tiles_total / s < 8 && s > 1) break;
+  const int min_split = (int)ceil_div(pl.tiles_total, TC_MAX_RUN_TILES);
+  int best = min_split; double best_eff = 0.0;
+  for (int s = min_split; s <= min_split + 8; ++s) {
+    if (s > pl.tiles_total) break;
+    if (pl.tiles_total / s < 8 && s > min_split) break;
     const int64_t ctas = row_blocks * s;
     const double eff = (double)ctas / (double)(ceil_div(ctas, sms) * sms);
     if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
   }
   pl.nsplit = best;
+  if (const char* env = getenv("NSVGD_TC_NSPLIT")) {   // accuracy / tuning experiments
+    const int v = atoi(env);
+    if (v >= 1 && v <= 64) pl.nsplit = std::min(v, pl.tiles_total);
+  }
   pl.tiles_per_split = (int)ceil_div(pl.tiles_total, pl.nsplit);
   return pl;
 }
@@ -489,14 +516,10 @@ int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dr
 
   NSVGD_PROPAGATE(launch_colmean(st, a.X, a.n, a.d, a.ldx, mpart, mu));
   NSVGD_CUDA(cudaMemsetAsync(err_flag, 0, 16, st));
-  tc_prep_kernel<<<(unsigned)(pl.n_pad / 64), 256, 0, st>>>(a.X, a.S, a.n, a.d, a.ldx, pl.n_pad, dp, mu, Xb0, Xb1, Vt0,
-                                                            Vt1, xn, cv);
-  NSVGD_LAUNCH_CHECK();
-  if (!pl.q_is_x) {
-    tc_prep_kernel<<<(unsigned)(pl.m_pad / 64), 256, 0, st>>>(a.Q, nullptr, a.m, a.d, a.ldq, pl.m_pad, dp, mu, Qb0, Qb1,
-                                                              nullptr, nullptr, qn, nullptr);
-    NSVGD_LAUNCH_CHECK();
-  }
+  NSVGD_PROPAGATE(launch_tc_prep(st, a.X, a.S, a.n, a.d, a.ldx, pl.n_pad, dp, mu, 1.f, Xb0, Xb1, Vt0, Vt1, xn, cv));
+  if (!pl.q_is_x)
+    NSVGD_PROPAGATE(launch_tc_prep(st, a.Q, nullptr, a.m, a.d, a.ldq, pl.m_pad, dp, mu, 1.f, Qb0, Qb1, nullptr, nullptr, qn,
+                                   nullptr));
   CUtensorMap maps[6];
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[0], Qb0, dp, pl.m_pad, (uint64_t)dp * 2, 64, TC_BM));
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[1], Qb1, dp, pl.m_pad, (uint64_t)dp * 2, 64, TC_BM));

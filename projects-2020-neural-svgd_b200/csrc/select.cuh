@@ -1,0 +1,74 @@
+// select.cuh — device state of the exact radix select (shared by pair_engine.cu and median_tc.cu)
+#pragma once
+#include "common.cuh"
+
+namespace nsvgd {
+
+struct SelectState {
+  uint32_t prefix[2];          // bits decided so far for the two target ranks
+  uint32_t mask;               // which bits are decided
+  uint32_t nan_flag;           // any NaN distance -> h = NaN (jnp.median semantics)
+  unsigned long long rank[2];  // remaining rank inside the current prefix
+  int32_t is_zero[2];          // target is one of the n diagonal zeros (full / literal modes)
+  float value[2];              // resolved order statistics
+  float log_np1;
+  int32_t done;
+};
+static_assert(sizeof(SelectState) <= NSVGD_SELECT_STATE_BYTES, "state too large");
+
+// state of the tensor-core-filtered fast path (median_tc.cu)
+struct FastMedState {
+  unsigned long long below;    // pairs with exact distance < L
+  uint32_t list_count;         // uncertain pairs emitted by the filter
+  uint32_t cand_count;         // exact distances inside [L, U]
+  uint32_t overflow;           // a list overflowed
+  uint32_t fallback;           // 1 -> the bracket missed or a list overflowed: run the SIMT 3-pass select
+  float L, U;
+  uint32_t u_is_inf, pad;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int pass_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
+__device__ __forceinline__ int pass_bins(int pass) { return pass == 2 ? 1024 : 2048; }
+
+// DEFINED-ORDER fp32 squared distance of one pair (oracle/svgd_oracle.py::pair_sqdist_f32):
+// sequential over coordinates, separate mul and add, last coordinate weighted by w.
+__device__ __forceinline__ float exact_pair_sqdist(const float* __restrict__ a, const float* __restrict__ b,
+                                                    int64_t d, float w_last) {
+  float acc = 0.f;
+  for (int64_t c = 0; c + 1 < d; ++c) {
+    const float diff = a[c] - b[c];
+    acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+  }
+  const float diff = a[d - 1] - b[d - 1];
+  float t = __fmul_rn(diff, diff);
+  t = __fmul_rn(w_last, t);
+  return __fadd_rn(acc, t);
+}
+#endif
+
+// pair_engine.cu
+int launch_select_init(cudaStream_t st, SelectState* s, long long r_lo, long long r_hi, float log_np1);
+int launch_buffer_hist(cudaStream_t st, const float* vals, const uint32_t* count_dev, uint32_t count_host,
+                       const SelectState* state, int pass, uint64_t* hist, const uint32_t* run_flag);
+int launch_select_advance(cudaStream_t st, SelectState* s, const uint64_t* hist, int pass, const uint32_t* run_flag);
+int launch_pair_hist(cudaStream_t st, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last,
+                     int64_t tile_row_start, int64_t tile_row_stride, const SelectState* state, int pass,
+                     uint64_t* hist, const uint32_t* run_flag);
+void median_ranks_host(int64_t n, int mode, long long* r_lo, long long* r_hi);
+
+// median_tc.cu: tensor-core filtered exact median.  Returns NSVGD_ERR_UNSUPPORTED when the shape is
+// outside its range (caller then uses the SIMT 3-pass select).
+bool median_fast_supported(int64_t n, int64_t dz);
+size_t median_fast_workspace(int64_t n, int64_t dz);
+int median_fast(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, long long r_lo,
+                long long r_hi, int64_t tile_row_start, int64_t tile_row_stride, SelectState* main_state, uint64_t* hist,
+                void* ws, size_t ws_bytes);
+
+// phi_tc.cu: centre + bf16 2-piece split (+ optional transposed [S|Xc] pieces); last_scale multiplies the
+// centred last coordinate (literal median mode)
+int launch_tc_prep(cudaStream_t st, const float* X, const float* S, int64_t n, int64_t d, int64_t ldx, int64_t rows_pad,
+                   int dp, const float* mu, float last_scale, void* Xb0, void* Xb1, void* Vt0, void* Vt1, float* xn,
+                   float* cv);
+
+}  // namespace nsvgd

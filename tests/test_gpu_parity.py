@@ -182,3 +182,48 @@ def test_full_size_rows_sampled_against_oracle():
     perm = torch.randperm(n, device="cuda")
     phi_p = engine.phistar(Xd[perm].contiguous(), Xd[perm].contiguous(), Sd[perm].contiguous(), h)
     assert rel_fro(phi_p.cpu(), phi[perm].cpu()) < 2e-5
+
+
+def _median_dataset(kind, n, d, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "gauss":
+        return (rng.standard_normal((n, d)) * 1.3 + 0.5).astype(np.float32)
+    if kind == "far":          # tight cloud far from the origin: centring + error radius must hold
+        return (rng.standard_normal((n, d)) * 0.05 + 30.0).astype(np.float32)
+    if kind == "cluster":      # well separated tight clusters: bimodal distance distribution
+        c = rng.standard_normal((8, d)) * 6.0
+        return (c[rng.integers(0, 8, n)] + rng.standard_normal((n, d)) * 0.02).astype(np.float32)
+    if kind == "ties":         # every row duplicated many times: massive ties -> device-side fallback
+        base = (rng.standard_normal((16, d))).astype(np.float32)
+        return base[rng.integers(0, 16, n)]
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("n,d,kind", [(8192, 128, "gauss"), (8192, 64, "gauss"), (9000, 100, "far"), (8192, 40, "cluster"),
+                                      (8200, 128, "ties"), (12000, 128, "gauss"), (8192, 33, "far")])
+@pytest.mark.parametrize("mode", so.MEDIAN_MODES)
+def test_fast_median_bit_identical_to_simt_select(n, d, kind, mode, monkeypatch):
+    """tensor-core filtered select == 3-pass SIMT select, bit for bit, on benign and adversarial clouds"""
+    from nsvgd import engine
+    X = dev(_median_dataset(kind, n, d, seed=n + d))
+    monkeypatch.setenv("NSVGD_MEDIAN_FAST", "0")
+    slow = engine.median_heuristic(X, mode).cpu().numpy()[0]
+    monkeypatch.setenv("NSVGD_MEDIAN_FAST", "1")
+    fast = engine.median_heuristic(X, mode).cpu().numpy()[0]
+    assert np.float32(fast).tobytes() == np.float32(slow).tobytes(), (fast, slow)
+
+
+@pytest.mark.parametrize("mode", ["literal", "offdiag"])
+def test_fast_median_bit_exact_vs_oracle_n8192(mode):
+    from nsvgd import engine
+    X = _median_dataset("gauss", 8192, 128, seed=5)
+    want = so.median_heuristic(X, mode)
+    got = engine.median_heuristic(dev(X), mode).cpu().numpy()[0]
+    assert np.float32(got).tobytes() == np.float32(want).tobytes(), (got, want)
+
+
+def test_fast_median_nan():
+    from nsvgd import engine
+    X = _median_dataset("gauss", 8192, 128, seed=6)
+    X[4000, 17] = np.nan
+    assert np.isnan(engine.median_heuristic(dev(X), "offdiag").item())
