@@ -229,6 +229,9 @@ def main():
     hist_ms, hist_cnt = _lib.profile_read(1)
     phi_op_ms, _ = _lib.profile_read(2)
     med_op_ms, _ = _lib.profile_read(3)
+    med_sample_ms, _ = _lib.profile_read(4)
+    med_exact_ms, _ = _lib.profile_read(5)
+    med_filter_ms, _ = _lib.profile_read(6)
     _lib.profile_enable(False)
     t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -301,7 +304,9 @@ def main():
                    "bandwidth": "median heuristic (%s) every step" % args.median_mode if not fixed_h else f"fixed {fixed_h}",
                    "scaled": True, "optimizer": "sgd", "parallelism": f"row-sharded x{world}", "l2_flush": "192 MiB fill between steps",
                    "path": args.path},
-        "breakdown_ms_per_step": {"median_op": med_op_ms / K, "median_hist_kernels": hist_ms / K, "phi_op": phi_op_ms / K,
+        "breakdown_ms_per_step": {"median_op": med_op_ms / K, "median_tc_filter_kernel": med_filter_ms / K,
+                                  "median_sample_kernel": med_sample_ms / K, "median_exact_list_kernel": med_exact_ms / K,
+                                  "median_simt_hist_kernels": hist_ms / K, "phi_op": phi_op_ms / K,
                                   "phi_main_kernel": phi_main_ms / K},
         "phi_only_value": (K * float(m_local) * n * d / (phi_op_ms * 1e-3)) if phi_op_ms else None,
         "result": {"h": h_val, "ksd": float(aux_host[0]), "l2": float(aux_host[1]), "alpha": float(aux_host[2])},

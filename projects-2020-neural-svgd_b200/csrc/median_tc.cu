@@ -27,6 +27,8 @@ using namespace tc;
 
 constexpr int MF_BM = 128, MF_BN = 64, MF_CHUNK = 64, MF_THREADS = 192, MF_XSTAGES = 4;
 constexpr uint32_t MF_SAMPLES = 1u << 22;
+constexpr int MF_NSEG = 64;          // independent append segments (one atomic counter per 128-byte line)
+constexpr int MF_CSTRIDE = 32;       // counter stride in uint32
 // error radius of the filter relative to |z_i|^2 + |z_j|^2: bf16 2-piece products 2^-15, norms 2^-17,
 // defined-order rounding of the exact value 2^-16, centring 2^-22  =>  < 2^-14.2; kappa = 2^-13.
 constexpr float MF_KAPPA = 1.220703125e-4f;
@@ -46,14 +48,15 @@ struct FastWs {
   FastMedState* fs; SelectState* bracket; SelectState* cand_state;
   float* mu; double* mpart; __nv_bfloat16* Zb0; __nv_bfloat16* Zb1; float* zn; float* Ds;
   unsigned long long* list; float* cand; uint32_t* err_flag;
-  uint32_t list_cap, cand_cap; int64_t n_pad; int dp;
+  uint32_t* list_counts; uint32_t* cand_counts;     // MF_NSEG counters each, MF_CSTRIDE apart
+  uint32_t list_cap, cand_cap; int64_t n_pad; int dp;   // capacities PER SEGMENT
 };
 
 static size_t fast_layout(int64_t n, int64_t dz, WsCarver& w, FastWs* o) {
   const int dp = dz <= 64 ? 64 : 128;
   const int64_t n_pad = round_up(n, 128);
   FastWs f{};
-  f.dp = dp; f.n_pad = n_pad; f.list_cap = list_capacity(n); f.cand_cap = cand_capacity(n);
+  f.dp = dp; f.n_pad = n_pad; f.list_cap = list_capacity(n) / MF_NSEG; f.cand_cap = cand_capacity(n) / MF_NSEG;
   f.fs = w.take<FastMedState>(1);
   f.bracket = (SelectState*)w.take<char>(NSVGD_SELECT_STATE_BYTES);
   f.cand_state = (SelectState*)w.take<char>(NSVGD_SELECT_STATE_BYTES);
@@ -63,9 +66,11 @@ static size_t fast_layout(int64_t n, int64_t dz, WsCarver& w, FastWs* o) {
   f.Zb1 = w.take<__nv_bfloat16>((size_t)(n_pad * dp), 1024);
   f.zn = w.take<float>((size_t)n_pad);
   f.Ds = w.take<float>(MF_SAMPLES);
-  f.list = w.take<unsigned long long>(f.list_cap);
-  f.cand = w.take<float>(f.cand_cap);
+  f.list = w.take<unsigned long long>((size_t)f.list_cap * MF_NSEG);
+  f.cand = w.take<float>((size_t)f.cand_cap * MF_NSEG);
   f.err_flag = w.take<uint32_t>(4);
+  f.list_counts = w.take<uint32_t>(MF_NSEG * MF_CSTRIDE);
+  f.cand_counts = w.take<uint32_t>(MF_NSEG * MF_CSTRIDE);
   if (o) *o = f;
   return w.off;
 }
@@ -144,7 +149,8 @@ struct MfParams {
   int64_t rb_start, rb_stride; // 128-row blocks handled by this rank
   FastMedState* fs;
   unsigned long long* list;
-  uint32_t list_cap;
+  uint32_t* list_counts;
+  uint32_t list_cap;           // per segment
   uint32_t* err_flag;
 };
 
@@ -266,6 +272,7 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     const float qe = MF_KAPPA * qn;
     const float Lv = p.fs->L, Uv = p.fs->U;
     uint32_t cnt = 0;
+    const int seg = (int)((blockIdx.y * gridDim.x + blockIdx.x) % MF_NSEG);
     for (int t = 0; t < T; ++t) {
       const int b = t & 1, ub = t >> 1;
       const int tile = t_begin + t;
@@ -306,17 +313,33 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
           else unc_hi |= (unc ? 1u : 0u) << (col - 32);
         }
       }
-      while (unc_lo) {
-        const int c = __ffs(unc_lo) - 1;
-        unc_lo &= unc_lo - 1;
-        const uint32_t pos = atomicAdd(&p.fs->list_count, 1u);
-        if (pos < p.list_cap) p.list[pos] = ((unsigned long long)gi << 32) | (unsigned long long)(j0 + c);
-      }
-      while (unc_hi) {
-        const int c = __ffs(unc_hi) - 1;
-        unc_hi &= unc_hi - 1;
-        const uint32_t pos = atomicAdd(&p.fs->list_count, 1u);
-        if (pos < p.list_cap) p.list[pos] = ((unsigned long long)gi << 32) | (unsigned long long)(j0 + 32 + c);
+      // warp-aggregated append: one atomic per warp and tile on this CTA's segment counter
+      const uint32_t c = __popc(unc_lo) + __popc(unc_hi);
+      if (__any_sync(0xffffffffu, c != 0u)) {
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&p.list_counts[seg * MF_CSTRIDE], total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        uint32_t pos = base + incl - c;
+        unsigned long long* seg_list = p.list + (size_t)seg * p.list_cap;
+        while (unc_lo) {
+          const int cc = __ffs(unc_lo) - 1;
+          unc_lo &= unc_lo - 1;
+          if (pos < p.list_cap) seg_list[pos] = ((unsigned long long)gi << 32) | (unsigned long long)(j0 + cc);
+          ++pos;
+        }
+        while (unc_hi) {
+          const int cc = __ffs(unc_hi) - 1;
+          unc_hi &= unc_hi - 1;
+          if (pos < p.list_cap) seg_list[pos] = ((unsigned long long)gi << 32) | (unsigned long long)(j0 + 32 + cc);
+          ++pos;
+        }
       }
     }
     uint32_t tot = cnt;
@@ -332,24 +355,43 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
 // ---------------------------------------------------------------------------- exact evaluation of the uncertain list
 __global__ void __launch_bounds__(256) exact_list_kernel(const float* __restrict__ P, int d, int64_t ldp, float w_last,
                                                          int vec, FastMedState* fs, const unsigned long long* __restrict__ list,
-                                                         uint32_t list_cap, float* __restrict__ cand, uint32_t cand_cap,
+                                                         const uint32_t* __restrict__ list_counts, uint32_t list_cap,
+                                                         float* __restrict__ cand, uint32_t* cand_counts, uint32_t cand_cap,
                                                          SelectState* main_state) {
   __shared__ unsigned int sh_below;
   if (threadIdx.x == 0) sh_below = 0u;
   __syncthreads();
-  const uint32_t count = min(fs->list_count, list_cap);
   const float Lv = fs->L, Uv = fs->U;
+  const int lane = threadIdx.x & 31;
   uint32_t below = 0;
   bool any_nan = false;
-  for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < count; t += gridDim.x * 256u) {
-    const unsigned long long e = list[t];
-    const int64_t i = (int64_t)(e >> 32), j = (int64_t)(e & 0xFFFFFFFFull);
-    const float dv = exact_pair(P, ldp, i, j, d, w_last, vec != 0);
-    if (dv != dv) { any_nan = true; continue; }
-    if (dv < Lv) ++below;
-    else if (dv <= Uv) {
-      const uint32_t pos = atomicAdd(&fs->cand_count, 1u);
-      if (pos < cand_cap) cand[pos] = dv;
+  for (int seg = blockIdx.y; seg < MF_NSEG; seg += gridDim.y) {
+    const uint32_t count = min(list_counts[seg * MF_CSTRIDE], list_cap);
+    const unsigned long long* seg_list = list + (size_t)seg * list_cap;
+    float* seg_cand = cand + (size_t)seg * cand_cap;
+    // warp-uniform trip count so that the ballot below sees the whole warp
+    for (uint32_t t0 = (blockIdx.x * 256u + threadIdx.x) & ~31u; t0 < count; t0 += gridDim.x * 256u) {
+      const uint32_t t = t0 + lane;
+      bool is_cand = false;
+      float dv = 0.f;
+      if (t < count) {
+        const unsigned long long e = seg_list[t];
+        const int64_t i = (int64_t)(e >> 32), j = (int64_t)(e & 0xFFFFFFFFull);
+        dv = exact_pair(P, ldp, i, j, d, w_last, vec != 0);
+        if (dv != dv) any_nan = true;
+        else if (dv < Lv) ++below;
+        else if (dv <= Uv) is_cand = true;
+      }
+      const uint32_t ball = __ballot_sync(0xffffffffu, is_cand);
+      if (ball) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&cand_counts[seg * MF_CSTRIDE], (uint32_t)__popc(ball));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (is_cand) {
+          const uint32_t pos = base + __popc(ball & ((1u << lane) - 1u));
+          if (pos < cand_cap) seg_cand[pos] = dv;
+        }
+      }
     }
   }
   if (any_nan) atomicOr(&main_state->nan_flag, 1u);
@@ -358,10 +400,20 @@ __global__ void __launch_bounds__(256) exact_list_kernel(const float* __restrict
   if (threadIdx.x == 0 && sh_below) atomicAdd(&fs->below, (unsigned long long)sh_below);
 }
 
-__global__ void fast_resolve_kernel(FastMedState* fs, const SelectState* main_state, SelectState* cs, uint32_t list_cap,
+__global__ void fast_resolve_kernel(FastMedState* fs, const SelectState* main_state, SelectState* cs,
+                                    const uint32_t* list_counts, uint32_t list_cap, uint32_t* cand_counts,
                                     uint32_t cand_cap, const uint32_t* err_flag) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  uint32_t fb = (fs->list_count > list_cap || fs->cand_count > cand_cap || *err_flag != 0u) ? 1u : 0u;
+  uint32_t fb = *err_flag != 0u ? 1u : 0u;
+  unsigned long long ncand = 0ull, nlist = 0ull;
+  for (int sgm = 0; sgm < MF_NSEG; ++sgm) {
+    const uint32_t lc = list_counts[sgm * MF_CSTRIDE], cc = cand_counts[sgm * MF_CSTRIDE];
+    if (lc > list_cap || cc > cand_cap) fb = 1u;                 // a list overflowed (massive ties)
+    if (cc > cand_cap) cand_counts[sgm * MF_CSTRIDE] = cand_cap;
+    ncand += min(cc, cand_cap); nlist += lc;
+  }
+  fs->list_count = (uint32_t)min(nlist, 0xFFFFFFFFull);
+  fs->cand_count = (uint32_t)min(ncand, 0xFFFFFFFFull);
   cs->prefix[0] = cs->prefix[1] = 0u; cs->mask = 0u; cs->nan_flag = 0u;
   cs->value[0] = cs->value[1] = 0.f; cs->log_np1 = main_state->log_np1; cs->done = 0;
   for (int t = 0; t < 2; ++t) {
@@ -369,11 +421,10 @@ __global__ void fast_resolve_kernel(FastMedState* fs, const SelectState* main_st
     cs->rank[t] = 0ull;
     if (main_state->is_zero[t]) continue;
     const unsigned long long r = main_state->rank[t];
-    if (r < fs->below || r - fs->below >= (unsigned long long)fs->cand_count) fb = 1u;   // bracket missed
+    if (r < fs->below || r - fs->below >= ncand) fb = 1u;          // the sampled bracket missed the target
     else cs->rank[t] = r - fs->below;
   }
   fs->fallback = fb;
-  if (fs->cand_count > cand_cap) fs->cand_count = cand_cap;
 }
 
 __global__ void fast_commit_kernel(const FastMedState* fs, const SelectState* cs, SelectState* main_state) {
@@ -395,10 +446,10 @@ static int launch_filter(cudaStream_t st, const CUtensorMap* maps, const MfParam
   if (my_blocks == 0) return NSVGD_OK;
   const unsigned chunks = (unsigned)ceil_div(prm.n_tiles, MF_CHUNK);
   NSVGD_REQUIRE(my_blocks <= 65535, NSVGD_ERR_INVALID, "median filter: too many row blocks");
-  prof_begin(1, st);
+  prof_begin(6, st);
   median_filter_tc_kernel<DP><<<dim3(chunks, (unsigned)my_blocks), MF_THREADS, L::DYN_BYTES, st>>>(maps[0], maps[1], maps[2],
                                                                                                   maps[3], prm);
-  prof_end(1, st);
+  prof_end(6, st);
   NSVGD_LAUNCH_CHECK();
   return NSVGD_OK;
 }
@@ -418,6 +469,8 @@ int median_fast(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t 
   // --- 0. centred bf16 pieces + norms (weighted last coordinate scaled by sqrt(w) after centring)
   NSVGD_PROPAGATE(launch_colmean(st, P, n, dz, ldp, f.mpart, f.mu));
   NSVGD_CUDA(cudaMemsetAsync(f.err_flag, 0, 16, st));
+  NSVGD_CUDA(cudaMemsetAsync(f.list_counts, 0, sizeof(uint32_t) * MF_NSEG * MF_CSTRIDE, st));
+  NSVGD_CUDA(cudaMemsetAsync(f.cand_counts, 0, sizeof(uint32_t) * MF_NSEG * MF_CSTRIDE, st));
   NSVGD_PROPAGATE(launch_tc_prep(st, P, nullptr, n, dz, ldp, f.n_pad, f.dp, f.mu, sqrtf(w_last), f.Zb0, f.Zb1, nullptr,
                                  nullptr, f.zn, nullptr));
 
@@ -431,11 +484,13 @@ int median_fast(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t 
   const int l_is_zero = a < 0, u_is_inf = b >= (long long)MF_SAMPLES;
   if (a < 0) a = 0;
   if (b >= (long long)MF_SAMPLES) b = (long long)MF_SAMPLES - 1;
+  prof_begin(4, st);
   sample_pairs_kernel<<<sms * 8, 256, 0, st>>>(P, n, (int)dz, ldp, w_last, vec, MF_SAMPLES, f.Ds);
+  prof_end(4, st);
   NSVGD_LAUNCH_CHECK();
   NSVGD_PROPAGATE(launch_select_init(st, f.bracket, a, b, 1.f));
   for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
-    NSVGD_PROPAGATE(launch_buffer_hist(st, f.Ds, nullptr, MF_SAMPLES, f.bracket, pass, hist, nullptr));
+    NSVGD_PROPAGATE(launch_buffer_hist(st, f.Ds, nullptr, 0, 1, 0, MF_SAMPLES, f.bracket, pass, hist, nullptr));
     NSVGD_PROPAGATE(launch_select_advance(st, f.bracket, hist, pass, nullptr));
   }
   bracket_set_kernel<<<1, 32, 0, st>>>(f.fs, f.bracket, l_is_zero, u_is_inf);
@@ -449,21 +504,25 @@ int median_fast(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t 
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[3], f.Zb1, f.dp, f.n_pad, (uint64_t)f.dp * 2, 64, MF_BN));
   MfParams prm{};
   prm.zn = f.zn; prm.n = n; prm.n_tiles = (int)(f.n_pad / MF_BN); prm.rb_start = tile_row_start; prm.rb_stride = tile_row_stride;
-  prm.fs = f.fs; prm.list = f.list; prm.list_cap = f.list_cap; prm.err_flag = f.err_flag;
+  prm.fs = f.fs; prm.list = f.list; prm.list_counts = f.list_counts; prm.list_cap = f.list_cap; prm.err_flag = f.err_flag;
   const int64_t row_blocks = f.n_pad / MF_BM;
   if (f.dp == 64) NSVGD_PROPAGATE(launch_filter<64>(st, maps, prm, row_blocks));
   else NSVGD_PROPAGATE(launch_filter<128>(st, maps, prm, row_blocks));
 
   // --- 3. exact evaluation of the uncertain pairs
-  exact_list_kernel<<<sms * 8, 256, 0, st>>>(P, (int)dz, ldp, w_last, vec, f.fs, f.list, f.list_cap, f.cand, f.cand_cap,
-                                             main_state);
+  prof_begin(5, st);
+  exact_list_kernel<<<dim3((unsigned)std::max(1, sms * 8 / MF_NSEG), MF_NSEG), 256, 0, st>>>(
+      P, (int)dz, ldp, w_last, vec, f.fs, f.list, f.list_counts, f.list_cap, f.cand, f.cand_counts, f.cand_cap, main_state);
+  prof_end(5, st);
   NSVGD_LAUNCH_CHECK();
 
   // --- 4. resolve among the candidates, or flag the fallback
-  fast_resolve_kernel<<<1, 32, 0, st>>>(f.fs, main_state, f.cand_state, f.list_cap, f.cand_cap, f.err_flag);
+  fast_resolve_kernel<<<1, 32, 0, st>>>(f.fs, main_state, f.cand_state, f.list_counts, f.list_cap, f.cand_counts, f.cand_cap,
+                                        f.err_flag);
   NSVGD_LAUNCH_CHECK();
   for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
-    NSVGD_PROPAGATE(launch_buffer_hist(st, f.cand, &f.fs->cand_count, 0, f.cand_state, pass, hist, nullptr));
+    NSVGD_PROPAGATE(launch_buffer_hist(st, f.cand, f.cand_counts, MF_CSTRIDE, MF_NSEG, f.cand_cap, 0, f.cand_state, pass, hist,
+                                       nullptr));
     NSVGD_PROPAGATE(launch_select_advance(st, f.cand_state, hist, pass, nullptr));
   }
   fast_commit_kernel<<<1, 32, 0, st>>>(f.fs, f.cand_state, main_state);

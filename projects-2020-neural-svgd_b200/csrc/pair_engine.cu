@@ -384,25 +384,29 @@ __global__ void select_finish_kernel(const SelectState* s, float* h_dev) {
 }
 
 // histogram of an in-memory value buffer (sampled distances / candidate distances) for the same select
-__global__ void __launch_bounds__(256) buffer_hist_kernel(const float* __restrict__ vals, const uint32_t* count_dev,
-                                                          uint32_t count_host, const SelectState* state, int pass,
-                                                          unsigned long long* hist, const uint32_t* run_flag) {
+__global__ void __launch_bounds__(256) buffer_hist_kernel(const float* __restrict__ vals, const uint32_t* counts_dev,
+                                                          int count_stride, int nseg, uint32_t seg_cap, uint32_t count_host,
+                                                          const SelectState* state, int pass, unsigned long long* hist,
+                                                          const uint32_t* run_flag) {
   if (run_flag && *run_flag == 0u) return;
   __shared__ unsigned int hist_s[2 * NSVGD_SELECT_BINS];
   for (int t = threadIdx.x; t < 2 * NSVGD_SELECT_BINS; t += 256) hist_s[t] = 0u;
   __syncthreads();
-  const uint32_t count = count_dev ? *count_dev : count_host;
   const SelectState stt = *state;
   const int shift = pass_shift(pass);
   const unsigned int binmask = (unsigned int)pass_bins(pass) - 1u;
   bool any_nan = false;
-  for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < count; t += gridDim.x * 256u) {
-    const float v = vals[t];
-    if (v != v) { any_nan = true; continue; }
-    const unsigned int bits = __float_as_uint(v);
-    const unsigned int bin = (bits >> shift) & binmask;
-    if ((bits & stt.mask) == stt.prefix[0]) atomicAdd(&hist_s[bin], 1u);
-    if ((bits & stt.mask) == stt.prefix[1]) atomicAdd(&hist_s[NSVGD_SELECT_BINS + bin], 1u);
+  for (int sgm = 0; sgm < nseg; ++sgm) {
+    const uint32_t count = counts_dev ? min(counts_dev[sgm * count_stride], seg_cap) : count_host;
+    const float* v0 = vals + (size_t)sgm * seg_cap;
+    for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < count; t += gridDim.x * 256u) {
+      const float v = v0[t];
+      if (v != v) { any_nan = true; continue; }
+      const unsigned int bits = __float_as_uint(v);
+      const unsigned int bin = (bits >> shift) & binmask;
+      if ((bits & stt.mask) == stt.prefix[0]) atomicAdd(&hist_s[bin], 1u);
+      if ((bits & stt.mask) == stt.prefix[1]) atomicAdd(&hist_s[NSVGD_SELECT_BINS + bin], 1u);
+    }
   }
   if (any_nan) atomicOr(const_cast<uint32_t*>(&state->nan_flag), 1u);
   __syncthreads();
@@ -418,11 +422,12 @@ int launch_select_init(cudaStream_t st, SelectState* s, long long r_lo, long lon
   return NSVGD_OK;
 }
 
-int launch_buffer_hist(cudaStream_t st, const float* vals, const uint32_t* count_dev, uint32_t count_host,
-                       const SelectState* state, int pass, uint64_t* hist, const uint32_t* run_flag) {
+int launch_buffer_hist(cudaStream_t st, const float* vals, const uint32_t* counts_dev, int count_stride, int nseg,
+                       uint32_t seg_cap, uint32_t count_host, const SelectState* state, int pass, uint64_t* hist,
+                       const uint32_t* run_flag) {
   NSVGD_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint64_t) * 2 * NSVGD_SELECT_BINS, st));
-  buffer_hist_kernel<<<device_sm_count() * 4, 256, 0, st>>>(vals, count_dev, count_host, state, pass,
-                                                            (unsigned long long*)hist, run_flag);
+  buffer_hist_kernel<<<device_sm_count() * 4, 256, 0, st>>>(vals, counts_dev, count_stride, nseg, seg_cap, count_host, state,
+                                                            pass, (unsigned long long*)hist, run_flag);
   NSVGD_LAUNCH_CHECK();
   return NSVGD_OK;
 }

@@ -49,8 +49,9 @@ __device__ __forceinline__ float exact_pair_sqdist(const float* __restrict__ a, 
 
 // pair_engine.cu
 int launch_select_init(cudaStream_t st, SelectState* s, long long r_lo, long long r_hi, float log_np1);
-int launch_buffer_hist(cudaStream_t st, const float* vals, const uint32_t* count_dev, uint32_t count_host,
-                       const SelectState* state, int pass, uint64_t* hist, const uint32_t* run_flag);
+int launch_buffer_hist(cudaStream_t st, const float* vals, const uint32_t* counts_dev, int count_stride, int nseg,
+                       uint32_t seg_cap, uint32_t count_host, const SelectState* state, int pass, uint64_t* hist,
+                       const uint32_t* run_flag);
 int launch_select_advance(cudaStream_t st, SelectState* s, const uint64_t* hist, int pass, const uint32_t* run_flag);
 int launch_pair_hist(cudaStream_t st, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last,
                      int64_t tile_row_start, int64_t tile_row_stride, const SelectState* state, int pass,
