@@ -125,6 +125,7 @@ struct EpilogueArgs {
   const float* O;         // GRAM: nsplit x m_pad x ldo
   const float* scal;      // DIRECT: m x 4 ; GRAM: nsplit x m_pad x 4
   int nsplit;
+  int scal_parts;         // GRAM: number of scal slices to sum (0 -> nsplit)
   int64_t m_pad;
   int64_t ldo;
   int64_t dpad;           // GRAM: column offset of the K Xc block inside a row of O

@@ -145,7 +145,8 @@ struct TcParams {
 };
 
 constexpr int TC_BM = 128, TC_BN = 64;
-constexpr int TC_THREADS = 192;
+constexpr int TC_PAIR_WARPS = 8;                         // pair-function warps: 2 per TMEM lane quarter
+constexpr int TC_THREADS = 64 + 32 * TC_PAIR_WARPS;      // + TMA producer warp + MMA issuer warp
 constexpr int TC_MAX_RUN_TILES = 64;   // <= 768 sequential TMEM accumulations per run
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_O = 0, TM_G = 256, TM_P = 384;
@@ -158,15 +159,19 @@ struct TcSmem {
   static constexpr int VSLOT = 2 * DP * 128;            // [2DP rows x 64 j] bf16 = 32 KB (DP=128)
   static constexpr int XSTAGES = 2;
   static constexpr int VSLOTS = (DP == 128) ? 3 : 4;
+  static constexpr int NVEC = 3;                        // ring of per-tile column vectors {xn[64], cv[64]}
+  static constexpr int VEC_BYTES = 2 * TC_BN * 4;
   static constexpr int Q_BYTES = 2 * KH * QSLAB;
   static constexpr int X_STAGE_BYTES = 2 * KH * XSLAB;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_X = OFF_Q + Q_BYTES;
   static constexpr int OFF_V = OFF_X + XSTAGES * X_STAGE_BYTES;
-  static constexpr int OFF_BAR = OFF_V + VSLOTS * VSLOT;
-  static constexpr int NBARS = 1 + 2 * XSTAGES + 2 * VSLOTS + 8 + 1;
+  static constexpr int OFF_VEC = OFF_V + VSLOTS * VSLOT;
+  static constexpr int OFF_BAR = OFF_VEC + NVEC * VEC_BYTES;
+  static constexpr int NBARS = 1 + 2 * XSTAGES + 2 * VSLOTS + 2 * NVEC + 8 + 1;
   static constexpr int TOTAL = OFF_BAR + NBARS * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;         // slack for manual 1024-B alignment
+  static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
 };
 
 template <int DP>
@@ -182,13 +187,16 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
   uint8_t* sQ = smem + L::OFF_Q;
   uint8_t* sX = smem + L::OFF_X;
   uint8_t* sV = smem + L::OFF_V;
+  float* sVec = (float*)(smem + L::OFF_VEC);
   uint64_t* bars = (uint64_t*)(smem + L::OFF_BAR);
   uint64_t* q_full = bars;
   uint64_t* x_full = q_full + 1;
   uint64_t* x_empty = x_full + L::XSTAGES;
   uint64_t* v_full = x_empty + L::XSTAGES;
   uint64_t* v_empty = v_full + L::VSLOTS;
-  uint64_t* g_full = v_empty + L::VSLOTS;
+  uint64_t* n_full = v_empty + L::VSLOTS;
+  uint64_t* n_empty = n_full + L::NVEC;
+  uint64_t* g_full = n_empty + L::NVEC;
   uint64_t* g_empty = g_full + 2;
   uint64_t* p_full = g_empty + 2;
   uint64_t* p_empty = p_full + 2;
@@ -209,9 +217,10 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
     mbar_init(q_full, 1);
     for (int i = 0; i < L::XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
     for (int i = 0; i < L::VSLOTS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < L::NVEC; ++i) { mbar_init(&n_full[i], 1); mbar_init(&n_empty[i], TC_PAIR_WARPS); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 128);
-      mbar_init(&p_full[i], 128); mbar_init(&p_empty[i], 1);
+      mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 32 * TC_PAIR_WARPS);
+      mbar_init(&p_full[i], 32 * TC_PAIR_WARPS); mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_full, 1);
     fence_barrier_init();
@@ -240,14 +249,20 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
       int vcount = 0;
       auto load_x = [&](int t) {
         const int st = t % L::XSTAGES, u = t / L::XSTAGES;
+        const int j0 = (t_begin + t) * TC_BN;
         mbar_wait(&x_empty[st], (u & 1) ^ 1, watch, 0x100 + st);
         mbar_arrive_expect_tx(&x_full[st], L::X_STAGE_BYTES);
         uint8_t* dst = sX + st * L::X_STAGE_BYTES;
-        const int j0 = (t_begin + t) * TC_BN;
         for (int kh = 0; kh < KH; ++kh) {
           tma_load_2d(dst + (0 * KH + kh) * L::XSLAB, &tmX0, &x_full[st], kh * 64, j0);
           tma_load_2d(dst + (1 * KH + kh) * L::XSLAB, &tmX1, &x_full[st], kh * 64, j0);
         }
+        // per-tile column vectors |xc_j|^2 and s_j.xc_j for the pair-function warps
+        const int ns = t % L::NVEC, un = t / L::NVEC;
+        mbar_wait(&n_empty[ns], (un & 1) ^ 1, watch, 0x180 + ns);
+        mbar_arrive_expect_tx(&n_full[ns], L::VEC_BYTES);
+        bulk_load_1d(sVec + ns * 2 * TC_BN, p.xn + j0, TC_BN * 4, &n_full[ns]);
+        bulk_load_1d(sVec + ns * 2 * TC_BN + TC_BN, p.cv + j0, TC_BN * 4, &n_full[ns]);
       };
       auto load_v = [&](int t) {
         const int j0 = (t_begin + t) * TC_BN;
@@ -336,8 +351,11 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
       umma_commit(o_full);
     }
   } else {
-    // =============================== pair-function warps (one thread per query row) ===============
+    // =============================== pair-function warps ==========================================
+    // thread <-> (row, column half): quarter = warp % 4 selects the TMEM lanes (rows), half = which
+    // 32 of the tile's 64 columns.  Two warps per SM sub-partition hide each other's latencies.
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float h = *p.h_dev;
@@ -347,23 +365,23 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
     float rowsum = 0.f, kc = 0.f, ke = 0.f;
     for (int t = 0; t < T; ++t) {
       const int b = t & 1, ub = t >> 1;
-      const int j0 = (t_begin + t) * TC_BN;
-      const float4* xn4 = reinterpret_cast<const float4*>(p.xn + j0);
-      const float4* cv4 = reinterpret_cast<const float4*>(p.cv + j0);
+      const int ns = t % L::NVEC, un = t / L::NVEC;
       mbar_wait(&g_full[b], ub & 1, watch, 0x400 + b);
       __syncwarp();
       tc_fence_after();
-      uint32_t g[64];
-      tmem_ld32(tmem + lane_addr + TM_G + b * TC_BN, g);
-      tmem_ld32(tmem + lane_addr + TM_G + b * TC_BN + 32, g + 32);
+      uint32_t g[32];
+      tmem_ld32(tmem + lane_addr + TM_G + b * TC_BN + half * 32, g);
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(&g_empty[b]);
-      uint32_t pk0[32], pk1[32];
+      mbar_wait(&n_full[ns], un & 1, watch, 0x420 + ns);
+      const float4* xn4 = reinterpret_cast<const float4*>(sVec + ns * 2 * TC_BN + half * 32);
+      const float4* cv4 = reinterpret_cast<const float4*>(sVec + ns * 2 * TC_BN + TC_BN + half * 32);
+      uint32_t pk0[16], pk1[16];
 #pragma unroll
-      for (int q4 = 0; q4 < 16; ++q4) {
-        const float4 xv = __ldg(&xn4[q4]);
-        const float4 cvv = __ldg(&cv4[q4]);
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const float4 xv = xn4[q4];
+        const float4 cvv = cv4[q4];
         const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
         const float cc[4] = {cvv.x, cvv.y, cvv.z, cvv.w};
         float k[4], ex[4];
@@ -388,26 +406,29 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
           ke = fmaf(kq0, ex[e], ke); ke = fmaf(kq1, ex[e + 1], ke);
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&n_empty[ns]);
       mbar_wait(&p_empty[b], (ub & 1) ^ 1, watch, 0x410 + b);
       __syncwarp();
       tc_fence_after();
-      tmem_st32(tmem + lane_addr + TM_P + b * 64, pk0);
-      tmem_st32(tmem + lane_addr + TM_P + b * 64 + 32, pk1);
+      tmem_st16(tmem + lane_addr + TM_P + b * 64 + half * 16, pk0);
+      tmem_st16(tmem + lane_addr + TM_P + b * 64 + 32 + half * 16, pk1);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[b]);
     }
-    // ---- epilogue: O (TMEM) -> workspace, one row per thread
+    // ---- epilogue: O (TMEM) -> workspace; the two warps of a quarter take DP columns each
+    const int64_t row = (int64_t)m0 + row_in_tile;
+    float* orow = p.O + ((int64_t)split * p.m_pad + row) * (2 * DP) + half * DP;
+    float* srow = p.scal + (((int64_t)split * 2 + half) * p.m_pad + row) * 4;
     if (T > 0) {
       mbar_wait(o_full, 0, watch, 0x500);
       __syncwarp();
       tc_fence_after();
-      const int64_t row = (int64_t)m0 + row_in_tile;
-      float* orow = p.O + ((int64_t)split * p.m_pad + row) * (2 * DP);
 #pragma unroll 1
-      for (int c0 = 0; c0 < 2 * DP; c0 += 32) {
+      for (int c0 = 0; c0 < DP; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem + lane_addr + TM_O + c0, v);
+        tmem_ld32(tmem + lane_addr + TM_O + half * DP + c0, v);
         tmem_wait_ld();
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -415,16 +436,13 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
               make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
                           __uint_as_float(v[q * 4 + 3]));
       }
-      // b = sum k r2 = -sum k e / cs
-      *reinterpret_cast<float4*>(p.scal + ((int64_t)split * p.m_pad + row) * 4) =
-          make_float4(rowsum, kc, -ke / cs, 0.f);
+      // b = sum k r2 = -sum k e / cs  (this thread's half of the columns)
+      *reinterpret_cast<float4*>(srow) = make_float4(rowsum, kc, -ke / cs, 0.f);
       tc_fence_before();
     } else {
       // empty j-range (tail split): contribute zeros
-      const int64_t row = (int64_t)m0 + row_in_tile;
-      float* orow = p.O + ((int64_t)split * p.m_pad + row) * (2 * DP);
-      for (int c = 0; c < 2 * DP; c += 4) *reinterpret_cast<float4*>(orow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(p.scal + ((int64_t)split * p.m_pad + row) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < DP; c += 4) *reinterpret_cast<float4*>(orow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(srow) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   __syncthreads();
@@ -507,7 +525,7 @@ int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dr
     qn = w.take<float>((size_t)pl.m_pad);
   }
   float* O = w.take<float>((size_t)pl.nsplit * pl.m_pad * 2 * dp, 1024);
-  float* scal = w.take<float>((size_t)pl.nsplit * pl.m_pad * 4);
+  float* scal = w.take<float>((size_t)pl.nsplit * 2 * pl.m_pad * 4);   // two column halves per split
   uint32_t* err_flag = w.take<uint32_t>(4);
   double* partials = w.take<double>((size_t)(2 * epilogue_blocks(a.m)));
   if (need) *need = w.off;
@@ -534,7 +552,7 @@ int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dr
   else NSVGD_PROPAGATE(launch_tc<128>(st, pl, maps, prm));
 
   EpilogueArgs e{};
-  e.form = 1; e.O = O; e.scal = scal; e.nsplit = pl.nsplit; e.m_pad = pl.m_pad; e.ldo = 2 * dp; e.dpad = dp; e.mu = mu;
+  e.form = 1; e.O = O; e.scal = scal; e.nsplit = pl.nsplit; e.scal_parts = 2 * pl.nsplit; e.m_pad = pl.m_pad; e.ldo = 2 * dp; e.dpad = dp; e.mu = mu;
   e.Q = a.Q; e.ldq = a.ldq; e.Sq = a.Sq; e.m = a.m; e.n = a.n; e.d = a.d; e.h_dev = a.h_dev;
   e.phi = a.phi; e.ldphi = a.ldphi; e.aux = a.aux; e.stats_dev = a.stats_dev; e.partials = partials;
   return launch_epilogue(st, e);

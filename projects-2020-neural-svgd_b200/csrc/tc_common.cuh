@@ -67,6 +67,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (bytes multiple of 16, both sides 16-byte aligned)
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---- TMEM ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {   // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
@@ -102,6 +109,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
       ::NS_I4(v, 0), NS_I4(v, 4), NS_I4(v, 8), NS_I4(v, 12), NS_I4(v, 16), NS_I4(v, 20), NS_I4(v, 24), NS_I4(v, 28),
       "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};"
+      ::NS_I4(v, 0), NS_I4(v, 4), NS_I4(v, 8), NS_I4(v, 12), "r"(taddr)
       : "memory");
 }
 

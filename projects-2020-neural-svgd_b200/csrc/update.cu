@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const EpilogueArgs a) {
       const float4 sc = *reinterpret_cast<const float4*>(&a.scal[row * 4]);
       rowsum = sc.x; aval = sc.y; bval = sc.z;
     } else {
-      for (int s = 0; s < a.nsplit; ++s) {
+      const int parts = a.scal_parts > 0 ? a.scal_parts : a.nsplit;
+      for (int s = 0; s < parts; ++s) {
         const float4 sc = *reinterpret_cast<const float4*>(&a.scal[((int64_t)s * a.m_pad + row) * 4]);
         rowsum += sc.x; aval += sc.y; bval += sc.z;   // aval = kc so far
       }
