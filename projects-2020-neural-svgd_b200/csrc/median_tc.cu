@@ -25,7 +25,11 @@ namespace nsvgd {
 
 using namespace tc;
 
-constexpr int MF_BM = 128, MF_BN = 64, MF_CHUNK = 64, MF_THREADS = 192, MF_XSTAGES = 4;
+constexpr int MF_BM = 128, MF_BN = 64, MF_CHUNK = 64, MF_XSTAGES = 4;
+constexpr int MF_CLS_WARPS = 8;                          // classification warps: 2 per TMEM lane quarter
+constexpr int MF_THREADS = 64 + 32 * MF_CLS_WARPS;
+constexpr int MF_NVEC = 4;                               // ring of per-tile |z_j|^2 vectors
+constexpr int MF_STAGE = 256;                            // per-warp staging buffer (uncertain pairs) in shared memory
 constexpr uint32_t MF_SAMPLES = 1u << 22;
 constexpr int MF_NSEG = 64;          // independent append segments (one atomic counter per 128-byte line)
 constexpr int MF_CSTRIDE = 32;       // counter stride in uint32
@@ -162,9 +166,12 @@ struct MfSmem {
   static constexpr int Q_BYTES = 2 * KH * QSLAB;
   static constexpr int X_STAGE_BYTES = 2 * KH * XSLAB;
   static constexpr int OFF_X = Q_BYTES;
-  static constexpr int OFF_BAR = OFF_X + MF_XSTAGES * X_STAGE_BYTES;
-  static constexpr int NBARS = 1 + 2 * MF_XSTAGES + 4;
+  static constexpr int OFF_VEC = OFF_X + MF_XSTAGES * X_STAGE_BYTES;
+  static constexpr int OFF_STAGE = OFF_VEC + MF_NVEC * MF_BN * 4;
+  static constexpr int OFF_BAR = OFF_STAGE + MF_CLS_WARPS * MF_STAGE * 8;
+  static constexpr int NBARS = 1 + 2 * MF_XSTAGES + 2 * MF_NVEC + 4;
   static constexpr int DYN_BYTES = OFF_BAR + NBARS * 8 + 16 + 1024;
+  static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
 };
 
 template <int DP>
@@ -189,18 +196,23 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
   uint64_t* q_full = bars;
   uint64_t* x_full = q_full + 1;
   uint64_t* x_empty = x_full + MF_XSTAGES;
-  uint64_t* g_full = x_empty + MF_XSTAGES;
+  uint64_t* n_full = x_empty + MF_XSTAGES;
+  uint64_t* n_empty = n_full + MF_NVEC;
+  uint64_t* g_full = n_empty + MF_NVEC;
   uint64_t* g_empty = g_full + 2;
   uint32_t* tmem_slot = (uint32_t*)(g_empty + 2);
+  float* sVec = (float*)(smem + L::OFF_VEC);
+  unsigned long long* sStage = (unsigned long long*)(smem + L::OFF_STAGE);
   volatile uint32_t* abort_s = tmem_slot + 1;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   Watch watch{abort_s, p.err_flag};
 
   if (threadIdx.x == 0) {
     *abort_s = (*(volatile uint32_t*)p.err_flag) ? 1u : 0u;
     mbar_init(q_full, 1);
     for (int i = 0; i < MF_XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 128); }
+    for (int i = 0; i < MF_NVEC; ++i) { mbar_init(&n_full[i], 1); mbar_init(&n_empty[i], MF_CLS_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 32 * MF_CLS_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 128); tmem_relinquish(); }
@@ -210,26 +222,39 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, L::Q_BYTES);
-      for (int kh = 0; kh < KH; ++kh) {
-        tma_load_2d(sQ + (0 * KH + kh) * L::QSLAB, &tmA0, q_full, kh * 64, m0);
-        tma_load_2d(sQ + (1 * KH + kh) * L::QSLAB, &tmA1, q_full, kh * 64, m0);
+    {
+      const bool leader = elect_one();
+      if (leader) {
+        mbar_arrive_expect_tx(q_full, L::Q_BYTES);
+        for (int kh = 0; kh < KH; ++kh) {
+          tma_load_2d(sQ + (0 * KH + kh) * L::QSLAB, &tmA0, q_full, kh * 64, m0);
+          tma_load_2d(sQ + (1 * KH + kh) * L::QSLAB, &tmA1, q_full, kh * 64, m0);
+        }
       }
       for (int t = 0; t < T; ++t) {
         const int st = t % MF_XSTAGES, u = t / MF_XSTAGES;
         mbar_wait(&x_empty[st], (u & 1) ^ 1, watch, 0x100 + st);
-        mbar_arrive_expect_tx(&x_full[st], L::X_STAGE_BYTES);
         uint8_t* dst = sX + st * L::X_STAGE_BYTES;
         const int j0 = (t_begin + t) * MF_BN;
-        for (int kh = 0; kh < KH; ++kh) {
-          tma_load_2d(dst + (0 * KH + kh) * L::XSLAB, &tmB0, &x_full[st], kh * 64, j0);
-          tma_load_2d(dst + (1 * KH + kh) * L::XSLAB, &tmB1, &x_full[st], kh * 64, j0);
+        if (leader) {
+          mbar_arrive_expect_tx(&x_full[st], L::X_STAGE_BYTES);
+          for (int kh = 0; kh < KH; ++kh) {
+            tma_load_2d(dst + (0 * KH + kh) * L::XSLAB, &tmB0, &x_full[st], kh * 64, j0);
+            tma_load_2d(dst + (1 * KH + kh) * L::XSLAB, &tmB1, &x_full[st], kh * 64, j0);
+          }
         }
+        const int ns = t % MF_NVEC, un = t / MF_NVEC;
+        mbar_wait(&n_empty[ns], (un & 1) ^ 1, watch, 0x180 + ns);
+        if (leader) {
+          mbar_arrive_expect_tx(&n_full[ns], MF_BN * 4);
+          bulk_load_1d(sVec + ns * MF_BN, p.zn + j0, MF_BN * 4, &n_full[ns]);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(MF_BM, MF_BN);
       const uint32_t sQ_a = smem_u32(sQ), sX_a = smem_u32(sX);
       mbar_wait(q_full, 0, watch, 0x300);
@@ -242,29 +267,33 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         tc_fence_after();
         const uint32_t d_tm = tmem + b * MF_BN;
         const uint32_t xs = sX_a + st * L::X_STAGE_BYTES;
-        uint32_t acc = 0;
+        if (leader) {
+          uint32_t acc = 0;
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const int pa = pass == 2 ? 1 : 0;
-          const int pb = pass == 1 ? 1 : 0;
+          for (int pass = 0; pass < 3; ++pass) {
+            const int pa = pass == 2 ? 1 : 0;
+            const int pb = pass == 1 ? 1 : 0;
 #pragma unroll
-          for (int kh = 0; kh < KH; ++kh) {
-            const uint64_t ad = umma_desc_sw128(sQ_a + (pa * KH + kh) * L::QSLAB);
-            const uint64_t bd = umma_desc_sw128(xs + (pb * KH + kh) * L::XSLAB);
+            for (int kh = 0; kh < KH; ++kh) {
+              const uint64_t ad = umma_desc_sw128(sQ_a + (pa * KH + kh) * L::QSLAB);
+              const uint64_t bd = umma_desc_sw128(xs + (pb * KH + kh) * L::XSLAB);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              umma_ss(d_tm, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 32), idesc, acc);
-              acc = 1;
+              for (int ks = 0; ks < 4; ++ks) {
+                umma_ss(d_tm, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 32), idesc, acc);
+                acc = 1;
+              }
             }
           }
+          umma_commit(&x_empty[st]);
+          umma_commit(&g_full[b]);
         }
-        umma_commit(&x_empty[st]);
-        umma_commit(&g_full[b]);
+        __syncwarp();
       }
     }
   } else {
-    // ---- classification warps: one thread per row i
+    // ---- classification warps: thread <-> (row i, 32-column half of the tile)
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int64_t gi = (int64_t)m0 + row_in_tile;
@@ -273,26 +302,40 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     const float Lv = p.fs->L, Uv = p.fs->U;
     uint32_t cnt = 0;
     const int seg = (int)((blockIdx.y * gridDim.x + blockIdx.x) % MF_NSEG);
+    unsigned long long* seg_list = p.list + (size_t)seg * p.list_cap;
+    unsigned long long* stage = sStage + (warp - 2) * MF_STAGE;
+    uint32_t fill = 0;                                   // warp-uniform
+    auto flush = [&]() {
+      if (fill == 0u) return;
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&p.list_counts[seg * MF_CSTRIDE], fill);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (uint32_t e = lane; e < fill; e += 32)
+        if (base + e < p.list_cap) seg_list[base + e] = stage[e];
+      __syncwarp();
+      fill = 0u;
+    };
     for (int t = 0; t < T; ++t) {
       const int b = t & 1, ub = t >> 1;
+      const int ns = t % MF_NVEC, un = t / MF_NVEC;
       const int tile = t_begin + t;
-      const int64_t j0 = (int64_t)tile * MF_BN;
-      const float4* zn4 = reinterpret_cast<const float4*>(p.zn + j0);
+      const int64_t j0 = (int64_t)tile * MF_BN + half * 32;
       mbar_wait(&g_full[b], ub & 1, watch, 0x400 + b);
       __syncwarp();
       tc_fence_after();
-      uint32_t g[64];
-      tmem_ld32(tmem + lane_addr + b * MF_BN, g);
-      tmem_ld32(tmem + lane_addr + b * MF_BN + 32, g + 32);
+      uint32_t g[32];
+      tmem_ld32(tmem + lane_addr + b * MF_BN + half * 32, g);
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(&g_empty[b]);
+      mbar_wait(&n_full[ns], un & 1, watch, 0x420 + ns);
+      const float4* zn4 = reinterpret_cast<const float4*>(sVec + ns * MF_BN + half * 32);
       // boundary tiles (diagonal or padded) need the i < j < n mask
-      const bool boundary = (tile <= 2 * (int)rb + 1) || (j0 + MF_BN > p.n) || ((int64_t)m0 + MF_BM > p.n);
-      uint32_t unc_lo = 0u, unc_hi = 0u;
+      const bool boundary = (tile <= 2 * (int)rb + 1) || ((int64_t)(tile + 1) * MF_BN > p.n) || ((int64_t)m0 + MF_BM > p.n);
+      uint32_t unc = 0u;
 #pragma unroll
-      for (int q4 = 0; q4 < 16; ++q4) {
-        const float4 zv = __ldg(&zn4[q4]);
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const float4 zv = zn4[q4];
         const float zs[4] = {zv.x, zv.y, zv.z, zv.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -301,20 +344,21 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
           const float er = fmaf(MF_KAPPA, zs[e], qe);
           bool below = (u + er) < Lv;
           const bool above = (u - er) > Uv;
-          bool unc = !(below || above);
+          bool un_ = !(below || above);
           if (boundary) {
             const int64_t gj = j0 + col;
             const bool valid = (gi < gj) && (gj < p.n) && (gi < p.n);
             below = below && valid;
-            unc = unc && valid;
+            un_ = un_ && valid;
           }
           cnt += below ? 1u : 0u;
-          if (col < 32) unc_lo |= (unc ? 1u : 0u) << col;
-          else unc_hi |= (unc ? 1u : 0u) << (col - 32);
+          unc |= (un_ ? 1u : 0u) << col;
         }
       }
-      // warp-aggregated append: one atomic per warp and tile on this CTA's segment counter
-      const uint32_t c = __popc(unc_lo) + __popc(unc_hi);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&n_empty[ns]);
+      // uncertain pairs -> per-warp staging buffer in shared memory (flushed with ONE global atomic)
+      const uint32_t c = __popc(unc);
       if (__any_sync(0xffffffffu, c != 0u)) {
         uint32_t incl = c;
 #pragma unroll
@@ -323,25 +367,32 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
           if (lane >= o) incl += v;
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&p.list_counts[seg * MF_CSTRIDE], total);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        uint32_t pos = base + incl - c;
-        unsigned long long* seg_list = p.list + (size_t)seg * p.list_cap;
-        while (unc_lo) {
-          const int cc = __ffs(unc_lo) - 1;
-          unc_lo &= unc_lo - 1;
-          if (pos < p.list_cap) seg_list[pos] = ((unsigned long long)gi << 32) | (unsigned long long)(j0 + cc);
-          ++pos;
-        }
-        while (unc_hi) {
-          const int cc = __ffs(unc_hi) - 1;
-          unc_hi &= unc_hi - 1;
-          if (pos < p.list_cap) seg_list[pos] = ((unsigned long long)gi << 32) | (unsigned long long)(j0 + 32 + cc);
-          ++pos;
+        if (fill + total > (uint32_t)MF_STAGE) flush();
+        if (total > (uint32_t)MF_STAGE) {
+          // pathological tile (ties): straight to global memory with its own reservation
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(&p.list_counts[seg * MF_CSTRIDE], total);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          uint32_t pos = base + incl - c;
+          while (unc) {
+            const int cc = __ffs(unc) - 1;
+            unc &= unc - 1;
+            if (pos < p.list_cap) seg_list[pos] = ((unsigned long long)gi << 32) | (unsigned long long)(j0 + cc);
+            ++pos;
+          }
+        } else {
+          uint32_t pos = fill + incl - c;
+          while (unc) {
+            const int cc = __ffs(unc) - 1;
+            unc &= unc - 1;
+            stage[pos++] = ((unsigned long long)gi << 32) | (unsigned long long)(j0 + cc);
+          }
+          fill += total;
+          __syncwarp();
         }
       }
     }
+    flush();
     uint32_t tot = cnt;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);

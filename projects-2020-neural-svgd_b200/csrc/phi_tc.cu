@@ -204,7 +204,7 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
   uint32_t* tmem_slot = (uint32_t*)(o_full + 1);
   volatile uint32_t* abort_s = tmem_slot + 1;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TC_BM;
   const int split = blockIdx.y;
   const int t_begin = split * p.tiles_per_split;
@@ -240,29 +240,37 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0 && T > 0) {
-      mbar_arrive_expect_tx(q_full, L::Q_BYTES);
-      for (int kh = 0; kh < KH; ++kh) {
-        tma_load_2d(sQ + (0 * KH + kh) * L::QSLAB, &tmQ0, q_full, kh * 64, m0);
-        tma_load_2d(sQ + (1 * KH + kh) * L::QSLAB, &tmQ1, q_full, kh * 64, m0);
+    if (T > 0) {
+      const bool leader = elect_one();
+      if (leader) {
+        mbar_arrive_expect_tx(q_full, L::Q_BYTES);
+        for (int kh = 0; kh < KH; ++kh) {
+          tma_load_2d(sQ + (0 * KH + kh) * L::QSLAB, &tmQ0, q_full, kh * 64, m0);
+          tma_load_2d(sQ + (1 * KH + kh) * L::QSLAB, &tmQ1, q_full, kh * 64, m0);
+        }
       }
       int vcount = 0;
       auto load_x = [&](int t) {
         const int st = t % L::XSTAGES, u = t / L::XSTAGES;
         const int j0 = (t_begin + t) * TC_BN;
         mbar_wait(&x_empty[st], (u & 1) ^ 1, watch, 0x100 + st);
-        mbar_arrive_expect_tx(&x_full[st], L::X_STAGE_BYTES);
         uint8_t* dst = sX + st * L::X_STAGE_BYTES;
-        for (int kh = 0; kh < KH; ++kh) {
-          tma_load_2d(dst + (0 * KH + kh) * L::XSLAB, &tmX0, &x_full[st], kh * 64, j0);
-          tma_load_2d(dst + (1 * KH + kh) * L::XSLAB, &tmX1, &x_full[st], kh * 64, j0);
+        if (leader) {
+          mbar_arrive_expect_tx(&x_full[st], L::X_STAGE_BYTES);
+          for (int kh = 0; kh < KH; ++kh) {
+            tma_load_2d(dst + (0 * KH + kh) * L::XSLAB, &tmX0, &x_full[st], kh * 64, j0);
+            tma_load_2d(dst + (1 * KH + kh) * L::XSLAB, &tmX1, &x_full[st], kh * 64, j0);
+          }
         }
         // per-tile column vectors |xc_j|^2 and s_j.xc_j for the pair-function warps
         const int ns = t % L::NVEC, un = t / L::NVEC;
         mbar_wait(&n_empty[ns], (un & 1) ^ 1, watch, 0x180 + ns);
-        mbar_arrive_expect_tx(&n_full[ns], L::VEC_BYTES);
-        bulk_load_1d(sVec + ns * 2 * TC_BN, p.xn + j0, TC_BN * 4, &n_full[ns]);
-        bulk_load_1d(sVec + ns * 2 * TC_BN + TC_BN, p.cv + j0, TC_BN * 4, &n_full[ns]);
+        if (leader) {
+          mbar_arrive_expect_tx(&n_full[ns], L::VEC_BYTES);
+          bulk_load_1d(sVec + ns * 2 * TC_BN, p.xn + j0, TC_BN * 4, &n_full[ns]);
+          bulk_load_1d(sVec + ns * 2 * TC_BN + TC_BN, p.cv + j0, TC_BN * 4, &n_full[ns]);
+        }
+        __syncwarp();
       };
       auto load_v = [&](int t) {
         const int j0 = (t_begin + t) * TC_BN;
@@ -270,8 +278,11 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
           const int sl = vcount % L::VSLOTS, u = vcount / L::VSLOTS;
           ++vcount;
           mbar_wait(&v_empty[sl], (u & 1) ^ 1, watch, 0x200 + sl);
-          mbar_arrive_expect_tx(&v_full[sl], L::VSLOT);
-          tma_load_2d(sV + sl * L::VSLOT, piece == 0 ? &tmV0 : &tmV1, &v_full[sl], j0, 0);
+          if (leader) {
+            mbar_arrive_expect_tx(&v_full[sl], L::VSLOT);
+            tma_load_2d(sV + sl * L::VSLOT, piece == 0 ? &tmV0 : &tmV1, &v_full[sl], j0, 0);
+          }
+          __syncwarp();
         }
       };
       // same order as the MMA warp consumes: X(0), X(1), V(0), X(2), V(1), ...
@@ -281,7 +292,8 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0 && T > 0) {
+    if (T > 0) {
+      const bool leader = elect_one();
       constexpr uint32_t idesc_g = umma_idesc_bf16(TC_BM, TC_BN);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(TC_BM, 2 * DP);
       const uint32_t sQ_a = smem_u32(sQ), sX_a = smem_u32(sX), sV_a = smem_u32(sV);
@@ -296,24 +308,27 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
         tc_fence_after();
         const uint32_t d_tm = tmem + TM_G + b * TC_BN;
         const uint32_t xs = sX_a + st * L::X_STAGE_BYTES;
-        uint32_t acc = 0;
+        if (leader) {
+          uint32_t acc = 0;
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          const int pa = pass == 2 ? 1 : 0;     // Q piece: b0, b0, b1
-          const int pb = pass == 1 ? 1 : 0;     // X piece: b0, b1, b0
+          for (int pass = 0; pass < 3; ++pass) {
+            const int pa = pass == 2 ? 1 : 0;     // Q piece: b0, b0, b1
+            const int pb = pass == 1 ? 1 : 0;     // X piece: b0, b1, b0
 #pragma unroll
-          for (int kh = 0; kh < KH; ++kh) {
-            const uint64_t ad = umma_desc_sw128(sQ_a + (pa * KH + kh) * L::QSLAB);
-            const uint64_t bd = umma_desc_sw128(xs + (pb * KH + kh) * L::XSLAB);
+            for (int kh = 0; kh < KH; ++kh) {
+              const uint64_t ad = umma_desc_sw128(sQ_a + (pa * KH + kh) * L::QSLAB);
+              const uint64_t bd = umma_desc_sw128(xs + (pb * KH + kh) * L::XSLAB);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              umma_ss(d_tm, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 32), idesc_g, acc);
-              acc = 1;
+              for (int ks = 0; ks < 4; ++ks) {
+                umma_ss(d_tm, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 32), idesc_g, acc);
+                acc = 1;
+              }
             }
           }
+          umma_commit(&x_empty[st]);
+          umma_commit(&g_full[b]);
         }
-        umma_commit(&x_empty[st]);
-        umma_commit(&g_full[b]);
+        __syncwarp();
       };
       auto issue_pv = [&](int u) {
         const int pb = u & 1, up = u >> 1;
@@ -325,30 +340,37 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
           mbar_wait(&v_full[sl], uv & 1, watch, 0x340 + sl);
           tc_fence_after();
           const uint64_t bd = umma_desc_sw128(sV_a + sl * L::VSLOT);
+          if (leader) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_ts(tmem + TM_O, p0 + ks * 8, umma_desc_advance(bd, ks * 32), idesc_pv, (u > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ts(tmem + TM_O, p0 + ks * 8, umma_desc_advance(bd, ks * 32), idesc_pv, (u > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_ts(tmem + TM_O, p1 + ks * 8, umma_desc_advance(bd, ks * 32), idesc_pv, 1u);
-          umma_commit(&v_empty[sl]);
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ts(tmem + TM_O, p1 + ks * 8, umma_desc_advance(bd, ks * 32), idesc_pv, 1u);
+            umma_commit(&v_empty[sl]);
+          }
+          __syncwarp();
         }
         {
           const int sl = vcount % L::VSLOTS, uv = vcount / L::VSLOTS; ++vcount;
           mbar_wait(&v_full[sl], uv & 1, watch, 0x350 + sl);
           tc_fence_after();
           const uint64_t bd = umma_desc_sw128(sV_a + sl * L::VSLOT);
+          if (leader) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_ts(tmem + TM_O, p0 + ks * 8, umma_desc_advance(bd, ks * 32), idesc_pv, 1u);
-          umma_commit(&v_empty[sl]);
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ts(tmem + TM_O, p0 + ks * 8, umma_desc_advance(bd, ks * 32), idesc_pv, 1u);
+            umma_commit(&v_empty[sl]);
+            umma_commit(&p_empty[pb]);
+          }
+          __syncwarp();
         }
-        umma_commit(&p_empty[pb]);
       };
       issue_gram(0);
       for (int t = 1; t < T; ++t) { issue_gram(t); issue_pv(t - 1); }
       issue_pv(T - 1);
-      umma_commit(o_full);
+      if (leader) umma_commit(o_full);
+      __syncwarp();
     }
   } else {
     // =============================== pair-function warps ==========================================
@@ -570,7 +592,7 @@ __global__ void __launch_bounds__(128) tc_probe_gram_kernel(const __grid_constan
   uint64_t* bars = (uint64_t*)(smem + 49152);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2);
   volatile uint32_t* abort_s = tmem_slot + 1;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   Watch watch{abort_s, err_flag};
   if (threadIdx.x == 0) {
     *abort_s = 0u;
@@ -627,7 +649,7 @@ __global__ void __launch_bounds__(128) tc_probe_pv_kernel(const __grid_constant_
   uint64_t* bars = (uint64_t*)(smem + 32768);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2);
   volatile uint32_t* abort_s = tmem_slot + 1;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   Watch watch{abort_s, err_flag};
   if (threadIdx.x == 0) {
     *abort_s = 0u;
