@@ -105,6 +105,33 @@ int nsvgd_median_hist_pass(void* stream, const float* Z, int64_t n, int64_t dz, 
 int nsvgd_median_advance(void* stream, void* state_dev, const uint64_t* hist_dev, int pass);
 int nsvgd_median_finish(void* stream, const void* state_dev, int64_t n, float* h_dev);
 
+/* Tensor-core filtered variant of the same exact select (n >= 8192, 32 < dz <= 128),
+ * split into stages so that a row-sharded run can all-reduce between them:
+ *   stage1  : bracket from sampled pairs (identical on every rank), tcgen05 filter over the 128-row blocks
+ *             block_row_start, +block_row_stride, ..., exact re-evaluation of the uncertain pairs;
+ *             reduce_dev (int64[4]) = {pairs below the bracket, candidates, overflow flag, listed pairs}
+ *   [host: all-reduce(sum) reduce_dev]
+ *   resolve : ranks inside the candidates, or raise the device-side fallback flag
+ *   3 x { cand_hist -> [all-reduce(sum) hist] -> cand_advance },  commit
+ *   3 x { fallback_hist -> [all-reduce] -> fallback_advance }   (kernels return at once unless flagged)
+ *   nsvgd_median_finish.
+ * `ws` is a scratch region of nsvgd_median_fast_workspace_bytes() that must stay untouched between stages. */
+int nsvgd_median_fast_supported(int64_t n, int64_t dz);
+int nsvgd_median_fast_workspace_bytes(int64_t n, int64_t dz, size_t* out_bytes);
+int nsvgd_median_fast_stage1(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last, int mode,
+                             int64_t block_row_start, int64_t block_row_stride, void* state_dev, uint64_t* hist_dev,
+                             void* ws, size_t ws_bytes, int64_t* reduce_dev);
+int nsvgd_median_fast_resolve(void* stream, void* state_dev, void* ws, size_t ws_bytes, int64_t n, int64_t dz,
+                              const int64_t* reduce_dev);
+int nsvgd_median_fast_cand_hist(void* stream, void* ws, size_t ws_bytes, int64_t n, int64_t dz, int pass, uint64_t* hist_dev);
+int nsvgd_median_fast_cand_advance(void* stream, void* ws, size_t ws_bytes, int64_t n, int64_t dz, const uint64_t* hist_dev, int pass);
+int nsvgd_median_fast_commit(void* stream, void* state_dev, void* ws, size_t ws_bytes, int64_t n, int64_t dz);
+int nsvgd_median_fallback_hist(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last,
+                               int64_t tile_row_start, int64_t tile_row_stride, const void* state_dev, void* ws,
+                               size_t ws_bytes, int pass, uint64_t* hist_dev);
+int nsvgd_median_fallback_advance(void* stream, void* state_dev, void* ws, size_t ws_bytes, int64_t n, int64_t dz,
+                                  const uint64_t* hist_dev, int pass);
+
 /* ---- A1/A3/A4: phi*  (stein.py:71-96, 180-222; kernels.py:52-65)
  * phi[i,:] = (1/n) sum_j k_ij s_j + k_ij (q_i - x_j)/h^2,  k_ij = exp(-|q_i-x_j|^2/(2h^2)).
  * Optional outputs (NULL to skip):

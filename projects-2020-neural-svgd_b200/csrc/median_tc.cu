@@ -72,7 +72,7 @@ static size_t fast_layout(int64_t n, int64_t dz, WsCarver& w, FastWs* o) {
   f.Ds = w.take<float>(MF_SAMPLES);
   f.list = w.take<unsigned long long>((size_t)f.list_cap * MF_NSEG);
   f.cand = w.take<float>((size_t)f.cand_cap * MF_NSEG);
-  f.err_flag = w.take<uint32_t>(4);
+  f.err_flag = w.take<uint32_t>(64);   // [0] error flag; bytes 64.. = the single-GPU reduce block
   f.list_counts = w.take<uint32_t>(MF_NSEG * MF_CSTRIDE);
   f.cand_counts = w.take<uint32_t>(MF_NSEG * MF_CSTRIDE);
   if (o) *o = f;
@@ -451,20 +451,28 @@ __global__ void __launch_bounds__(256) exact_list_kernel(const float* __restrict
   if (threadIdx.x == 0 && sh_below) atomicAdd(&fs->below, (unsigned long long)sh_below);
 }
 
-__global__ void fast_resolve_kernel(FastMedState* fs, const SelectState* main_state, SelectState* cs,
-                                    const uint32_t* list_counts, uint32_t list_cap, uint32_t* cand_counts,
-                                    uint32_t cand_cap, const uint32_t* err_flag) {
+// local summary of stage 1 (per rank): red = {below, candidates (clamped), overflow|error, listed pairs}
+__global__ void fast_pack_kernel(FastMedState* fs, const uint32_t* list_counts, uint32_t list_cap, uint32_t* cand_counts,
+                                 uint32_t cand_cap, const uint32_t* err_flag, long long* red) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  uint32_t fb = *err_flag != 0u ? 1u : 0u;
+  long long bad = *err_flag != 0u ? 1 : 0;
   unsigned long long ncand = 0ull, nlist = 0ull;
   for (int sgm = 0; sgm < MF_NSEG; ++sgm) {
     const uint32_t lc = list_counts[sgm * MF_CSTRIDE], cc = cand_counts[sgm * MF_CSTRIDE];
-    if (lc > list_cap || cc > cand_cap) fb = 1u;                 // a list overflowed (massive ties)
+    if (lc > list_cap || cc > cand_cap) bad = 1;                   // a list overflowed (massive ties)
     if (cc > cand_cap) cand_counts[sgm * MF_CSTRIDE] = cand_cap;
     ncand += min(cc, cand_cap); nlist += lc;
   }
   fs->list_count = (uint32_t)min(nlist, 0xFFFFFFFFull);
   fs->cand_count = (uint32_t)min(ncand, 0xFFFFFFFFull);
+  red[0] = (long long)fs->below; red[1] = (long long)ncand; red[2] = bad; red[3] = (long long)nlist;
+}
+
+// red holds the GLOBAL sums (all-reduced across ranks when row-sharded)
+__global__ void fast_resolve_kernel(FastMedState* fs, const SelectState* main_state, SelectState* cs, const long long* red) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const unsigned long long below = (unsigned long long)red[0], ncand = (unsigned long long)red[1];
+  uint32_t fb = red[2] != 0 ? 1u : 0u;
   cs->prefix[0] = cs->prefix[1] = 0u; cs->mask = 0u; cs->nan_flag = 0u;
   cs->value[0] = cs->value[1] = 0.f; cs->log_np1 = main_state->log_np1; cs->done = 0;
   for (int t = 0; t < 2; ++t) {
@@ -472,8 +480,8 @@ __global__ void fast_resolve_kernel(FastMedState* fs, const SelectState* main_st
     cs->rank[t] = 0ull;
     if (main_state->is_zero[t]) continue;
     const unsigned long long r = main_state->rank[t];
-    if (r < fs->below || r - fs->below >= ncand) fb = 1u;          // the sampled bracket missed the target
-    else cs->rank[t] = r - fs->below;
+    if (r < below || r - below >= ncand) fb = 1u;          // the sampled bracket missed the target
+    else cs->rank[t] = r - below;
   }
   fs->fallback = fb;
 }
@@ -505,9 +513,9 @@ static int launch_filter(cudaStream_t st, const CUtensorMap* maps, const MfParam
   return NSVGD_OK;
 }
 
-int median_fast(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, long long r_lo,
-                long long r_hi, int64_t tile_row_start, int64_t tile_row_stride, SelectState* main_state, uint64_t* hist,
-                void* ws, size_t ws_bytes) {
+int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, long long r_lo,
+                       long long r_hi, int64_t block_row_start, int64_t block_row_stride, SelectState* main_state,
+                       uint64_t* hist, void* ws, size_t ws_bytes, long long* red) {
   NSVGD_REQUIRE(median_fast_supported(n, dz), NSVGD_ERR_UNSUPPORTED, "median_fast: unsupported shape");
   NSVGD_REQUIRE(r_lo >= 0 && r_hi >= r_lo, NSVGD_ERR_UNSUPPORTED, "median_fast: needs genuine pair ranks");
   WsCarver w(ws, ws_bytes);
@@ -526,6 +534,7 @@ int median_fast(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t 
                                  nullptr, f.zn, nullptr));
 
   // --- 1. bracket [L, U] from the sample quantiles: 7 sigma of the binomial rank error + slack
+  //        (deterministic pseudo-random pairs: every rank computes the identical bracket)
   const double Ppairs = 0.5 * (double)n * (double)(n - 1);
   const double ns = (double)MF_SAMPLES;
   const double p_lo = ((double)r_lo + 0.5) / Ppairs, p_hi = ((double)r_hi + 0.5) / Ppairs;
@@ -547,14 +556,14 @@ int median_fast(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t 
   bracket_set_kernel<<<1, 32, 0, st>>>(f.fs, f.bracket, l_is_zero, u_is_inf);
   NSVGD_LAUNCH_CHECK();
 
-  // --- 2. tensor-core filter over the upper triangle (row blocks strided across ranks)
+  // --- 2. tensor-core filter over the upper triangle (128-row blocks strided across ranks)
   CUtensorMap maps[4];
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[0], f.Zb0, f.dp, f.n_pad, (uint64_t)f.dp * 2, 64, MF_BM));
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[1], f.Zb1, f.dp, f.n_pad, (uint64_t)f.dp * 2, 64, MF_BM));
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[2], f.Zb0, f.dp, f.n_pad, (uint64_t)f.dp * 2, 64, MF_BN));
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[3], f.Zb1, f.dp, f.n_pad, (uint64_t)f.dp * 2, 64, MF_BN));
   MfParams prm{};
-  prm.zn = f.zn; prm.n = n; prm.n_tiles = (int)(f.n_pad / MF_BN); prm.rb_start = tile_row_start; prm.rb_stride = tile_row_stride;
+  prm.zn = f.zn; prm.n = n; prm.n_tiles = (int)(f.n_pad / MF_BN); prm.rb_start = block_row_start; prm.rb_stride = block_row_stride;
   prm.fs = f.fs; prm.list = f.list; prm.list_counts = f.list_counts; prm.list_cap = f.list_cap; prm.err_flag = f.err_flag;
   const int64_t row_blocks = f.n_pad / MF_BM;
   if (f.dp == 64) NSVGD_PROPAGATE(launch_filter<64>(st, maps, prm, row_blocks));
@@ -566,20 +575,71 @@ int median_fast(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t 
       P, (int)dz, ldp, w_last, vec, f.fs, f.list, f.list_counts, f.list_cap, f.cand, f.cand_counts, f.cand_cap, main_state);
   prof_end(5, st);
   NSVGD_LAUNCH_CHECK();
-
-  // --- 4. resolve among the candidates, or flag the fallback
-  fast_resolve_kernel<<<1, 32, 0, st>>>(f.fs, main_state, f.cand_state, f.list_counts, f.list_cap, f.cand_counts, f.cand_cap,
-                                        f.err_flag);
+  fast_pack_kernel<<<1, 32, 0, st>>>(f.fs, f.list_counts, f.list_cap, f.cand_counts, f.cand_cap, f.err_flag, red);
   NSVGD_LAUNCH_CHECK();
-  for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
-    NSVGD_PROPAGATE(launch_buffer_hist(st, f.cand, f.cand_counts, MF_CSTRIDE, MF_NSEG, f.cand_cap, 0, f.cand_state, pass, hist,
-                                       nullptr));
-    NSVGD_PROPAGATE(launch_select_advance(st, f.cand_state, hist, pass, nullptr));
-  }
+  return NSVGD_OK;
+}
+
+static int fast_ws(int64_t n, int64_t dz, void* ws, size_t ws_bytes, FastWs* f) {
+  NSVGD_REQUIRE(median_fast_supported(n, dz), NSVGD_ERR_UNSUPPORTED, "median_fast: unsupported shape");
+  WsCarver w(ws, ws_bytes);
+  fast_layout(n, dz, w, f);
+  NSVGD_REQUIRE(ws && w.ok(), NSVGD_ERR_WORKSPACE, "median_fast: workspace too small (%zu < %zu)", ws_bytes, w.off);
+  return NSVGD_OK;
+}
+
+int median_fast_resolve(cudaStream_t st, SelectState* main_state, void* ws, size_t ws_bytes, int64_t n, int64_t dz,
+                        const long long* red) {
+  FastWs f;
+  NSVGD_PROPAGATE(fast_ws(n, dz, ws, ws_bytes, &f));
+  fast_resolve_kernel<<<1, 32, 0, st>>>(f.fs, main_state, f.cand_state, red);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
+int median_fast_cand_hist(cudaStream_t st, void* ws, size_t ws_bytes, int64_t n, int64_t dz, int pass, uint64_t* hist) {
+  FastWs f;
+  NSVGD_PROPAGATE(fast_ws(n, dz, ws, ws_bytes, &f));
+  return launch_buffer_hist(st, f.cand, f.cand_counts, MF_CSTRIDE, MF_NSEG, f.cand_cap, 0, f.cand_state, pass, hist, nullptr);
+}
+
+int median_fast_cand_advance(cudaStream_t st, void* ws, size_t ws_bytes, int64_t n, int64_t dz, const uint64_t* hist, int pass) {
+  FastWs f;
+  NSVGD_PROPAGATE(fast_ws(n, dz, ws, ws_bytes, &f));
+  return launch_select_advance(st, f.cand_state, hist, pass, nullptr);
+}
+
+int median_fast_commit(cudaStream_t st, SelectState* main_state, void* ws, size_t ws_bytes, int64_t n, int64_t dz) {
+  FastWs f;
+  NSVGD_PROPAGATE(fast_ws(n, dz, ws, ws_bytes, &f));
   fast_commit_kernel<<<1, 32, 0, st>>>(f.fs, f.cand_state, main_state);
   NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
 
-  // --- 5. conditional fallback: the SIMT 3-pass select, kernels return at once unless fs->fallback
+const uint32_t* median_fast_fallback_flag(void* ws, size_t ws_bytes, int64_t n, int64_t dz) {
+  FastWs f;
+  if (fast_ws(n, dz, ws, ws_bytes, &f) != NSVGD_OK) return nullptr;
+  return &f.fs->fallback;
+}
+
+// single-GPU composition of the stages
+int median_fast(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, long long r_lo,
+                long long r_hi, int64_t tile_row_start, int64_t tile_row_stride, SelectState* main_state, uint64_t* hist,
+                void* ws, size_t ws_bytes) {
+  // red lives at the tail of the workspace region reserved by median_fast_workspace()
+  FastWs f;
+  NSVGD_PROPAGATE(fast_ws(n, dz, ws, ws_bytes, &f));
+  long long* red = (long long*)(f.err_flag) + 8;      // err_flag block is 256-byte aligned, 16 bytes used
+  NSVGD_PROPAGATE(median_fast_stage1(st, P, n, dz, ldp, w_last, r_lo, r_hi, tile_row_start, tile_row_stride, main_state, hist,
+                                     ws, ws_bytes, red));
+  NSVGD_PROPAGATE(median_fast_resolve(st, main_state, ws, ws_bytes, n, dz, red));
+  for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
+    NSVGD_PROPAGATE(median_fast_cand_hist(st, ws, ws_bytes, n, dz, pass, hist));
+    NSVGD_PROPAGATE(median_fast_cand_advance(st, ws, ws_bytes, n, dz, hist, pass));
+  }
+  NSVGD_PROPAGATE(median_fast_commit(st, main_state, ws, ws_bytes, n, dz));
+  // conditional fallback: the SIMT 3-pass select; kernels return at once unless fs->fallback is set
   for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
     NSVGD_PROPAGATE(launch_pair_hist(st, P, n, dz, ldp, w_last, tile_row_start, tile_row_stride, main_state, pass, hist,
                                      &f.fs->fallback));
@@ -589,3 +649,59 @@ int median_fast(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t 
 }
 
 }  // namespace nsvgd
+
+using namespace nsvgd;
+
+// ---- C ABI: building blocks of the tensor-core filtered select for row-sharded runs (include/nsvgd.h)
+extern "C" int nsvgd_median_fast_supported(int64_t n, int64_t dz) { return median_fast_supported(n, dz) ? 1 : 0; }
+
+extern "C" int nsvgd_median_fast_workspace_bytes(int64_t n, int64_t dz, size_t* out_bytes) {
+  NSVGD_REQUIRE(out_bytes, NSVGD_ERR_INVALID, "median_fast_workspace_bytes: null pointer");
+  NSVGD_REQUIRE(median_fast_supported(n, dz), NSVGD_ERR_UNSUPPORTED, "median_fast: unsupported shape (n=%lld dz=%lld)", (long long)n, (long long)dz);
+  *out_bytes = median_fast_workspace(n, dz);
+  return NSVGD_OK;
+}
+
+extern "C" int nsvgd_median_fast_stage1(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last, int mode,
+                                        int64_t block_row_start, int64_t block_row_stride, void* state_dev, uint64_t* hist_dev,
+                                        void* ws, size_t ws_bytes, int64_t* reduce_dev) {
+  NSVGD_REQUIRE(Z && state_dev && hist_dev && ws && reduce_dev, NSVGD_ERR_INVALID, "median_fast_stage1: null pointer");
+  NSVGD_REQUIRE(mode >= 0 && mode <= 2 && block_row_start >= 0 && block_row_stride >= 1, NSVGD_ERR_INVALID, "median_fast_stage1: bad arguments");
+  long long r_lo, r_hi;
+  median_ranks_host(n, mode, &r_lo, &r_hi);
+  return median_fast_stage1((cudaStream_t)stream, Z, n, dz, ldz, w_last, r_lo, r_hi, block_row_start, block_row_stride,
+                            (SelectState*)state_dev, hist_dev, ws, ws_bytes, (long long*)reduce_dev);
+}
+extern "C" int nsvgd_median_fast_resolve(void* stream, void* state_dev, void* ws, size_t ws_bytes, int64_t n, int64_t dz,
+                                         const int64_t* reduce_dev) {
+  NSVGD_REQUIRE(state_dev && reduce_dev, NSVGD_ERR_INVALID, "median_fast_resolve: null pointer");
+  return median_fast_resolve((cudaStream_t)stream, (SelectState*)state_dev, ws, ws_bytes, n, dz, (const long long*)reduce_dev);
+}
+extern "C" int nsvgd_median_fast_cand_hist(void* stream, void* ws, size_t ws_bytes, int64_t n, int64_t dz, int pass, uint64_t* hist_dev) {
+  NSVGD_REQUIRE(hist_dev && pass >= 0 && pass < NSVGD_SELECT_PASSES, NSVGD_ERR_INVALID, "median_fast_cand_hist: bad arguments");
+  return median_fast_cand_hist((cudaStream_t)stream, ws, ws_bytes, n, dz, pass, hist_dev);
+}
+extern "C" int nsvgd_median_fast_cand_advance(void* stream, void* ws, size_t ws_bytes, int64_t n, int64_t dz, const uint64_t* hist_dev, int pass) {
+  NSVGD_REQUIRE(hist_dev && pass >= 0 && pass < NSVGD_SELECT_PASSES, NSVGD_ERR_INVALID, "median_fast_cand_advance: bad arguments");
+  return median_fast_cand_advance((cudaStream_t)stream, ws, ws_bytes, n, dz, hist_dev, pass);
+}
+extern "C" int nsvgd_median_fast_commit(void* stream, void* state_dev, void* ws, size_t ws_bytes, int64_t n, int64_t dz) {
+  NSVGD_REQUIRE(state_dev, NSVGD_ERR_INVALID, "median_fast_commit: null pointer");
+  return median_fast_commit((cudaStream_t)stream, (SelectState*)state_dev, ws, ws_bytes, n, dz);
+}
+extern "C" int nsvgd_median_fallback_hist(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last,
+                                          int64_t tile_row_start, int64_t tile_row_stride, const void* state_dev, void* ws,
+                                          size_t ws_bytes, int pass, uint64_t* hist_dev) {
+  NSVGD_REQUIRE(Z && state_dev && hist_dev && pass >= 0 && pass < NSVGD_SELECT_PASSES, NSVGD_ERR_INVALID, "median_fallback_hist: bad arguments");
+  const uint32_t* flag = median_fast_fallback_flag(ws, ws_bytes, n, dz);
+  NSVGD_REQUIRE(flag, NSVGD_ERR_WORKSPACE, "median_fallback_hist: bad workspace");
+  return launch_pair_hist((cudaStream_t)stream, Z, n, dz, ldz, w_last, tile_row_start, tile_row_stride,
+                          (const SelectState*)state_dev, pass, hist_dev, flag);
+}
+extern "C" int nsvgd_median_fallback_advance(void* stream, void* state_dev, void* ws, size_t ws_bytes, int64_t n, int64_t dz,
+                                             const uint64_t* hist_dev, int pass) {
+  NSVGD_REQUIRE(state_dev && hist_dev && pass >= 0 && pass < NSVGD_SELECT_PASSES, NSVGD_ERR_INVALID, "median_fallback_advance: bad arguments");
+  const uint32_t* flag = median_fast_fallback_flag(ws, ws_bytes, n, dz);
+  NSVGD_REQUIRE(flag, NSVGD_ERR_WORKSPACE, "median_fallback_advance: bad workspace");
+  return launch_select_advance((cudaStream_t)stream, (SelectState*)state_dev, hist_dev, pass, flag);
+}

@@ -81,6 +81,79 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const EpilogueArgs a) {
   }
 }
 
+
+// GRAM form, vectorised: one warp per row, each lane owns 4 consecutive columns (float4), all split
+// partials of a column group in flight at once.  Requires d, ldo, dpad, ldq, ldphi multiples of 4.
+__global__ void __launch_bounds__(256) epilogue_gram4_kernel(const EpilogueArgs a) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * EPI_ROWS + w;
+  __shared__ double sh_t[EPI_ROWS], sh_l[EPI_ROWS];
+  const float h = *a.h_dev;
+  const float inv_h2 = 1.f / (h * h);
+  const float inv_n = 1.f / (float)a.n;
+  double t_row = 0.0, l_row = 0.0;
+  if (row < a.m) {
+    float rowsum = 0.f, aval = 0.f, bval = 0.f;
+    const int parts = a.scal_parts > 0 ? a.scal_parts : a.nsplit;
+    for (int s = lane; s < parts; s += 32) {
+      const float4 sc = *reinterpret_cast<const float4*>(&a.scal[((int64_t)s * a.m_pad + row) * 4]);
+      rowsum += sc.x; aval += sc.y; bval += sc.z;
+    }
+    rowsum = warp_sum(rowsum); aval = warp_sum(aval); bval = warp_sum(bval);
+    float sphi = 0.f, l2 = 0.f, qks = 0.f;
+    for (int64_t c = 4 * lane; c < a.d; c += 128) {
+      float4 ks = make_float4(0.f, 0.f, 0.f, 0.f), kx = ks;
+      for (int s = 0; s < a.nsplit; ++s) {
+        const float* o = a.O + ((int64_t)s * a.m_pad + row) * a.ldo;
+        const float4 v0 = *reinterpret_cast<const float4*>(o + c);
+        const float4 v1 = *reinterpret_cast<const float4*>(o + a.dpad + c);
+        ks.x += v0.x; ks.y += v0.y; ks.z += v0.z; ks.w += v0.w;
+        kx.x += v1.x; kx.y += v1.y; kx.z += v1.z; kx.w += v1.w;
+      }
+      const float4 q4 = *reinterpret_cast<const float4*>(a.Q + row * a.ldq + c);
+      const float4 m4 = *reinterpret_cast<const float4*>(a.mu + c);
+      const float qc[4] = {q4.x - m4.x, q4.y - m4.y, q4.z - m4.z, q4.w - m4.w};
+      const float ksv[4] = {ks.x, ks.y, ks.z, ks.w}, kxv[4] = {kx.x, kx.y, kx.z, kx.w};
+      float pv[4], dr[4], rp[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float rr = rowsum * qc[e] - kxv[e];
+        qks = fmaf(qc[e], ksv[e], qks);
+        dr[e] = ksv[e] * inv_n;
+        rp[e] = rr * inv_h2 * inv_n;
+        pv[e] = dr[e] + rp[e];
+        l2 = fmaf(pv[e], pv[e], l2);
+      }
+      *reinterpret_cast<float4*>(a.phi + row * a.ldphi + c) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+      if (a.aux) {
+        *reinterpret_cast<float4*>(a.aux + (row * 2 + 0) * a.d + c) = make_float4(dr[0], dr[1], dr[2], dr[3]);
+        *reinterpret_cast<float4*>(a.aux + (row * 2 + 1) * a.d + c) = make_float4(rp[0], rp[1], rp[2], rp[3]);
+      }
+      if (a.Sq) {
+        const float4 s4 = *reinterpret_cast<const float4*>(a.Sq + row * a.ldq + c);
+        sphi = fmaf(s4.x, pv[0], sphi); sphi = fmaf(s4.y, pv[1], sphi);
+        sphi = fmaf(s4.z, pv[2], sphi); sphi = fmaf(s4.w, pv[3], sphi);
+      }
+    }
+    sphi = warp_sum(sphi); l2 = warp_sum(l2); qks = warp_sum(qks);
+    aval = aval - qks;                                           // a_i = (K c)_i - qc_i.(K S)_i
+    const float div = (aval * inv_h2 + (float)a.d * inv_h2 * rowsum - bval * inv_h2 * inv_h2) * inv_n;
+    t_row = (double)sphi + (double)div;
+    l_row = (double)l2;
+  }
+  if (a.stats_dev) {
+    if (lane == 0) { sh_t[w] = t_row; sh_l[w] = l_row; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0, l = 0.0;
+#pragma unroll
+      for (int i = 0; i < EPI_ROWS; ++i) { t += sh_t[i]; l += sh_l[i]; }
+      a.partials[2 * (int64_t)blockIdx.x + 0] = t;
+      a.partials[2 * (int64_t)blockIdx.x + 1] = l;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(1024) stats_final_kernel(const double* __restrict__ partials, int64_t blocks,
                                                            double m, double* stats) {
   __shared__ double sh[32];
@@ -94,7 +167,11 @@ __global__ void __launch_bounds__(1024) stats_final_kernel(const double* __restr
 int launch_epilogue(cudaStream_t st, const EpilogueArgs& a) {
   const int blocks = epilogue_blocks(a.m);
   NSVGD_REQUIRE(!a.stats_dev || a.Sq, NSVGD_ERR_INVALID, "phi: stats need the scores at the queries (Sq)");
-  epilogue_kernel<<<blocks, 256, 0, st>>>(a);
+  auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  const bool vec4 = a.form == 1 && a.d % 4 == 0 && a.ldo % 4 == 0 && a.dpad % 4 == 0 && a.ldq % 4 == 0 && a.ldphi % 4 == 0 &&
+                    al16(a.O) && al16(a.Q) && al16(a.mu) && al16(a.phi) && (!a.Sq || al16(a.Sq)) && (!a.aux || al16(a.aux));
+  if (vec4) epilogue_gram4_kernel<<<blocks, 256, 0, st>>>(a);
+  else epilogue_kernel<<<blocks, 256, 0, st>>>(a);
   NSVGD_LAUNCH_CHECK();
   if (a.stats_dev) {
     stats_final_kernel<<<1, 1024, 0, st>>>(a.partials, blocks, (double)a.m, a.stats_dev);

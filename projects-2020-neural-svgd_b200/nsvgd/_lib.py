@@ -28,7 +28,10 @@ SYMBOLS = [
     "nsvgd_version", "nsvgd_last_error", "nsvgd_launch_count", "nsvgd_workspace_bytes",
     "nsvgd_profile_enable", "nsvgd_profile_read",
     "nsvgd_median_h_f32", "nsvgd_median_prepare", "nsvgd_median_hist_pass", "nsvgd_median_advance",
-    "nsvgd_median_finish", "nsvgd_phi_f32", "nsvgd_step_sgd_f32", "nsvgd_apply_update_f32",
+    "nsvgd_median_finish", "nsvgd_median_fast_supported", "nsvgd_median_fast_workspace_bytes",
+    "nsvgd_median_fast_stage1", "nsvgd_median_fast_resolve", "nsvgd_median_fast_cand_hist",
+    "nsvgd_median_fast_cand_advance", "nsvgd_median_fast_commit", "nsvgd_median_fallback_hist",
+    "nsvgd_median_fallback_advance", "nsvgd_phi_f32", "nsvgd_step_sgd_f32", "nsvgd_apply_update_f32",
     "nsvgd_ksd_f32", "nsvgd_mmd_f32", "nsvgd_ksum_f32", "nsvgd_adam_update_f32",
     "nsvgd_tc_probe_gram", "nsvgd_tc_probe_pv",
 ]
@@ -63,6 +66,15 @@ def load():
     lib.nsvgd_median_hist_pass.argtypes = [vp, vp, i64, i64, i64, f32, i64, i64, vp, i32, vp]
     lib.nsvgd_median_advance.argtypes = [vp, vp, vp, i32]
     lib.nsvgd_median_finish.argtypes = [vp, vp, i64, vp]
+    lib.nsvgd_median_fast_supported.argtypes = [i64, i64]
+    lib.nsvgd_median_fast_workspace_bytes.argtypes = [i64, i64, C.POINTER(sz)]
+    lib.nsvgd_median_fast_stage1.argtypes = [vp, vp, i64, i64, i64, f32, i32, i64, i64, vp, vp, vp, sz, vp]
+    lib.nsvgd_median_fast_resolve.argtypes = [vp, vp, vp, sz, i64, i64, vp]
+    lib.nsvgd_median_fast_cand_hist.argtypes = [vp, vp, sz, i64, i64, i32, vp]
+    lib.nsvgd_median_fast_cand_advance.argtypes = [vp, vp, sz, i64, i64, vp, i32]
+    lib.nsvgd_median_fast_commit.argtypes = [vp, vp, vp, sz, i64, i64]
+    lib.nsvgd_median_fallback_hist.argtypes = [vp, vp, i64, i64, i64, f32, i64, i64, vp, vp, sz, i32, vp]
+    lib.nsvgd_median_fallback_advance.argtypes = [vp, vp, vp, sz, i64, i64, vp, i32]
     lib.nsvgd_phi_f32.argtypes = [vp, vp, vp, i64, i64, vp, vp, i64, i64, i64, vp, vp, i64, vp, vp, i32, vp, sz]
     lib.nsvgd_step_sgd_f32.argtypes = [vp, vp, vp, i64, i64, i64, vp, f32, i32, f32, vp, vp, i32, vp, sz]
     lib.nsvgd_apply_update_f32.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp, f32, i32, f32, vp, vp]

@@ -161,6 +161,53 @@ class MedianSelect:
                                           C.byref(dz), C.byref(w), ptr(self.state)))
         self.dz, self.w_last = int(dz.value), float(w.value)
         self.P = self.Z if mode == "literal" else x
+        self.fast_supported = bool(load().nsvgd_median_fast_supported(n, self.dz)) and os.environ.get("NSVGD_MEDIAN_FAST", "1") != "0"
+        self._fast_ws = None
+        self.reduce = torch.zeros(4, dtype=torch.int64, device=x.device)
+
+    # ---- tensor-core filtered select, staged for all-reduces in between (include/nsvgd.h) ----------
+    def _fws(self):
+        if self._fast_ws is None:
+            need = C.c_size_t(0)
+            check(load().nsvgd_median_fast_workspace_bytes(self.n, self.dz, C.byref(need)))
+            self._fast_ws = torch.empty(int(need.value), dtype=torch.uint8, device=self.x.device)
+        return self._fast_ws
+
+    def fast_stage1(self, block_row_start=0, block_row_stride=1) -> torch.Tensor:
+        ws = self._fws()
+        check(load().nsvgd_median_fast_stage1(stream_ptr(self.x.device), ptr(self.P), self.n, self.dz, ld(self.P), self.w_last,
+                                              _lib.MEDIAN_MODES[self.mode], block_row_start, block_row_stride, ptr(self.state),
+                                              ptr(self.hist), ptr(ws), ws.numel(), ptr(self.reduce)))
+        return self.reduce
+
+    def fast_resolve(self):
+        ws = self._fws()
+        check(load().nsvgd_median_fast_resolve(stream_ptr(self.x.device), ptr(self.state), ptr(ws), ws.numel(), self.n, self.dz,
+                                               ptr(self.reduce)))
+
+    def fast_cand_hist(self, p: int) -> torch.Tensor:
+        ws = self._fws()
+        check(load().nsvgd_median_fast_cand_hist(stream_ptr(self.x.device), ptr(ws), ws.numel(), self.n, self.dz, p, ptr(self.hist)))
+        return self.hist
+
+    def fast_cand_advance(self, p: int):
+        ws = self._fws()
+        check(load().nsvgd_median_fast_cand_advance(stream_ptr(self.x.device), ptr(ws), ws.numel(), self.n, self.dz, ptr(self.hist), p))
+
+    def fast_commit(self):
+        ws = self._fws()
+        check(load().nsvgd_median_fast_commit(stream_ptr(self.x.device), ptr(self.state), ptr(ws), ws.numel(), self.n, self.dz))
+
+    def fallback_hist(self, p: int, tile_row_start=0, tile_row_stride=1) -> torch.Tensor:
+        ws = self._fws()
+        check(load().nsvgd_median_fallback_hist(stream_ptr(self.x.device), ptr(self.P), self.n, self.dz, ld(self.P), self.w_last,
+                                                tile_row_start, tile_row_stride, ptr(self.state), ptr(ws), ws.numel(), p, ptr(self.hist)))
+        return self.hist
+
+    def fallback_advance(self, p: int):
+        ws = self._fws()
+        check(load().nsvgd_median_fallback_advance(stream_ptr(self.x.device), ptr(self.state), ptr(ws), ws.numel(), self.n, self.dz,
+                                                   ptr(self.hist), p))
 
     def hist_pass(self, p: int, tile_row_start=0, tile_row_stride=1) -> torch.Tensor:
         check(load().nsvgd_median_hist_pass(stream_ptr(self.x.device), ptr(self.P), self.n, self.dz, ld(self.P), self.w_last,

@@ -60,6 +60,20 @@ class ShardedSVGD:
 
     def median_heuristic(self, X_all: torch.Tensor) -> torch.Tensor:
         sel = self.engine.MedianSelect(X_all, self.median_mode)
+        sum_ = dict(op=dist.ReduceOp.SUM, group=self.group)
+        if getattr(sel, "fast_supported", False):
+            # tensor-core filtered select: the bracket is identical on every rank (deterministic sample of
+            # the gathered particles); counts and candidate histograms are all-reduced between the stages.
+            dist.all_reduce(sel.fast_stage1(self.rank, self.world), **sum_)
+            sel.fast_resolve()
+            for p in range(3):
+                dist.all_reduce(sel.fast_cand_hist(p), **sum_)
+                sel.fast_cand_advance(p)
+            sel.fast_commit()
+            for p in range(3):      # conditional SIMT fallback: kernels return at once unless flagged
+                dist.all_reduce(sel.fallback_hist(p, self.rank, self.world), **sum_)
+                sel.fallback_advance(p)
+            return sel.finish()
         for p in range(3):
             hist = sel.hist_pass(p, tile_row_start=self.rank, tile_row_stride=self.world)
             dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
