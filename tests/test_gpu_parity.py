@@ -227,3 +227,31 @@ def test_fast_median_nan():
     X = _median_dataset("gauss", 8192, 128, seed=6)
     X[4000, 17] = np.nan
     assert np.isnan(engine.median_heuristic(dev(X), "offdiag").item())
+
+
+@pytest.mark.parametrize("mode", ["literal", "offdiag"])
+def test_fast_median_staged_two_ranks_on_one_gpu(mode):
+    """the staged (row-sharded) form of the tensor-core filtered select: two simulated ranks on one
+    GPU, reduce tensors and histograms summed by hand exactly as parallel.py all-reduces them."""
+    from nsvgd import engine
+    X = dev(_median_dataset("gauss", 8192, 128, seed=21))
+    want = engine.median_heuristic(X, mode).cpu().numpy()[0]
+    sels = [engine.MedianSelect(X, mode) for _ in range(2)]
+    assert all(s.fast_supported for s in sels)
+    red = sum(s.fast_stage1(r, 2).clone() for r, s in enumerate(sels))
+    for s in sels:
+        s.reduce.copy_(red); s.fast_resolve()
+    for p in range(3):
+        hist = sum(s.fast_cand_hist(p).clone() for s in sels)
+        for s in sels:
+            s.hist.copy_(hist); s.fast_cand_advance(p)
+    for s in sels:
+        s.fast_commit()
+    for p in range(3):
+        hist = sum(s.fallback_hist(p, r, 2).clone() for r, s in enumerate(sels))
+        for s in sels:
+            s.hist.copy_(hist); s.fallback_advance(p)
+    for s in sels:
+        got = s.finish().cpu().numpy()[0]
+        assert np.float32(got).tobytes() == np.float32(want).tobytes()
+    assert red[1].item() > 0 and red[2].item() == 0
