@@ -4,7 +4,7 @@
 // can influence the result is recomputed with the defined-order fp32 arithmetic.
 //
 //   1. sample  : 2^22 pseudo-random pairs, exact distances, radix-select two sample quantiles
-//                L <= (target order statistics) <= U   (7 sigma + slack of the binomial rank error)
+//                L <= (target order statistics) <= U   (6 sigma + slack of the binomial rank error)
 //   2. filter  : ONE pass over all pairs on the tensor cores: Gram tile (bf16 2-piece split, 3 MMA
 //                passes, TMEM accumulator) -> dt = |z_i|^2 + |z_j|^2 - 2 g.  With the rigorous error
 //                radius eps_ij = kappa (|z_i|^2 + |z_j|^2):  dt + eps < L -> counted "below";
@@ -50,7 +50,7 @@ static uint32_t cand_capacity(int64_t n) {
 
 struct FastWs {
   FastMedState* fs; SelectState* bracket; SelectState* cand_state;
-  float* mu; double* mpart; __nv_bfloat16* Zb0; __nv_bfloat16* Zb1; float* zn; float* Ds;
+  float* mu; double* mpart; __nv_bfloat16* Zb0; __nv_bfloat16* Zb1; float* zn; float* zlo; float* zhi; float* Ds;
   unsigned long long* list; float* cand; uint32_t* err_flag;
   uint32_t* list_counts; uint32_t* cand_counts;     // MF_NSEG counters each, MF_CSTRIDE apart
   uint32_t list_cap, cand_cap; int64_t n_pad; int dp;   // capacities PER SEGMENT
@@ -69,6 +69,8 @@ static size_t fast_layout(int64_t n, int64_t dz, WsCarver& w, FastWs* o) {
   f.Zb0 = w.take<__nv_bfloat16>((size_t)(n_pad * dp), 1024);
   f.Zb1 = w.take<__nv_bfloat16>((size_t)(n_pad * dp), 1024);
   f.zn = w.take<float>((size_t)n_pad);
+  f.zlo = w.take<float>((size_t)n_pad);
+  f.zhi = w.take<float>((size_t)n_pad);
   f.Ds = w.take<float>(MF_SAMPLES);
   f.list = w.take<unsigned long long>((size_t)f.list_cap * MF_NSEG);
   f.cand = w.take<float>((size_t)f.cand_cap * MF_NSEG);
@@ -125,6 +127,38 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   return x ^ (x >> 31);
 }
 
+
+// ---- warp-cooperative exact distances: 32 pairs per warp, rows read with fully coalesced 128-byte
+// requests (lane l loads coordinates l, l+32, l+64, l+96), squared differences parked in shared
+// memory, then lane p adds pair p's terms in the DEFINED sequential order.  Bit-identical to
+// exact_pair_sqdist; halves the L2 sector traffic of the one-thread-per-pair gather.
+constexpr int WX_STRIDE = 129;                       // floats per pair row in shared memory (dz <= 128)
+constexpr int WX_WARPS = 4;
+__device__ __forceinline__ float warp_exact32(const float* __restrict__ P, int64_t ldp, int d, float w_last, int64_t i,
+                                              int64_t j, float* __restrict__ sq, int lane) {
+  for (int pp = 0; pp < 32; ++pp) {
+    const int64_t ip = __shfl_sync(0xffffffffu, i, pp), jp = __shfl_sync(0xffffffffu, j, pp);
+    const float* a = P + ip * ldp;
+    const float* b = P + jp * ldp;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = lane + 32 * e;
+      if (c < d) {
+        const float diff = __ldg(a + c) - __ldg(b + c);
+        float t = __fmul_rn(diff, diff);
+        if (c == d - 1) t = __fmul_rn(w_last, t);
+        sq[pp * WX_STRIDE + c] = t;
+      }
+    }
+  }
+  __syncwarp();
+  float acc = 0.f;
+  const float* mine = sq + lane * WX_STRIDE;
+  for (int c = 0; c < d; ++c) acc = __fadd_rn(acc, mine[c]);
+  __syncwarp();
+  return acc;
+}
+
 __global__ void __launch_bounds__(256) sample_pairs_kernel(const float* __restrict__ P, int64_t n, int d, int64_t ldp,
                                                            float w_last, int vec, uint32_t ns, float* __restrict__ Ds) {
   for (uint32_t s = blockIdx.x * 256u + threadIdx.x; s < ns; s += gridDim.x * 256u) {
@@ -133,6 +167,33 @@ __global__ void __launch_bounds__(256) sample_pairs_kernel(const float* __restri
     uint64_t j = ((z & 0xFFFFFFFFull) * (uint64_t)(n - 1)) >> 32;
     if (j >= i) ++j;
     Ds[s] = exact_pair(P, ldp, (int64_t)min(i, j), (int64_t)max(i, j), d, w_last, vec != 0);
+  }
+}
+
+__global__ void __launch_bounds__(32 * WX_WARPS) sample_pairs_warp_kernel(const float* __restrict__ P, int64_t n, int d,
+                                                                         int64_t ldp, float w_last, uint32_t ns,
+                                                                         float* __restrict__ Ds) {
+  extern __shared__ float wx_smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* sq = wx_smem + w * 32 * WX_STRIDE;
+  for (uint32_t s0 = (blockIdx.x * WX_WARPS + w) * 32u; s0 < ns; s0 += gridDim.x * WX_WARPS * 32u) {
+    const uint32_t sidx = min(s0 + lane, ns - 1);
+    const uint64_t z = splitmix64(sidx);
+    const uint64_t i = ((z >> 32) * (uint64_t)n) >> 32;
+    uint64_t j = ((z & 0xFFFFFFFFull) * (uint64_t)(n - 1)) >> 32;
+    if (j >= i) ++j;
+    const float dv = warp_exact32(P, ldp, d, w_last, (int64_t)min(i, j), (int64_t)max(i, j), sq, lane);
+    if (s0 + lane < ns) Ds[s0 + lane] = dv;
+  }
+}
+
+// per-column classification thresholds: below <=> fma(g,-2,A1) < zlo[j], above <=> fma(g,-2,A2) > zhi[j]
+__global__ void filter_vectors_kernel(const float* __restrict__ zn, int64_t n_pad, float* __restrict__ zlo,
+                                      float* __restrict__ zhi) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_pad; t += (int64_t)gridDim.x * blockDim.x) {
+    const float z = zn[t];
+    zlo[t] = -z * (1.f + MF_KAPPA);
+    zhi[t] = -z * (1.f - MF_KAPPA);
   }
 }
 
@@ -147,7 +208,7 @@ __global__ void bracket_set_kernel(FastMedState* fs, const SelectState* bracket,
 
 // ---------------------------------------------------------------------------- the tensor-core filter
 struct MfParams {
-  const float* zn;
+  const float* zn; const float* zlo; const float* zhi;
   int64_t n;
   int n_tiles;                 // n_pad / 64
   int64_t rb_start, rb_stride; // 128-row blocks handled by this rank
@@ -167,7 +228,7 @@ struct MfSmem {
   static constexpr int X_STAGE_BYTES = 2 * KH * XSLAB;
   static constexpr int OFF_X = Q_BYTES;
   static constexpr int OFF_VEC = OFF_X + MF_XSTAGES * X_STAGE_BYTES;
-  static constexpr int OFF_STAGE = OFF_VEC + MF_NVEC * MF_BN * 4;
+  static constexpr int OFF_STAGE = OFF_VEC + MF_NVEC * 2 * MF_BN * 4;
   static constexpr int OFF_BAR = OFF_STAGE + MF_CLS_WARPS * MF_STAGE * 8;
   static constexpr int NBARS = 1 + 2 * MF_XSTAGES + 2 * MF_NVEC + 4;
   static constexpr int DYN_BYTES = OFF_BAR + NBARS * 8 + 16 + 1024;
@@ -246,8 +307,9 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         const int ns = t % MF_NVEC, un = t / MF_NVEC;
         mbar_wait(&n_empty[ns], (un & 1) ^ 1, watch, 0x180 + ns);
         if (leader) {
-          mbar_arrive_expect_tx(&n_full[ns], MF_BN * 4);
-          bulk_load_1d(sVec + ns * MF_BN, p.zn + j0, MF_BN * 4, &n_full[ns]);
+          mbar_arrive_expect_tx(&n_full[ns], 2 * MF_BN * 4);
+          bulk_load_1d(sVec + ns * 2 * MF_BN, p.zlo + j0, MF_BN * 4, &n_full[ns]);
+          bulk_load_1d(sVec + ns * 2 * MF_BN + MF_BN, p.zhi + j0, MF_BN * 4, &n_full[ns]);
         }
         __syncwarp();
       }
@@ -298,8 +360,10 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int64_t gi = (int64_t)m0 + row_in_tile;
     const float qn = p.zn[gi];
-    const float qe = MF_KAPPA * qn;
     const float Lv = p.fs->L, Uv = p.fs->U;
+    // below  <=>  -2g + qn(1+k) - L < -zn_j(1+k)       above  <=>  -2g + qn(1-k) - U > -zn_j(1-k)
+    const float A1 = fmaf(qn, 1.f + MF_KAPPA, -Lv), A2 = fmaf(qn, 1.f - MF_KAPPA, -Uv);
+    const float2 A1_2 = make_float2(A1, A1), A2_2 = make_float2(A2, A2), m2_2 = make_float2(-2.f, -2.f);
     uint32_t cnt = 0;
     const int seg = (int)((blockIdx.y * gridDim.x + blockIdx.x) % MF_NSEG);
     unsigned long long* seg_list = p.list + (size_t)seg * p.list_cap;
@@ -329,30 +393,38 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
       tc_fence_before();
       mbar_arrive(&g_empty[b]);
       mbar_wait(&n_full[ns], un & 1, watch, 0x420 + ns);
-      const float4* zn4 = reinterpret_cast<const float4*>(sVec + ns * MF_BN + half * 32);
+      const float4* zlo4 = reinterpret_cast<const float4*>(sVec + ns * 2 * MF_BN + half * 32);
+      const float4* zhi4 = reinterpret_cast<const float4*>(sVec + ns * 2 * MF_BN + MF_BN + half * 32);
       // boundary tiles (diagonal or padded) need the i < j < n mask
       const bool boundary = (tile <= 2 * (int)rb + 1) || ((int64_t)(tile + 1) * MF_BN > p.n) || ((int64_t)m0 + MF_BM > p.n);
       uint32_t unc = 0u;
 #pragma unroll
       for (int q4 = 0; q4 < 8; ++q4) {
-        const float4 zv = zn4[q4];
-        const float zs[4] = {zv.x, zv.y, zv.z, zv.w};
+        const float4 lo4 = zlo4[q4];
+        const float4 hi4 = zhi4[q4];
+        const float los[4] = {lo4.x, lo4.y, lo4.z, lo4.w};
+        const float his[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int col = q4 * 4 + e;
-          const float u = fmaf(__uint_as_float(g[col]), -2.f, qn) + zs[e];
-          const float er = fmaf(MF_KAPPA, zs[e], qe);
-          bool below = (u + er) < Lv;
-          const bool above = (u - er) > Uv;
-          bool un_ = !(below || above);
-          if (boundary) {
-            const int64_t gj = j0 + col;
-            const bool valid = (gi < gj) && (gj < p.n) && (gi < p.n);
-            below = below && valid;
-            un_ = un_ && valid;
+        for (int e = 0; e < 4; e += 2) {
+          const float2 gg = make_float2(__uint_as_float(g[q4 * 4 + e]), __uint_as_float(g[q4 * 4 + e + 1]));
+          const float2 t1 = __ffma2_rn(gg, m2_2, A1_2);
+          const float2 t2 = __ffma2_rn(gg, m2_2, A2_2);
+          const float t1v[2] = {t1.x, t1.y}, t2v[2] = {t2.x, t2.y};
+#pragma unroll
+          for (int f = 0; f < 2; ++f) {
+            const int col = q4 * 4 + e + f;
+            bool below = t1v[f] < los[e + f];
+            const bool above = t2v[f] > his[e + f];
+            bool un_ = !(below || above);
+            if (boundary) {
+              const int64_t gj = j0 + col;
+              const bool valid = (gi < gj) && (gj < p.n) && (gi < p.n);
+              below = below && valid;
+              un_ = un_ && valid;
+            }
+            cnt += below ? 1u : 0u;
+            unc |= (un_ ? 1u : 0u) << col;
           }
-          cnt += below ? 1u : 0u;
-          unc |= (un_ ? 1u : 0u) << col;
         }
       }
       __syncwarp();
@@ -404,6 +476,54 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
 }
 
 // ---------------------------------------------------------------------------- exact evaluation of the uncertain list
+__global__ void __launch_bounds__(32 * WX_WARPS) exact_list_warp_kernel(const float* __restrict__ P, int d, int64_t ldp,
+                                                                       float w_last, FastMedState* fs,
+                                                                       const unsigned long long* __restrict__ list,
+                                                                       const uint32_t* __restrict__ list_counts,
+                                                                       uint32_t list_cap, float* __restrict__ cand,
+                                                                       uint32_t* cand_counts, uint32_t cand_cap,
+                                                                       SelectState* main_state) {
+  extern __shared__ float wx_smem[];
+  __shared__ unsigned int sh_below;
+  if (threadIdx.x == 0) sh_below = 0u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* sq = wx_smem + w * 32 * WX_STRIDE;
+  const float Lv = fs->L, Uv = fs->U;
+  uint32_t below = 0;
+  bool any_nan = false;
+  for (int seg = blockIdx.y; seg < MF_NSEG; seg += gridDim.y) {
+    const uint32_t count = min(list_counts[seg * MF_CSTRIDE], list_cap);
+    const unsigned long long* seg_list = list + (size_t)seg * list_cap;
+    float* seg_cand = cand + (size_t)seg * cand_cap;
+    for (uint32_t t0 = (blockIdx.x * WX_WARPS + w) * 32u; t0 < count; t0 += gridDim.x * WX_WARPS * 32u) {
+      const uint32_t t = t0 + lane;
+      const unsigned long long e = seg_list[min(t, count - 1)];
+      const float dv = warp_exact32(P, ldp, d, w_last, (int64_t)(e >> 32), (int64_t)(e & 0xFFFFFFFFull), sq, lane);
+      bool is_cand = false;
+      if (t < count) {
+        if (dv != dv) any_nan = true;
+        else if (dv < Lv) ++below;
+        else if (dv <= Uv) is_cand = true;
+      }
+      const uint32_t ball = __ballot_sync(0xffffffffu, is_cand);
+      if (ball) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&cand_counts[seg * MF_CSTRIDE], (uint32_t)__popc(ball));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (is_cand) {
+          const uint32_t pos = base + __popc(ball & ((1u << lane) - 1u));
+          if (pos < cand_cap) seg_cand[pos] = dv;
+        }
+      }
+    }
+  }
+  if (any_nan) atomicOr(&main_state->nan_flag, 1u);
+  if (below) atomicAdd(&sh_below, below);
+  __syncthreads();
+  if (threadIdx.x == 0 && sh_below) atomicAdd(&fs->below, (unsigned long long)sh_below);
+}
+
 __global__ void __launch_bounds__(256) exact_list_kernel(const float* __restrict__ P, int d, int64_t ldp, float w_last,
                                                          int vec, FastMedState* fs, const unsigned long long* __restrict__ list,
                                                          const uint32_t* __restrict__ list_counts, uint32_t list_cap,
@@ -523,6 +643,7 @@ int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   fast_layout(n, dz, w, &f);
   NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "median_fast: workspace too small (%zu < %zu)", ws_bytes, w.off);
   const int vec = (ldp % 4 == 0) && (((uintptr_t)P & 15) == 0);
+  (void)vec;
   const int sms = device_sm_count();
 
   // --- 0. centred bf16 pieces + norms (weighted last coordinate scaled by sqrt(w) after centring)
@@ -533,19 +654,26 @@ int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   NSVGD_PROPAGATE(launch_tc_prep(st, P, nullptr, n, dz, ldp, f.n_pad, f.dp, f.mu, sqrtf(w_last), f.Zb0, f.Zb1, nullptr,
                                  nullptr, f.zn, nullptr));
 
-  // --- 1. bracket [L, U] from the sample quantiles: 7 sigma of the binomial rank error + slack
+  // --- 1. bracket [L, U] from the sample quantiles: 6 sigma of the binomial rank error + slack
   //        (deterministic pseudo-random pairs: every rank computes the identical bracket)
   const double Ppairs = 0.5 * (double)n * (double)(n - 1);
   const double ns = (double)MF_SAMPLES;
   const double p_lo = ((double)r_lo + 0.5) / Ppairs, p_hi = ((double)r_hi + 0.5) / Ppairs;
   const double sig_lo = sqrt(ns * p_lo * (1.0 - p_lo)), sig_hi = sqrt(ns * p_hi * (1.0 - p_hi));
-  long long a = (long long)floor(p_lo * ns - 7.0 * sig_lo - 16.0);
-  long long b = (long long)ceil(p_hi * ns + 7.0 * sig_hi + 16.0);
+  long long a = (long long)floor(p_lo * ns - 6.0 * sig_lo - 16.0);
+  long long b = (long long)ceil(p_hi * ns + 6.0 * sig_hi + 16.0);
   const int l_is_zero = a < 0, u_is_inf = b >= (long long)MF_SAMPLES;
   if (a < 0) a = 0;
   if (b >= (long long)MF_SAMPLES) b = (long long)MF_SAMPLES - 1;
+  constexpr int WX_SMEM = WX_WARPS * 32 * WX_STRIDE * (int)sizeof(float);
+  static bool wx_attr = false;
+  if (!wx_attr) {
+    NSVGD_CUDA(cudaFuncSetAttribute(sample_pairs_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WX_SMEM));
+    NSVGD_CUDA(cudaFuncSetAttribute(exact_list_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WX_SMEM));
+    wx_attr = true;
+  }
   prof_begin(4, st);
-  sample_pairs_kernel<<<sms * 8, 256, 0, st>>>(P, n, (int)dz, ldp, w_last, vec, MF_SAMPLES, f.Ds);
+  sample_pairs_warp_kernel<<<sms * 3, 32 * WX_WARPS, WX_SMEM, st>>>(P, n, (int)dz, ldp, w_last, MF_SAMPLES, f.Ds);
   prof_end(4, st);
   NSVGD_LAUNCH_CHECK();
   NSVGD_PROPAGATE(launch_select_init(st, f.bracket, a, b, 1.f));
@@ -556,6 +684,9 @@ int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   bracket_set_kernel<<<1, 32, 0, st>>>(f.fs, f.bracket, l_is_zero, u_is_inf);
   NSVGD_LAUNCH_CHECK();
 
+  filter_vectors_kernel<<<(unsigned)std::min<int64_t>(ceil_div(f.n_pad, 256), 1024), 256, 0, st>>>(f.zn, f.n_pad, f.zlo, f.zhi);
+  NSVGD_LAUNCH_CHECK();
+
   // --- 2. tensor-core filter over the upper triangle (128-row blocks strided across ranks)
   CUtensorMap maps[4];
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[0], f.Zb0, f.dp, f.n_pad, (uint64_t)f.dp * 2, 64, MF_BM));
@@ -563,7 +694,7 @@ int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[2], f.Zb0, f.dp, f.n_pad, (uint64_t)f.dp * 2, 64, MF_BN));
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[3], f.Zb1, f.dp, f.n_pad, (uint64_t)f.dp * 2, 64, MF_BN));
   MfParams prm{};
-  prm.zn = f.zn; prm.n = n; prm.n_tiles = (int)(f.n_pad / MF_BN); prm.rb_start = block_row_start; prm.rb_stride = block_row_stride;
+  prm.zn = f.zn; prm.zlo = f.zlo; prm.zhi = f.zhi; prm.n = n; prm.n_tiles = (int)(f.n_pad / MF_BN); prm.rb_start = block_row_start; prm.rb_stride = block_row_stride;
   prm.fs = f.fs; prm.list = f.list; prm.list_counts = f.list_counts; prm.list_cap = f.list_cap; prm.err_flag = f.err_flag;
   const int64_t row_blocks = f.n_pad / MF_BM;
   if (f.dp == 64) NSVGD_PROPAGATE(launch_filter<64>(st, maps, prm, row_blocks));
@@ -571,8 +702,8 @@ int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
 
   // --- 3. exact evaluation of the uncertain pairs
   prof_begin(5, st);
-  exact_list_kernel<<<dim3((unsigned)std::max(1, sms * 8 / MF_NSEG), MF_NSEG), 256, 0, st>>>(
-      P, (int)dz, ldp, w_last, vec, f.fs, f.list, f.list_counts, f.list_cap, f.cand, f.cand_counts, f.cand_cap, main_state);
+  exact_list_warp_kernel<<<dim3((unsigned)std::max(1, sms * 3 / MF_NSEG + 1), MF_NSEG), 32 * WX_WARPS, WX_SMEM, st>>>(
+      P, (int)dz, ldp, w_last, f.fs, f.list, f.list_counts, f.list_cap, f.cand, f.cand_counts, f.cand_cap, main_state);
   prof_end(5, st);
   NSVGD_LAUNCH_CHECK();
   fast_pack_kernel<<<1, 32, 0, st>>>(f.fs, f.list_counts, f.list_cap, f.cand_counts, f.cand_cap, f.err_flag, red);

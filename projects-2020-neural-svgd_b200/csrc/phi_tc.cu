@@ -384,7 +384,9 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
     const float cs = NSVGD_HALF_LOG2E / (h * h);          // k = exp2(-cs r2)
     const float two_cs = 2.f * cs, neg_cs = -cs;
     const float ai = neg_cs * p.qn[m0 + row_in_tile];
-    float rowsum = 0.f, kc = 0.f, ke = 0.f;
+    const float2 two_cs2 = make_float2(two_cs, two_cs), neg_cs2 = make_float2(neg_cs, neg_cs), ai2 = make_float2(ai, ai);
+    const float2 neg_one2 = make_float2(-1.f, -1.f);
+    float2 rowsum2 = make_float2(0.f, 0.f), kc2 = rowsum2, ke2 = rowsum2;
     for (int t = 0; t < T; ++t) {
       const int b = t & 1, ub = t >> 1;
       const int ns = t % L::NVEC, un = t / L::NVEC;
@@ -400,32 +402,31 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
       const float4* xn4 = reinterpret_cast<const float4*>(sVec + ns * 2 * TC_BN + half * 32);
       const float4* cv4 = reinterpret_cast<const float4*>(sVec + ns * 2 * TC_BN + TC_BN + half * 32);
       uint32_t pk0[16], pk1[16];
+      // packed fp32x2 math (FFMA2/FADD2): two columns per instruction
 #pragma unroll
       for (int q4 = 0; q4 < 8; ++q4) {
         const float4 xv = xn4[q4];
         const float4 cvv = cv4[q4];
-        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-        const float cc[4] = {cvv.x, cvv.y, cvv.z, cvv.w};
-        float k[4], ex[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          ex[e] = fmaf(__uint_as_float(g[q4 * 4 + e]), two_cs, ai);
-          ex[e] = fmaf(xs[e], neg_cs, ex[e]);
-          k[e] = ex2_approx(ex[e]);
-        }
 #pragma unroll
         for (int e = 0; e < 4; e += 2) {
+          const float2 gg = make_float2(__uint_as_float(g[q4 * 4 + e]), __uint_as_float(g[q4 * 4 + e + 1]));
+          const float2 xs = e == 0 ? make_float2(xv.x, xv.y) : make_float2(xv.z, xv.w);
+          const float2 cc = e == 0 ? make_float2(cvv.x, cvv.y) : make_float2(cvv.z, cvv.w);
+          float2 ex = __ffma2_rn(gg, two_cs2, ai2);
+          ex = __ffma2_rn(xs, neg_cs2, ex);
+          const float2 k = make_float2(ex2_approx(ex.x), ex2_approx(ex.y));
           // k = p0 + p1 (+ <= 2^-18 k): the MMA consumes the pieces, so the row statistics use
           // kq = p0 + p1 as well -> rowsum*q_i - K X cancels the self term exactly
-          const uint32_t a0 = pack_bf16x2(k[e], k[e + 1]);
-          const float h0 = bf16lo_to_float(a0), h1 = bf16hi_to_float(a0);
-          const uint32_t a1 = pack_bf16x2(k[e] - h0, k[e + 1] - h1);
+          const uint32_t a0 = pack_bf16x2(k.x, k.y);
+          const float2 h = make_float2(bf16lo_to_float(a0), bf16hi_to_float(a0));
+          const float2 r = __ffma2_rn(h, neg_one2, k);
+          const uint32_t a1 = pack_bf16x2(r.x, r.y);
           pk0[q4 * 2 + (e >> 1)] = a0;
           pk1[q4 * 2 + (e >> 1)] = a1;
-          const float kq0 = h0 + bf16lo_to_float(a1), kq1 = h1 + bf16hi_to_float(a1);
-          rowsum += kq0; rowsum += kq1;
-          kc = fmaf(kq0, cc[e], kc); kc = fmaf(kq1, cc[e + 1], kc);
-          ke = fmaf(kq0, ex[e], ke); ke = fmaf(kq1, ex[e + 1], ke);
+          const float2 kq = __fadd2_rn(h, make_float2(bf16lo_to_float(a1), bf16hi_to_float(a1)));
+          rowsum2 = __fadd2_rn(rowsum2, kq);
+          kc2 = __ffma2_rn(kq, cc, kc2);
+          ke2 = __ffma2_rn(kq, ex, ke2);
         }
       }
       __syncwarp();
@@ -459,7 +460,7 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
                           __uint_as_float(v[q * 4 + 3]));
       }
       // b = sum k r2 = -sum k e / cs  (this thread's half of the columns)
-      *reinterpret_cast<float4*>(srow) = make_float4(rowsum, kc, -ke / cs, 0.f);
+      *reinterpret_cast<float4*>(srow) = make_float4(rowsum2.x + rowsum2.y, kc2.x + kc2.y, -(ke2.x + ke2.y) / cs, 0.f);
       tc_fence_before();
     } else {
       // empty j-range (tail split): contribute zeros
