@@ -643,7 +643,6 @@ int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   fast_layout(n, dz, w, &f);
   NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "median_fast: workspace too small (%zu < %zu)", ws_bytes, w.off);
   const int vec = (ldp % 4 == 0) && (((uintptr_t)P & 15) == 0);
-  (void)vec;
   const int sms = device_sm_count();
 
   // --- 0. centred bf16 pieces + norms (weighted last coordinate scaled by sqrt(w) after centring)
@@ -702,8 +701,15 @@ int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
 
   // --- 3. exact evaluation of the uncertain pairs
   prof_begin(5, st);
-  exact_list_warp_kernel<<<dim3((unsigned)std::max(1, sms * 3 / MF_NSEG + 1), MF_NSEG), 32 * WX_WARPS, WX_SMEM, st>>>(
-      P, (int)dz, ldp, w_last, f.fs, f.list, f.list_counts, f.list_cap, f.cand, f.cand_counts, f.cand_cap, main_state);
+  // listed pairs come out of the filter grouped by row quarter and tile, so the one-thread-per-pair
+  // gather re-uses rows through L1 and beats the warp-cooperative variant here (1.85 vs 2.5 ms at cfg4)
+  if (vec) {
+    exact_list_kernel<<<dim3((unsigned)std::max(1, sms * 8 / MF_NSEG), MF_NSEG), 256, 0, st>>>(
+        P, (int)dz, ldp, w_last, vec, f.fs, f.list, f.list_counts, f.list_cap, f.cand, f.cand_counts, f.cand_cap, main_state);
+  } else {
+    exact_list_warp_kernel<<<dim3((unsigned)std::max(1, sms * 3 / MF_NSEG + 1), MF_NSEG), 32 * WX_WARPS, WX_SMEM, st>>>(
+        P, (int)dz, ldp, w_last, f.fs, f.list, f.list_counts, f.list_cap, f.cand, f.cand_counts, f.cand_cap, main_state);
+  }
   prof_end(5, st);
   NSVGD_LAUNCH_CHECK();
   fast_pack_kernel<<<1, 32, 0, st>>>(f.fs, f.list_counts, f.list_cap, f.cand_counts, f.cand_cap, f.err_flag, red);
