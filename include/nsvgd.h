@@ -107,7 +107,9 @@ int nsvgd_median_finish(void* stream, const void* state_dev, int64_t n, float* h
 
 /* Tensor-core filtered variant of the same exact select (n >= 8192, 32 < dz <= 128),
  * split into stages so that a row-sharded run can all-reduce between them:
- *   stage1  : bracket from sampled pairs (identical on every rank), tcgen05 filter over the 128-row blocks
+ *   sample  : centred bf16 pieces + this rank's slice (part of nparts) of the 2^22 sampled pair distances;
+ *             returns where the sample buffer lives inside ws  [host: all-gather the slices in place]
+ *   stage1  : bracket from the sampled distances (identical on every rank), tcgen05 filter over the 128-row blocks
  *             block_row_start, +block_row_stride, ..., exact re-evaluation of the uncertain pairs;
  *             reduce_dev (int64[4]) = {pairs below the bracket, candidates, overflow flag, listed pairs}
  *   [host: all-reduce(sum) reduce_dev]
@@ -118,6 +120,9 @@ int nsvgd_median_finish(void* stream, const void* state_dev, int64_t n, float* h
  * `ws` is a scratch region of nsvgd_median_fast_workspace_bytes() that must stay untouched between stages. */
 int nsvgd_median_fast_supported(int64_t n, int64_t dz);
 int nsvgd_median_fast_workspace_bytes(int64_t n, int64_t dz, size_t* out_bytes);
+int nsvgd_median_fast_sample(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last,
+                             int64_t part, int64_t nparts, void* ws, size_t ws_bytes, size_t* samples_offset_bytes,
+                             int64_t* samples_count);
 int nsvgd_median_fast_stage1(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last, int mode,
                              int64_t block_row_start, int64_t block_row_stride, void* state_dev, uint64_t* hist_dev,
                              void* ws, size_t ws_bytes, int64_t* reduce_dev);

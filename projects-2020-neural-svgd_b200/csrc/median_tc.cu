@@ -171,12 +171,13 @@ __global__ void __launch_bounds__(256) sample_pairs_kernel(const float* __restri
 }
 
 __global__ void __launch_bounds__(32 * WX_WARPS) sample_pairs_warp_kernel(const float* __restrict__ P, int64_t n, int d,
-                                                                         int64_t ldp, float w_last, uint32_t ns,
-                                                                         float* __restrict__ Ds) {
+                                                                         int64_t ldp, float w_last, uint32_t s_begin,
+                                                                         uint32_t ns, float* __restrict__ Ds) {
+  // samples [s_begin, ns): sample s is a pure function of s, so ranks can each take a slice
   extern __shared__ float wx_smem[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* sq = wx_smem + w * 32 * WX_STRIDE;
-  for (uint32_t s0 = (blockIdx.x * WX_WARPS + w) * 32u; s0 < ns; s0 += gridDim.x * WX_WARPS * 32u) {
+  for (uint32_t s0 = s_begin + (blockIdx.x * WX_WARPS + w) * 32u; s0 < ns; s0 += gridDim.x * WX_WARPS * 32u) {
     const uint32_t sidx = min(s0 + lane, ns - 1);
     const uint64_t z = splitmix64(sidx);
     const uint64_t i = ((z >> 32) * (uint64_t)n) >> 32;
@@ -633,6 +634,47 @@ static int launch_filter(cudaStream_t st, const CUtensorMap* maps, const MfParam
   return NSVGD_OK;
 }
 
+// stage 0: centred bf16 pieces, norms, thresholds, and this rank's slice of the sampled pair distances
+int median_fast_sample(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, int64_t part,
+                       int64_t nparts, void* ws, size_t ws_bytes, size_t* samples_off, int64_t* samples_count) {
+  NSVGD_REQUIRE(median_fast_supported(n, dz), NSVGD_ERR_UNSUPPORTED, "median_fast: unsupported shape");
+  NSVGD_REQUIRE(nparts >= 1 && part >= 0 && part < nparts && MF_SAMPLES % nparts == 0 && (MF_SAMPLES / nparts) % 32 == 0,
+                NSVGD_ERR_INVALID, "median_fast_sample: the sample count %u must split evenly over %lld parts", MF_SAMPLES,
+                (long long)nparts);
+  WsCarver w(ws, ws_bytes);
+  FastWs f;
+  fast_layout(n, dz, w, &f);
+  NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "median_fast: workspace too small (%zu < %zu)", ws_bytes, w.off);
+  const int sms = device_sm_count();
+  NSVGD_PROPAGATE(launch_colmean(st, P, n, dz, ldp, f.mpart, f.mu));
+  NSVGD_CUDA(cudaMemsetAsync(f.err_flag, 0, 16, st));
+  NSVGD_CUDA(cudaMemsetAsync(f.list_counts, 0, sizeof(uint32_t) * MF_NSEG * MF_CSTRIDE, st));
+  NSVGD_CUDA(cudaMemsetAsync(f.cand_counts, 0, sizeof(uint32_t) * MF_NSEG * MF_CSTRIDE, st));
+  // weighted last coordinate scaled by sqrt(w) AFTER centring
+  NSVGD_PROPAGATE(launch_tc_prep(st, P, nullptr, n, dz, ldp, f.n_pad, f.dp, f.mu, sqrtf(w_last), f.Zb0, f.Zb1, nullptr,
+                                 nullptr, f.zn, nullptr));
+  filter_vectors_kernel<<<(unsigned)std::min<int64_t>(ceil_div(f.n_pad, 256), 1024), 256, 0, st>>>(f.zn, f.n_pad, f.zlo, f.zhi);
+  NSVGD_LAUNCH_CHECK();
+  constexpr int WX_SMEM = WX_WARPS * 32 * WX_STRIDE * (int)sizeof(float);
+  static bool wx_attr = false;
+  if (!wx_attr) {
+    NSVGD_CUDA(cudaFuncSetAttribute(sample_pairs_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WX_SMEM));
+    NSVGD_CUDA(cudaFuncSetAttribute(exact_list_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WX_SMEM));
+    wx_attr = true;
+  }
+  const uint32_t per = MF_SAMPLES / (uint32_t)nparts;
+  const uint32_t s_begin = per * (uint32_t)part, s_end = s_begin + per;
+  const unsigned blocks = (unsigned)std::min<int64_t>(sms * 3, ceil_div(per, 32 * WX_WARPS));
+  prof_begin(4, st);
+  sample_pairs_warp_kernel<<<blocks, 32 * WX_WARPS, WX_SMEM, st>>>(P, n, (int)dz, ldp, w_last, s_begin, s_end, f.Ds);
+  prof_end(4, st);
+  NSVGD_LAUNCH_CHECK();
+  if (samples_off) *samples_off = (size_t)((char*)f.Ds - (char*)ws);
+  if (samples_count) *samples_count = (int64_t)MF_SAMPLES;
+  return NSVGD_OK;
+}
+
+// stage 1 (all MF_SAMPLES sampled distances present in the workspace): bracket, filter, exact list, summary
 int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, long long r_lo,
                        long long r_hi, int64_t block_row_start, int64_t block_row_stride, SelectState* main_state,
                        uint64_t* hist, void* ws, size_t ws_bytes, long long* red) {
@@ -644,14 +686,7 @@ int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "median_fast: workspace too small (%zu < %zu)", ws_bytes, w.off);
   const int vec = (ldp % 4 == 0) && (((uintptr_t)P & 15) == 0);
   const int sms = device_sm_count();
-
-  // --- 0. centred bf16 pieces + norms (weighted last coordinate scaled by sqrt(w) after centring)
-  NSVGD_PROPAGATE(launch_colmean(st, P, n, dz, ldp, f.mpart, f.mu));
-  NSVGD_CUDA(cudaMemsetAsync(f.err_flag, 0, 16, st));
-  NSVGD_CUDA(cudaMemsetAsync(f.list_counts, 0, sizeof(uint32_t) * MF_NSEG * MF_CSTRIDE, st));
-  NSVGD_CUDA(cudaMemsetAsync(f.cand_counts, 0, sizeof(uint32_t) * MF_NSEG * MF_CSTRIDE, st));
-  NSVGD_PROPAGATE(launch_tc_prep(st, P, nullptr, n, dz, ldp, f.n_pad, f.dp, f.mu, sqrtf(w_last), f.Zb0, f.Zb1, nullptr,
-                                 nullptr, f.zn, nullptr));
+  constexpr int WX_SMEM = WX_WARPS * 32 * WX_STRIDE * (int)sizeof(float);
 
   // --- 1. bracket [L, U] from the sample quantiles: 6 sigma of the binomial rank error + slack
   //        (deterministic pseudo-random pairs: every rank computes the identical bracket)
@@ -664,26 +699,12 @@ int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   const int l_is_zero = a < 0, u_is_inf = b >= (long long)MF_SAMPLES;
   if (a < 0) a = 0;
   if (b >= (long long)MF_SAMPLES) b = (long long)MF_SAMPLES - 1;
-  constexpr int WX_SMEM = WX_WARPS * 32 * WX_STRIDE * (int)sizeof(float);
-  static bool wx_attr = false;
-  if (!wx_attr) {
-    NSVGD_CUDA(cudaFuncSetAttribute(sample_pairs_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WX_SMEM));
-    NSVGD_CUDA(cudaFuncSetAttribute(exact_list_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WX_SMEM));
-    wx_attr = true;
-  }
-  prof_begin(4, st);
-  sample_pairs_warp_kernel<<<sms * 3, 32 * WX_WARPS, WX_SMEM, st>>>(P, n, (int)dz, ldp, w_last, MF_SAMPLES, f.Ds);
-  prof_end(4, st);
-  NSVGD_LAUNCH_CHECK();
   NSVGD_PROPAGATE(launch_select_init(st, f.bracket, a, b, 1.f));
   for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
     NSVGD_PROPAGATE(launch_buffer_hist(st, f.Ds, nullptr, 0, 1, 0, MF_SAMPLES, f.bracket, pass, hist, nullptr));
     NSVGD_PROPAGATE(launch_select_advance(st, f.bracket, hist, pass, nullptr));
   }
   bracket_set_kernel<<<1, 32, 0, st>>>(f.fs, f.bracket, l_is_zero, u_is_inf);
-  NSVGD_LAUNCH_CHECK();
-
-  filter_vectors_kernel<<<(unsigned)std::min<int64_t>(ceil_div(f.n_pad, 256), 1024), 256, 0, st>>>(f.zn, f.n_pad, f.zlo, f.zhi);
   NSVGD_LAUNCH_CHECK();
 
   // --- 2. tensor-core filter over the upper triangle (128-row blocks strided across ranks)
@@ -768,6 +789,7 @@ int median_fast(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t 
   FastWs f;
   NSVGD_PROPAGATE(fast_ws(n, dz, ws, ws_bytes, &f));
   long long* red = (long long*)(f.err_flag) + 8;      // err_flag block is 256-byte aligned, 16 bytes used
+  NSVGD_PROPAGATE(median_fast_sample(st, P, n, dz, ldp, w_last, 0, 1, ws, ws_bytes, nullptr, nullptr));
   NSVGD_PROPAGATE(median_fast_stage1(st, P, n, dz, ldp, w_last, r_lo, r_hi, tile_row_start, tile_row_stride, main_state, hist,
                                      ws, ws_bytes, red));
   NSVGD_PROPAGATE(median_fast_resolve(st, main_state, ws, ws_bytes, n, dz, red));
@@ -797,6 +819,14 @@ extern "C" int nsvgd_median_fast_workspace_bytes(int64_t n, int64_t dz, size_t* 
   NSVGD_REQUIRE(median_fast_supported(n, dz), NSVGD_ERR_UNSUPPORTED, "median_fast: unsupported shape (n=%lld dz=%lld)", (long long)n, (long long)dz);
   *out_bytes = median_fast_workspace(n, dz);
   return NSVGD_OK;
+}
+
+extern "C" int nsvgd_median_fast_sample(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last,
+                                        int64_t part, int64_t nparts, void* ws, size_t ws_bytes, size_t* samples_offset_bytes,
+                                        int64_t* samples_count) {
+  NSVGD_REQUIRE(Z && ws, NSVGD_ERR_INVALID, "median_fast_sample: null pointer");
+  return median_fast_sample((cudaStream_t)stream, Z, n, dz, ldz, w_last, part, nparts, ws, ws_bytes, samples_offset_bytes,
+                            samples_count);
 }
 
 extern "C" int nsvgd_median_fast_stage1(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last, int mode,

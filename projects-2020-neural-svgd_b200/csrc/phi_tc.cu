@@ -145,8 +145,8 @@ struct TcParams {
 };
 
 constexpr int TC_BM = 128, TC_BN = 64;
-constexpr int TC_PAIR_WARPS = 8;                         // pair-function warps: 2 per TMEM lane quarter
-constexpr int TC_THREADS = 64 + 32 * TC_PAIR_WARPS;      // + TMA producer warp + MMA issuer warp
+constexpr int TC_DEFAULT_PAIR_WARPS = 8;
+constexpr bool TC_DEFAULT_INTERLEAVE = false;
 constexpr int TC_MAX_RUN_TILES = 64;   // <= 768 sequential TMEM accumulations per run
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_O = 0, TM_G = 256, TM_P = 384;
@@ -174,8 +174,11 @@ struct TcSmem {
   static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
 };
 
-template <int DP>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// NW = pair-function warps (8: 2 per TMEM lane quarter x 32 columns each; 16: 4 per quarter x 16 columns)
+// IL = issue the Gram MMAs of tile t+1 interleaved with the P.V MMAs of tile t-1 (spreads the
+//      shared-memory operand traffic of the N=64 Gram MMAs over the TMEM-fed P.V MMAs)
+template <int DP, int NW, bool IL>
+__global__ void __launch_bounds__(64 + 32 * NW, 1)
 phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ CUtensorMap tmQ1,
               const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
               const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmV1,
@@ -217,10 +220,10 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
     mbar_init(q_full, 1);
     for (int i = 0; i < L::XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
     for (int i = 0; i < L::VSLOTS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < L::NVEC; ++i) { mbar_init(&n_full[i], 1); mbar_init(&n_empty[i], TC_PAIR_WARPS); }
+    for (int i = 0; i < L::NVEC; ++i) { mbar_init(&n_full[i], 1); mbar_init(&n_empty[i], NW); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 32 * TC_PAIR_WARPS);
-      mbar_init(&p_full[i], 32 * TC_PAIR_WARPS); mbar_init(&p_empty[i], 1);
+      mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 32 * NW);
+      mbar_init(&p_full[i], 32 * NW); mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_full, 1);
     fence_barrier_init();
@@ -285,10 +288,20 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
           __syncwarp();
         }
       };
-      // same order as the MMA warp consumes: X(0), X(1), V(0), X(2), V(1), ...
-      load_x(0);
-      for (int t = 1; t < T; ++t) { load_x(t); load_v(t - 1); }
-      load_v(T - 1);
+      // same order as the MMA warp consumes
+      if (!IL) {          // X(0), X(1), V(0), X(2), V(1), ...
+        load_x(0);
+        for (int t = 1; t < T; ++t) { load_x(t); load_v(t - 1); }
+        load_v(T - 1);
+      } else {            // X(0), X(1), X(2), V(0), X(3), V(1), ...
+        load_x(0);
+        if (T > 1) load_x(1);
+        for (int t = 1; t < T; ++t) {
+          if (t + 1 < T) load_x(t + 1);
+          load_v(t - 1);
+        }
+        load_v(T - 1);
+      }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
@@ -366,18 +379,74 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
           __syncwarp();
         }
       };
-      issue_gram(0);
-      for (int t = 1; t < T; ++t) { issue_gram(t); issue_pv(t - 1); }
-      issue_pv(T - 1);
+      // Gram(tg) and P.V(tp) interleaved on the tensor pipe: 2 Gram MMAs (N=64, smem A+B) per P.V MMA (N=2DP, A in TMEM)
+      auto issue_mixed = [&](int tg, int tp) {
+        const int b = tg & 1, ub = tg >> 1;
+        const int st = tg % L::XSTAGES, us = tg / L::XSTAGES;
+        const int pb = tp & 1, up = tp >> 1;
+        const int s0 = vcount % L::VSLOTS, u0 = vcount / L::VSLOTS; ++vcount;
+        const int s1 = vcount % L::VSLOTS, u1 = vcount / L::VSLOTS; ++vcount;
+        mbar_wait(&g_empty[b], (ub & 1) ^ 1, watch, 0x310 + b);
+        mbar_wait(&x_full[st], us & 1, watch, 0x320 + st);
+        mbar_wait(&p_full[pb], up & 1, watch, 0x330 + pb);
+        mbar_wait(&v_full[s0], u0 & 1, watch, 0x340 + s0);
+        mbar_wait(&v_full[s1], u1 & 1, watch, 0x350 + s1);
+        tc_fence_after();
+        const uint32_t d_tm = tmem + TM_G + b * TC_BN;
+        const uint32_t xs = sX_a + st * L::X_STAGE_BYTES;
+        const uint32_t p0 = tmem + TM_P + pb * 64, p1 = p0 + 32;
+        const uint64_t bd0 = umma_desc_sw128(sV_a + s0 * L::VSLOT), bd1 = umma_desc_sw128(sV_a + s1 * L::VSLOT);
+        if (leader) {
+          constexpr int NG = 3 * KH * 4;           // Gram MMAs per tile
+          constexpr int GPK = NG / 12;             // per P.V MMA
+#pragma unroll
+          for (int k = 0; k < 12; ++k) {
+#pragma unroll
+            for (int gi = 0; gi < GPK; ++gi) {
+              const int gm = k * GPK + gi;
+              const int pass = gm / (KH * 4), kh = (gm / 4) % KH, ks = gm % 4;
+              const int pa = pass == 2 ? 1 : 0, pbx = pass == 1 ? 1 : 0;
+              const uint64_t ad = umma_desc_sw128(sQ_a + (pa * KH + kh) * L::QSLAB);
+              const uint64_t bd = umma_desc_sw128(xs + (pbx * KH + kh) * L::XSLAB);
+              umma_ss(d_tm, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 32), idesc_g, gm > 0 ? 1u : 0u);
+              if (gm == NG - 1) { umma_commit(&x_empty[st]); umma_commit(&g_full[b]); }
+            }
+            const int ks = k & 3;
+            if (k < 4) umma_ts(tmem + TM_O, p0 + ks * 8, umma_desc_advance(bd0, ks * 32), idesc_pv, (tp > 0 || ks > 0) ? 1u : 0u);
+            else if (k < 8) umma_ts(tmem + TM_O, p1 + ks * 8, umma_desc_advance(bd0, ks * 32), idesc_pv, 1u);
+            else umma_ts(tmem + TM_O, p0 + ks * 8, umma_desc_advance(bd1, ks * 32), idesc_pv, 1u);
+            if (k == 7) umma_commit(&v_empty[s0]);
+          }
+          umma_commit(&v_empty[s1]);
+          umma_commit(&p_empty[pb]);
+        }
+        __syncwarp();
+      };
+      if (!IL) {
+        issue_gram(0);
+        for (int t = 1; t < T; ++t) { issue_gram(t); issue_pv(t - 1); }
+        issue_pv(T - 1);
+      } else {
+        issue_gram(0);
+        if (T > 1) issue_gram(1);
+        for (int t = 1; t < T; ++t) {
+          if (t + 1 < T) issue_mixed(t + 1, t - 1);
+          else issue_pv(t - 1);
+        }
+        issue_pv(T - 1);
+      }
       if (leader) umma_commit(o_full);
       __syncwarp();
     }
   } else {
     // =============================== pair-function warps ==========================================
-    // thread <-> (row, column half): quarter = warp % 4 selects the TMEM lanes (rows), half = which
-    // 32 of the tile's 64 columns.  Two warps per SM sub-partition hide each other's latencies.
+    // thread <-> (row, column part): quarter = warp % 4 selects the TMEM lanes (rows), part = which CPT
+    // of the tile's 64 columns.  Several warps per SM sub-partition hide each other's latencies.
+    constexpr int NPART = NW / 4;
+    constexpr int CPT = TC_BN / NPART;                 // columns per thread and tile (32 or 16)
+    constexpr int OCOLS = 2 * DP / NPART;              // accumulator columns per thread in the epilogue
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float h = *p.h_dev;
@@ -393,18 +462,19 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
       mbar_wait(&g_full[b], ub & 1, watch, 0x400 + b);
       __syncwarp();
       tc_fence_after();
-      uint32_t g[32];
-      tmem_ld32(tmem + lane_addr + TM_G + b * TC_BN + half * 32, g);
+      uint32_t g[CPT];
+      if (CPT == 32) tmem_ld32(tmem + lane_addr + TM_G + b * TC_BN + part * CPT, g);
+      else tmem_ld16(tmem + lane_addr + TM_G + b * TC_BN + part * CPT, g);
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(&g_empty[b]);
       mbar_wait(&n_full[ns], un & 1, watch, 0x420 + ns);
-      const float4* xn4 = reinterpret_cast<const float4*>(sVec + ns * 2 * TC_BN + half * 32);
-      const float4* cv4 = reinterpret_cast<const float4*>(sVec + ns * 2 * TC_BN + TC_BN + half * 32);
-      uint32_t pk0[16], pk1[16];
+      const float4* xn4 = reinterpret_cast<const float4*>(sVec + ns * 2 * TC_BN + part * CPT);
+      const float4* cv4 = reinterpret_cast<const float4*>(sVec + ns * 2 * TC_BN + TC_BN + part * CPT);
+      uint32_t pk0[CPT / 2], pk1[CPT / 2];
       // packed fp32x2 math (FFMA2/FADD2): two columns per instruction
 #pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {
+      for (int q4 = 0; q4 < CPT / 4; ++q4) {
         const float4 xv = xn4[q4];
         const float4 cvv = cv4[q4];
 #pragma unroll
@@ -415,15 +485,15 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
           float2 ex = __ffma2_rn(gg, two_cs2, ai2);
           ex = __ffma2_rn(xs, neg_cs2, ex);
           const float2 k = make_float2(ex2_approx(ex.x), ex2_approx(ex.y));
-          // k = p0 + p1 (+ <= 2^-18 k): the MMA consumes the pieces, so the row statistics use
+          // k = p0 + p1 (+ <= 2^-16 k): the MMA consumes the pieces, so the row statistics use
           // kq = p0 + p1 as well -> rowsum*q_i - K X cancels the self term exactly
           const uint32_t a0 = pack_bf16x2(k.x, k.y);
-          const float2 h = make_float2(bf16lo_to_float(a0), bf16hi_to_float(a0));
-          const float2 r = __ffma2_rn(h, neg_one2, k);
+          const float2 hh = make_float2(bf16lo_to_float(a0), bf16hi_to_float(a0));
+          const float2 r = __ffma2_rn(hh, neg_one2, k);
           const uint32_t a1 = pack_bf16x2(r.x, r.y);
           pk0[q4 * 2 + (e >> 1)] = a0;
           pk1[q4 * 2 + (e >> 1)] = a1;
-          const float2 kq = __fadd2_rn(h, make_float2(bf16lo_to_float(a1), bf16hi_to_float(a1)));
+          const float2 kq = __fadd2_rn(hh, make_float2(bf16lo_to_float(a1), bf16hi_to_float(a1)));
           rowsum2 = __fadd2_rn(rowsum2, kq);
           kc2 = __ffma2_rn(kq, cc, kc2);
           ke2 = __ffma2_rn(kq, ex, ke2);
@@ -434,24 +504,29 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
       mbar_wait(&p_empty[b], (ub & 1) ^ 1, watch, 0x410 + b);
       __syncwarp();
       tc_fence_after();
-      tmem_st16(tmem + lane_addr + TM_P + b * 64 + half * 16, pk0);
-      tmem_st16(tmem + lane_addr + TM_P + b * 64 + 32 + half * 16, pk1);
+      if (CPT == 32) {
+        tmem_st16(tmem + lane_addr + TM_P + b * 64 + part * 16, pk0);
+        tmem_st16(tmem + lane_addr + TM_P + b * 64 + 32 + part * 16, pk1);
+      } else {
+        tmem_st8(tmem + lane_addr + TM_P + b * 64 + part * 8, pk0);
+        tmem_st8(tmem + lane_addr + TM_P + b * 64 + 32 + part * 8, pk1);
+      }
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[b]);
     }
-    // ---- epilogue: O (TMEM) -> workspace; the two warps of a quarter take DP columns each
+    // ---- epilogue: O (TMEM) -> workspace; the NPART warps of a quarter take OCOLS columns each
     const int64_t row = (int64_t)m0 + row_in_tile;
-    float* orow = p.O + ((int64_t)split * p.m_pad + row) * (2 * DP) + half * DP;
-    float* srow = p.scal + (((int64_t)split * 2 + half) * p.m_pad + row) * 4;
+    float* orow = p.O + ((int64_t)split * p.m_pad + row) * (2 * DP) + part * OCOLS;
+    float* srow = p.scal + (((int64_t)split * NPART + part) * p.m_pad + row) * 4;
     if (T > 0) {
       mbar_wait(o_full, 0, watch, 0x500);
       __syncwarp();
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < DP; c0 += 32) {
+      for (int c0 = 0; c0 < OCOLS; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem + lane_addr + TM_O + half * DP + c0, v);
+        tmem_ld32(tmem + lane_addr + TM_O + part * OCOLS + c0, v);
         tmem_wait_ld();
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -459,12 +534,12 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
               make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]), __uint_as_float(v[q * 4 + 2]),
                           __uint_as_float(v[q * 4 + 3]));
       }
-      // b = sum k r2 = -sum k e / cs  (this thread's half of the columns)
+      // b = sum k r2 = -sum k e / cs  (this thread's part of the columns)
       *reinterpret_cast<float4*>(srow) = make_float4(rowsum2.x + rowsum2.y, kc2.x + kc2.y, -(ke2.x + ke2.y) / cs, 0.f);
       tc_fence_before();
     } else {
       // empty j-range (tail split): contribute zeros
-      for (int c = 0; c < DP; c += 4) *reinterpret_cast<float4*>(orow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < OCOLS; c += 4) *reinterpret_cast<float4*>(orow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
       *reinterpret_cast<float4*>(srow) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
@@ -511,20 +586,38 @@ static TcPlan make_plan(const PhiArgs& a) {
   return pl;
 }
 
-template <int DP>
-static int launch_tc(cudaStream_t st, const TcPlan& pl, const CUtensorMap* maps, const TcParams& prm) {
+template <int DP, int NW, bool IL>
+static int launch_tc_variant(cudaStream_t st, const TcPlan& pl, const CUtensorMap* maps, const TcParams& prm) {
   using L = TcSmem<DP>;
   static bool attr_set = false;
   if (!attr_set) {
-    NSVGD_CUDA(cudaFuncSetAttribute(phi_tc_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    NSVGD_CUDA(cudaFuncSetAttribute(phi_tc_kernel<DP, NW, IL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
     attr_set = true;
   }
   dim3 grid((unsigned)(pl.m_pad / TC_BM), (unsigned)pl.nsplit);
   prof_begin(0, st);
-  phi_tc_kernel<DP><<<grid, TC_THREADS, L::DYN_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], prm);
+  phi_tc_kernel<DP, NW, IL><<<grid, 64 + 32 * NW, L::DYN_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], prm);
   prof_end(0, st);
   NSVGD_LAUNCH_CHECK();
   return NSVGD_OK;
+}
+
+// kernel variant: NSVGD_TC_PAIR_WARPS in {8,16}, NSVGD_TC_INTERLEAVE in {0,1} (tuning knobs; defaults measured best)
+static int tc_pair_warps() {
+  const char* e = getenv("NSVGD_TC_PAIR_WARPS");
+  return (e && atoi(e) == 16) ? 16 : ((e && atoi(e) == 8) ? 8 : TC_DEFAULT_PAIR_WARPS);
+}
+static bool tc_interleave() {
+  const char* e = getenv("NSVGD_TC_INTERLEAVE");
+  return e ? atoi(e) != 0 : TC_DEFAULT_INTERLEAVE;
+}
+
+template <int DP>
+static int launch_tc(cudaStream_t st, const TcPlan& pl, const CUtensorMap* maps, const TcParams& prm) {
+  const int nw = tc_pair_warps();
+  const bool il = tc_interleave();
+  if (nw == 16) return il ? launch_tc_variant<DP, 16, true>(st, pl, maps, prm) : launch_tc_variant<DP, 16, false>(st, pl, maps, prm);
+  return il ? launch_tc_variant<DP, 8, true>(st, pl, maps, prm) : launch_tc_variant<DP, 8, false>(st, pl, maps, prm);
 }
 
 int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dry, size_t* need) {
@@ -548,7 +641,7 @@ int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dr
     qn = w.take<float>((size_t)pl.m_pad);
   }
   float* O = w.take<float>((size_t)pl.nsplit * pl.m_pad * 2 * dp, 1024);
-  float* scal = w.take<float>((size_t)pl.nsplit * 2 * pl.m_pad * 4);   // two column halves per split
+  float* scal = w.take<float>((size_t)pl.nsplit * 4 * pl.m_pad * 4);   // up to 4 column parts per split
   uint32_t* err_flag = w.take<uint32_t>(4);
   double* partials = w.take<double>((size_t)(2 * epilogue_blocks(a.m)));
   if (need) *need = w.off;
@@ -575,7 +668,7 @@ int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dr
   else NSVGD_PROPAGATE(launch_tc<128>(st, pl, maps, prm));
 
   EpilogueArgs e{};
-  e.form = 1; e.O = O; e.scal = scal; e.nsplit = pl.nsplit; e.scal_parts = 2 * pl.nsplit; e.m_pad = pl.m_pad; e.ldo = 2 * dp; e.dpad = dp; e.mu = mu;
+  e.form = 1; e.O = O; e.scal = scal; e.nsplit = pl.nsplit; e.scal_parts = (tc_pair_warps() / 4) * pl.nsplit; e.m_pad = pl.m_pad; e.ldo = 2 * dp; e.dpad = dp; e.mu = mu;
   e.Q = a.Q; e.ldq = a.ldq; e.Sq = a.Sq; e.m = a.m; e.n = a.n; e.d = a.d; e.h_dev = a.h_dev;
   e.phi = a.phi; e.ldphi = a.ldphi; e.aux = a.aux; e.stats_dev = a.stats_dev; e.partials = partials;
   return launch_epilogue(st, e);

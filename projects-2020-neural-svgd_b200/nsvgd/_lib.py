@@ -29,7 +29,7 @@ SYMBOLS = [
     "nsvgd_profile_enable", "nsvgd_profile_read",
     "nsvgd_median_h_f32", "nsvgd_median_prepare", "nsvgd_median_hist_pass", "nsvgd_median_advance",
     "nsvgd_median_finish", "nsvgd_median_fast_supported", "nsvgd_median_fast_workspace_bytes",
-    "nsvgd_median_fast_stage1", "nsvgd_median_fast_resolve", "nsvgd_median_fast_cand_hist",
+    "nsvgd_median_fast_sample", "nsvgd_median_fast_stage1", "nsvgd_median_fast_resolve", "nsvgd_median_fast_cand_hist",
     "nsvgd_median_fast_cand_advance", "nsvgd_median_fast_commit", "nsvgd_median_fallback_hist",
     "nsvgd_median_fallback_advance", "nsvgd_phi_f32", "nsvgd_step_sgd_f32", "nsvgd_apply_update_f32",
     "nsvgd_ksd_f32", "nsvgd_mmd_f32", "nsvgd_ksum_f32", "nsvgd_adam_update_f32",
@@ -68,6 +68,7 @@ def load():
     lib.nsvgd_median_finish.argtypes = [vp, vp, i64, vp]
     lib.nsvgd_median_fast_supported.argtypes = [i64, i64]
     lib.nsvgd_median_fast_workspace_bytes.argtypes = [i64, i64, C.POINTER(sz)]
+    lib.nsvgd_median_fast_sample.argtypes = [vp, vp, i64, i64, i64, f32, i64, i64, vp, sz, C.POINTER(sz), C.POINTER(i64)]
     lib.nsvgd_median_fast_stage1.argtypes = [vp, vp, i64, i64, i64, f32, i32, i64, i64, vp, vp, vp, sz, vp]
     lib.nsvgd_median_fast_resolve.argtypes = [vp, vp, vp, sz, i64, i64, vp]
     lib.nsvgd_median_fast_cand_hist.argtypes = [vp, vp, sz, i64, i64, i32, vp]

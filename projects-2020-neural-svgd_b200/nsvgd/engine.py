@@ -173,6 +173,17 @@ class MedianSelect:
             self._fast_ws = torch.empty(int(need.value), dtype=torch.uint8, device=self.x.device)
         return self._fast_ws
 
+    def fast_sample(self, part=0, nparts=1):
+        """stage 0: prep + this rank's slice of the sampled distances.  Returns (full sample buffer, local
+        slice) as float32 views into the workspace; all-gather the slices into the full buffer when sharded."""
+        ws = self._fws()
+        off, cnt = C.c_size_t(0), C.c_int64(0)
+        check(load().nsvgd_median_fast_sample(stream_ptr(self.x.device), ptr(self.P), self.n, self.dz, ld(self.P), self.w_last,
+                                              part, nparts, ptr(ws), ws.numel(), C.byref(off), C.byref(cnt)))
+        full = ws[off.value: off.value + 4 * cnt.value].view(torch.float32)
+        per = cnt.value // nparts
+        return full, full[part * per: (part + 1) * per]
+
     def fast_stage1(self, block_row_start=0, block_row_stride=1) -> torch.Tensor:
         ws = self._fws()
         check(load().nsvgd_median_fast_stage1(stream_ptr(self.x.device), ptr(self.P), self.n, self.dz, ld(self.P), self.w_last,

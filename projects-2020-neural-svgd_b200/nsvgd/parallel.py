@@ -64,6 +64,10 @@ class ShardedSVGD:
         if getattr(sel, "fast_supported", False):
             # tensor-core filtered select: the bracket is identical on every rank (deterministic sample of
             # the gathered particles); counts and candidate histograms are all-reduced between the stages.
+            nparts = self.world if (1 << 22) % self.world == 0 and ((1 << 22) // self.world) % 32 == 0 else 1
+            full, mine = sel.fast_sample(self.rank if nparts > 1 else 0, nparts)
+            if nparts > 1:
+                dist.all_gather_into_tensor(full, mine, group=self.group)
             dist.all_reduce(sel.fast_stage1(self.rank, self.world), **sum_)
             sel.fast_resolve()
             for p in range(3):

@@ -238,6 +238,11 @@ def test_fast_median_staged_two_ranks_on_one_gpu(mode):
     want = engine.median_heuristic(X, mode).cpu().numpy()[0]
     sels = [engine.MedianSelect(X, mode) for _ in range(2)]
     assert all(s.fast_supported for s in sels)
+    for r, s in enumerate(sels):                      # each simulated rank samples its half ...
+        s.fast_sample(r, 2)
+    full0, _ = sels[0].fast_sample(0, 2); full1, _ = sels[1].fast_sample(1, 2)
+    half = full0.numel() // 2                          # ... and the halves are exchanged (all-gather)
+    full0[half:].copy_(full1[half:]); full1[:half].copy_(full0[:half])
     red = sum(s.fast_stage1(r, 2).clone() for r, s in enumerate(sels))
     for s in sels:
         s.reduce.copy_(red); s.fast_resolve()
