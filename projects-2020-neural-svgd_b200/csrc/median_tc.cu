@@ -274,7 +274,7 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     mbar_init(q_full, 1);
     for (int i = 0; i < MF_XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
     for (int i = 0; i < MF_NVEC; ++i) { mbar_init(&n_full[i], 1); mbar_init(&n_empty[i], MF_CLS_WARPS); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 32 * MF_CLS_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], MF_CLS_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 128); tmem_relinquish(); }
@@ -392,7 +392,8 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
       tmem_ld32(tmem + lane_addr + b * MF_BN + half * 32, g);
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(&g_empty[b]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&g_empty[b]);
       mbar_wait(&n_full[ns], un & 1, watch, 0x420 + ns);
       const float4* zlo4 = reinterpret_cast<const float4*>(sVec + ns * 2 * MF_BN + half * 32);
       const float4* zhi4 = reinterpret_cast<const float4*>(sVec + ns * 2 * MF_BN + MF_BN + half * 32);

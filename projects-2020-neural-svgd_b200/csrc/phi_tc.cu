@@ -222,8 +222,10 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
     for (int i = 0; i < L::VSLOTS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     for (int i = 0; i < L::NVEC; ++i) { mbar_init(&n_full[i], 1); mbar_init(&n_empty[i], NW); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 32 * NW);
-      mbar_init(&p_full[i], 32 * NW); mbar_init(&p_empty[i], 1);
+      // one arrival per pair-function warp (lane 0 after __syncwarp): 256 per-thread arrivals on one
+      // mbarrier serialise and sat on the G -> P -> PV critical path
+      mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], NW);
+      mbar_init(&p_full[i], NW); mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_full, 1);
     fence_barrier_init();
@@ -467,7 +469,8 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
       else tmem_ld16(tmem + lane_addr + TM_G + b * TC_BN + part * CPT, g);
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(&g_empty[b]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&g_empty[b]);
       mbar_wait(&n_full[ns], un & 1, watch, 0x420 + ns);
       const float4* xn4 = reinterpret_cast<const float4*>(sVec + ns * 2 * TC_BN + part * CPT);
       const float4* cv4 = reinterpret_cast<const float4*>(sVec + ns * 2 * TC_BN + TC_BN + part * CPT);
@@ -513,7 +516,8 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
       }
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&p_full[b]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[b]);
     }
     // ---- epilogue: O (TMEM) -> workspace; the NPART warps of a quarter take OCOLS columns each
     const int64_t row = (int64_t)m0 + row_in_tile;
