@@ -251,7 +251,7 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
   const int m0 = (int)(rb * MF_BM);
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned, stays in the shared address space
   uint8_t* sQ = smem;
   uint8_t* sX = smem + L::OFF_X;
   uint64_t* bars = (uint64_t*)(smem + L::OFF_BAR);

@@ -186,7 +186,7 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
   using L = TcSmem<DP>;
   constexpr int KH = L::KH;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned, stays in the shared address space
   uint8_t* sQ = smem + L::OFF_Q;
   uint8_t* sX = smem + L::OFF_X;
   uint8_t* sV = smem + L::OFF_V;
@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(128) tc_probe_gram_kernel(const __grid_constan
                                                             const __grid_constant__ CUtensorMap tmB, float* G,
                                                             uint32_t* err_flag) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned, stays in the shared address space
   uint8_t* sA = smem;                 // 2 slabs x 16 KB
   uint8_t* sB = smem + 32768;         // 2 slabs x 8 KB
   uint64_t* bars = (uint64_t*)(smem + 49152);
@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(128) tc_probe_gram_kernel(const __grid_constan
 __global__ void __launch_bounds__(128) tc_probe_pv_kernel(const __grid_constant__ CUtensorMap tmV, const float* P,
                                                           float* O, uint32_t* err_flag) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned, stays in the shared address space
   uint8_t* sV = smem;                 // 256 rows x 128 B = 32 KB
   uint64_t* bars = (uint64_t*)(smem + 32768);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2);
