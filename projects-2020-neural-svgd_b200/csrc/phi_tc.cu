@@ -13,7 +13,9 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
 // warps 2-5 = pair-function / epilogue warps (TMEM lane quarter = warp_idx % 4).
-// TMEM map (512 cols): O [0,256) | G0 [256,320) | G1 [320,384) | P(0) [384,448) | P(1) [448,512)
+// TMEM map (512 cols): O [0,256) | G0 [256,320) | G1 [320,384) | G2 [384,448) | P [448,512)
+// The Gram runs two tiles ahead of P.V (three G buffers, one P buffer): the pair-function latency
+// G -> ld -> exp -> split -> st has two tile-times of slack instead of one (measured +: profiles/).
 #include <stdlib.h>
 
 #include <algorithm>
@@ -146,10 +148,10 @@ struct TcParams {
 
 constexpr int TC_BM = 128, TC_BN = 64;
 constexpr int TC_DEFAULT_PAIR_WARPS = 8;
-constexpr bool TC_DEFAULT_INTERLEAVE = false;
 constexpr int TC_MAX_RUN_TILES = 64;   // <= 768 sequential TMEM accumulations per run
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TM_O = 0, TM_G = 256, TM_P = 384;
+constexpr uint32_t TM_O = 0, TM_G = 256, TM_P = 448;   // O 256 | G x3 (192) | P x1 (64: b0 32 + b1 32)
+constexpr int TC_NG = 3;                                 // Gram accumulators in flight
 
 template <int DP>
 struct TcSmem {
@@ -168,16 +170,14 @@ struct TcSmem {
   static constexpr int OFF_V = OFF_X + XSTAGES * X_STAGE_BYTES;
   static constexpr int OFF_VEC = OFF_V + VSLOTS * VSLOT;
   static constexpr int OFF_BAR = OFF_VEC + NVEC * VEC_BYTES;
-  static constexpr int NBARS = 1 + 2 * XSTAGES + 2 * VSLOTS + 2 * NVEC + 8 + 1;
+  static constexpr int NBARS = 1 + 2 * XSTAGES + 2 * VSLOTS + 2 * NVEC + 2 * TC_NG + 2 + 1;
   static constexpr int TOTAL = OFF_BAR + NBARS * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;         // slack for manual 1024-B alignment
   static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
 };
 
 // NW = pair-function warps (8: 2 per TMEM lane quarter x 32 columns each; 16: 4 per quarter x 16 columns)
-// IL = issue the Gram MMAs of tile t+1 interleaved with the P.V MMAs of tile t-1 (spreads the
-//      shared-memory operand traffic of the N=64 Gram MMAs over the TMEM-fed P.V MMAs)
-template <int DP, int NW, bool IL>
+template <int DP, int NW>
 __global__ void __launch_bounds__(64 + 32 * NW, 1)
 phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ CUtensorMap tmQ1,
               const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
@@ -200,10 +200,10 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
   uint64_t* n_full = v_empty + L::VSLOTS;
   uint64_t* n_empty = n_full + L::NVEC;
   uint64_t* g_full = n_empty + L::NVEC;
-  uint64_t* g_empty = g_full + 2;
-  uint64_t* p_full = g_empty + 2;
-  uint64_t* p_empty = p_full + 2;
-  uint64_t* o_full = p_empty + 2;
+  uint64_t* g_empty = g_full + TC_NG;
+  uint64_t* p_full = g_empty + TC_NG;
+  uint64_t* p_empty = p_full + 1;
+  uint64_t* o_full = p_empty + 1;
   uint32_t* tmem_slot = (uint32_t*)(o_full + 1);
   volatile uint32_t* abort_s = tmem_slot + 1;
 
@@ -221,12 +221,9 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
     for (int i = 0; i < L::XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
     for (int i = 0; i < L::VSLOTS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     for (int i = 0; i < L::NVEC; ++i) { mbar_init(&n_full[i], 1); mbar_init(&n_empty[i], NW); }
-    for (int i = 0; i < 2; ++i) {
-      // one arrival per pair-function warp (lane 0 after __syncwarp): 256 per-thread arrivals on one
-      // mbarrier serialise and sat on the G -> P -> PV critical path
-      mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], NW);
-      mbar_init(&p_full[i], NW); mbar_init(&p_empty[i], 1);
-    }
+    // one arrival per pair-function warp (lane 0 after __syncwarp)
+    for (int i = 0; i < TC_NG; ++i) { mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], NW); }
+    mbar_init(p_full, NW); mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -290,19 +287,12 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
           __syncwarp();
         }
       };
-      // same order as the MMA warp consumes
-      if (!IL) {          // X(0), X(1), V(0), X(2), V(1), ...
-        load_x(0);
-        for (int t = 1; t < T; ++t) { load_x(t); load_v(t - 1); }
-        load_v(T - 1);
-      } else {            // X(0), X(1), X(2), V(0), X(3), V(1), ...
-        load_x(0);
-        if (T > 1) load_x(1);
-        for (int t = 1; t < T; ++t) {
-          if (t + 1 < T) load_x(t + 1);
-          load_v(t - 1);
-        }
-        load_v(T - 1);
+      // same order as the MMA warp consumes: X(0), X(1), X(2), V(0), X(3), V(1), ...
+      load_x(0);
+      if (T > 1) load_x(1);
+      for (int t = 0; t < T; ++t) {
+        if (t + 2 < T) load_x(t + 2);
+        load_v(t);
       }
     }
   } else if (warp == 1) {
@@ -316,7 +306,7 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
       mbar_wait(q_full, 0, watch, 0x300);
       tc_fence_after();
       auto issue_gram = [&](int t) {
-        const int b = t & 1, ub = t >> 1;
+        const int b = t % TC_NG, ub = t / TC_NG;
         const int st = t % L::XSTAGES, us = t / L::XSTAGES;
         mbar_wait(&g_empty[b], (ub & 1) ^ 1, watch, 0x310 + b);
         mbar_wait(&x_full[st], us & 1, watch, 0x320 + st);
@@ -346,10 +336,9 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
         __syncwarp();
       };
       auto issue_pv = [&](int u) {
-        const int pb = u & 1, up = u >> 1;
-        mbar_wait(&p_full[pb], up & 1, watch, 0x330 + pb);
+        mbar_wait(p_full, u & 1, watch, 0x330);
         tc_fence_after();
-        const uint32_t p0 = tmem + TM_P + pb * 64, p1 = p0 + 32;
+        const uint32_t p0 = tmem + TM_P, p1 = p0 + 32;
         {
           const int sl = vcount % L::VSLOTS, uv = vcount / L::VSLOTS; ++vcount;
           mbar_wait(&v_full[sl], uv & 1, watch, 0x340 + sl);
@@ -376,66 +365,17 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
             for (int ks = 0; ks < 4; ++ks)
               umma_ts(tmem + TM_O, p0 + ks * 8, umma_desc_advance(bd, ks * 32), idesc_pv, 1u);
             umma_commit(&v_empty[sl]);
-            umma_commit(&p_empty[pb]);
+            umma_commit(p_empty);
           }
           __syncwarp();
         }
       };
-      // Gram(tg) and P.V(tp) interleaved on the tensor pipe: 2 Gram MMAs (N=64, smem A+B) per P.V MMA (N=2DP, A in TMEM)
-      auto issue_mixed = [&](int tg, int tp) {
-        const int b = tg & 1, ub = tg >> 1;
-        const int st = tg % L::XSTAGES, us = tg / L::XSTAGES;
-        const int pb = tp & 1, up = tp >> 1;
-        const int s0 = vcount % L::VSLOTS, u0 = vcount / L::VSLOTS; ++vcount;
-        const int s1 = vcount % L::VSLOTS, u1 = vcount / L::VSLOTS; ++vcount;
-        mbar_wait(&g_empty[b], (ub & 1) ^ 1, watch, 0x310 + b);
-        mbar_wait(&x_full[st], us & 1, watch, 0x320 + st);
-        mbar_wait(&p_full[pb], up & 1, watch, 0x330 + pb);
-        mbar_wait(&v_full[s0], u0 & 1, watch, 0x340 + s0);
-        mbar_wait(&v_full[s1], u1 & 1, watch, 0x350 + s1);
-        tc_fence_after();
-        const uint32_t d_tm = tmem + TM_G + b * TC_BN;
-        const uint32_t xs = sX_a + st * L::X_STAGE_BYTES;
-        const uint32_t p0 = tmem + TM_P + pb * 64, p1 = p0 + 32;
-        const uint64_t bd0 = umma_desc_sw128(sV_a + s0 * L::VSLOT), bd1 = umma_desc_sw128(sV_a + s1 * L::VSLOT);
-        if (leader) {
-          constexpr int NG = 3 * KH * 4;           // Gram MMAs per tile
-          constexpr int GPK = NG / 12;             // per P.V MMA
-#pragma unroll
-          for (int k = 0; k < 12; ++k) {
-#pragma unroll
-            for (int gi = 0; gi < GPK; ++gi) {
-              const int gm = k * GPK + gi;
-              const int pass = gm / (KH * 4), kh = (gm / 4) % KH, ks = gm % 4;
-              const int pa = pass == 2 ? 1 : 0, pbx = pass == 1 ? 1 : 0;
-              const uint64_t ad = umma_desc_sw128(sQ_a + (pa * KH + kh) * L::QSLAB);
-              const uint64_t bd = umma_desc_sw128(xs + (pbx * KH + kh) * L::XSLAB);
-              umma_ss(d_tm, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 32), idesc_g, gm > 0 ? 1u : 0u);
-              if (gm == NG - 1) { umma_commit(&x_empty[st]); umma_commit(&g_full[b]); }
-            }
-            const int ks = k & 3;
-            if (k < 4) umma_ts(tmem + TM_O, p0 + ks * 8, umma_desc_advance(bd0, ks * 32), idesc_pv, (tp > 0 || ks > 0) ? 1u : 0u);
-            else if (k < 8) umma_ts(tmem + TM_O, p1 + ks * 8, umma_desc_advance(bd0, ks * 32), idesc_pv, 1u);
-            else umma_ts(tmem + TM_O, p0 + ks * 8, umma_desc_advance(bd1, ks * 32), idesc_pv, 1u);
-            if (k == 7) umma_commit(&v_empty[s0]);
-          }
-          umma_commit(&v_empty[s1]);
-          umma_commit(&p_empty[pb]);
-        }
-        __syncwarp();
-      };
-      if (!IL) {
-        issue_gram(0);
-        for (int t = 1; t < T; ++t) { issue_gram(t); issue_pv(t - 1); }
-        issue_pv(T - 1);
-      } else {
-        issue_gram(0);
-        if (T > 1) issue_gram(1);
-        for (int t = 1; t < T; ++t) {
-          if (t + 1 < T) issue_mixed(t + 1, t - 1);
-          else issue_pv(t - 1);
-        }
-        issue_pv(T - 1);
+      // tensor-pipe order: G0 G1 | G2 PV0 | G3 PV1 | ...  (Gram two tiles ahead of P.V)
+      issue_gram(0);
+      if (T > 1) issue_gram(1);
+      for (int t = 0; t < T; ++t) {
+        if (t + 2 < T) issue_gram(t + 2);
+        issue_pv(t);
       }
       if (leader) umma_commit(o_full);
       __syncwarp();
@@ -459,7 +399,7 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
     const float2 neg_one2 = make_float2(-1.f, -1.f);
     float2 rowsum2 = make_float2(0.f, 0.f), kc2 = rowsum2, ke2 = rowsum2;
     for (int t = 0; t < T; ++t) {
-      const int b = t & 1, ub = t >> 1;
+      const int b = t % TC_NG, ub = t / TC_NG;
       const int ns = t % L::NVEC, un = t / L::NVEC;
       mbar_wait(&g_full[b], ub & 1, watch, 0x400 + b);
       __syncwarp();
@@ -504,20 +444,21 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&n_empty[ns]);
-      mbar_wait(&p_empty[b], (ub & 1) ^ 1, watch, 0x410 + b);
+      // single P buffer: P(t) is stored as soon as P.V(t-1) has consumed P(t-1); G(t+2) keeps the tensor pipe busy meanwhile
+      mbar_wait(p_empty, (t & 1) ^ 1, watch, 0x410);
       __syncwarp();
       tc_fence_after();
       if (CPT == 32) {
-        tmem_st16(tmem + lane_addr + TM_P + b * 64 + part * 16, pk0);
-        tmem_st16(tmem + lane_addr + TM_P + b * 64 + 32 + part * 16, pk1);
+        tmem_st16(tmem + lane_addr + TM_P + part * 16, pk0);
+        tmem_st16(tmem + lane_addr + TM_P + 32 + part * 16, pk1);
       } else {
-        tmem_st8(tmem + lane_addr + TM_P + b * 64 + part * 8, pk0);
-        tmem_st8(tmem + lane_addr + TM_P + b * 64 + 32 + part * 8, pk1);
+        tmem_st8(tmem + lane_addr + TM_P + part * 8, pk0);
+        tmem_st8(tmem + lane_addr + TM_P + 32 + part * 8, pk1);
       }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[b]);
+      if (lane == 0) mbar_arrive(p_full);
     }
     // ---- epilogue: O (TMEM) -> workspace; the NPART warps of a quarter take OCOLS columns each
     const int64_t row = (int64_t)m0 + row_in_tile;
@@ -590,38 +531,32 @@ static TcPlan make_plan(const PhiArgs& a) {
   return pl;
 }
 
-template <int DP, int NW, bool IL>
+template <int DP, int NW>
 static int launch_tc_variant(cudaStream_t st, const TcPlan& pl, const CUtensorMap* maps, const TcParams& prm) {
   using L = TcSmem<DP>;
   static bool attr_set = false;
   if (!attr_set) {
-    NSVGD_CUDA(cudaFuncSetAttribute(phi_tc_kernel<DP, NW, IL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    NSVGD_CUDA(cudaFuncSetAttribute(phi_tc_kernel<DP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
     attr_set = true;
   }
   dim3 grid((unsigned)(pl.m_pad / TC_BM), (unsigned)pl.nsplit);
   prof_begin(0, st);
-  phi_tc_kernel<DP, NW, IL><<<grid, 64 + 32 * NW, L::DYN_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], prm);
+  phi_tc_kernel<DP, NW><<<grid, 64 + 32 * NW, L::DYN_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], prm);
   prof_end(0, st);
   NSVGD_LAUNCH_CHECK();
   return NSVGD_OK;
 }
 
-// kernel variant: NSVGD_TC_PAIR_WARPS in {8,16}, NSVGD_TC_INTERLEAVE in {0,1} (tuning knobs; defaults measured best)
+// kernel variant: NSVGD_TC_PAIR_WARPS in {8,16} (tuning knob; 8 measured best, profiles/r01_phi_variants.txt)
 static int tc_pair_warps() {
   const char* e = getenv("NSVGD_TC_PAIR_WARPS");
   return (e && atoi(e) == 16) ? 16 : ((e && atoi(e) == 8) ? 8 : TC_DEFAULT_PAIR_WARPS);
 }
-static bool tc_interleave() {
-  const char* e = getenv("NSVGD_TC_INTERLEAVE");
-  return e ? atoi(e) != 0 : TC_DEFAULT_INTERLEAVE;
-}
 
 template <int DP>
 static int launch_tc(cudaStream_t st, const TcPlan& pl, const CUtensorMap* maps, const TcParams& prm) {
-  const int nw = tc_pair_warps();
-  const bool il = tc_interleave();
-  if (nw == 16) return il ? launch_tc_variant<DP, 16, true>(st, pl, maps, prm) : launch_tc_variant<DP, 16, false>(st, pl, maps, prm);
-  return il ? launch_tc_variant<DP, 8, true>(st, pl, maps, prm) : launch_tc_variant<DP, 8, false>(st, pl, maps, prm);
+  if (tc_pair_warps() == 16) return launch_tc_variant<DP, 16>(st, pl, maps, prm);
+  return launch_tc_variant<DP, 8>(st, pl, maps, prm);
 }
 
 int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dry, size_t* need) {

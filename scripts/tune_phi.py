@@ -14,9 +14,8 @@ rows = np.random.default_rng(0).choice(n, 16, replace=False)
 h = 6.0
 ref = so.phistar(X[rows], X, S, h)
 flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")
-for nw, il in itertools.product(("8", "16"), ("0", "1")):
+for nw, il in itertools.product(("8", "16"), ("-",)):
     os.environ["NSVGD_TC_PAIR_WARPS"] = nw
-    os.environ["NSVGD_TC_INTERLEAVE"] = il
     for _ in range(2):
         phi, st = engine.phistar(Xd, Xd, Sd, h, Sq=Sd, stats=True)
     torch.cuda.synchronize()
