@@ -13,9 +13,10 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
 // warps 2-5 = pair-function / epilogue warps (TMEM lane quarter = warp_idx % 4).
-// TMEM map (512 cols): O [0,256) | G0 [256,320) | G1 [320,384) | G2 [384,448) | P [448,512)
-// The Gram runs two tiles ahead of P.V (three G buffers, one P buffer): the pair-function latency
-// G -> ld -> exp -> split -> st has two tile-times of slack instead of one (measured +: profiles/).
+// TMEM map (512 cols): O [0,256) | Q piece b0 [256,320) | Q piece b1 [320,384) | G [384,448) | P [448,512)
+// The query block lives in TENSOR MEMORY as the A operand of the Gram MMAs (tcgen05.mma TS form) instead
+// of shared memory: the SM's 128 B/clk shared-memory port was the binding resource (Q re-read by every
+// Gram MMA = 96 KB of the 336 KB moved per tile; profiles/r01_phi_tc_notes.txt).
 #include <stdlib.h>
 
 #include <algorithm>
@@ -138,6 +139,7 @@ int launch_tc_prep(cudaStream_t st, const float* X, const float* S, int64_t n, i
 
 // ---------------------------------------------------------------------------- main kernel
 struct TcParams {
+  const uint32_t* Qb0; const uint32_t* Qb1;   // query pieces, [m_pad x DP] bf16 viewed as packed pairs
   const float* xn; const float* cv; const float* qn;
   const float* h_dev;
   float* O; float* scal;          // [nsplit][m_pad][2*DP], [nsplit][m_pad][4]
@@ -150,44 +152,37 @@ constexpr int TC_BM = 128, TC_BN = 64;
 constexpr int TC_DEFAULT_PAIR_WARPS = 8;
 constexpr int TC_MAX_RUN_TILES = 64;   // <= 768 sequential TMEM accumulations per run
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t TM_O = 0, TM_G = 256, TM_P = 448;   // O 256 | G x3 (192) | P x1 (64: b0 32 + b1 32)
-constexpr int TC_NG = 3;                                 // Gram accumulators in flight
+constexpr uint32_t TM_O = 0, TM_Q = 256, TM_G = 384, TM_P = 448;   // O 256 | Q 2x64 | G 64 | P 64 (b0 32 + b1 32)
 
 template <int DP>
 struct TcSmem {
-  static constexpr int KH = DP / 64;                    // 64-column (128-byte) K slabs of the Gram operands
-  static constexpr int QSLAB = TC_BM * 128;             // 16 KB: 128 rows x 128 B
+  static constexpr int KH = DP / 64;                    // 64-column (128-byte) K slabs of the Gram B operand
   static constexpr int XSLAB = TC_BN * 128;             // 8 KB
   static constexpr int VSLOT = 2 * DP * 128;            // [2DP rows x 64 j] bf16 = 32 KB (DP=128)
   static constexpr int XSTAGES = 2;
-  static constexpr int VSLOTS = (DP == 128) ? 3 : 4;
-  static constexpr int NVEC = 3;                        // ring of per-tile column vectors {xn[64], cv[64]}
+  static constexpr int VSLOTS = 4;
+  static constexpr int NVEC = 4;                        // ring of per-tile column vectors {xn[64], cv[64]}
   static constexpr int VEC_BYTES = 2 * TC_BN * 4;
-  static constexpr int Q_BYTES = 2 * KH * QSLAB;
   static constexpr int X_STAGE_BYTES = 2 * KH * XSLAB;
-  static constexpr int OFF_Q = 0;
-  static constexpr int OFF_X = OFF_Q + Q_BYTES;
+  static constexpr int OFF_X = 0;
   static constexpr int OFF_V = OFF_X + XSTAGES * X_STAGE_BYTES;
   static constexpr int OFF_VEC = OFF_V + VSLOTS * VSLOT;
   static constexpr int OFF_BAR = OFF_VEC + NVEC * VEC_BYTES;
-  static constexpr int NBARS = 1 + 2 * XSTAGES + 2 * VSLOTS + 2 * NVEC + 2 * TC_NG + 2 + 1;
+  static constexpr int NBARS = 1 + 2 * XSTAGES + 2 * VSLOTS + 2 * NVEC + 4 + 1;
   static constexpr int TOTAL = OFF_BAR + NBARS * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;         // slack for manual 1024-B alignment
   static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
 };
 
-// NW = pair-function warps (8: 2 per TMEM lane quarter x 32 columns each; 16: 4 per quarter x 16 columns)
 template <int DP, int NW>
 __global__ void __launch_bounds__(64 + 32 * NW, 1)
-phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ CUtensorMap tmQ1,
-              const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
+phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
               const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmV1,
               const TcParams p) {
   using L = TcSmem<DP>;
   constexpr int KH = L::KH;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned, stays in the shared address space
-  uint8_t* sQ = smem + L::OFF_Q;
   uint8_t* sX = smem + L::OFF_X;
   uint8_t* sV = smem + L::OFF_V;
   float* sVec = (float*)(smem + L::OFF_VEC);
@@ -200,8 +195,8 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
   uint64_t* n_full = v_empty + L::VSLOTS;
   uint64_t* n_empty = n_full + L::NVEC;
   uint64_t* g_full = n_empty + L::NVEC;
-  uint64_t* g_empty = g_full + TC_NG;
-  uint64_t* p_full = g_empty + TC_NG;
+  uint64_t* g_empty = g_full + 1;
+  uint64_t* p_full = g_empty + 1;
   uint64_t* p_empty = p_full + 1;
   uint64_t* o_full = p_empty + 1;
   uint32_t* tmem_slot = (uint32_t*)(o_full + 1);
@@ -217,19 +212,18 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     *abort_s = (*(volatile uint32_t*)p.err_flag) ? 1u : 0u;
-    mbar_init(q_full, 1);
+    mbar_init(q_full, NW);                       // query pieces stored to TMEM by the pair-function warps
     for (int i = 0; i < L::XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
     for (int i = 0; i < L::VSLOTS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     for (int i = 0; i < L::NVEC; ++i) { mbar_init(&n_full[i], 1); mbar_init(&n_empty[i], NW); }
     // one arrival per pair-function warp (lane 0 after __syncwarp)
-    for (int i = 0; i < TC_NG; ++i) { mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], NW); }
+    mbar_init(g_full, 1); mbar_init(g_empty, NW);
     mbar_init(p_full, NW); mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ0); tma_prefetch_desc(&tmQ1); tma_prefetch_desc(&tmX0);
-    tma_prefetch_desc(&tmX1); tma_prefetch_desc(&tmV0); tma_prefetch_desc(&tmV1);
+    tma_prefetch_desc(&tmX0); tma_prefetch_desc(&tmX1); tma_prefetch_desc(&tmV0); tma_prefetch_desc(&tmV1);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, TMEM_COLS);
@@ -244,13 +238,6 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
     // =============================== TMA producer ===============================
     if (T > 0) {
       const bool leader = elect_one();
-      if (leader) {
-        mbar_arrive_expect_tx(q_full, L::Q_BYTES);
-        for (int kh = 0; kh < KH; ++kh) {
-          tma_load_2d(sQ + (0 * KH + kh) * L::QSLAB, &tmQ0, q_full, kh * 64, m0);
-          tma_load_2d(sQ + (1 * KH + kh) * L::QSLAB, &tmQ1, q_full, kh * 64, m0);
-        }
-      }
       int vcount = 0;
       auto load_x = [&](int t) {
         const int st = t % L::XSTAGES, u = t / L::XSTAGES;
@@ -287,11 +274,10 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
           __syncwarp();
         }
       };
-      // same order as the MMA warp consumes: X(0), X(1), X(2), V(0), X(3), V(1), ...
+      // same order as the MMA warp consumes: X(0), X(1), V(0), X(2), V(1), ...
       load_x(0);
-      if (T > 1) load_x(1);
       for (int t = 0; t < T; ++t) {
-        if (t + 2 < T) load_x(t + 2);
+        if (t + 1 < T) load_x(t + 1);
         load_v(t);
       }
     }
@@ -301,37 +287,35 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
       const bool leader = elect_one();
       constexpr uint32_t idesc_g = umma_idesc_bf16(TC_BM, TC_BN);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(TC_BM, 2 * DP);
-      const uint32_t sQ_a = smem_u32(sQ), sX_a = smem_u32(sX), sV_a = smem_u32(sV);
+      const uint32_t sX_a = smem_u32(sX), sV_a = smem_u32(sV);
       int vcount = 0;
       mbar_wait(q_full, 0, watch, 0x300);
       tc_fence_after();
       auto issue_gram = [&](int t) {
-        const int b = t % TC_NG, ub = t / TC_NG;
         const int st = t % L::XSTAGES, us = t / L::XSTAGES;
-        mbar_wait(&g_empty[b], (ub & 1) ^ 1, watch, 0x310 + b);
+        mbar_wait(g_empty, (t & 1) ^ 1, watch, 0x310);
         mbar_wait(&x_full[st], us & 1, watch, 0x320 + st);
         tc_fence_after();
-        const uint32_t d_tm = tmem + TM_G + b * TC_BN;
+        const uint32_t d_tm = tmem + TM_G;
         const uint32_t xs = sX_a + st * L::X_STAGE_BYTES;
         if (leader) {
           uint32_t acc = 0;
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
-            const int pa = pass == 2 ? 1 : 0;     // Q piece: b0, b0, b1
-            const int pb = pass == 1 ? 1 : 0;     // X piece: b0, b1, b0
+            const int pa = pass == 2 ? 1 : 0;     // Q piece: b0, b0, b1   (A operand, in TMEM)
+            const int pb = pass == 1 ? 1 : 0;     // X piece: b0, b1, b0   (B operand, shared memory)
 #pragma unroll
             for (int kh = 0; kh < KH; ++kh) {
-              const uint64_t ad = umma_desc_sw128(sQ_a + (pa * KH + kh) * L::QSLAB);
               const uint64_t bd = umma_desc_sw128(xs + (pb * KH + kh) * L::XSLAB);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                umma_ss(d_tm, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 32), idesc_g, acc);
+                umma_ts(d_tm, tmem + TM_Q + pa * 64 + (kh * 4 + ks) * 8, umma_desc_advance(bd, ks * 32), idesc_g, acc);
                 acc = 1;
               }
             }
           }
           umma_commit(&x_empty[st]);
-          umma_commit(&g_full[b]);
+          umma_commit(g_full);
         }
         __syncwarp();
       };
@@ -370,11 +354,11 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
           __syncwarp();
         }
       };
-      // tensor-pipe order: G0 G1 | G2 PV0 | G3 PV1 | ...  (Gram two tiles ahead of P.V)
+      // tensor-pipe order: G0 | G1 PV0 | G2 PV1 | ...  (single G and P buffers: G(t+1) is issued once the
+      // pair warps have loaded G(t), and runs while they compute P(t); P.V(t-1) covers the load itself)
       issue_gram(0);
-      if (T > 1) issue_gram(1);
       for (int t = 0; t < T; ++t) {
-        if (t + 2 < T) issue_gram(t + 2);
+        if (t + 1 < T) issue_gram(t + 1);
         issue_pv(t);
       }
       if (leader) umma_commit(o_full);
@@ -398,19 +382,43 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
     const float2 two_cs2 = make_float2(two_cs, two_cs), neg_cs2 = make_float2(neg_cs, neg_cs), ai2 = make_float2(ai, ai);
     const float2 neg_one2 = make_float2(-1.f, -1.f);
     float2 rowsum2 = make_float2(0.f, 0.f), kc2 = rowsum2, ke2 = rowsum2;
+    if (T > 0) {
+      // the CTA's 128 query rows (two bf16 pieces) -> TMEM, once: A operand of every Gram MMA
+      constexpr int QW = DP / 2 / NPART;               // packed words per thread and piece
+      const int64_t qoff = ((int64_t)m0 + row_in_tile) * (DP / 2) + part * QW;
+#pragma unroll
+      for (int piece = 0; piece < 2; ++piece) {
+        const uint4* src = reinterpret_cast<const uint4*>((piece == 0 ? p.Qb0 : p.Qb1) + qoff);
+        constexpr int QSTEP = QW >= 16 ? 16 : 8;
+#pragma unroll
+        for (int c0 = 0; c0 < QW; c0 += QSTEP) {
+          uint32_t qv[QSTEP];
+#pragma unroll
+          for (int q = 0; q < QSTEP / 4; ++q) {
+            const uint4 v = __ldg(src + c0 / 4 + q);
+            qv[q * 4] = v.x; qv[q * 4 + 1] = v.y; qv[q * 4 + 2] = v.z; qv[q * 4 + 3] = v.w;
+          }
+          if (QSTEP == 16) tmem_st16(tmem + lane_addr + TM_Q + piece * 64 + part * QW + c0, qv);
+          else tmem_st8(tmem + lane_addr + TM_Q + piece * 64 + part * QW + c0, qv);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_full);
+    }
     for (int t = 0; t < T; ++t) {
-      const int b = t % TC_NG, ub = t / TC_NG;
       const int ns = t % L::NVEC, un = t / L::NVEC;
-      mbar_wait(&g_full[b], ub & 1, watch, 0x400 + b);
+      mbar_wait(g_full, t & 1, watch, 0x400);
       __syncwarp();
       tc_fence_after();
       uint32_t g[CPT];
-      if (CPT == 32) tmem_ld32(tmem + lane_addr + TM_G + b * TC_BN + part * CPT, g);
-      else tmem_ld16(tmem + lane_addr + TM_G + b * TC_BN + part * CPT, g);
+      if (CPT == 32) tmem_ld32(tmem + lane_addr + TM_G + part * CPT, g);
+      else tmem_ld16(tmem + lane_addr + TM_G + part * CPT, g);
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&g_empty[b]);
+      if (lane == 0) mbar_arrive(g_empty);
       mbar_wait(&n_full[ns], un & 1, watch, 0x420 + ns);
       const float4* xn4 = reinterpret_cast<const float4*>(sVec + ns * 2 * TC_BN + part * CPT);
       const float4* cv4 = reinterpret_cast<const float4*>(sVec + ns * 2 * TC_BN + TC_BN + part * CPT);
@@ -444,7 +452,7 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmQ0, const __grid_constant__ 
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&n_empty[ns]);
-      // single P buffer: P(t) is stored as soon as P.V(t-1) has consumed P(t-1); G(t+2) keeps the tensor pipe busy meanwhile
+      // single P buffer: P(t) is stored as soon as P.V(t-1) has consumed P(t-1); G(t+1) keeps the tensor pipe busy meanwhile
       mbar_wait(p_empty, (t & 1) ^ 1, watch, 0x410);
       __syncwarp();
       tc_fence_after();
@@ -541,7 +549,7 @@ static int launch_tc_variant(cudaStream_t st, const TcPlan& pl, const CUtensorMa
   }
   dim3 grid((unsigned)(pl.m_pad / TC_BM), (unsigned)pl.nsplit);
   prof_begin(0, st);
-  phi_tc_kernel<DP, NW><<<grid, 64 + 32 * NW, L::DYN_BYTES, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], prm);
+  phi_tc_kernel<DP, NW><<<grid, 64 + 32 * NW, L::DYN_BYTES, st>>>(maps[2], maps[3], maps[4], maps[5], prm);
   prof_end(0, st);
   NSVGD_LAUNCH_CHECK();
   return NSVGD_OK;
@@ -594,14 +602,12 @@ int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dr
     NSVGD_PROPAGATE(launch_tc_prep(st, a.Q, nullptr, a.m, a.d, a.ldq, pl.m_pad, dp, mu, 1.f, Qb0, Qb1, nullptr, nullptr, qn,
                                    nullptr));
   CUtensorMap maps[6];
-  NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[0], Qb0, dp, pl.m_pad, (uint64_t)dp * 2, 64, TC_BM));
-  NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[1], Qb1, dp, pl.m_pad, (uint64_t)dp * 2, 64, TC_BM));
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[2], Xb0, dp, pl.n_pad, (uint64_t)dp * 2, 64, TC_BN));
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[3], Xb1, dp, pl.n_pad, (uint64_t)dp * 2, 64, TC_BN));
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[4], Vt0, pl.n_pad, 2 * dp, (uint64_t)pl.n_pad * 2, TC_BN, 2 * dp));
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[5], Vt1, pl.n_pad, 2 * dp, (uint64_t)pl.n_pad * 2, TC_BN, 2 * dp));
   TcParams prm{};
-  prm.xn = xn; prm.cv = cv; prm.qn = qn; prm.h_dev = a.h_dev; prm.O = O; prm.scal = scal; prm.m_pad = pl.m_pad;
+  prm.Qb0 = (const uint32_t*)Qb0; prm.Qb1 = (const uint32_t*)Qb1; prm.xn = xn; prm.cv = cv; prm.qn = qn; prm.h_dev = a.h_dev; prm.O = O; prm.scal = scal; prm.m_pad = pl.m_pad;
   prm.tiles_total = pl.tiles_total; prm.tiles_per_split = pl.tiles_per_split; prm.err_flag = err_flag;
   if (dp == 64) NSVGD_PROPAGATE(launch_tc<64>(st, pl, maps, prm));
   else NSVGD_PROPAGATE(launch_tc<128>(st, pl, maps, prm));
