@@ -400,33 +400,36 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
       // boundary tiles (diagonal or padded) need the i < j < n mask
       const bool boundary = (tile <= 2 * (int)rb + 1) || ((int64_t)(tile + 1) * MF_BN > p.n) || ((int64_t)m0 + MF_BM > p.n);
       uint32_t unc = 0u;
+      if (!boundary) {
+        // interior tile (the common case): 2 compares per element, no index arithmetic
 #pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {
-        const float4 lo4 = zlo4[q4];
-        const float4 hi4 = zhi4[q4];
-        const float los[4] = {lo4.x, lo4.y, lo4.z, lo4.w};
-        const float his[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
-#pragma unroll
-        for (int e = 0; e < 4; e += 2) {
-          const float2 gg = make_float2(__uint_as_float(g[q4 * 4 + e]), __uint_as_float(g[q4 * 4 + e + 1]));
-          const float2 t1 = __ffma2_rn(gg, m2_2, A1_2);
-          const float2 t2 = __ffma2_rn(gg, m2_2, A2_2);
-          const float t1v[2] = {t1.x, t1.y}, t2v[2] = {t2.x, t2.y};
-#pragma unroll
-          for (int f = 0; f < 2; ++f) {
-            const int col = q4 * 4 + e + f;
-            bool below = t1v[f] < los[e + f];
-            const bool above = t2v[f] > his[e + f];
-            bool un_ = !(below || above);
-            if (boundary) {
-              const int64_t gj = j0 + col;
-              const bool valid = (gi < gj) && (gj < p.n) && (gi < p.n);
-              below = below && valid;
-              un_ = un_ && valid;
-            }
-            cnt += below ? 1u : 0u;
-            unc |= (un_ ? 1u : 0u) << col;
-          }
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 lo4 = zlo4[q4];
+          const float4 hi4 = zhi4[q4];
+          const float2 ta = __ffma2_rn(make_float2(__uint_as_float(g[q4 * 4]), __uint_as_float(g[q4 * 4 + 1])), m2_2, A1_2);
+          const float2 tb = __ffma2_rn(make_float2(__uint_as_float(g[q4 * 4 + 2]), __uint_as_float(g[q4 * 4 + 3])), m2_2, A1_2);
+          const float2 ua = __ffma2_rn(make_float2(__uint_as_float(g[q4 * 4]), __uint_as_float(g[q4 * 4 + 1])), m2_2, A2_2);
+          const float2 ub2 = __ffma2_rn(make_float2(__uint_as_float(g[q4 * 4 + 2]), __uint_as_float(g[q4 * 4 + 3])), m2_2, A2_2);
+          const bool b0 = ta.x < lo4.x, b1 = ta.y < lo4.y, b2 = tb.x < lo4.z, b3 = tb.y < lo4.w;
+          const bool a0 = ua.x > hi4.x, a1 = ua.y > hi4.y, a2 = ub2.x > hi4.z, a3 = ub2.y > hi4.w;
+          cnt += (uint32_t)b0 + (uint32_t)b1 + (uint32_t)b2 + (uint32_t)b3;
+          if (!(b0 || a0)) unc |= 1u << (q4 * 4);
+          if (!(b1 || a1)) unc |= 1u << (q4 * 4 + 1);
+          if (!(b2 || a2)) unc |= 1u << (q4 * 4 + 2);
+          if (!(b3 || a3)) unc |= 1u << (q4 * 4 + 3);
+        }
+      } else {
+        // diagonal / padded tile: mask to i < j < n
+#pragma unroll 4
+        for (int col = 0; col < 32; ++col) {
+          const float gv = __uint_as_float(g[col]);
+          const float lo = sVec[ns * 2 * MF_BN + half * 32 + col], hi = sVec[ns * 2 * MF_BN + MF_BN + half * 32 + col];
+          const int64_t gj = j0 + col;
+          const bool valid = (gi < gj) && (gj < p.n) && (gi < p.n);
+          const bool below = fmaf(gv, -2.f, A1) < lo;
+          const bool above = fmaf(gv, -2.f, A2) > hi;
+          cnt += (below && valid) ? 1u : 0u;
+          if (valid && !(below || above)) unc |= 1u << col;
         }
       }
       __syncwarp();
