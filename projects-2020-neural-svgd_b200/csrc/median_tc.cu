@@ -120,6 +120,18 @@ __device__ __forceinline__ float exact_pair(const float* P, int64_t ldp, int64_t
              : exact_pair_sqdist(P + i * ldp, P + j * ldp, d, w_last);
 }
 
+// one element of the filter: below = (t1 < lo) -> ++cnt;  uncertain = !(below || t2 > hi) -> set `bit` in unc.
+// Four SASS instructions: FSETP, FSETP.OR, @p IADD, @!q LOP.
+__device__ __forceinline__ void classify(uint32_t& cnt, uint32_t& unc, float t1, float lo, float t2, float hi, uint32_t bit) {
+  asm("{\n\t.reg .pred p, q;\n\t"
+      "setp.lt.f32 p, %2, %3;\n\t"
+      "setp.gt.or.f32 q, %4, %5, p;\n\t"
+      "@p add.u32 %0, %0, 1;\n\t"
+      "@!q or.b32 %1, %1, %6;\n\t}"
+      : "+r"(cnt), "+r"(unc)
+      : "f"(t1), "f"(lo), "f"(t2), "f"(hi), "r"(bit));
+}
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -401,26 +413,23 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
       const bool boundary = (tile <= 2 * (int)rb + 1) || ((int64_t)(tile + 1) * MF_BN > p.n) || ((int64_t)m0 + MF_BM > p.n);
       uint32_t unc = 0u;
       if (!boundary) {
-        // interior tile (the common case): 2 compares per element, no index arithmetic
+        // interior tile (the common case): per element 2 FSETP (the second OR-combined), 1 predicated IADD, 1 predicated LOP
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
           const float4 lo4 = zlo4[q4];
           const float4 hi4 = zhi4[q4];
-          const float2 ta = __ffma2_rn(make_float2(__uint_as_float(g[q4 * 4]), __uint_as_float(g[q4 * 4 + 1])), m2_2, A1_2);
-          const float2 tb = __ffma2_rn(make_float2(__uint_as_float(g[q4 * 4 + 2]), __uint_as_float(g[q4 * 4 + 3])), m2_2, A1_2);
-          const float2 ua = __ffma2_rn(make_float2(__uint_as_float(g[q4 * 4]), __uint_as_float(g[q4 * 4 + 1])), m2_2, A2_2);
-          const float2 ub2 = __ffma2_rn(make_float2(__uint_as_float(g[q4 * 4 + 2]), __uint_as_float(g[q4 * 4 + 3])), m2_2, A2_2);
-          const bool b0 = ta.x < lo4.x, b1 = ta.y < lo4.y, b2 = tb.x < lo4.z, b3 = tb.y < lo4.w;
-          const bool a0 = ua.x > hi4.x, a1 = ua.y > hi4.y, a2 = ub2.x > hi4.z, a3 = ub2.y > hi4.w;
-          cnt += (uint32_t)b0 + (uint32_t)b1 + (uint32_t)b2 + (uint32_t)b3;
-          if (!(b0 || a0)) unc |= 1u << (q4 * 4);
-          if (!(b1 || a1)) unc |= 1u << (q4 * 4 + 1);
-          if (!(b2 || a2)) unc |= 1u << (q4 * 4 + 2);
-          if (!(b3 || a3)) unc |= 1u << (q4 * 4 + 3);
+          const float2 g01 = make_float2(__uint_as_float(g[q4 * 4]), __uint_as_float(g[q4 * 4 + 1]));
+          const float2 g23 = make_float2(__uint_as_float(g[q4 * 4 + 2]), __uint_as_float(g[q4 * 4 + 3]));
+          const float2 ta = __ffma2_rn(g01, m2_2, A1_2), tb = __ffma2_rn(g23, m2_2, A1_2);
+          const float2 ua = __ffma2_rn(g01, m2_2, A2_2), ub2 = __ffma2_rn(g23, m2_2, A2_2);
+          classify(cnt, unc, ta.x, lo4.x, ua.x, hi4.x, 1u << (q4 * 4));
+          classify(cnt, unc, ta.y, lo4.y, ua.y, hi4.y, 1u << (q4 * 4 + 1));
+          classify(cnt, unc, tb.x, lo4.z, ub2.x, hi4.z, 1u << (q4 * 4 + 2));
+          classify(cnt, unc, tb.y, lo4.w, ub2.y, hi4.w, 1u << (q4 * 4 + 3));
         }
       } else {
-        // diagonal / padded tile: mask to i < j < n
-#pragma unroll 4
+        // diagonal / padded tile: mask to i < j < n  (fully unrolled: g[] must stay in registers)
+#pragma unroll
         for (int col = 0; col < 32; ++col) {
           const float gv = __uint_as_float(g[col]);
           const float lo = sVec[ns * 2 * MF_BN + half * 32 + col], hi = sVec[ns * 2 * MF_BN + MF_BN + half * 32 + col];
