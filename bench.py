@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--cpu-rows", type=int, default=2048, help="query rows of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step as one CUDA graph (auto: when row-sharded, where host issue time limits the step)")
     return ap.parse_args()
 
 
@@ -188,7 +190,13 @@ def main():
     sharded = ShardedSVGD(n, d, median_mode=args.median_mode) if world > 1 else None
     flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    use_graph = args.graph == "on" or (args.graph == "auto" and world > 1)
+    graphed = None
+    launches_per_replay = 0
+
     def one_step():
+        if graphed is not None:
+            return graphed.replay()
         if world > 1:
             h, aux, _ = sharded.step(X_loc, S_loc, lr, scaled=True, lambda_reg=lam, bandwidth=fixed_h)
         else:
@@ -201,6 +209,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if use_graph:
+        l0 = _lib.launch_count()
+        if world > 1:
+            graphed = sharded.capture(X_loc, S_loc, lr, scaled=True, lambda_reg=lam, bandwidth=fixed_h)
+        else:
+            from nsvgd.parallel import GraphedStep
+            one_step(); torch.cuda.synchronize()
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                h_, aux_ = one_step()
+            graphed = GraphedStep(g_, h_, aux_)
+        launches_per_replay = (_lib.launch_count() - l0) // 2       # warm-up pass + captured pass
+        X_loc.copy_(X0)
     for _ in range(W):
         flush.fill_(1)
         one_step()
@@ -210,7 +231,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    _lib.profile_enable(True)
+    _lib.profile_enable(graphed is None)      # library-side events cannot be recorded inside a replayed graph
     launches0 = _lib.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
@@ -222,9 +243,24 @@ def main():
         ev[i][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches = _lib.launch_count() - launches0
+    launches = _lib.launch_count() - launches0 if graphed is None else launches_per_replay * K
     clocks = sampler.stop() if rank == 0 else None
     step_ms = sum(a.elapsed_time(b) for a, b in ev)
+    h_val = float(h) if not isinstance(h, torch.Tensor) else float(h.item())
+    aux_host = aux.cpu().numpy()
+    if graphed is not None:
+        # per-kernel breakdown / roofline: a second, un-graphed pass of min(K, 5) steps with the library-side
+        # CUDA events on (not part of `value`; says so in roofline.note)
+        g_keep, graphed = graphed, None
+        _lib.profile_enable(True)
+        KP = max(1, min(K, 5))
+        for i in range(KP):
+            flush.fill_(i & 1)
+            one_step()
+        barrier()
+        graphed = g_keep
+    else:
+        KP = K
     phi_main_ms, phi_main_cnt = _lib.profile_read(0)
     hist_ms, hist_cnt = _lib.profile_read(1)
     phi_op_ms, _ = _lib.profile_read(2)
@@ -238,8 +274,6 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = K * float(n) * n * d / (total_ms * 1e-3)
-    h_val = float(h) if not isinstance(h, torch.Tensor) else float(h.item())
-    aux_host = aux.cpu().numpy()
 
     # ---- e2e: the reference-facing call with HOST buffers, copies inside the timed region -------------
     e2e = None
@@ -288,7 +322,8 @@ def main():
                     "traffic": None, "avg_kernel_ms": avg_ms, "launches": phi_main_cnt,
                     "executed_mma_frac": 3 * achieved / pk["bf16_tflops"],
                     "note": "achieved = algorithmic 6*m*n*d flop / CUDA-event time of the kernel; the bf16 2-piece split "
-                            "executes 3 MMA passes per algorithmic flop (executed_mma_frac); peak = " + pk["source"]}
+                            "executes 3 MMA passes per algorithmic flop (executed_mma_frac); peak = " + pk["source"]
+                            + ("" if graphed is None else "; kernel events from an un-graphed pass after the graph-replayed timed region")}
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         rate, secs, cores = cpu_port_rate(Xh, Sh, h_val if np.isfinite(h_val) and h_val > 0 else 6.0, args.cpu_rows)
@@ -303,12 +338,15 @@ def main():
         "config": {"workload": f"svgd_step n={n} d={d} (BASELINE configs[3])", "n": n, "d": d, "rows_per_gpu": m_local,
                    "bandwidth": "median heuristic (%s) every step" % args.median_mode if not fixed_h else f"fixed {fixed_h}",
                    "scaled": True, "optimizer": "sgd", "parallelism": f"row-sharded x{world}", "l2_flush": "192 MiB fill between steps",
-                   "path": args.path},
-        "breakdown_ms_per_step": {"median_op": med_op_ms / K, "median_tc_filter_kernel": med_filter_ms / K,
-                                  "median_sample_kernel": med_sample_ms / K, "median_exact_list_kernel": med_exact_ms / K,
-                                  "median_simt_hist_kernels": hist_ms / K, "phi_op": phi_op_ms / K,
-                                  "phi_main_kernel": phi_main_ms / K},
-        "phi_only_value": (K * float(m_local) * n * d / (phi_op_ms * 1e-3)) if phi_op_ms else None,
+                   "path": args.path,
+                   "launch": "one CUDA graph replay per step (collectives captured)" if graphed is not None else "eager (C-ABI calls per op)"},
+        "breakdown_ms_per_step": {"median_op": med_op_ms / KP, "median_tc_filter_kernel": med_filter_ms / KP,
+                                  "median_sample_kernel": med_sample_ms / KP, "median_exact_list_kernel": med_exact_ms / KP,
+                                  "median_simt_hist_kernels": hist_ms / KP, "phi_op": phi_op_ms / KP,
+                                  "phi_main_kernel": phi_main_ms / KP,
+                                  "source": "library-side CUDA events, " + ("the timed region" if graphed is None else
+                                            f"a separate un-graphed pass of {KP} steps after the timed region")},
+        "phi_only_value": (KP * float(m_local) * n * d / (phi_op_ms * 1e-3)) if phi_op_ms else None,
         "result": {"h": h_val, "ksd": float(aux_host[0]), "l2": float(aux_host[1]), "alpha": float(aux_host[2])},
         "wall_s": t_wall, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "cpu_baseline": cpu_baseline, "e2e": e2e,

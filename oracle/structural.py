@@ -1,5 +1,5 @@
 """Structural mirror of nvgd/src/stein.py, kernels.py, metrics.py, models.py in torch.func.
-TEST INFRASTRUCTURE ONLY (see oracle/svgd_oracle.py header; PARITY UNPINNED).
+TEST INFRASTRUCTURE ONLY (see oracle/svgd_oracle.py header; parity pin: tests/golden/refshim + ref_*.npz).
 
 The reference writes the hot path as nested ``vmap`` over per-pair closures with
 ``grad`` / ``jacfwd`` inside.  JAX is not installable here, so this file re-states

@@ -5,14 +5,16 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
 path (``projects-2020-neural-svgd_b200/``) never does: it fails loudly when the
 CUDA library is missing.
 
-PARITY UNPINNED: the reference (ratschlab/projects-2020-Neural-SVGD) ships no
-tests, golden vectors or fixtures for this path and cannot be imported here
-(JAX/jaxlib/haiku/optax absent, no network).  This file is therefore a CPU
-*restatement* of the reference algorithm in NumPy; it is cross-checked against
-an independent structural mirror (``oracle/structural.py``, torch.func
-vmap/grad/jacfwd written line-for-line after ``nvgd/src/stein.py``) and the
-golden vectors under ``tests/golden`` are produced by that mirror
-(``tests/golden/make_golden.py``).
+PARITY PIN: the reference (ratschlab/projects-2020-Neural-SVGD) ships no
+tests, golden vectors or fixtures for this path, and JAX/jaxlib/haiku/optax are
+absent (no network).  The pin is therefore the reference's own UNMODIFIED
+sources executed in this container under torch-backed stand-ins for those
+dependencies (tests/golden/refshim/, tests/golden/make_reference_golden.py ->
+tests/golden/ref_*.npz); tests/test_reference_golden.py checks every function
+of this file against those fixtures.  What stays unpinned is XLA's last-ulp
+floating-point behaviour (the stand-in computes with torch).  A second witness:
+oracle/structural.py, an independent torch.func mirror of nvgd/src/stein.py
+(tests/golden/make_golden.py).
 
 Every function cites the reference file:line it restates (paths relative to
 the reference checkout).

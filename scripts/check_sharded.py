@@ -26,6 +26,28 @@ for n, d, mode in ((8192, 128, "literal"), (3000, 7, "offdiag"), (9001, 100, "fu
     err = (Xl - Xs[r0:r1]).norm().item() / Xs[r0:r1].norm().item()
     print(f"rank {rank} n={n} d={d} {mode}: h bit-identical={same_h} ({h.item():.7f}) X rel err={err:.2e}", flush=True)
     ok = ok and same_h and err < 2e-6
+# the same step captured as ONE CUDA graph (collectives included), replayed three times
+n, d, mode = 8192, 128, "literal"
+X, S = gaussian_diag_workload(n, d, seed=5)
+S = (S * 0.02).astype(np.float32)
+Xd, Sd = torch.tensor(X).cuda(), torch.tensor(S).cuda()
+Xs = Xd.clone()
+hs = []
+for _ in range(3):
+    hs.append(engine.median_heuristic(Xs, mode))
+    engine.svgd_step_sgd(Xs, Sd, hs[-1], 1e-2, scaled=True, lambda_reg=0.5)
+r0, r1 = row_partition(n, world, rank)
+Xl, Sl = Xd[r0:r1].clone(), Sd[r0:r1].clone()
+sh = ShardedSVGD(n, d, median_mode=mode)
+g = sh.capture(Xl, Sl, 1e-2, scaled=True, lambda_reg=0.5)
+Xl.copy_(Xd[r0:r1])
+same = True
+for i in range(3):
+    h, aux = g.replay()
+    same = same and (h.item() == hs[i].item())
+err = (Xl - Xs[r0:r1]).norm().item() / Xs[r0:r1].norm().item()
+print(f"rank {rank} graphed x3: h bit-identical={same} X rel err={err:.2e}", flush=True)
+ok = ok and same and err < 2e-6
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

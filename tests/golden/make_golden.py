@@ -3,7 +3,8 @@
 The reference cannot be imported in this image (no JAX), so the golden vectors
 come from oracle/structural.py — a torch.func vmap/grad/jacfwd mirror written
 line-for-line after nvgd/src/stein.py — in fp64, plus the literal (O(n^3)-style)
-median-heuristic emulation.  PARITY UNPINNED by the reference itself.
+median-heuristic emulation.  (The fixtures produced by executing the reference's own sources are
+ref_*.npz, see make_reference_golden.py; these are the second, independent witness.)
 Inputs are float32 (what the CUDA path consumes); all outputs float64 except h
 (float32, the bit-exact contract, from oracle/svgd_oracle.py's defined-order path).
 """
