@@ -304,9 +304,25 @@ def main():
                "h2d_bytes_per_step": int(2 * (r1 - r0) * d * 4), "d2h_bytes_per_step": int((r1 - r0) * d * 4 + 64),
                "steps": KE, "api": "nsvgd.engine.median_heuristic + svgd_step_sgd (C ABI nsvgd_median_h_f32 / nsvgd_step_sgd_f32), pinned host buffers"}
 
+    def shutdown():
+        """A CUDA graph that captured NCCL kernels must be released before the communicator goes away, and
+        destroy_process_group() was observed to hang after graph replays (torch 2.11 / NCCL 2.28): synchronise,
+        drop the graph, barrier, and leave without tearing the communicator down."""
+        nonlocal graphed
+        if world == 1:
+            return
+        torch.cuda.synchronize()
+        if graphed is not None:
+            graphed = None
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(0)
+        dist.destroy_process_group()
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown()
         return
 
     # ---- roofline of the dominant kernel (phi* main kernel) --------------------------------------------
@@ -351,9 +367,8 @@ def main():
         "wall_s": t_wall, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "cpu_baseline": cpu_baseline, "e2e": e2e,
     }
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(out), flush=True)
+    shutdown()
 
 
 if __name__ == "__main__":

@@ -118,8 +118,11 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 //                scal[m x 4] = {rowsum, a = sum_j k s_j.(x_j - q_i), b = sum_j k r2, 0}
 //   GRAM form  : O[split][m_pad x ldo] = [K S | K Xc] partial over j-splits;
 //                scal[split][m_pad x 4] = {rowsum, kc = sum_j k c_j, b, 0}; needs mu (column mean)
+//   GRAMW form : O[split][m_pad x ldo] = K W partial, W = S - Xc/h^2 (one block: the second GEMM is half as wide);
+//                scal[...] = {rowsum, kc, b, kg = sum_j k g_ij = qc_i.(K Xc)_i};
+//                phi_i = (1/n)[(K W)_i + rowsum_i qc_i/h^2],  qc_i.(K S)_i = qc_i.(K W)_i + kg_i/h^2
 struct EpilogueArgs {
-  int form;               // 0 = DIRECT, 1 = GRAM
+  int form;               // 0 = DIRECT, 1 = GRAM, 2 = GRAMW
   const float* KS;        // DIRECT: m x d (ld = d)
   const float* R;         // DIRECT
   const float* O;         // GRAM: nsplit x m_pad x ldo

@@ -72,30 +72,40 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
                                                       const float* __restrict__ mu, float last_scale,
                                                       __nv_bfloat16* __restrict__ Xb0, __nv_bfloat16* __restrict__ Xb1,
                                                       __nv_bfloat16* __restrict__ Vt0, __nv_bfloat16* __restrict__ Vt1,
-                                                      float* __restrict__ xn, float* __restrict__ cv) {
+                                                      float* __restrict__ xn, float* __restrict__ cv,
+                                                      const float* __restrict__ h_combine) {
+  // h_combine != null: COMBINED form, one transposed block W^T = (S - Xc/h^2)^T in rows [0, dp) of Vt
+  // (phi_i = (1/n)[(K W)_i + rowsum_i qc_i / h^2]: the second GEMM has N = dp instead of 2 dp columns)
   __shared__ float T[64][129];   // one half (S or Xc) of the block, fp32
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t r0 = (int64_t)blockIdx.x * 64;
+  const bool combine = h_combine != nullptr;
+  float inv_h2 = 0.f;
+  if (combine) { const float h = *h_combine; inv_h2 = 1.f / (h * h); }
   for (int half = 0; half < 2; ++half) {      // 0: Xc (also writes Xb, xn, cv), 1: S
-    if (half == 1 && !Vt0) break;
+    if (half == 1 && (!Vt0 || combine)) break;
     __syncthreads();
     for (int rr = w; rr < 64; rr += 8) {
       const int64_t row = r0 + rr;
       const bool rv = row < n;
       float acc_n = 0.f, acc_c = 0.f;
       for (int c = lane; c < dp; c += 32) {
-        float v = 0.f;
+        float v = 0.f, tv = 0.f;
         if (rv && c < d) {
           if (half == 0) {
             v = X[row * ldx + c] - mu[c];
             if (c == d - 1) v *= last_scale;
             acc_n = fmaf(v, v, acc_n);
-            if (S) acc_c = fmaf(S[row * ldx + c], v, acc_c);
+            if (S) {
+              const float sv = S[row * ldx + c];
+              acc_c = fmaf(sv, v, acc_c);
+              if (combine) tv = fmaf(-v, inv_h2, sv);
+            }
           } else {
             v = S[row * ldx + c];
           }
         }
-        T[rr][c] = v;
+        T[rr][c] = combine ? tv : v;
         if (half == 0) {
           const __nv_bfloat16 b0 = __float2bfloat16_rn(v);
           const __nv_bfloat16 b1 = __float2bfloat16_rn(v - __bfloat162float(b0));
@@ -114,7 +124,7 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
     __syncthreads();
     if (Vt0) {
       // transposed write: warp handles one coordinate c at a time, lane -> rows (2 lane, 2 lane + 1)
-      const int64_t vrow0 = half == 0 ? dp : 0;   // Xc^T goes to rows [dp, 2dp), S^T to [0, dp)
+      const int64_t vrow0 = (half == 0 && !combine) ? dp : 0;   // Xc^T goes to rows [dp, 2dp), S^T (or W^T) to [0, dp)
       for (int c = w; c < dp; c += 8) {
         const float a = T[2 * lane][c], b = T[2 * lane + 1][c];
         const uint32_t p0 = pack_bf16x2(a, b);
@@ -129,10 +139,10 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
 
 int launch_tc_prep(cudaStream_t st, const float* X, const float* S, int64_t n, int64_t d, int64_t ldx, int64_t rows_pad,
                    int dp, const float* mu, float last_scale, void* Xb0, void* Xb1, void* Vt0, void* Vt1, float* xn,
-                   float* cv) {
+                   float* cv, const float* h_combine) {
   tc_prep_kernel<<<(unsigned)(rows_pad / 64), 256, 0, st>>>(X, S, n, d, ldx, rows_pad, dp, mu, last_scale,
                                                             (__nv_bfloat16*)Xb0, (__nv_bfloat16*)Xb1, (__nv_bfloat16*)Vt0,
-                                                            (__nv_bfloat16*)Vt1, xn, cv);
+                                                            (__nv_bfloat16*)Vt1, xn, cv, h_combine);
   NSVGD_LAUNCH_CHECK();
   return NSVGD_OK;
 }
@@ -154,11 +164,11 @@ constexpr int TC_MAX_RUN_TILES = 64;   // <= 768 sequential TMEM accumulations p
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_O = 0, TM_Q = 256, TM_G = 384, TM_P = 448;   // O 256 | Q 2x64 | G 64 | P 64 (b0 32 + b1 32)
 
-template <int DP>
+template <int DP, int VC>
 struct TcSmem {
   static constexpr int KH = DP / 64;                    // 64-column (128-byte) K slabs of the Gram B operand
   static constexpr int XSLAB = TC_BN * 128;             // 8 KB
-  static constexpr int VSLOT = 2 * DP * 128;            // [2DP rows x 64 j] bf16 = 32 KB (DP=128)
+  static constexpr int VSLOT = VC * 128;                // [VC rows x 64 j] bf16 = 32 KB (VC = 2 DP = 256)
   static constexpr int XSTAGES = 2;
   static constexpr int VSLOTS = 4;
   static constexpr int NVEC = 4;                        // ring of per-tile column vectors {xn[64], cv[64]}
@@ -174,13 +184,16 @@ struct TcSmem {
   static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
 };
 
-template <int DP, int NW>
+// VC = columns of the second GEMM: 2*DP -> O = P [S | Xc] (drift and repulsion separately: aux output),
+//                                  DP   -> O = P W, W = S - Xc/h^2 (COMBINED form: 1/3 fewer MMA flops)
+template <int DP, int NW, int VC>
 __global__ void __launch_bounds__(64 + 32 * NW, 1)
 phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
               const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmV1,
               const TcParams p) {
-  using L = TcSmem<DP>;
+  using L = TcSmem<DP, VC>;
   constexpr int KH = L::KH;
+  constexpr bool COMBINED = (VC == DP);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned, stays in the shared address space
   uint8_t* sX = smem + L::OFF_X;
@@ -286,7 +299,7 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
     if (T > 0) {
       const bool leader = elect_one();
       constexpr uint32_t idesc_g = umma_idesc_bf16(TC_BM, TC_BN);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(TC_BM, 2 * DP);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(TC_BM, VC);
       const uint32_t sX_a = smem_u32(sX), sV_a = smem_u32(sV);
       int vcount = 0;
       mbar_wait(q_full, 0, watch, 0x300);
@@ -370,7 +383,8 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
     // of the tile's 64 columns.  Several warps per SM sub-partition hide each other's latencies.
     constexpr int NPART = NW / 4;
     constexpr int CPT = TC_BN / NPART;                 // columns per thread and tile (32 or 16)
-    constexpr int OCOLS = 2 * DP / NPART;              // accumulator columns per thread in the epilogue
+    constexpr int OCOLS = VC / NPART;                  // accumulator columns per thread in the epilogue
+    static_assert(OCOLS % 32 == 0, "epilogue reads 32 accumulator columns per tcgen05.ld");
     const int quarter = warp & 3;
     const int part = (warp - 2) >> 2;
     const int row_in_tile = quarter * 32 + lane;
@@ -381,7 +395,7 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
     const float ai = neg_cs * p.qn[m0 + row_in_tile];
     const float2 two_cs2 = make_float2(two_cs, two_cs), neg_cs2 = make_float2(neg_cs, neg_cs), ai2 = make_float2(ai, ai);
     const float2 neg_one2 = make_float2(-1.f, -1.f);
-    float2 rowsum2 = make_float2(0.f, 0.f), kc2 = rowsum2, ke2 = rowsum2;
+    float2 rowsum2 = make_float2(0.f, 0.f), kc2 = rowsum2, ke2 = rowsum2, kg2 = rowsum2;
     if (T > 0) {
       // the CTA's 128 query rows (two bf16 pieces) -> TMEM, once: A operand of every Gram MMA
       constexpr int QW = DP / 2 / NPART;               // packed words per thread and piece
@@ -448,6 +462,7 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
           rowsum2 = __fadd2_rn(rowsum2, kq);
           kc2 = __ffma2_rn(kq, cc, kc2);
           ke2 = __ffma2_rn(kq, ex, ke2);
+          if (COMBINED) kg2 = __ffma2_rn(kq, gg, kg2);      // sum_j k g_ij = qc_i . (K Xc)_i, recovers qc_i . (K S)_i
         }
       }
       __syncwarp();
@@ -470,7 +485,7 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
     }
     // ---- epilogue: O (TMEM) -> workspace; the NPART warps of a quarter take OCOLS columns each
     const int64_t row = (int64_t)m0 + row_in_tile;
-    float* orow = p.O + ((int64_t)split * p.m_pad + row) * (2 * DP) + part * OCOLS;
+    float* orow = p.O + ((int64_t)split * p.m_pad + row) * VC + part * OCOLS;
     float* srow = p.scal + (((int64_t)split * NPART + part) * p.m_pad + row) * 4;
     if (T > 0) {
       mbar_wait(o_full, 0, watch, 0x500);
@@ -488,7 +503,7 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
                           __uint_as_float(v[q * 4 + 3]));
       }
       // b = sum k r2 = -sum k e / cs  (this thread's part of the columns)
-      *reinterpret_cast<float4*>(srow) = make_float4(rowsum2.x + rowsum2.y, kc2.x + kc2.y, -(ke2.x + ke2.y) / cs, 0.f);
+      *reinterpret_cast<float4*>(srow) = make_float4(rowsum2.x + rowsum2.y, kc2.x + kc2.y, -(ke2.x + ke2.y) / cs, kg2.x + kg2.y);
       tc_fence_before();
     } else {
       // empty j-range (tail split): contribute zeros
@@ -539,17 +554,17 @@ static TcPlan make_plan(const PhiArgs& a) {
   return pl;
 }
 
-template <int DP, int NW>
+template <int DP, int NW, int VC>
 static int launch_tc_variant(cudaStream_t st, const TcPlan& pl, const CUtensorMap* maps, const TcParams& prm) {
-  using L = TcSmem<DP>;
+  using L = TcSmem<DP, VC>;
   static bool attr_set = false;
   if (!attr_set) {
-    NSVGD_CUDA(cudaFuncSetAttribute(phi_tc_kernel<DP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    NSVGD_CUDA(cudaFuncSetAttribute(phi_tc_kernel<DP, NW, VC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
     attr_set = true;
   }
   dim3 grid((unsigned)(pl.m_pad / TC_BM), (unsigned)pl.nsplit);
   prof_begin(0, st);
-  phi_tc_kernel<DP, NW><<<grid, 64 + 32 * NW, L::DYN_BYTES, st>>>(maps[2], maps[3], maps[4], maps[5], prm);
+  phi_tc_kernel<DP, NW, VC><<<grid, 64 + 32 * NW, L::DYN_BYTES, st>>>(maps[2], maps[3], maps[4], maps[5], prm);
   prof_end(0, st);
   NSVGD_LAUNCH_CHECK();
   return NSVGD_OK;
@@ -562,15 +577,26 @@ static int tc_pair_warps() {
 }
 
 template <int DP>
-static int launch_tc(cudaStream_t st, const TcPlan& pl, const CUtensorMap* maps, const TcParams& prm) {
-  if (tc_pair_warps() == 16) return launch_tc_variant<DP, 16>(st, pl, maps, prm);
-  return launch_tc_variant<DP, 8>(st, pl, maps, prm);
+static int launch_tc(cudaStream_t st, const TcPlan& pl, const CUtensorMap* maps, const TcParams& prm, bool combined) {
+  if (combined) return launch_tc_variant<DP, 8, DP>(st, pl, maps, prm);
+  if (tc_pair_warps() == 16) return launch_tc_variant<DP, 16, 2 * DP>(st, pl, maps, prm);
+  return launch_tc_variant<DP, 8, 2 * DP>(st, pl, maps, prm);
+}
+
+// COMBINED form (second GEMM against W = S - Xc/h^2, N = dp): whenever the caller does not ask for the
+// separate [drift, repulsion] aux output.  NSVGD_TC_COMBINE=0 forces the [S | Xc] form (A/B measurements).
+static bool tc_combined(const PhiArgs& a) {
+  const char* e = getenv("NSVGD_TC_COMBINE");
+  if (e && atoi(e) == 0) return false;
+  return a.aux == nullptr;
 }
 
 int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dry, size_t* need) {
   if (!dry) NSVGD_REQUIRE(a.d <= 128, NSVGD_ERR_UNSUPPORTED, "phi_tc: tensor-core path supports d <= 128 (d=%lld)", (long long)a.d);
   const TcPlan pl = make_plan(a);
   const int dp = pl.dp;
+  const bool combined = !dry && tc_combined(a);      // dry run sizes for the larger [S | Xc] form
+  const int vc = combined ? dp : 2 * dp;
   WsCarver w(ws, ws_bytes, dry);
   float* mu = w.take<float>((size_t)a.d);
   double* mpart = w.take<double>((size_t)colmean_partials(a.n, a.d));
@@ -597,23 +623,25 @@ int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dr
 
   NSVGD_PROPAGATE(launch_colmean(st, a.X, a.n, a.d, a.ldx, mpart, mu));
   NSVGD_CUDA(cudaMemsetAsync(err_flag, 0, 16, st));
-  NSVGD_PROPAGATE(launch_tc_prep(st, a.X, a.S, a.n, a.d, a.ldx, pl.n_pad, dp, mu, 1.f, Xb0, Xb1, Vt0, Vt1, xn, cv));
+  NSVGD_PROPAGATE(launch_tc_prep(st, a.X, a.S, a.n, a.d, a.ldx, pl.n_pad, dp, mu, 1.f, Xb0, Xb1, Vt0, Vt1, xn, cv,
+                                 combined ? a.h_dev : nullptr));
   if (!pl.q_is_x)
     NSVGD_PROPAGATE(launch_tc_prep(st, a.Q, nullptr, a.m, a.d, a.ldq, pl.m_pad, dp, mu, 1.f, Qb0, Qb1, nullptr, nullptr, qn,
-                                   nullptr));
+                                   nullptr, nullptr));
   CUtensorMap maps[6];
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[2], Xb0, dp, pl.n_pad, (uint64_t)dp * 2, 64, TC_BN));
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[3], Xb1, dp, pl.n_pad, (uint64_t)dp * 2, 64, TC_BN));
-  NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[4], Vt0, pl.n_pad, 2 * dp, (uint64_t)pl.n_pad * 2, TC_BN, 2 * dp));
-  NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[5], Vt1, pl.n_pad, 2 * dp, (uint64_t)pl.n_pad * 2, TC_BN, 2 * dp));
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[4], Vt0, pl.n_pad, vc, (uint64_t)pl.n_pad * 2, TC_BN, vc));
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[5], Vt1, pl.n_pad, vc, (uint64_t)pl.n_pad * 2, TC_BN, vc));
   TcParams prm{};
   prm.Qb0 = (const uint32_t*)Qb0; prm.Qb1 = (const uint32_t*)Qb1; prm.xn = xn; prm.cv = cv; prm.qn = qn; prm.h_dev = a.h_dev; prm.O = O; prm.scal = scal; prm.m_pad = pl.m_pad;
   prm.tiles_total = pl.tiles_total; prm.tiles_per_split = pl.tiles_per_split; prm.err_flag = err_flag;
-  if (dp == 64) NSVGD_PROPAGATE(launch_tc<64>(st, pl, maps, prm));
-  else NSVGD_PROPAGATE(launch_tc<128>(st, pl, maps, prm));
+  if (dp == 64) NSVGD_PROPAGATE(launch_tc<64>(st, pl, maps, prm, combined));
+  else NSVGD_PROPAGATE(launch_tc<128>(st, pl, maps, prm, combined));
 
   EpilogueArgs e{};
-  e.form = 1; e.O = O; e.scal = scal; e.nsplit = pl.nsplit; e.scal_parts = (tc_pair_warps() / 4) * pl.nsplit; e.m_pad = pl.m_pad; e.ldo = 2 * dp; e.dpad = dp; e.mu = mu;
+  e.form = combined ? 2 : 1; e.O = O; e.scal = scal; e.nsplit = pl.nsplit;
+  e.scal_parts = ((combined ? 8 : tc_pair_warps()) / 4) * pl.nsplit; e.m_pad = pl.m_pad; e.ldo = vc; e.dpad = dp; e.mu = mu;
   e.Q = a.Q; e.ldq = a.ldq; e.Sq = a.Sq; e.m = a.m; e.n = a.n; e.d = a.d; e.h_dev = a.h_dev;
   e.phi = a.phi; e.ldphi = a.ldphi; e.aux = a.aux; e.stats_dev = a.stats_dev; e.partials = partials;
   return launch_epilogue(st, e);

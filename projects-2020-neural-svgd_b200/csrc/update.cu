@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const EpilogueArgs a) {
   const float inv_n = 1.f / (float)a.n;
   double t_row = 0.0, l_row = 0.0;
   if (row < a.m) {
-    float rowsum = 0.f, aval = 0.f, bval = 0.f;
+    float rowsum = 0.f, aval = 0.f, bval = 0.f, kg = 0.f;
     if (a.form == 0) {
       const float4 sc = *reinterpret_cast<const float4*>(&a.scal[row * 4]);
       rowsum = sc.x; aval = sc.y; bval = sc.z;
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const EpilogueArgs a) {
       const int parts = a.scal_parts > 0 ? a.scal_parts : a.nsplit;
       for (int s = 0; s < parts; ++s) {
         const float4 sc = *reinterpret_cast<const float4*>(&a.scal[((int64_t)s * a.m_pad + row) * 4]);
-        rowsum += sc.x; aval += sc.y; bval += sc.z;   // aval = kc so far
+        rowsum += sc.x; aval += sc.y; bval += sc.z; kg += sc.w;   // aval = kc so far
       }
     }
     float sphi = 0.f, l2 = 0.f, qks = 0.f;
@@ -39,6 +39,16 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const EpilogueArgs a) {
       if (a.form == 0) {
         ks = a.KS[row * a.d + c];
         rr = a.R[row * a.d + c];
+      } else if (a.form == 2) {
+        float kw = 0.f;
+        for (int s = 0; s < a.nsplit; ++s) kw += a.O[((int64_t)s * a.m_pad + row) * a.ldo + c];
+        const float qc = a.Q[row * a.ldq + c] - a.mu[c];
+        qks = fmaf(qc, kw, qks);
+        const float p = fmaf(rowsum * qc, inv_h2, kw) * inv_n;
+        a.phi[row * a.ldphi + c] = p;
+        if (a.Sq) sphi = fmaf(a.Sq[row * a.ldq + c], p, sphi);
+        l2 = fmaf(p, p, l2);
+        continue;
       } else {
         ks = 0.f;
         float kx = 0.f;
@@ -64,6 +74,7 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const EpilogueArgs a) {
     }
     sphi = warp_sum(sphi); l2 = warp_sum(l2);
     if (a.form == 1) { qks = warp_sum(qks); aval = aval - qks; }   // a_i = (K c)_i - qc_i.(K S)_i
+    if (a.form == 2) { qks = warp_sum(qks); aval = aval - fmaf(kg, inv_h2, qks); }   // qc.(K S) = qc.(K W) + kg/h^2
     const float div = (aval * inv_h2 + (float)a.d * inv_h2 * rowsum - bval * inv_h2 * inv_h2) * inv_n;
     t_row = (double)sphi + (double)div;
     l_row = (double)l2;
@@ -93,22 +104,25 @@ __global__ void __launch_bounds__(256) epilogue_gram4_kernel(const EpilogueArgs 
   const float inv_n = 1.f / (float)a.n;
   double t_row = 0.0, l_row = 0.0;
   if (row < a.m) {
-    float rowsum = 0.f, aval = 0.f, bval = 0.f;
+    float rowsum = 0.f, aval = 0.f, bval = 0.f, kg = 0.f;
     const int parts = a.scal_parts > 0 ? a.scal_parts : a.nsplit;
     for (int s = lane; s < parts; s += 32) {
       const float4 sc = *reinterpret_cast<const float4*>(&a.scal[((int64_t)s * a.m_pad + row) * 4]);
-      rowsum += sc.x; aval += sc.y; bval += sc.z;
+      rowsum += sc.x; aval += sc.y; bval += sc.z; kg += sc.w;
     }
-    rowsum = warp_sum(rowsum); aval = warp_sum(aval); bval = warp_sum(bval);
+    rowsum = warp_sum(rowsum); aval = warp_sum(aval); bval = warp_sum(bval); kg = warp_sum(kg);
+    const bool gramw = a.form == 2;
     float sphi = 0.f, l2 = 0.f, qks = 0.f;
     for (int64_t c = 4 * lane; c < a.d; c += 128) {
       float4 ks = make_float4(0.f, 0.f, 0.f, 0.f), kx = ks;
       for (int s = 0; s < a.nsplit; ++s) {
         const float* o = a.O + ((int64_t)s * a.m_pad + row) * a.ldo;
         const float4 v0 = *reinterpret_cast<const float4*>(o + c);
-        const float4 v1 = *reinterpret_cast<const float4*>(o + a.dpad + c);
         ks.x += v0.x; ks.y += v0.y; ks.z += v0.z; ks.w += v0.w;
-        kx.x += v1.x; kx.y += v1.y; kx.z += v1.z; kx.w += v1.w;
+        if (!gramw) {
+          const float4 v1 = *reinterpret_cast<const float4*>(o + a.dpad + c);
+          kx.x += v1.x; kx.y += v1.y; kx.z += v1.z; kx.w += v1.w;
+        }
       }
       const float4 q4 = *reinterpret_cast<const float4*>(a.Q + row * a.ldq + c);
       const float4 m4 = *reinterpret_cast<const float4*>(a.mu + c);
@@ -118,10 +132,10 @@ __global__ void __launch_bounds__(256) epilogue_gram4_kernel(const EpilogueArgs 
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float rr = rowsum * qc[e] - kxv[e];
-        qks = fmaf(qc[e], ksv[e], qks);
+        qks = fmaf(qc[e], ksv[e], qks);              // GRAMW: ksv = (K W), qks = qc.(K W)
         dr[e] = ksv[e] * inv_n;
         rp[e] = rr * inv_h2 * inv_n;
-        pv[e] = dr[e] + rp[e];
+        pv[e] = gramw ? fmaf(rowsum * qc[e], inv_h2, ksv[e]) * inv_n : dr[e] + rp[e];
         l2 = fmaf(pv[e], pv[e], l2);
       }
       *reinterpret_cast<float4*>(a.phi + row * a.ldphi + c) = make_float4(pv[0], pv[1], pv[2], pv[3]);
@@ -136,6 +150,7 @@ __global__ void __launch_bounds__(256) epilogue_gram4_kernel(const EpilogueArgs 
       }
     }
     sphi = warp_sum(sphi); l2 = warp_sum(l2); qks = warp_sum(qks);
+    if (gramw) qks = fmaf(kg, inv_h2, qks);                      // qc.(K S) = qc.(K W) + (sum_j k g_ij)/h^2
     aval = aval - qks;                                           // a_i = (K c)_i - qc_i.(K S)_i
     const float div = (aval * inv_h2 + (float)a.d * inv_h2 * rowsum - bval * inv_h2 * inv_h2) * inv_n;
     t_row = (double)sphi + (double)div;
@@ -168,7 +183,7 @@ int launch_epilogue(cudaStream_t st, const EpilogueArgs& a) {
   const int blocks = epilogue_blocks(a.m);
   NSVGD_REQUIRE(!a.stats_dev || a.Sq, NSVGD_ERR_INVALID, "phi: stats need the scores at the queries (Sq)");
   auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
-  const bool vec4 = a.form == 1 && a.d % 4 == 0 && a.ldo % 4 == 0 && a.dpad % 4 == 0 && a.ldq % 4 == 0 && a.ldphi % 4 == 0 &&
+  const bool vec4 = a.form >= 1 && a.d % 4 == 0 && a.ldo % 4 == 0 && a.dpad % 4 == 0 && a.ldq % 4 == 0 && a.ldphi % 4 == 0 &&
                     al16(a.O) && al16(a.Q) && al16(a.mu) && al16(a.phi) && (!a.Sq || al16(a.Sq)) && (!a.aux || al16(a.aux));
   if (vec4) epilogue_gram4_kernel<<<blocks, 256, 0, st>>>(a);
   else epilogue_kernel<<<blocks, 256, 0, st>>>(a);

@@ -48,6 +48,9 @@ for i in range(3):
 err = (Xl - Xs[r0:r1]).norm().item() / Xs[r0:r1].norm().item()
 print(f"rank {rank} graphed x3: h bit-identical={same} X rel err={err:.2e}", flush=True)
 ok = ok and same and err < 2e-6
+torch.cuda.synchronize()
+del g
 dist.barrier()
-dist.destroy_process_group()
-sys.exit(0 if ok else 1)
+torch.cuda.synchronize()
+sys.stdout.flush()
+os._exit(0 if ok else 1)      # destroy_process_group() hangs after NCCL graph replays (torch 2.11 / NCCL 2.28)

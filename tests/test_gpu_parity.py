@@ -124,6 +124,20 @@ def test_phi_paths_vs_oracle(path, n, d, h):
     assert st[1] / n == pytest.approx(so.l2_norm_squared(ref), rel=2 * TOL)
     got_rect = engine.phistar(Qd, Xd, Sd, h, path=path)
     assert rel_fro(got_rect.cpu(), so.phistar(Q, X, S, h)) < TOL
+    # without the aux output the tensor-core path runs its COMBINED form (second GEMM against W = S - Xc/h^2);
+    # the KSD statistic is then recovered from qc.(K W) + sum_j k g_ij / h^2: square and rectangular
+    phi2, st2 = engine.phistar(Xd, Xd, Sd, h, Sq=Sd, stats=True, path=path)
+    assert rel_fro(phi2.cpu(), ref) < TOL and max_row_rel(phi2.cpu(), ref) < 10 * TOL
+    st2 = st2.cpu().numpy()
+    assert st2[0] / n == pytest.approx(sd_ref, rel=2 * TOL, abs=2 * TOL * abs(so.l2_norm_squared(ref)) ** 0.5)
+    assert st2[1] / n == pytest.approx(so.l2_norm_squared(ref), rel=2 * TOL)
+    Sq = (np.random.default_rng(2).standard_normal((m, d)) * 0.3).astype(np.float32)
+    phi3, st3 = engine.phistar(Qd, Xd, Sd, h, Sq=dev(Sq), stats=True, path=path)
+    ref3 = so.phistar(Q, X, S, h)
+    t_ref = float(np.sum(np.sum(Sq.astype(np.float64) * ref3, axis=1) + so.div_phistar(Q, X, S, h)))
+    scale = float(np.sum(np.abs(np.sum(Sq.astype(np.float64) * ref3, axis=1)) + np.abs(so.div_phistar(Q, X, S, h))))
+    assert rel_fro(phi3.cpu(), ref3) < TOL
+    assert st3.cpu().numpy()[0] == pytest.approx(t_ref, abs=2 * TOL * scale)
 
 
 def test_phi_far_from_origin_and_tight_cloud():
