@@ -156,6 +156,7 @@ struct TcParams {
   int64_t m_pad;
   int tiles_total, tiles_per_split;
   uint32_t* err_flag;
+  int dbg;                        // NSVGD_TC_DEBUG timing experiments: 1 = no MMAs issued, 2 = pair math skipped (results invalid)
 };
 
 constexpr int TC_BM = 128, TC_BN = 64;
@@ -163,14 +164,21 @@ constexpr int TC_DEFAULT_PAIR_WARPS = 8;
 constexpr int TC_MAX_RUN_TILES = 64;   // <= 768 sequential TMEM accumulations per run
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_O = 0, TM_Q = 256, TM_G = 384, TM_P = 448;   // O 256 | Q 2x64 | G 64 | P 64 (b0 32 + b1 32)
+// ping-pong (PP = 2, COMBINED form only: O needs 128 columns): a second G/P pair in the freed columns
+//   O [0,128) | G1 [128,192) | P1 [192,256) | Q [256,384) | G0 [384,448) | P0 [448,512)
+__device__ __forceinline__ constexpr uint32_t tm_g(int b) { return b == 0 ? TM_G : 128u; }
+__device__ __forceinline__ constexpr uint32_t tm_p(int b) { return b == 0 ? TM_P : 192u; }
 
-template <int DP, int VC>
+template <int DP, int VC, int PP = 1>
 struct TcSmem {
   static constexpr int KH = DP / 64;                    // 64-column (128-byte) K slabs of the Gram B operand
   static constexpr int XSLAB = TC_BN * 128;             // 8 KB
   static constexpr int VSLOT = VC * 128;                // [VC rows x 64 j] bf16 = 32 KB (VC = 2 DP = 256)
-  static constexpr int XSTAGES = 2;
-  static constexpr int VSLOTS = 4;
+  // TMA prefetch depth.  The COMBINED form spends ~1600 cycles per tile on the tensor pipe, about one L2 round trip
+  // of a 16 KB TMA box: with 2 X stages / 2 tiles of V the pipe starved (70 % active, pair warps parked on g_full,
+  // profiles/r01_ncu_phi_tc_combined.txt); 3 tiles of X and 3 tiles of V in flight hide it.
+  static constexpr int XSTAGES = VC <= 128 ? 3 : 2;
+  static constexpr int VSLOTS = VC <= 128 ? 6 : 4;
   static constexpr int NVEC = 4;                        // ring of per-tile column vectors {xn[64], cv[64]}
   static constexpr int VEC_BYTES = 2 * TC_BN * 4;
   static constexpr int X_STAGE_BYTES = 2 * KH * XSLAB;
@@ -178,7 +186,7 @@ struct TcSmem {
   static constexpr int OFF_V = OFF_X + XSTAGES * X_STAGE_BYTES;
   static constexpr int OFF_VEC = OFF_V + VSLOTS * VSLOT;
   static constexpr int OFF_BAR = OFF_VEC + NVEC * VEC_BYTES;
-  static constexpr int NBARS = 1 + 2 * XSTAGES + 2 * VSLOTS + 2 * NVEC + 4 + 1;
+  static constexpr int NBARS = 1 + 2 * XSTAGES + 2 * VSLOTS + 2 * NVEC + 4 * PP + 1;
   static constexpr int TOTAL = OFF_BAR + NBARS * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;         // slack for manual 1024-B alignment
   static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
@@ -186,14 +194,19 @@ struct TcSmem {
 
 // VC = columns of the second GEMM: 2*DP -> O = P [S | Xc] (drift and repulsion separately: aux output),
 //                                  DP   -> O = P W, W = S - Xc/h^2 (COMBINED form: 1/3 fewer MMA flops)
-template <int DP, int NW, int VC>
+// PP = 2: PING-PONG.  The pair-function warps form two groups that take alternate tiles, each with its own G and P
+// buffer in TMEM, so one group's TMEM read + exp + TMEM write (~1400-2200 cycles per tile, profiles/r01_phi_pipeline.md)
+// overlaps the other group's and the tensor pipe (~1570 cycles per tile) never waits for a P tile.
+template <int DP, int NW, int VC, int PP>
 __global__ void __launch_bounds__(64 + 32 * NW, 1)
 phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
               const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmV1,
               const TcParams p) {
-  using L = TcSmem<DP, VC>;
+  using L = TcSmem<DP, VC, PP>;
   constexpr int KH = L::KH;
   constexpr bool COMBINED = (VC == DP);
+  static_assert(PP == 1 || (COMBINED && NW % 8 == 0), "ping-pong needs the COMBINED TMEM map and two equal groups");
+  constexpr int GW = NW / PP;                          // pair-function warps per group
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned, stays in the shared address space
   uint8_t* sX = smem + L::OFF_X;
@@ -207,11 +220,11 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
   uint64_t* v_empty = v_full + L::VSLOTS;
   uint64_t* n_full = v_empty + L::VSLOTS;
   uint64_t* n_empty = n_full + L::NVEC;
-  uint64_t* g_full = n_empty + L::NVEC;
-  uint64_t* g_empty = g_full + 1;
-  uint64_t* p_full = g_empty + 1;
-  uint64_t* p_empty = p_full + 1;
-  uint64_t* o_full = p_empty + 1;
+  uint64_t* g_full = n_empty + L::NVEC;          // [PP] each
+  uint64_t* g_empty = g_full + PP;
+  uint64_t* p_full = g_empty + PP;
+  uint64_t* p_empty = p_full + PP;
+  uint64_t* o_full = p_empty + PP;
   uint32_t* tmem_slot = (uint32_t*)(o_full + 1);
   volatile uint32_t* abort_s = tmem_slot + 1;
 
@@ -228,10 +241,12 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
     mbar_init(q_full, NW);                       // query pieces stored to TMEM by the pair-function warps
     for (int i = 0; i < L::XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
     for (int i = 0; i < L::VSLOTS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < L::NVEC; ++i) { mbar_init(&n_full[i], 1); mbar_init(&n_empty[i], NW); }
-    // one arrival per pair-function warp (lane 0 after __syncwarp)
-    mbar_init(g_full, 1); mbar_init(g_empty, NW);
-    mbar_init(p_full, NW); mbar_init(p_empty, 1);
+    for (int i = 0; i < L::NVEC; ++i) { mbar_init(&n_full[i], 1); mbar_init(&n_empty[i], GW); }
+    // one arrival per pair-function warp of the group that owns the buffer (lane 0 after __syncwarp)
+    for (int b = 0; b < PP; ++b) {
+      mbar_init(&g_full[b], 1); mbar_init(&g_empty[b], GW);
+      mbar_init(&p_full[b], GW); mbar_init(&p_empty[b], 1);
+    }
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -258,7 +273,9 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
         mbar_wait(&x_empty[st], (u & 1) ^ 1, watch, 0x100 + st);
         uint8_t* dst = sX + st * L::X_STAGE_BYTES;
         if (leader) {
-          mbar_arrive_expect_tx(&x_full[st], L::X_STAGE_BYTES);
+          if (p.dbg & 4) { if (t < L::XSTAGES) mbar_arrive_expect_tx(&x_full[st], L::X_STAGE_BYTES); else mbar_arrive(&x_full[st]); }
+          else mbar_arrive_expect_tx(&x_full[st], L::X_STAGE_BYTES);
+          if (!(p.dbg & 4) || t < L::XSTAGES)
           for (int kh = 0; kh < KH; ++kh) {
             tma_load_2d(dst + (0 * KH + kh) * L::XSLAB, &tmX0, &x_full[st], kh * 64, j0);
             tma_load_2d(dst + (1 * KH + kh) * L::XSLAB, &tmX1, &x_full[st], kh * 64, j0);
@@ -281,16 +298,19 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
           ++vcount;
           mbar_wait(&v_empty[sl], (u & 1) ^ 1, watch, 0x200 + sl);
           if (leader) {
-            mbar_arrive_expect_tx(&v_full[sl], L::VSLOT);
-            tma_load_2d(sV + sl * L::VSLOT, piece == 0 ? &tmV0 : &tmV1, &v_full[sl], j0, 0);
+            if ((p.dbg & 4) && vcount > L::VSLOTS) mbar_arrive(&v_full[sl]);      // timing experiment: no L2 -> smem traffic
+            else {
+              mbar_arrive_expect_tx(&v_full[sl], L::VSLOT);
+              tma_load_2d(sV + sl * L::VSLOT, piece == 0 ? &tmV0 : &tmV1, &v_full[sl], j0, 0);
+            }
           }
           __syncwarp();
         }
       };
-      // same order as the MMA warp consumes: X(0), X(1), V(0), X(2), V(1), ...
-      load_x(0);
+      // same order as the MMA warp consumes: X(0) .. X(PP-1), then X(t+PP), V(t)
+      for (int t = 0; t < PP && t < T; ++t) load_x(t);
       for (int t = 0; t < T; ++t) {
-        if (t + 1 < T) load_x(t + 1);
+        if (t + PP < T) load_x(t + PP);
         load_v(t);
       }
     }
@@ -306,13 +326,15 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
       tc_fence_after();
       auto issue_gram = [&](int t) {
         const int st = t % L::XSTAGES, us = t / L::XSTAGES;
-        mbar_wait(g_empty, (t & 1) ^ 1, watch, 0x310);
+        const int b = t % PP, ub = t / PP;
+        mbar_wait(&g_empty[b], (ub & 1) ^ 1, watch, 0x310);
         mbar_wait(&x_full[st], us & 1, watch, 0x320 + st);
         tc_fence_after();
-        const uint32_t d_tm = tmem + TM_G;
+        const uint32_t d_tm = tmem + (b == 0 ? tm_g(0) : tm_g(1));
         const uint32_t xs = sX_a + st * L::X_STAGE_BYTES;
         if (leader) {
           uint32_t acc = 0;
+          if (!(p.dbg & 1))
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
             const int pa = pass == 2 ? 1 : 0;     // Q piece: b0, b0, b1   (A operand, in TMEM)
@@ -328,26 +350,29 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
             }
           }
           umma_commit(&x_empty[st]);
-          umma_commit(g_full);
+          umma_commit(&g_full[b]);
         }
         __syncwarp();
       };
       auto issue_pv = [&](int u) {
-        mbar_wait(p_full, u & 1, watch, 0x330);
+        const int b = u % PP, ub = u / PP;
+        mbar_wait(&p_full[b], ub & 1, watch, 0x330);
         tc_fence_after();
-        const uint32_t p0 = tmem + TM_P, p1 = p0 + 32;
+        const uint32_t p0 = tmem + (b == 0 ? tm_p(0) : tm_p(1)), p1 = p0 + 32;
         {
           const int sl = vcount % L::VSLOTS, uv = vcount / L::VSLOTS; ++vcount;
           mbar_wait(&v_full[sl], uv & 1, watch, 0x340 + sl);
           tc_fence_after();
           const uint64_t bd = umma_desc_sw128(sV_a + sl * L::VSLOT);
           if (leader) {
+            if (!(p.dbg & 1)) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_ts(tmem + TM_O, p0 + ks * 8, umma_desc_advance(bd, ks * 32), idesc_pv, (u > 0 || ks > 0) ? 1u : 0u);
+              for (int ks = 0; ks < 4; ++ks)
+                umma_ts(tmem + TM_O, p0 + ks * 8, umma_desc_advance(bd, ks * 32), idesc_pv, (u > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_ts(tmem + TM_O, p1 + ks * 8, umma_desc_advance(bd, ks * 32), idesc_pv, 1u);
+              for (int ks = 0; ks < 4; ++ks)
+                umma_ts(tmem + TM_O, p1 + ks * 8, umma_desc_advance(bd, ks * 32), idesc_pv, 1u);
+            }
             umma_commit(&v_empty[sl]);
           }
           __syncwarp();
@@ -358,20 +383,22 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
           tc_fence_after();
           const uint64_t bd = umma_desc_sw128(sV_a + sl * L::VSLOT);
           if (leader) {
+            if (!(p.dbg & 1))
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               umma_ts(tmem + TM_O, p0 + ks * 8, umma_desc_advance(bd, ks * 32), idesc_pv, 1u);
             umma_commit(&v_empty[sl]);
-            umma_commit(p_empty);
+            umma_commit(&p_empty[b]);
           }
           __syncwarp();
         }
       };
       // tensor-pipe order: G0 | G1 PV0 | G2 PV1 | ...  (single G and P buffers: G(t+1) is issued once the
       // pair warps have loaded G(t), and runs while they compute P(t); P.V(t-1) covers the load itself)
-      issue_gram(0);
+      // ping-pong (PP = 2): G0 G1 | G2 PV0 | G3 PV1 | ...  (G(t+2) is issued once group t%2 has loaded G(t))
+      for (int t = 0; t < PP && t < T; ++t) issue_gram(t);
       for (int t = 0; t < T; ++t) {
-        if (t + 1 < T) issue_gram(t + 1);
+        if (t + PP < T) issue_gram(t + PP);
         issue_pv(t);
       }
       if (leader) umma_commit(o_full);
@@ -381,12 +408,15 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
     // =============================== pair-function warps ==========================================
     // thread <-> (row, column part): quarter = warp % 4 selects the TMEM lanes (rows), part = which CPT
     // of the tile's 64 columns.  Several warps per SM sub-partition hide each other's latencies.
-    constexpr int NPART = NW / 4;
-    constexpr int CPT = TC_BN / NPART;                 // columns per thread and tile (32 or 16)
+    constexpr int NPART = NW / 4;                      // warps per TMEM lane quarter (epilogue / Q-load column parts)
+    constexpr int GPART = GW / 4;                      // column parts of a tile within one group
+    constexpr int CPT = TC_BN / GPART;                 // columns per thread and tile (32 or 16)
     constexpr int OCOLS = VC / NPART;                  // accumulator columns per thread in the epilogue
     static_assert(OCOLS % 32 == 0, "epilogue reads 32 accumulator columns per tcgen05.ld");
     const int quarter = warp & 3;
-    const int part = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;                  // 0 .. NPART-1
+    const int group = part / GPART;                    // which tiles: t % PP == group
+    const int gpart = part % GPART;                    // column part inside the group's tile
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const float h = *p.h_dev;
@@ -421,22 +451,29 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(q_full);
     }
-    for (int t = 0; t < T; ++t) {
+    const uint32_t tm_g_mine = tmem + lane_addr + (group == 0 ? tm_g(0) : tm_g(1)) + gpart * CPT;
+    const uint32_t tm_p_mine = tmem + lane_addr + (group == 0 ? tm_p(0) : tm_p(1));
+    for (int t = group; t < T; t += PP) {
       const int ns = t % L::NVEC, un = t / L::NVEC;
-      mbar_wait(g_full, t & 1, watch, 0x400);
+      const int ub = t / PP;
+      mbar_wait(&g_full[group], ub & 1, watch, 0x400);
       __syncwarp();
       tc_fence_after();
       uint32_t g[CPT];
-      if (CPT == 32) tmem_ld32(tmem + lane_addr + TM_G + part * CPT, g);
-      else tmem_ld16(tmem + lane_addr + TM_G + part * CPT, g);
+      if (CPT == 32) tmem_ld32(tm_g_mine, g);
+      else tmem_ld16(tm_g_mine, g);
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(g_empty);
+      if (lane == 0) mbar_arrive(&g_empty[group]);
       mbar_wait(&n_full[ns], un & 1, watch, 0x420 + ns);
-      const float4* xn4 = reinterpret_cast<const float4*>(sVec + ns * 2 * TC_BN + part * CPT);
-      const float4* cv4 = reinterpret_cast<const float4*>(sVec + ns * 2 * TC_BN + TC_BN + part * CPT);
+      const float4* xn4 = reinterpret_cast<const float4*>(sVec + ns * 2 * TC_BN + gpart * CPT);
+      const float4* cv4 = reinterpret_cast<const float4*>(sVec + ns * 2 * TC_BN + TC_BN + gpart * CPT);
       uint32_t pk0[CPT / 2], pk1[CPT / 2];
+      if (p.dbg & 2) {
+#pragma unroll
+        for (int q = 0; q < CPT / 2; ++q) { pk0[q] = g[2 * q]; pk1[q] = g[2 * q + 1]; }
+      } else
       // packed fp32x2 math (FFMA2/FADD2): two columns per instruction
 #pragma unroll
       for (int q4 = 0; q4 < CPT / 4; ++q4) {
@@ -468,20 +505,20 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(&n_empty[ns]);
       // single P buffer: P(t) is stored as soon as P.V(t-1) has consumed P(t-1); G(t+1) keeps the tensor pipe busy meanwhile
-      mbar_wait(p_empty, (t & 1) ^ 1, watch, 0x410);
+      mbar_wait(&p_empty[group], (ub & 1) ^ 1, watch, 0x410);
       __syncwarp();
       tc_fence_after();
       if (CPT == 32) {
-        tmem_st16(tmem + lane_addr + TM_P + part * 16, pk0);
-        tmem_st16(tmem + lane_addr + TM_P + 32 + part * 16, pk1);
+        tmem_st16(tm_p_mine + gpart * 16, pk0);
+        tmem_st16(tm_p_mine + 32 + gpart * 16, pk1);
       } else {
-        tmem_st8(tmem + lane_addr + TM_P + part * 8, pk0);
-        tmem_st8(tmem + lane_addr + TM_P + 32 + part * 8, pk1);
+        tmem_st8(tm_p_mine + gpart * 8, pk0);
+        tmem_st8(tm_p_mine + 32 + gpart * 8, pk1);
       }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[group]);
     }
     // ---- epilogue: O (TMEM) -> workspace; the NPART warps of a quarter take OCOLS columns each
     const int64_t row = (int64_t)m0 + row_in_tile;
@@ -554,17 +591,17 @@ static TcPlan make_plan(const PhiArgs& a) {
   return pl;
 }
 
-template <int DP, int NW, int VC>
+template <int DP, int NW, int VC, int PP>
 static int launch_tc_variant(cudaStream_t st, const TcPlan& pl, const CUtensorMap* maps, const TcParams& prm) {
-  using L = TcSmem<DP, VC>;
+  using L = TcSmem<DP, VC, PP>;
   static bool attr_set = false;
   if (!attr_set) {
-    NSVGD_CUDA(cudaFuncSetAttribute(phi_tc_kernel<DP, NW, VC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+    NSVGD_CUDA(cudaFuncSetAttribute(phi_tc_kernel<DP, NW, VC, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
     attr_set = true;
   }
   dim3 grid((unsigned)(pl.m_pad / TC_BM), (unsigned)pl.nsplit);
   prof_begin(0, st);
-  phi_tc_kernel<DP, NW, VC><<<grid, 64 + 32 * NW, L::DYN_BYTES, st>>>(maps[2], maps[3], maps[4], maps[5], prm);
+  phi_tc_kernel<DP, NW, VC, PP><<<grid, 64 + 32 * NW, L::DYN_BYTES, st>>>(maps[2], maps[3], maps[4], maps[5], prm);
   prof_end(0, st);
   NSVGD_LAUNCH_CHECK();
   return NSVGD_OK;
@@ -576,11 +613,23 @@ static int tc_pair_warps() {
   return (e && atoi(e) == 16) ? 16 : ((e && atoi(e) == 8) ? 8 : TC_DEFAULT_PAIR_WARPS);
 }
 
+// NSVGD_TC_PINGPONG=1: ping-pong, 2 x 8 pair warps.  Default off: measured 5.04 vs 4.99 ms at n=65536, d=128
+// (profiles/r01_phi_pipeline.md) -- the kernel is not latency-bound, so the extra warps buy nothing.
+static bool tc_pingpong() {
+  const char* e = getenv("NSVGD_TC_PINGPONG");
+  return e && atoi(e) == 1;
+}
+
 template <int DP>
 static int launch_tc(cudaStream_t st, const TcPlan& pl, const CUtensorMap* maps, const TcParams& prm, bool combined) {
-  if (combined) return launch_tc_variant<DP, 8, DP>(st, pl, maps, prm);
-  if (tc_pair_warps() == 16) return launch_tc_variant<DP, 16, 2 * DP>(st, pl, maps, prm);
-  return launch_tc_variant<DP, 8, 2 * DP>(st, pl, maps, prm);
+  if (combined) {
+    if constexpr (DP == 128) {      // ping-pong needs 128 accumulator columns per lane quarter split over 4 warps
+      if (tc_pingpong()) return launch_tc_variant<DP, 16, DP, 2>(st, pl, maps, prm);
+    }
+    return launch_tc_variant<DP, 8, DP, 1>(st, pl, maps, prm);
+  }
+  if (tc_pair_warps() == 16) return launch_tc_variant<DP, 16, 2 * DP, 1>(st, pl, maps, prm);
+  return launch_tc_variant<DP, 8, 2 * DP, 1>(st, pl, maps, prm);
 }
 
 // COMBINED form (second GEMM against W = S - Xc/h^2, N = dp): whenever the caller does not ask for the
@@ -636,12 +685,13 @@ int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dr
   TcParams prm{};
   prm.Qb0 = (const uint32_t*)Qb0; prm.Qb1 = (const uint32_t*)Qb1; prm.xn = xn; prm.cv = cv; prm.qn = qn; prm.h_dev = a.h_dev; prm.O = O; prm.scal = scal; prm.m_pad = pl.m_pad;
   prm.tiles_total = pl.tiles_total; prm.tiles_per_split = pl.tiles_per_split; prm.err_flag = err_flag;
+  if (const char* env = getenv("NSVGD_TC_DEBUG")) prm.dbg = atoi(env);
   if (dp == 64) NSVGD_PROPAGATE(launch_tc<64>(st, pl, maps, prm, combined));
   else NSVGD_PROPAGATE(launch_tc<128>(st, pl, maps, prm, combined));
 
   EpilogueArgs e{};
   e.form = combined ? 2 : 1; e.O = O; e.scal = scal; e.nsplit = pl.nsplit;
-  e.scal_parts = ((combined ? 8 : tc_pair_warps()) / 4) * pl.nsplit; e.m_pad = pl.m_pad; e.ldo = vc; e.dpad = dp; e.mu = mu;
+  e.scal_parts = ((combined ? ((tc_pingpong() && dp == 128) ? 16 : 8) : tc_pair_warps()) / 4) * pl.nsplit; e.m_pad = pl.m_pad; e.ldo = vc; e.dpad = dp; e.mu = mu;
   e.Q = a.Q; e.ldq = a.ldq; e.Sq = a.Sq; e.m = a.m; e.n = a.n; e.d = a.d; e.h_dev = a.h_dev;
   e.phi = a.phi; e.ldphi = a.ldphi; e.aux = a.aux; e.stats_dev = a.stats_dev; e.partials = partials;
   return launch_epilogue(st, e);

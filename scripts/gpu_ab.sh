@@ -1,0 +1,7 @@
+#!/bin/bash
+# quick bench A/B (+ optional parity subset): bash scripts/gpu_ab.sh [pytest -k expr]
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+if [ -n "$1" ]; then timeout 600 python -m pytest tests/test_gpu_parity.py -x -q --tb=short -p no:cacheprovider -k "$1" 2>&1 | tail -3; fi
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ab.log 2>&1; echo "exit $?"
+grep '^{' gpurun_out/ab.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['breakdown_ms_per_step'], d['result'], d['clocks'])"
