@@ -355,6 +355,8 @@ def main():
                    "bandwidth": "median heuristic (%s) every step" % args.median_mode if not fixed_h else f"fixed {fixed_h}",
                    "scaled": True, "optimizer": "sgd", "parallelism": f"row-sharded x{world}", "l2_flush": "192 MiB fill between steps",
                    "path": args.path,
+                   "small_allreduces": ("peer memory over NVLink, fused into the consumer kernels (csrc/p2p.cuh)"
+                                        if (sharded is not None and sharded.comm is not None) else ("nccl" if world > 1 else "none")),
                    "launch": "one CUDA graph replay per step (collectives captured)" if graphed is not None else "eager (C-ABI calls per op)"},
         "breakdown_ms_per_step": {"median_op": med_op_ms / KP, "median_tc_filter_kernel": med_filter_ms / KP,
                                   "median_sample_kernel": med_sample_ms / KP, "median_exact_list_kernel": med_exact_ms / KP,

@@ -137,6 +137,38 @@ int nsvgd_median_fallback_hist(void* stream, const float* Z, int64_t n, int64_t 
 int nsvgd_median_fallback_advance(void* stream, void* state_dev, void* ws, size_t ws_bytes, int64_t n, int64_t dz,
                                   const uint64_t* hist_dev, int pass);
 
+/* ---- row-sharded runs — small all-reduces over NVLink PEER MEMORY, fused into their consumer kernels.
+ * Between the heavy kernels a row-sharded step exchanges only tiny vectors (radix-select histograms, candidate counts,
+ * the KSD/l2 sums).  Instead of one NCCL all-reduce (launch + ~20 us) each, the consumer kernel publishes its vector in a
+ * peer-mapped block, flags every peer (st.release.sys), waits for theirs (ld.acquire.sys) and sums the peers' vectors in
+ * rank order — integer sums and fixed-order double sums are bit-identical on every rank (csrc/p2p.cuh).
+ * Plumbing: each rank allocates ONE block (nsvgd_p2p_alloc: cudaMalloc + zero + cudaIpcGetMemHandle, 64-byte handle), the
+ * host layer exchanges the handles (any transport; nsvgd/parallel.py uses one torch.distributed all-gather), opens the
+ * peers' blocks (nsvgd_p2p_open) and passes `blocks[world]` (own block at index `rank`) to the calls below.  All ranks
+ * must issue the same sequence of p2p calls.  Enqueue-only, CUDA-graph capturable (epochs live in device memory); a peer
+ * that does not arrive within ~2 s raises the block's timeout flag instead of hanging (nsvgd_p2p_timeout_flag). */
+size_t nsvgd_p2p_block_bytes(void);
+int nsvgd_p2p_alloc(void** dev_ptr, unsigned char* handle_out /* 64 bytes */);
+int nsvgd_p2p_open(const unsigned char* handle /* 64 bytes */, void** peer_ptr);
+int nsvgd_p2p_close(void* peer_ptr);
+int nsvgd_p2p_free(void* dev_ptr);
+int nsvgd_p2p_timeout_flag(const void* own_block, int* flag_out);
+/* stand-alone form: in-place sum of buf[0..nwords) (uint64 adds, or doubles in rank order), nwords <= 8192 */
+int nsvgd_p2p_allreduce(void* stream, int rank, int world, void* const* blocks, void* buf, int64_t nwords, int is_f64);
+/* = all-reduce(hist) + nsvgd_median_advance */
+int nsvgd_p2p_median_advance(void* stream, int rank, int world, void* const* blocks, void* state_dev, uint64_t* hist_dev, int pass);
+/* = all-reduce(reduce_dev[4]) + nsvgd_median_fast_resolve */
+int nsvgd_p2p_median_fast_resolve(void* stream, int rank, int world, void* const* blocks, void* state_dev, void* ws,
+                                  size_t ws_bytes, int64_t n, int64_t dz, int64_t* reduce_dev);
+/* hist_dev = uint64[4*2048]: [candidate histogram | fallback histogram] of radix pass `pass`;
+ * = all-reduce(hist) + nsvgd_median_fast_cand_advance + (iff the fallback flag is set) nsvgd_median_fallback_advance */
+int nsvgd_p2p_median_fast_advance2(void* stream, int rank, int world, void* const* blocks, void* state_dev, void* ws,
+                                   size_t ws_bytes, int64_t n, int64_t dz, uint64_t* hist_dev, int pass);
+/* = all-reduce(stats_dev[4], doubles) + nsvgd_apply_update_f32 */
+int nsvgd_p2p_apply_update_f32(void* stream, int rank, int world, void* const* blocks, float* Xrows, const float* phi,
+                               int64_t m, int64_t d, int64_t ldx, int64_t ldphi, double* stats_dev, float lr, int scaled,
+                               float lambda_reg, float* grads, double* step_aux_dev);
+
 /* ---- A1/A3/A4: phi*  (stein.py:71-96, 180-222; kernels.py:52-65)
  * phi[i,:] = (1/n) sum_j k_ij s_j + k_ij (q_i - x_j)/h^2,  k_ij = exp(-|q_i-x_j|^2/(2h^2)).
  * Optional outputs (NULL to skip):

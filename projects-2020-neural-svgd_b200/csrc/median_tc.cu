@@ -18,6 +18,7 @@
 
 #include <algorithm>
 
+#include "p2p.cuh"
 #include "select.cuh"
 #include "tc_common.cuh"
 
@@ -603,8 +604,32 @@ __global__ void fast_pack_kernel(FastMedState* fs, const uint32_t* list_counts, 
 }
 
 // red holds the GLOBAL sums (all-reduced across ranks when row-sharded)
+__device__ __forceinline__ void fast_resolve_body(FastMedState* fs, const SelectState* main_state, SelectState* cs,
+                                                  const long long* red);
+
 __global__ void fast_resolve_kernel(FastMedState* fs, const SelectState* main_state, SelectState* cs, const long long* red) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  fast_resolve_body(fs, main_state, cs, red);
+}
+
+// row-sharded: the all-reduce of {below, candidates, bad, listed} over peer memory fused into the resolve step
+__global__ void __launch_bounds__(64) fast_resolve_p2p_kernel(const P2PComm c, FastMedState* fs, const SelectState* main_state,
+                                                              SelectState* cs, long long* red) {
+  p2p_allreduce_cta(c, reinterpret_cast<unsigned long long*>(red), 4, false);
+  if (threadIdx.x == 0) fast_resolve_body(fs, main_state, cs, red);
+}
+
+// row-sharded: ONE kernel per radix pass = all-reduce of [candidate histogram | fallback histogram] over peer memory
+// + the candidate-select decision + (only when the fallback flag is set) the SIMT-select decision
+__global__ void __launch_bounds__(1024) fast_advance2_p2p_kernel(const P2PComm c, const FastMedState* fs, SelectState* cand_state,
+                                                                 SelectState* main_state, unsigned long long* hist, int pass) {
+  p2p_allreduce_cta(c, hist, 4 * NSVGD_SELECT_BINS, false);
+  select_advance_body(cand_state, hist, pass);
+  if (fs->fallback) select_advance_body(main_state, hist + 2 * NSVGD_SELECT_BINS, pass);
+}
+
+__device__ __forceinline__ void fast_resolve_body(FastMedState* fs, const SelectState* main_state, SelectState* cs,
+                                                  const long long* red) {
   const unsigned long long below = (unsigned long long)red[0], ncand = (unsigned long long)red[1];
   uint32_t fb = red[2] != 0 ? 1u : 0u;
   cs->prefix[0] = cs->prefix[1] = 0u; cs->mask = 0u; cs->nan_flag = 0u;
@@ -857,6 +882,34 @@ extern "C" int nsvgd_median_fast_resolve(void* stream, void* state_dev, void* ws
   NSVGD_REQUIRE(state_dev && reduce_dev, NSVGD_ERR_INVALID, "median_fast_resolve: null pointer");
   return median_fast_resolve((cudaStream_t)stream, (SelectState*)state_dev, ws, ws_bytes, n, dz, (const long long*)reduce_dev);
 }
+extern "C" int nsvgd_p2p_median_fast_resolve(void* stream, int rank, int world, void* const* blocks, void* state_dev, void* ws,
+                                             size_t ws_bytes, int64_t n, int64_t dz, int64_t* reduce_dev) {
+  P2PComm c;
+  NSVGD_REQUIRE(p2p_make_comm(&c, rank, world, blocks), NSVGD_ERR_INVALID, "p2p_median_fast_resolve: bad communicator");
+  NSVGD_REQUIRE(state_dev && reduce_dev, NSVGD_ERR_INVALID, "p2p_median_fast_resolve: null pointer");
+  FastWs f;
+  NSVGD_PROPAGATE(fast_ws(n, dz, ws, ws_bytes, &f));
+  fast_resolve_p2p_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(c, f.fs, (const SelectState*)state_dev, f.cand_state,
+                                                             (long long*)reduce_dev);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
+/* hist_dev: uint64[4 * NSVGD_SELECT_BINS] = [candidate histogram (2 targets) | fallback histogram (2 targets)] */
+extern "C" int nsvgd_p2p_median_fast_advance2(void* stream, int rank, int world, void* const* blocks, void* state_dev, void* ws,
+                                              size_t ws_bytes, int64_t n, int64_t dz, uint64_t* hist_dev, int pass) {
+  P2PComm c;
+  NSVGD_REQUIRE(p2p_make_comm(&c, rank, world, blocks), NSVGD_ERR_INVALID, "p2p_median_fast_advance2: bad communicator");
+  NSVGD_REQUIRE(state_dev && hist_dev, NSVGD_ERR_INVALID, "p2p_median_fast_advance2: null pointer");
+  NSVGD_REQUIRE(pass >= 0 && pass < NSVGD_SELECT_PASSES, NSVGD_ERR_INVALID, "p2p_median_fast_advance2: bad pass %d", pass);
+  FastWs f;
+  NSVGD_PROPAGATE(fast_ws(n, dz, ws, ws_bytes, &f));
+  fast_advance2_p2p_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(c, f.fs, f.cand_state, (SelectState*)state_dev,
+                                                                (unsigned long long*)hist_dev, pass);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
 extern "C" int nsvgd_median_fast_cand_hist(void* stream, void* ws, size_t ws_bytes, int64_t n, int64_t dz, int pass, uint64_t* hist_dev) {
   NSVGD_REQUIRE(hist_dev && pass >= 0 && pass < NSVGD_SELECT_PASSES, NSVGD_ERR_INVALID, "median_fast_cand_hist: bad arguments");
   return median_fast_cand_hist((cudaStream_t)stream, ws, ws_bytes, n, dz, pass, hist_dev);

@@ -13,6 +13,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include "p2p.cuh"
 #include "select.cuh"
 
 namespace nsvgd {
@@ -322,52 +323,14 @@ __global__ void literal_z_kernel(const float* __restrict__ X, int64_t n, int64_t
 __global__ void __launch_bounds__(1024) select_advance_kernel(SelectState* s, const unsigned long long* hist, int pass,
                                                               const uint32_t* run_flag) {
   if (run_flag && *run_flag == 0u) return;
-  // warp t (t = 0,1) resolves target t: find the bin whose cumulative count exceeds rank[t]
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ uint32_t new_prefix[2];
-  __shared__ unsigned long long new_rank[2];
-  const int nb = pass == 2 ? 1024 : 2048;
-  const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
-  if (w < 2) {
-    const unsigned long long* hh = hist + (size_t)w * NSVGD_SELECT_BINS;
-    const unsigned long long target = s->rank[w];
-    const int per = nb / 32;
-    unsigned long long lsum = 0;
-    for (int b = 0; b < per; ++b) lsum += hh[lane * per + b];
-    unsigned long long incl = lsum;   // inclusive scan over lanes
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const unsigned long long excl = incl - lsum;
-    const bool mine = target >= excl && target < incl;
-    const unsigned int ball = __ballot_sync(0xffffffffu, mine);
-    if (ball == 0u) {  // rank beyond the population (cannot happen for valid ranks)
-      if (lane == 0) { new_prefix[w] = s->prefix[w]; new_rank[w] = target; }
-    } else if (lane == (__ffs(ball) - 1)) {
-      unsigned long long cum = excl;
-      int b = 0;
-      for (; b < per; ++b) {
-        const unsigned long long c = hh[lane * per + b];
-        if (target < cum + c) break;
-        cum += c;
-      }
-      new_prefix[w] = s->prefix[w] | ((uint32_t)(lane * per + b) << shift);
-      new_rank[w] = target - cum;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    s->prefix[0] = new_prefix[0]; s->prefix[1] = new_prefix[1];
-    s->rank[0] = new_rank[0]; s->rank[1] = new_rank[1];
-    s->mask |= ((uint32_t)(nb - 1)) << shift;
-    if (pass == NSVGD_SELECT_PASSES - 1) {
-      s->value[0] = s->is_zero[0] ? 0.f : __uint_as_float(s->prefix[0]);
-      s->value[1] = s->is_zero[1] ? 0.f : __uint_as_float(s->prefix[1]);
-      s->done = 1;
-    }
-  }
+  select_advance_body(s, hist, pass);
+}
+
+// row-sharded SIMT select: all-reduce of the histogram over peer memory fused into the decision kernel
+__global__ void __launch_bounds__(1024) select_advance_p2p_kernel(const P2PComm c, SelectState* s, unsigned long long* hist,
+                                                                  int pass) {
+  p2p_allreduce_cta(c, hist, 2 * NSVGD_SELECT_BINS, false);
+  select_advance_body(s, hist, pass);
 }
 
 __global__ void select_finish_kernel(const SelectState* s, float* h_dev) {
@@ -434,6 +397,12 @@ int launch_buffer_hist(cudaStream_t st, const float* vals, const uint32_t* count
 
 int launch_select_advance(cudaStream_t st, SelectState* s, const uint64_t* hist, int pass, const uint32_t* run_flag) {
   select_advance_kernel<<<1, 64, 0, st>>>(s, (const unsigned long long*)hist, pass, run_flag);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
+int launch_select_advance_p2p(cudaStream_t st, const P2PComm& c, SelectState* s, uint64_t* hist, int pass) {
+  select_advance_p2p_kernel<<<1, 1024, 0, st>>>(c, s, (unsigned long long*)hist, pass);
   NSVGD_LAUNCH_CHECK();
   return NSVGD_OK;
 }
@@ -518,6 +487,15 @@ extern "C" int nsvgd_median_advance(void* stream, void* state_dev, const uint64_
   NSVGD_REQUIRE(state_dev && hist_dev, NSVGD_ERR_INVALID, "median_advance: null pointer");
   NSVGD_REQUIRE(pass >= 0 && pass < NSVGD_SELECT_PASSES, NSVGD_ERR_INVALID, "median_advance: bad pass %d", pass);
   return launch_select_advance((cudaStream_t)stream, (SelectState*)state_dev, hist_dev, pass, nullptr);
+}
+
+extern "C" int nsvgd_p2p_median_advance(void* stream, int rank, int world, void* const* blocks, void* state_dev,
+                                        uint64_t* hist_dev, int pass) {
+  P2PComm c;
+  NSVGD_REQUIRE(p2p_make_comm(&c, rank, world, blocks), NSVGD_ERR_INVALID, "p2p_median_advance: bad communicator");
+  NSVGD_REQUIRE(state_dev && hist_dev, NSVGD_ERR_INVALID, "p2p_median_advance: null pointer");
+  NSVGD_REQUIRE(pass >= 0 && pass < NSVGD_SELECT_PASSES, NSVGD_ERR_INVALID, "p2p_median_advance: bad pass %d", pass);
+  return launch_select_advance_p2p((cudaStream_t)stream, c, (SelectState*)state_dev, hist_dev, pass);
 }
 
 extern "C" int nsvgd_median_finish(void* stream, const void* state_dev, int64_t n, float* h_dev) {

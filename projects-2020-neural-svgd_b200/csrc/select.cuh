@@ -1,6 +1,7 @@
 // select.cuh — device state of the exact radix select (shared by pair_engine.cu and median_tc.cu)
 #pragma once
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace nsvgd {
 
@@ -31,6 +32,58 @@ struct FastMedState {
 __device__ __forceinline__ int pass_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
 __device__ __forceinline__ int pass_bins(int pass) { return pass == 2 ? 1024 : 2048; }
 
+// One radix-select decision (both target ranks) from a histogram: warp t (t = 0,1) resolves target t.  Shared by the
+// plain advance kernel and the kernels that first all-reduce the histogram over peer memory (p2p.cuh).
+// Call from ALL threads of a CTA with blockDim.x >= 64.
+__device__ __forceinline__ void select_advance_body(SelectState* s, const unsigned long long* hist, int pass) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ uint32_t new_prefix[2];
+  __shared__ unsigned long long new_rank[2];
+  const int nb = pass == 2 ? 1024 : 2048;
+  const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+  if (w < 2) {
+    const unsigned long long* hh = hist + (size_t)w * NSVGD_SELECT_BINS;
+    const unsigned long long target = s->rank[w];
+    const int per = nb / 32;
+    unsigned long long lsum = 0;
+    for (int b = 0; b < per; ++b) lsum += hh[lane * per + b];
+    unsigned long long incl = lsum;   // inclusive scan over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned long long excl = incl - lsum;
+    const bool mine = target >= excl && target < incl;
+    const unsigned int ball = __ballot_sync(0xffffffffu, mine);
+    if (ball == 0u) {  // rank beyond the population (cannot happen for valid ranks)
+      if (lane == 0) { new_prefix[w] = s->prefix[w]; new_rank[w] = target; }
+    } else if (lane == (__ffs(ball) - 1)) {
+      unsigned long long cum = excl;
+      int b = 0;
+      for (; b < per; ++b) {
+        const unsigned long long c = hh[lane * per + b];
+        if (target < cum + c) break;
+        cum += c;
+      }
+      new_prefix[w] = s->prefix[w] | ((uint32_t)(lane * per + b) << shift);
+      new_rank[w] = target - cum;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s->prefix[0] = new_prefix[0]; s->prefix[1] = new_prefix[1];
+    s->rank[0] = new_rank[0]; s->rank[1] = new_rank[1];
+    s->mask |= ((uint32_t)(nb - 1)) << shift;
+    if (pass == NSVGD_SELECT_PASSES - 1) {
+      s->value[0] = s->is_zero[0] ? 0.f : __uint_as_float(s->prefix[0]);
+      s->value[1] = s->is_zero[1] ? 0.f : __uint_as_float(s->prefix[1]);
+      s->done = 1;
+    }
+  }
+  __syncthreads();
+}
+
 // DEFINED-ORDER fp32 squared distance of one pair (oracle/svgd_oracle.py::pair_sqdist_f32):
 // sequential over coordinates, separate mul and add, last coordinate weighted by w.
 __device__ __forceinline__ float exact_pair_sqdist(const float* __restrict__ a, const float* __restrict__ b,
@@ -53,6 +106,7 @@ int launch_buffer_hist(cudaStream_t st, const float* vals, const uint32_t* count
                        uint32_t seg_cap, uint32_t count_host, const SelectState* state, int pass, uint64_t* hist,
                        const uint32_t* run_flag);
 int launch_select_advance(cudaStream_t st, SelectState* s, const uint64_t* hist, int pass, const uint32_t* run_flag);
+int launch_select_advance_p2p(cudaStream_t st, const P2PComm& c, SelectState* s, uint64_t* hist, int pass);
 int launch_pair_hist(cudaStream_t st, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last,
                      int64_t tile_row_start, int64_t tile_row_stride, const SelectState* state, int pass,
                      uint64_t* hist, const uint32_t* run_flag);

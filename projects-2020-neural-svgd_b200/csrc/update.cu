@@ -6,6 +6,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace nsvgd {
 
@@ -196,9 +197,23 @@ int launch_epilogue(cudaStream_t st, const EpilogueArgs& a) {
 }
 
 // ---- update ----------------------------------------------------------------------------------
+__device__ __forceinline__ void step_aux_body(const double* stats, int scaled, float lambda_reg, float lr, double* aux);
+
 __global__ void step_aux_kernel(const double* __restrict__ stats, int scaled, float lambda_reg, float lr,
                                 double* __restrict__ aux) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) step_aux_body(stats, scaled, lambda_reg, lr, aux);
+}
+
+// row-sharded: the all-reduce of the KSD / l2 sums (4 doubles, fixed rank order -> bit-identical alpha on every
+// rank) over peer memory fused into the kernel that turns them into the step scaling
+__global__ void __launch_bounds__(64) step_aux_p2p_kernel(const P2PComm c, double* stats, int scaled, float lambda_reg, float lr,
+                                                          double* aux) {
+  p2p_allreduce_cta(c, reinterpret_cast<unsigned long long*>(stats), 4, true);
+  if (threadIdx.x == 0) step_aux_body(stats, scaled, lambda_reg, lr, aux);
+}
+
+__device__ __forceinline__ void step_aux_body(const double* stats, int scaled, float lambda_reg, float lr, double* aux) {
+  {
     double ksd = 0.0, l2 = 0.0, alpha = 1.0, sum_l = 0.0;
     if (stats) {
       const double m = stats[2];
@@ -255,6 +270,24 @@ extern "C" int nsvgd_apply_update_f32(void* stream, float* Xrows, const float* p
   const int64_t total = m * d;
   const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)device_sm_count() * 8);
   apply_update_kernel<<<blocks, 256, 0, st>>>(Xrows, phi, m, d, ldx, ldphi, step_aux_dev, lr, grads);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
+extern "C" int nsvgd_p2p_apply_update_f32(void* stream, int rank, int world, void* const* blocks, float* Xrows,
+                                          const float* phi, int64_t m, int64_t d, int64_t ldx, int64_t ldphi,
+                                          double* stats_dev, float lr, int scaled, float lambda_reg, float* grads,
+                                          double* step_aux_dev) {
+  cudaStream_t st = (cudaStream_t)stream;
+  P2PComm c;
+  NSVGD_REQUIRE(p2p_make_comm(&c, rank, world, blocks), NSVGD_ERR_INVALID, "p2p_apply_update: bad communicator");
+  NSVGD_REQUIRE(Xrows && phi && step_aux_dev && stats_dev, NSVGD_ERR_INVALID, "p2p_apply_update: null pointer");
+  NSVGD_REQUIRE(m >= 1 && d >= 1 && ldx >= d && ldphi >= d, NSVGD_ERR_INVALID, "p2p_apply_update: bad shape");
+  step_aux_p2p_kernel<<<1, 64, 0, st>>>(c, stats_dev, scaled, lambda_reg, lr, step_aux_dev);
+  NSVGD_LAUNCH_CHECK();
+  const int64_t total = m * d;
+  const unsigned blocks_ = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)device_sm_count() * 8);
+  apply_update_kernel<<<blocks_, 256, 0, st>>>(Xrows, phi, m, d, ldx, ldphi, step_aux_dev, lr, grads);
   NSVGD_LAUNCH_CHECK();
   return NSVGD_OK;
 }

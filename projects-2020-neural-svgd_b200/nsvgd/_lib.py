@@ -34,6 +34,9 @@ SYMBOLS = [
     "nsvgd_median_fallback_advance", "nsvgd_phi_f32", "nsvgd_step_sgd_f32", "nsvgd_apply_update_f32",
     "nsvgd_ksd_f32", "nsvgd_mmd_f32", "nsvgd_ksum_f32", "nsvgd_adam_update_f32",
     "nsvgd_tc_probe_gram", "nsvgd_tc_probe_pv",
+    "nsvgd_p2p_block_bytes", "nsvgd_p2p_alloc", "nsvgd_p2p_open", "nsvgd_p2p_close", "nsvgd_p2p_free",
+    "nsvgd_p2p_timeout_flag", "nsvgd_p2p_allreduce", "nsvgd_p2p_median_advance", "nsvgd_p2p_median_fast_resolve",
+    "nsvgd_p2p_median_fast_advance2", "nsvgd_p2p_apply_update_f32",
 ]
 
 
@@ -85,9 +88,22 @@ def load():
     lib.nsvgd_adam_update_f32.argtypes = [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, i64]
     lib.nsvgd_tc_probe_gram.argtypes = [vp, vp, vp, vp, vp, sz]
     lib.nsvgd_tc_probe_pv.argtypes = [vp, vp, vp, vp, vp, sz]
+    pvp = C.POINTER(vp)
+    lib.nsvgd_p2p_alloc.argtypes = [pvp, vp]
+    lib.nsvgd_p2p_open.argtypes = [vp, pvp]
+    lib.nsvgd_p2p_close.argtypes = [vp]
+    lib.nsvgd_p2p_free.argtypes = [vp]
+    lib.nsvgd_p2p_timeout_flag.argtypes = [vp, C.POINTER(i32)]
+    lib.nsvgd_p2p_allreduce.argtypes = [vp, i32, i32, pvp, vp, i64, i32]
+    lib.nsvgd_p2p_median_advance.argtypes = [vp, i32, i32, pvp, vp, vp, i32]
+    lib.nsvgd_p2p_median_fast_resolve.argtypes = [vp, i32, i32, pvp, vp, vp, sz, i64, i64, vp]
+    lib.nsvgd_p2p_median_fast_advance2.argtypes = [vp, i32, i32, pvp, vp, vp, sz, i64, i64, vp, i32]
+    lib.nsvgd_p2p_apply_update_f32.argtypes = [vp, i32, i32, pvp, vp, vp, i64, i64, i64, i64, vp, f32, i32, f32, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("nsvgd_version", "nsvgd_last_error", "nsvgd_launch_count"):
+        if name == "nsvgd_p2p_block_bytes":
+            fn.restype = sz
+        elif name not in ("nsvgd_version", "nsvgd_last_error", "nsvgd_launch_count"):
             fn.restype = i32
     _lib = lib
     return lib

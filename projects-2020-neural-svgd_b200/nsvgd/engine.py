@@ -107,6 +107,62 @@ def apply_update(Xrows, phi, stats, lr, scaled, lambda_reg, want_grads=False):
     return step_aux, grads
 
 
+def apply_update_p2p(comm, Xrows, phi, stats, lr, scaled, lambda_reg, want_grads=False):
+    """apply_update with the all-reduce of `stats` (float64[4], summed in place in rank order) over peer memory
+    fused into the kernel that derives the step scaling."""
+    m, d = Xrows.shape
+    grads = torch.empty_like(phi) if want_grads else None
+    step_aux = torch.empty(8, dtype=torch.float64, device=Xrows.device)
+    check(load().nsvgd_p2p_apply_update_f32(stream_ptr(Xrows.device), comm.rank, comm.world, comm.blocks, ptr(Xrows), ptr(phi),
+                                            m, d, ld(Xrows), ld(phi), ptr(stats), float(lr), int(bool(scaled)), float(lambda_reg),
+                                            ptr(grads), ptr(step_aux)))
+    return step_aux, grads
+
+
+class PeerComm:
+    """Peer-mapped blocks for the fused small all-reduces (csrc/p2p.cuh): one cudaMalloc'ed block per rank, shared
+    through cudaIpc handles that are exchanged with one all-gather of the process group."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        lib = load()
+        own = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        check(lib.nsvgd_p2p_alloc(C.byref(own), handle))            # zero-filled and synchronised
+        self.own = own.value
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=dev)
+        allh = torch.empty(self.world * 64, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=group)         # also orders every rank's zero-fill before any flag write
+        allh = allh.cpu().numpy().tobytes()
+        self.peers = []
+        ptrs = (C.c_void_p * self.world)()
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs[r] = self.own
+                continue
+            pp = C.c_void_p()
+            buf = (C.c_ubyte * 64).from_buffer_copy(allh[64 * r: 64 * r + 64])
+            check(lib.nsvgd_p2p_open(buf, C.byref(pp)))
+            ptrs[r] = pp.value
+            self.peers.append(pp.value)
+        self.blocks = ptrs
+        dist.barrier(group=group)
+
+    def timed_out(self) -> bool:
+        flag = C.c_int(0)
+        check(load().nsvgd_p2p_timeout_flag(self.own, C.byref(flag)))
+        return bool(flag.value)
+
+    def allreduce(self, t: torch.Tensor) -> torch.Tensor:
+        """stand-alone in-place sum (int64 or float64 tensors of <= 8192 elements)"""
+        assert t.is_cuda and t.is_contiguous() and t.dtype in (torch.int64, torch.float64) and t.numel() <= 8192
+        check(load().nsvgd_p2p_allreduce(stream_ptr(t.device), self.rank, self.world, self.blocks, ptr(t), t.numel(),
+                                         int(t.dtype == torch.float64)))
+        return t
+
+
 def ksd(X, Sx, h, variant="v", Y=None, Sy=None) -> torch.Tensor:
     """KSD^2 closed form (stein.py:273-349) -> 0-dim float64 device tensor."""
     X = require_cuda_f32(X, "X").contiguous(); Sx = require_cuda_f32(Sx, "Sx").contiguous()
@@ -153,7 +209,11 @@ class MedianSelect:
         n, d = x.shape
         self.n = n
         self.state = torch.zeros(_lib.SELECT_STATE_BYTES, dtype=torch.uint8, device=x.device)
-        self.hist = torch.zeros(2 * _lib.SELECT_BINS, dtype=torch.int64, device=x.device)
+        # [select histogram (2 targets) | fallback-select histogram (2 targets)]: contiguous so that a row-sharded
+        # run reduces both with ONE all-reduce per radix pass
+        self.hist_all = torch.zeros(4 * _lib.SELECT_BINS, dtype=torch.int64, device=x.device)
+        self.hist = self.hist_all[: 2 * _lib.SELECT_BINS]
+        self.hist_fb = self.hist_all[2 * _lib.SELECT_BINS:]
         dz_max = d if n > d else n - 1
         self.Z = torch.empty((n, dz_max), dtype=torch.float32, device=x.device) if mode == "literal" else None
         dz, w = C.c_int64(0), C.c_float(0)
@@ -212,13 +272,28 @@ class MedianSelect:
     def fallback_hist(self, p: int, tile_row_start=0, tile_row_stride=1) -> torch.Tensor:
         ws = self._fws()
         check(load().nsvgd_median_fallback_hist(stream_ptr(self.x.device), ptr(self.P), self.n, self.dz, ld(self.P), self.w_last,
-                                                tile_row_start, tile_row_stride, ptr(self.state), ptr(ws), ws.numel(), p, ptr(self.hist)))
-        return self.hist
+                                                tile_row_start, tile_row_stride, ptr(self.state), ptr(ws), ws.numel(), p, ptr(self.hist_fb)))
+        return self.hist_fb
 
     def fallback_advance(self, p: int):
         ws = self._fws()
         check(load().nsvgd_median_fallback_advance(stream_ptr(self.x.device), ptr(self.state), ptr(ws), ws.numel(), self.n, self.dz,
-                                                   ptr(self.hist), p))
+                                                   ptr(self.hist_fb), p))
+
+    # ---- peer-memory variants: the all-reduce happens inside the consumer kernel (include/nsvgd.h, csrc/p2p.cuh) ----
+    def p2p_fast_resolve(self, comm):
+        ws = self._fws()
+        check(load().nsvgd_p2p_median_fast_resolve(stream_ptr(self.x.device), comm.rank, comm.world, comm.blocks, ptr(self.state),
+                                                   ptr(ws), ws.numel(), self.n, self.dz, ptr(self.reduce)))
+
+    def p2p_fast_advance2(self, comm, p: int):
+        ws = self._fws()
+        check(load().nsvgd_p2p_median_fast_advance2(stream_ptr(self.x.device), comm.rank, comm.world, comm.blocks, ptr(self.state),
+                                                    ptr(ws), ws.numel(), self.n, self.dz, ptr(self.hist_all), p))
+
+    def p2p_advance(self, comm, p: int):
+        check(load().nsvgd_p2p_median_advance(stream_ptr(self.x.device), comm.rank, comm.world, comm.blocks, ptr(self.state),
+                                              ptr(self.hist), p))
 
     def hist_pass(self, p: int, tile_row_start=0, tile_row_stride=1) -> torch.Tensor:
         check(load().nsvgd_median_hist_pass(stream_ptr(self.x.device), ptr(self.P), self.n, self.dz, ld(self.P), self.w_last,

@@ -24,7 +24,11 @@ def row_partition(n: int, world: int, rank: int):
 
 
 class ShardedSVGD:
-    def __init__(self, n: int, d: int, group=None, median_mode: str = "literal", engine=None):
+    def __init__(self, n: int, d: int, group=None, median_mode: str = "literal", engine=None, p2p="auto"):
+        """p2p: "auto" -> the small all-reduces (select histograms, counts, KSD/l2 sums) run over NVLink peer memory
+        inside their consumer kernels (csrc/p2p.cuh) when the CUDA engine is used and every rank could map its peers;
+        "off" -> NCCL all-reduces; "on" -> peer memory or raise."""
+        real_engine = engine is None
         if engine is None:
             from . import engine as _engine
             engine = _engine
@@ -37,6 +41,22 @@ class ShardedSVGD:
         self.r0, self.r1 = row_partition(n, self.world, self.rank)
         self.max_rows = row_partition(n, self.world, 0)[1]
         self._buf = {}
+        self.comm = None
+        import os
+        if p2p == "auto" and os.environ.get("NSVGD_P2P", "1") == "0":
+            p2p = "off"
+        if p2p != "off" and real_engine and self.world > 1 and torch.cuda.is_available():
+            ok, err = 1, None
+            try:
+                self.comm = engine.PeerComm(group)
+            except Exception as e:          # cudaIpc not permitted in this container, no peer access, ...
+                ok, err = 0, e
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)      # all ranks take the same path
+            if int(flag.item()) == 0:
+                self.comm = None
+                if p2p == "on":
+                    raise RuntimeError(f"peer-memory communicator unavailable: {err}")
 
     # ---- collectives -----------------------------------------------------------------------------
     def all_gather_rows(self, local: torch.Tensor, tag: str) -> torch.Tensor:
@@ -68,20 +88,33 @@ class ShardedSVGD:
             full, mine = sel.fast_sample(self.rank if nparts > 1 else 0, nparts)
             if nparts > 1:
                 dist.all_gather_into_tensor(full, mine, group=self.group)
-            dist.all_reduce(sel.fast_stage1(self.rank, self.world), **sum_)
-            sel.fast_resolve()
+            red = sel.fast_stage1(self.rank, self.world)
+            if self.comm is not None:
+                sel.p2p_fast_resolve(self.comm)                      # all-reduce(red) fused into the resolve kernel
+            else:
+                dist.all_reduce(red, **sum_)
+                sel.fast_resolve()
+            # per radix pass ONE exchange of [candidate histogram | fallback histogram]: the conditional SIMT
+            # fallback (kernels return at once unless the device-side flag is set) rides along with the
+            # candidate select instead of costing three more collectives
             for p in range(3):
-                dist.all_reduce(sel.fast_cand_hist(p), **sum_)
-                sel.fast_cand_advance(p)
+                sel.fast_cand_hist(p)
+                sel.fallback_hist(p, self.rank, self.world)
+                if self.comm is not None:
+                    sel.p2p_fast_advance2(self.comm, p)              # all-reduce + both decisions in one kernel
+                else:
+                    dist.all_reduce(sel.hist_all, **sum_)
+                    sel.fast_cand_advance(p)
+                    sel.fallback_advance(p)
             sel.fast_commit()
-            for p in range(3):      # conditional SIMT fallback: kernels return at once unless flagged
-                dist.all_reduce(sel.fallback_hist(p, self.rank, self.world), **sum_)
-                sel.fallback_advance(p)
             return sel.finish()
         for p in range(3):
             hist = sel.hist_pass(p, tile_row_start=self.rank, tile_row_stride=self.world)
-            dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
-            sel.advance(p)
+            if self.comm is not None:
+                sel.p2p_advance(self.comm, p)
+            else:
+                dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
+                sel.advance(p)
         return sel.finish()
 
     # ---- one step --------------------------------------------------------------------------------
@@ -91,8 +124,12 @@ class ShardedSVGD:
         S_all = self.all_gather_rows(S_local, "S")
         h = bandwidth if bandwidth else self.median_heuristic(X_all)      # truthiness as in models.py:657
         phi, stats = self.engine.phistar(X_local, X_all, S_all, h, Sq=S_local, stats=True)
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)
-        step_aux, grads = self.engine.apply_update(X_local, phi, stats, lr, scaled, lambda_reg, want_grads=want_grads)
+        if self.comm is not None:
+            step_aux, grads = self.engine.apply_update_p2p(self.comm, X_local, phi, stats, lr, scaled, lambda_reg,
+                                                           want_grads=want_grads)
+        else:
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.group)
+            step_aux, grads = self.engine.apply_update(X_local, phi, stats, lr, scaled, lambda_reg, want_grads=want_grads)
         return h, step_aux, grads
 
     # ---- the same step as ONE CUDA graph --------------------------------------------------------

@@ -24,7 +24,10 @@ for n, d, mode in ((8192, 128, "literal"), (3000, 7, "offdiag"), (9001, 100, "fu
     h, aux, _ = sh.step(Xl, Sl, 1e-2, scaled=True, lambda_reg=0.5)
     same_h = h.item() == h_ref.item()
     err = (Xl - Xs[r0:r1]).norm().item() / Xs[r0:r1].norm().item()
-    print(f"rank {rank} n={n} d={d} {mode}: h bit-identical={same_h} ({h.item():.7f}) X rel err={err:.2e}", flush=True)
+    p2p = sh.comm is not None
+    tmo = sh.comm.timed_out() if p2p else False
+    print(f"rank {rank} n={n} d={d} {mode}: h bit-identical={same_h} ({h.item():.7f}) X rel err={err:.2e} peer-memory={p2p} timeout={tmo}", flush=True)
+    ok = ok and not tmo
     ok = ok and same_h and err < 2e-6
 # the same step captured as ONE CUDA graph (collectives included), replayed three times
 n, d, mode = 8192, 128, "literal"
@@ -46,7 +49,18 @@ for i in range(3):
     h, aux = g.replay()
     same = same and (h.item() == hs[i].item())
 err = (Xl - Xs[r0:r1]).norm().item() / Xs[r0:r1].norm().item()
-print(f"rank {rank} graphed x3: h bit-identical={same} X rel err={err:.2e}", flush=True)
+print(f"rank {rank} graphed x3: h bit-identical={same} X rel err={err:.2e} peer-memory={sh.comm is not None}", flush=True)
+if sh.comm is not None:
+    # stand-alone peer-memory all-reduce: integers and doubles (fixed rank order)
+    t = torch.arange(5000, dtype=torch.int64, device="cuda") * (rank + 1)
+    sh.comm.allreduce(t)
+    exp = torch.arange(5000, dtype=torch.int64, device="cuda") * (world * (world + 1) // 2)
+    f = torch.full((7,), 0.1 * (rank + 1), dtype=torch.float64, device="cuda")
+    sh.comm.allreduce(f)
+    fe = sum(0.1 * (r + 1) for r in range(world))
+    good = bool((t == exp).all()) and abs(f[0].item() - fe) < 1e-15 and not sh.comm.timed_out()
+    print(f"rank {rank} p2p allreduce int/double ok={good}", flush=True)
+    ok = ok and good
 ok = ok and same and err < 2e-6
 torch.cuda.synchronize()
 del g
