@@ -89,28 +89,35 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
       const int64_t row = r0 + rr;
       const bool rv = row < n;
       float acc_n = 0.f, acc_c = 0.f;
-      for (int c = lane; c < dp; c += 32) {
-        float v = 0.f, tv = 0.f;
-        if (rv && c < d) {
-          if (half == 0) {
-            v = X[row * ldx + c] - mu[c];
-            if (c == d - 1) v *= last_scale;
-            acc_n = fmaf(v, v, acc_n);
-            if (S) {
-              const float sv = S[row * ldx + c];
-              acc_c = fmaf(sv, v, acc_c);
-              if (combine) tv = fmaf(-v, inv_h2, sv);
+      // two adjacent columns per lane: packed bf16x2 (4-byte) stores, 128 bytes per warp store
+      for (int c0 = 2 * lane; c0 < dp; c0 += 64) {
+        float v2[2] = {0.f, 0.f}, t2[2] = {0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = c0 + e;
+          float v = 0.f, tv = 0.f;
+          if (rv && c < d) {
+            if (half == 0) {
+              v = X[row * ldx + c] - mu[c];
+              if (c == d - 1) v *= last_scale;
+              acc_n = fmaf(v, v, acc_n);
+              if (S) {
+                const float sv = S[row * ldx + c];
+                acc_c = fmaf(sv, v, acc_c);
+                if (combine) tv = fmaf(-v, inv_h2, sv);
+              }
+            } else {
+              v = S[row * ldx + c];
             }
-          } else {
-            v = S[row * ldx + c];
           }
+          v2[e] = v; t2[e] = combine ? tv : v;
         }
-        T[rr][c] = combine ? tv : v;
+        T[rr][c0] = t2[0]; T[rr][c0 + 1] = t2[1];
         if (half == 0) {
-          const __nv_bfloat16 b0 = __float2bfloat16_rn(v);
-          const __nv_bfloat16 b1 = __float2bfloat16_rn(v - __bfloat162float(b0));
-          Xb0[row * dp + c] = b0;
-          Xb1[row * dp + c] = b1;
+          const uint32_t p0 = pack_bf16x2(v2[0], v2[1]);
+          const uint32_t p1 = pack_bf16x2(v2[0] - bf16lo_to_float(p0), v2[1] - bf16hi_to_float(p0));
+          *reinterpret_cast<uint32_t*>(&Xb0[row * dp + c0]) = p0;
+          *reinterpret_cast<uint32_t*>(&Xb1[row * dp + c0]) = p1;
         }
       }
       if (half == 0) {
