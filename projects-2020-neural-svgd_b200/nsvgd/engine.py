@@ -126,16 +126,16 @@ class PeerComm:
     def __init__(self, group=None):
         import torch.distributed as dist
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        dev = torch.device("cuda", torch.cuda.current_device())
         lib = load()
         own = C.c_void_p()
         handle = (C.c_ubyte * 64)()
         check(lib.nsvgd_p2p_alloc(C.byref(own), handle))            # zero-filled and synchronised
         self.own = own.value
-        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=dev)
-        allh = torch.empty(self.world * 64, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(allh, mine, group=group)         # also orders every rank's zero-fill before any flag write
-        allh = allh.cpu().numpy().tobytes()
+        # handles travel as python objects: works on every backend (nccl, gloo) and also orders every rank's zero-fill
+        # before any peer can write a flag
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        allh = b"".join(handles)
         self.peers = []
         ptrs = (C.c_void_p * self.world)()
         for r in range(self.world):

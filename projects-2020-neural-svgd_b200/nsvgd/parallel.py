@@ -51,9 +51,9 @@ class ShardedSVGD:
                 self.comm = engine.PeerComm(group)
             except Exception as e:          # cudaIpc not permitted in this container, no peer access, ...
                 ok, err = 0, e
-            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)      # all ranks take the same path
-            if int(flag.item()) == 0:
+            oks = [None] * self.world
+            dist.all_gather_object(oks, ok, group=group)                  # all ranks take the same path
+            if min(oks) == 0:
                 self.comm = None
                 if p2p == "on":
                     raise RuntimeError(f"peer-memory communicator unavailable: {err}")
@@ -85,6 +85,8 @@ class ShardedSVGD:
             # tensor-core filtered select: the bracket is identical on every rank (deterministic sample of
             # the gathered particles); counts and candidate histograms are all-reduced between the stages.
             nparts = self.world if (1 << 22) % self.world == 0 and ((1 << 22) // self.world) % 32 == 0 else 1
+            if dist.get_backend(self.group) != "nccl":
+                nparts = 1          # device-tensor all-gather needs NCCL; every rank then samples everything
             full, mine = sel.fast_sample(self.rank if nparts > 1 else 0, nparts)
             if nparts > 1:
                 dist.all_gather_into_tensor(full, mine, group=self.group)

@@ -269,7 +269,7 @@ def test_fast_median_staged_two_ranks_on_one_gpu(mode):
     for p in range(3):
         hist = sum(s.fallback_hist(p, r, 2).clone() for r, s in enumerate(sels))
         for s in sels:
-            s.hist.copy_(hist); s.fallback_advance(p)
+            s.hist_fb.copy_(hist); s.fallback_advance(p)
     for s in sels:
         got = s.finish().cpu().numpy()[0]
         assert np.float32(got).tobytes() == np.float32(want).tobytes()
