@@ -50,7 +50,8 @@ typedef enum {
   NSVGD_PATH_AUTO = 0,
   NSVGD_PATH_SIMT = 1,       /* small-d direct-difference FP32/MUFU kernel (d <= 32) */
   NSVGD_PATH_TC = 2,         /* fused tcgen05/TMEM kernel, bf16 hi/lo split, 3 MMA passes (d <= 128) */
-  NSVGD_PATH_GENERIC = 3     /* any d: K row-chunks materialised in ws + SIMT GEMM */
+  NSVGD_PATH_GENERIC = 3,    /* any d: K row-chunks materialised in ws + SIMT GEMM */
+  NSVGD_PATH_LARGE = 4       /* d > 128: cuBLAS bf16 tensor-op GEMMs (2-piece split, 3 passes) around a fused pair kernel */
 } nsvgd_path;
 
 typedef enum {

@@ -73,20 +73,24 @@ static int choose_path(int path, int64_t n, int64_t m, int64_t d) {
       if (!strcmp(env, "simt")) path = NSVGD_PATH_SIMT;
       else if (!strcmp(env, "tc")) path = NSVGD_PATH_TC;
       else if (!strcmp(env, "generic")) path = NSVGD_PATH_GENERIC;
+      else if (!strcmp(env, "large")) path = NSVGD_PATH_LARGE;
     }
   }
   if (path != NSVGD_PATH_AUTO) return path;
   if (d <= 32) return NSVGD_PATH_SIMT;
   if (d <= 128 && n >= 1024 && m >= 256) return NSVGD_PATH_TC;
+  if (d > 128 && n >= 1024 && m >= 256) return NSVGD_PATH_LARGE;
   return NSVGD_PATH_GENERIC;
 }
 
 static int phi_dispatch(cudaStream_t st, const PhiArgs& a, int path, void* ws, size_t ws_bytes, bool dry, size_t* need) {
-  const int p = choose_path(path, a.n, a.m, a.d);
+  int p = choose_path(path, a.n, a.m, a.d);
+  if (p == NSVGD_PATH_LARGE && a.aux && path == NSVGD_PATH_AUTO) p = NSVGD_PATH_GENERIC;   // aux split: generic path
   switch (p) {
     case NSVGD_PATH_SIMT: return phi_simt(st, a, ws, ws_bytes, dry, need);
     case NSVGD_PATH_TC: return phi_tc(st, a, ws, ws_bytes, dry, need);
     case NSVGD_PATH_GENERIC: return phi_generic(st, a, ws, ws_bytes, dry, need);
+    case NSVGD_PATH_LARGE: return phi_large(st, a, ws, ws_bytes, dry, need);
     default: set_error("phi: bad path %d", path); return NSVGD_ERR_INVALID;
   }
 }
@@ -139,7 +143,7 @@ extern "C" int nsvgd_phi_f32(void* stream, const float* Q, const float* Sq, int6
   NSVGD_PROPAGATE(check_phi_shapes("phi", Q, m, ldq, X, S, n, ldx, d));
   NSVGD_REQUIRE(h_dev && phi && ldphi >= d, NSVGD_ERR_INVALID, "phi: null h_dev/phi or ldphi < d");
   NSVGD_REQUIRE(!stats_dev || Sq, NSVGD_ERR_INVALID, "phi: stats need the scores at the queries (Sq)");
-  NSVGD_REQUIRE(path >= 0 && path <= 3, NSVGD_ERR_INVALID, "phi: bad path %d", path);
+  NSVGD_REQUIRE(path >= 0 && path <= 4, NSVGD_ERR_INVALID, "phi: bad path %d", path);
   NSVGD_REQUIRE(ws, NSVGD_ERR_WORKSPACE, "phi: null workspace");
   NSVGD_PROPAGATE(have_device());
   PhiArgs a{Q, Sq, m, ldq, X, S, n, ldx, d, h_dev, phi, ldphi, aux, stats_dev};
@@ -154,7 +158,7 @@ extern "C" int nsvgd_step_sgd_f32(void* stream, float* X, const float* S, int64_
                                   double* step_aux_dev, int path, void* ws, size_t ws_bytes) {
   NSVGD_PROPAGATE(check_phi_shapes("step", X, n, ldx, X, S, n, ldx, d));
   NSVGD_REQUIRE(h_dev && step_aux_dev && ws, NSVGD_ERR_INVALID, "step: null pointer");
-  NSVGD_REQUIRE(path >= 0 && path <= 3, NSVGD_ERR_INVALID, "step: bad path %d", path);
+  NSVGD_REQUIRE(path >= 0 && path <= 4, NSVGD_ERR_INVALID, "step: bad path %d", path);
   NSVGD_PROPAGATE(have_device());
   WsCarver w(ws, ws_bytes);
   float* phi = w.take<float>((size_t)(n * d));
@@ -179,10 +183,11 @@ extern "C" int nsvgd_workspace_bytes(int op, int64_t n, int64_t m, int64_t d, in
     a.m = mm; a.n = n; a.d = d; a.ldq = d; a.ldx = d; a.ldphi = d;
     size_t best = 0;
     const int p0 = path == NSVGD_PATH_AUTO ? NSVGD_PATH_SIMT : path;
-    const int p1 = path == NSVGD_PATH_AUTO ? NSVGD_PATH_GENERIC : path;
+    const int p1 = path == NSVGD_PATH_AUTO ? NSVGD_PATH_LARGE : path;
     for (int p = p0; p <= p1; ++p) {
       if (p == NSVGD_PATH_SIMT && d > 32) continue;
       if (p == NSVGD_PATH_TC && d > 128) continue;
+      if (p == NSVGD_PATH_LARGE && d <= 128 && path == NSVGD_PATH_AUTO) continue;
       size_t s = 0;
       if (phi_dispatch(nullptr, a, p, nullptr, 0, true, &s) == NSVGD_OK) best = std::max(best, s);
     }

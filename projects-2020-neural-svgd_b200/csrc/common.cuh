@@ -155,6 +155,7 @@ struct PhiArgs {
 int phi_simt(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dry, size_t* need);
 int phi_generic(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dry, size_t* need);
 int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dry, size_t* need);
+int phi_large(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dry, size_t* need);
 
 // column mean (phi_generic.cu): deterministic two-stage; part needs colmean_partials(n,d) doubles
 int launch_colmean(cudaStream_t st, const float* X, int64_t n, int64_t d, int64_t ldx, double* part, float* mu);

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libnsvgd.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_WORKSPACE = range(5)
 MEDIAN_MODES = {"literal": 0, "offdiag": 1, "full": 2}
-PATHS = {"auto": 0, "simt": 1, "tc": 2, "generic": 3}
+PATHS = {"auto": 0, "simt": 1, "tc": 2, "generic": 3, "large": 4}
 OPS = {"median": 0, "phi": 1, "ksd": 2, "mmd": 3, "step": 4}
 KSD_VARIANTS = {"rect": 0, "u": 1, "v": 2}
 SELECT_BINS = 2048

@@ -100,6 +100,7 @@ PATH_CASES = [
     ("simt", 1000, 3, 1.3), ("simt", 333, 1, 0.7), ("simt", 257, 8, 2.0), ("simt", 300, 16, 3.0), ("simt", 130, 31, 4.0),
     ("generic", 700, 50, 5.0), ("generic", 300, 3, 1.3), ("generic", 129, 200, 12.0), ("generic", 64, 1030, 30.0),
     ("tc", 2048, 128, 8.0), ("tc", 1500, 100, 7.0), ("tc", 1024, 64, 5.5), ("tc", 1111, 50, 5.0), ("tc", 4096, 128, 3.0),
+    ("large", 1500, 200, 12.0), ("large", 1100, 515, 20.0), ("large", 4500, 130, 9.0),
 ]
 
 
@@ -113,8 +114,14 @@ def test_phi_paths_vs_oracle(path, n, d, h):
     m = 77
     Q = (np.random.default_rng(1).standard_normal((m, d)) * 0.9 + 0.4).astype(np.float32)
     Xd, Sd, Qd = dev(X), dev(S), dev(Q)
-    phi, aux, stats = engine.phistar(Xd, Xd, Sd, h, Sq=Sd, aux=True, stats=True, path=path)
     ref, ref_aux = so.phistar(X, X, S, h, aux=True)
+    if path == "large":       # cuBLAS path: COMBINED form only (the aux split of d > 128 is served by "generic")
+        with pytest.raises(NotImplementedError):
+            engine.phistar(Xd, Xd, Sd, h, Sq=Sd, aux=True, stats=True, path=path)
+        phi, stats = engine.phistar(Xd, Xd, Sd, h, Sq=Sd, stats=True, path=path)
+        _, aux = engine.phistar(Xd, Xd, Sd, h, aux=True)            # auto dispatch falls back to generic for aux
+    else:
+        phi, aux, stats = engine.phistar(Xd, Xd, Sd, h, Sq=Sd, aux=True, stats=True, path=path)
     assert rel_fro(phi.cpu(), ref) < TOL, rel_fro(phi.cpu(), ref)
     assert max_row_rel(phi.cpu(), ref) < 10 * TOL
     assert rel_fro(aux.cpu(), ref_aux) < TOL
