@@ -91,13 +91,35 @@ size_t median_fast_workspace(int64_t n, int64_t dz) {
 // ---------------------------------------------------------------------------- exact pair distance, vectorised loads
 __device__ __forceinline__ float exact_pair_sqdist_v4(const float* __restrict__ a, const float* __restrict__ b, int d,
                                                       float w_last) {
+  // Loads are issued in batches of 8 float4 per row BEFORE the (inherently sequential) defined-order adds: the kernel
+  // is latency-bound (ncu: issue 12 %, L2 26 %), and one round trip per 4 coordinates cost 32 serial L2 latencies per
+  // pair; batching makes it 4.  The arithmetic and its order are unchanged (bit-exact contract).
+  // Only the last float4 group (or the scalar tail) can hold the weighted coordinate d-1: the batched groups need no
+  // per-element test.
   float acc = 0.f;
   const int dm = d - 1;            // coordinates [0, dm) unweighted, dm weighted
   const int groups = d >> 2;
+  const int plain = (d & 3) ? groups : groups - 1;     // float4 groups made of unweighted coordinates only
   float last_diff = 0.f;
-  for (int g = 0; g < groups; ++g) {
-    const float4 av = __ldg(reinterpret_cast<const float4*>(a) + g);
-    const float4 bv = __ldg(reinterpret_cast<const float4*>(b) + g);
+  constexpr int B = 8;
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  int g0 = 0;
+  for (; g0 + B <= plain; g0 += B) {
+    float4 av[B], bv[B];
+#pragma unroll
+    for (int u = 0; u < B; ++u) { av[u] = __ldg(a4 + g0 + u); bv[u] = __ldg(b4 + g0 + u); }
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      const float d0 = av[u].x - bv[u].x, d1 = av[u].y - bv[u].y, d2 = av[u].z - bv[u].z, d3 = av[u].w - bv[u].w;
+      acc = __fadd_rn(acc, __fmul_rn(d0, d0));
+      acc = __fadd_rn(acc, __fmul_rn(d1, d1));
+      acc = __fadd_rn(acc, __fmul_rn(d2, d2));
+      acc = __fadd_rn(acc, __fmul_rn(d3, d3));
+    }
+  }
+  for (int g = g0; g < groups; ++g) {
+    const float4 av = __ldg(a4 + g), bv = __ldg(b4 + g);
     const float da[4] = {av.x - bv.x, av.y - bv.y, av.z - bv.z, av.w - bv.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -587,7 +609,7 @@ __global__ void __launch_bounds__(32 * WX_WARPS) exact_list_warp_kernel(const fl
   if (threadIdx.x == 0 && sh_below) atomicAdd(&fs->below, (unsigned long long)sh_below);
 }
 
-__global__ void __launch_bounds__(256) exact_list_kernel(const float* __restrict__ P, int d, int64_t ldp, float w_last,
+__global__ void __launch_bounds__(256, 2) exact_list_kernel(const float* __restrict__ P, int d, int64_t ldp, float w_last,
                                                          int vec, FastMedState* fs, const unsigned long long* __restrict__ list,
                                                          const uint32_t* __restrict__ list_counts, uint32_t list_cap,
                                                          float* __restrict__ cand, uint32_t* cand_counts, uint32_t cand_cap,
@@ -612,6 +634,104 @@ __global__ void __launch_bounds__(256) exact_list_kernel(const float* __restrict
         const unsigned long long e = seg_list[t];
         const int64_t i = (int64_t)(e >> 32), j = (int64_t)(e & 0xFFFFFFFFull);
         dv = exact_pair(P, ldp, i, j, d, w_last, vec != 0);
+        if (dv != dv) any_nan = true;
+        else if (dv < Lv) ++below;
+        else if (dv <= Uv) is_cand = true;
+      }
+      const uint32_t ball = __ballot_sync(0xffffffffu, is_cand);
+      if (ball) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&cand_counts[seg * MF_CSTRIDE], (uint32_t)__popc(ball));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (is_cand) {
+          const uint32_t pos = base + __popc(ball & ((1u << lane) - 1u));
+          if (pos < cand_cap) seg_cand[pos] = dv;
+        }
+      }
+    }
+  }
+  if (any_nan) atomicOr(&main_state->nan_flag, 1u);
+  if (below) atomicAdd(&sh_below, below);
+  __syncthreads();
+  if (threadIdx.x == 0 && sh_below) atomicAdd(&fs->below, (unsigned long long)sh_below);
+}
+
+// Slice-cooperative exact evaluation of the listed pairs.  exact_list_kernel (one thread per pair, each lane walking its
+// own two rows) is bound by the L1 tag stage: every LDG.128 of a warp touches 32 different lines and each line is looked up
+// 8 times (ncu: l1tex throughput 85 %, L2 26 %, issue 12 %; profiles/r01_ncu_exact_final.txt).  Here a warp takes 32 pairs
+// and moves their 64 rows through shared memory one 128-byte column slice at a time: 8 lanes read one line of one row
+// (one lookup per line, 16 loads in flight per lane), the slice is parked in two padded 32 x 32 tiles, and lane p then
+// adds pair p's 32 terms of the slice in the DEFINED sequential order (same arithmetic, bit-identical results).
+// Requires d % 4 == 0, ldp % 4 == 0, 16-byte aligned rows, d <= 128.
+constexpr int XL_STRIDE = 36;                         // floats per tile row: 32 + 4 pad -> conflict-free LDS.128 / STS.128
+constexpr int XL_TILE = 32 * XL_STRIDE;
+constexpr int XL_SMEM = 8 * 2 * XL_TILE * (int)sizeof(float);
+__global__ void __launch_bounds__(256, 2) exact_list_coop_kernel(const float* __restrict__ P, int d, int64_t ldp, float w_last,
+                                                                 FastMedState* fs, const unsigned long long* __restrict__ list,
+                                                                 const uint32_t* __restrict__ list_counts, uint32_t list_cap,
+                                                                 float* __restrict__ cand, uint32_t* cand_counts, uint32_t cand_cap,
+                                                                 SelectState* main_state) {
+  extern __shared__ __align__(16) float xl_smem[];
+  __shared__ unsigned int sh_below;
+  if (threadIdx.x == 0) sh_below = 0u;
+  __syncthreads();
+  const float Lv = fs->L, Uv = fs->U;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r = lane >> 3, q = lane & 7;              // cooperative loads: 8 lanes per row, 4 rows per instruction
+  float* tA = xl_smem + w * 2 * XL_TILE;
+  float* tB = tA + XL_TILE;
+  const int nslices = (d + 31) >> 5;
+  const int last_group = (d >> 2) - 1;                // the float4 group that holds the weighted coordinate d-1
+  uint32_t below = 0;
+  bool any_nan = false;
+  for (int seg = blockIdx.y; seg < MF_NSEG; seg += gridDim.y) {
+    const uint32_t count = min(list_counts[seg * MF_CSTRIDE], list_cap);
+    const unsigned long long* seg_list = list + (size_t)seg * list_cap;
+    float* seg_cand = cand + (size_t)seg * cand_cap;
+    for (uint32_t t0 = (blockIdx.x * 256u + threadIdx.x) & ~31u; t0 < count; t0 += gridDim.x * 256u) {
+      const uint32_t t = t0 + lane;
+      const unsigned long long e = seg_list[min(t, count - 1u)];      // idle lanes shadow the last pair (valid rows)
+      const uint32_t i = (uint32_t)(e >> 32), j = (uint32_t)(e & 0xFFFFFFFFull);
+      uint32_t ia[8], jb[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        ia[u] = __shfl_sync(0xffffffffu, i, 4 * u + r);
+        jb[u] = __shfl_sync(0xffffffffu, j, 4 * u + r);
+      }
+      float acc = 0.f, last_diff = 0.f;
+      for (int sl = 0; sl < nslices; ++sl) {
+        const int col = 32 * sl + 4 * q;
+        const bool inb = col < d;
+        float4 va[8], vb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          va[u] = inb ? __ldg(reinterpret_cast<const float4*>(P + (int64_t)ia[u] * ldp + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          vb[u] = inb ? __ldg(reinterpret_cast<const float4*>(P + (int64_t)jb[u] * ldp + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();                                  // the previous slice has been consumed
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          *reinterpret_cast<float4*>(tA + (4 * u + r) * XL_STRIDE + 4 * q) = va[u];
+          *reinterpret_cast<float4*>(tB + (4 * u + r) * XL_STRIDE + 4 * q) = vb[u];
+        }
+        __syncwarp();
+        const int kmax = min(8, (d - 32 * sl) >> 2);
+        for (int k = 0; k < kmax; ++k) {
+          const float4 a4 = *reinterpret_cast<const float4*>(tA + lane * XL_STRIDE + 4 * k);
+          const float4 b4 = *reinterpret_cast<const float4*>(tB + lane * XL_STRIDE + 4 * k);
+          const float d0 = a4.x - b4.x, d1 = a4.y - b4.y, d2 = a4.z - b4.z, d3 = a4.w - b4.w;
+          acc = __fadd_rn(acc, __fmul_rn(d0, d0));
+          acc = __fadd_rn(acc, __fmul_rn(d1, d1));
+          acc = __fadd_rn(acc, __fmul_rn(d2, d2));
+          if (8 * sl + k != last_group) acc = __fadd_rn(acc, __fmul_rn(d3, d3));
+          else last_diff = d3;
+        }
+      }
+      float tl = __fmul_rn(last_diff, last_diff);
+      tl = __fmul_rn(w_last, tl);
+      const float dv = __fadd_rn(acc, tl);
+      bool is_cand = false;
+      if (t < count) {
         if (dv != dv) any_nan = true;
         else if (dv < Lv) ++below;
         else if (dv <= Uv) is_cand = true;
@@ -816,7 +936,16 @@ int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   prof_begin(5, st);
   // listed pairs come out of the filter grouped by row quarter and tile, so the one-thread-per-pair
   // gather re-uses rows through L1 and beats the warp-cooperative variant here (1.85 vs 2.5 ms at cfg4)
-  if (vec) {
+  const char* xl_env = getenv("NSVGD_MEDIAN_EXACT");        // "thread": the one-thread-per-pair kernel (A/B measurements)
+  if (vec && dz % 4 == 0 && !(xl_env && xl_env[0] == 't')) {
+    static bool xl_attr = false;
+    if (!xl_attr) {
+      NSVGD_CUDA(cudaFuncSetAttribute(exact_list_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XL_SMEM));
+      xl_attr = true;
+    }
+    exact_list_coop_kernel<<<dim3((unsigned)std::max(1, sms * 8 / MF_NSEG), MF_NSEG), 256, XL_SMEM, st>>>(
+        P, (int)dz, ldp, w_last, f.fs, f.list, f.list_counts, f.list_cap, f.cand, f.cand_counts, f.cand_cap, main_state);
+  } else if (vec) {
     exact_list_kernel<<<dim3((unsigned)std::max(1, sms * 8 / MF_NSEG), MF_NSEG), 256, 0, st>>>(
         P, (int)dz, ldp, w_last, vec, f.fs, f.list, f.list_counts, f.list_cap, f.cand, f.cand_counts, f.cand_cap, main_state);
   } else {

@@ -168,7 +168,8 @@ struct TcParams {
 
 constexpr int TC_BM = 128, TC_BN = 64;
 constexpr int TC_DEFAULT_PAIR_WARPS = 8;
-constexpr int TC_MAX_RUN_TILES = 64;   // <= 768 sequential TMEM accumulations per run
+constexpr int TC_MAX_RUN_TILES = 64;   // [S | Xc] form: 12 accumulating MMAs per tile -> <= 768 sequential TMEM accumulations per run
+constexpr int TC_MAX_RUN_TILES_COMBINED = 96;   // COMBINED form: 8 per tile into O -> the same 768
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_O = 0, TM_Q = 256, TM_G = 384, TM_P = 448;   // O 256 | Q 2x64 | G 64 | P 64 (b0 32 + b1 32)
 // ping-pong (PP = 2, COMBINED form only: O needs 128 columns): a second G/P pair in the freed columns
@@ -567,7 +568,7 @@ struct TcPlan {
   int dp; int64_t n_pad, m_pad; int nsplit, tiles_total, tiles_per_split; bool q_is_x;
 };
 
-static TcPlan make_plan(const PhiArgs& a) {
+static TcPlan make_plan(const PhiArgs& a, bool combined) {
   TcPlan pl{};
   pl.dp = a.d <= 64 ? 64 : 128;
   pl.n_pad = round_up(a.n, 128);
@@ -580,7 +581,7 @@ static TcPlan make_plan(const PhiArgs& a) {
   // (2) Occupancy: row blocks x splits CTAs should cover the SMs in whole waves (1 CTA/SM).
   const int sms = device_sm_count();
   const int64_t row_blocks = pl.m_pad / TC_BM;
-  const int min_split = (int)ceil_div(pl.tiles_total, TC_MAX_RUN_TILES);
+  const int min_split = (int)ceil_div(pl.tiles_total, combined ? TC_MAX_RUN_TILES_COMBINED : TC_MAX_RUN_TILES);
   int best = min_split; double best_eff = 0.0;
   for (int s = min_split; s <= min_split + 8; ++s) {
     if (s > pl.tiles_total) break;
@@ -649,9 +650,9 @@ static bool tc_combined(const PhiArgs& a) {
 
 int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dry, size_t* need) {
   if (!dry) NSVGD_REQUIRE(a.d <= 128, NSVGD_ERR_UNSUPPORTED, "phi_tc: tensor-core path supports d <= 128 (d=%lld)", (long long)a.d);
-  const TcPlan pl = make_plan(a);
+  const bool combined = !dry && tc_combined(a);      // dry run sizes for the larger [S | Xc] form (more splits, wider O)
+  const TcPlan pl = make_plan(a, combined);
   const int dp = pl.dp;
-  const bool combined = !dry && tc_combined(a);      // dry run sizes for the larger [S | Xc] form
   const int vc = combined ? dp : 2 * dp;
   WsCarver w(ws, ws_bytes, dry);
   float* mu = w.take<float>((size_t)a.d);
