@@ -27,11 +27,11 @@ namespace nsvgd {
 
 using namespace tc;
 
-constexpr int MF_BM = 128, MF_BN = 64, MF_CHUNK = 64, MF_XSTAGES = 4;
+constexpr int MF_BM = 128, MF_BN = 64, MF_CHUNK = 64, MF_XSTAGES = 3;
 constexpr int MF_CLS_WARPS = 8;                          // classification warps: 2 per TMEM lane quarter
 constexpr int MF_THREADS = 64 + 32 * MF_CLS_WARPS;
 constexpr int MF_NVEC = 4;                               // ring of per-tile |z_j|^2 vectors
-constexpr int MF_STAGE = 256;                            // per-warp staging buffer (uncertain pairs) in shared memory
+constexpr int MF_STAGE = 128;                            // per-warp staging buffer (uncertain pairs) in shared memory
 constexpr uint32_t MF_SAMPLES = 1u << 22;
 constexpr int MF_NSEG = 64;          // independent append segments (one atomic counter per 128-byte line)
 constexpr int MF_CSTRIDE = 32;       // counter stride in uint32
@@ -292,6 +292,7 @@ __global__ void bracket_set_kernel(FastMedState* fs, const SelectState* bracket,
 
 // ---------------------------------------------------------------------------- the tensor-core filter
 struct MfParams {
+  const uint32_t* Qb0; const uint32_t* Qb1;   // centred bf16 pieces [n_pad x DP] viewed as packed pairs (query block -> TMEM)
   const float* zn; const float* zlo; const float* zhi;
   int64_t n;
   int n_tiles;                 // n_pad / 64
@@ -308,19 +309,23 @@ struct MfSmem {
   static constexpr int KH = DP / 64;
   static constexpr int QSLAB = MF_BM * 128;
   static constexpr int XSLAB = MF_BN * 128;
-  static constexpr int Q_BYTES = 2 * KH * QSLAB;
+  // The 128-row query block lives in TENSOR MEMORY (A operand of tcgen05.mma TS, as in phi_tc.cu): shared memory holds
+  // only the 3-stage ring of column tiles, 107 KB per CTA, so TWO CTAs share an SM (256 TMEM columns each) and one CTA's
+  // TMEM read + classification overlaps the other's MMAs.
   static constexpr int X_STAGE_BYTES = 2 * KH * XSLAB;
-  static constexpr int OFF_X = Q_BYTES;
+  static constexpr int OFF_X = 0;
   static constexpr int OFF_VEC = OFF_X + MF_XSTAGES * X_STAGE_BYTES;
   static constexpr int OFF_STAGE = OFF_VEC + MF_NVEC * 2 * MF_BN * 4;
   static constexpr int OFF_BAR = OFF_STAGE + MF_CLS_WARPS * MF_STAGE * 8;
   static constexpr int NBARS = 1 + 2 * MF_XSTAGES + 2 * MF_NVEC + 4;
   static constexpr int DYN_BYTES = OFF_BAR + NBARS * 8 + 16 + 1024;
-  static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
+  static_assert(2 * (DYN_BYTES + 1024) <= 232448, "two CTAs per SM must fit");
 };
 
+constexpr uint32_t MF_TMEM_COLS = 256, MF_TM_Q = 128;   // G double buffer [0,128) | Q piece b0 [128,192) | Q piece b1 [192,256)
+
 template <int DP>
-__global__ void __launch_bounds__(MF_THREADS, 1)
+__global__ void __launch_bounds__(MF_THREADS, 2)
 median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                         const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                         const MfParams p) {
@@ -335,7 +340,6 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned, stays in the shared address space
-  uint8_t* sQ = smem;
   uint8_t* sX = smem + L::OFF_X;
   uint64_t* bars = (uint64_t*)(smem + L::OFF_BAR);
   uint64_t* q_full = bars;
@@ -354,13 +358,13 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
 
   if (threadIdx.x == 0) {
     *abort_s = (*(volatile uint32_t*)p.err_flag) ? 1u : 0u;
-    mbar_init(q_full, 1);
+    mbar_init(q_full, MF_CLS_WARPS);             // query pieces stored to TMEM by the classification warps
     for (int i = 0; i < MF_XSTAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
     for (int i = 0; i < MF_NVEC; ++i) { mbar_init(&n_full[i], 1); mbar_init(&n_empty[i], MF_CLS_WARPS); }
     for (int i = 0; i < 2; ++i) { mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], MF_CLS_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 128); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, MF_TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -369,13 +373,6 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
   if (warp == 0) {
     {
       const bool leader = elect_one();
-      if (leader) {
-        mbar_arrive_expect_tx(q_full, L::Q_BYTES);
-        for (int kh = 0; kh < KH; ++kh) {
-          tma_load_2d(sQ + (0 * KH + kh) * L::QSLAB, &tmA0, q_full, kh * 64, m0);
-          tma_load_2d(sQ + (1 * KH + kh) * L::QSLAB, &tmA1, q_full, kh * 64, m0);
-        }
-      }
       for (int t = 0; t < T; ++t) {
         const int st = t % MF_XSTAGES, u = t / MF_XSTAGES;
         mbar_wait(&x_empty[st], (u & 1) ^ 1, watch, 0x100 + st);
@@ -402,7 +399,7 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     {
       const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(MF_BM, MF_BN);
-      const uint32_t sQ_a = smem_u32(sQ), sX_a = smem_u32(sX);
+      const uint32_t sX_a = smem_u32(sX);
       mbar_wait(q_full, 0, watch, 0x300);
       tc_fence_after();
       for (int t = 0; t < T; ++t) {
@@ -421,11 +418,10 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             const int pb = pass == 1 ? 1 : 0;
 #pragma unroll
             for (int kh = 0; kh < KH; ++kh) {
-              const uint64_t ad = umma_desc_sw128(sQ_a + (pa * KH + kh) * L::QSLAB);
               const uint64_t bd = umma_desc_sw128(xs + (pb * KH + kh) * L::XSLAB);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                umma_ss(d_tm, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 32), idesc, acc);
+                umma_ts(d_tm, tmem + MF_TM_Q + pa * 64 + (kh * 4 + ks) * 8, umma_desc_advance(bd, ks * 32), idesc, acc);
                 acc = 1;
               }
             }
@@ -443,6 +439,29 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int64_t gi = (int64_t)m0 + row_in_tile;
+    {
+      // the CTA's 128 query rows (two bf16 pieces) -> TMEM, once: A operand of every Gram MMA
+      constexpr int QW = DP / 4;                       // packed words per thread and piece (2 column halves per row)
+      const int64_t qoff = gi * (DP / 2) + half * QW;
+#pragma unroll
+      for (int piece = 0; piece < 2; ++piece) {
+        const uint4* src = reinterpret_cast<const uint4*>((piece == 0 ? p.Qb0 : p.Qb1) + qoff);
+#pragma unroll
+        for (int c0 = 0; c0 < QW; c0 += 16) {
+          uint32_t qv[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 v = __ldg(src + c0 / 4 + q);
+            qv[q * 4] = v.x; qv[q * 4 + 1] = v.y; qv[q * 4 + 2] = v.z; qv[q * 4 + 3] = v.w;
+          }
+          tmem_st16(tmem + lane_addr + MF_TM_Q + piece * 64 + half * QW + c0, qv);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_full);
+    }
     const float qn = p.zn[gi];
     const float Lv = p.fs->L, Uv = p.fs->U;
     // below  <=>  -2g + qn(1+k) - L < -zn_j(1+k)       above  <=>  -2g + qn(1-k) - U > -zn_j(1-k)
@@ -557,7 +576,7 @@ median_filter_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, 128); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem, MF_TMEM_COLS); }
 }
 
 // ---------------------------------------------------------------------------- exact evaluation of the uncertain list
@@ -926,6 +945,7 @@ int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[2], f.Zb0, f.dp, f.n_pad, (uint64_t)f.dp * 2, 64, MF_BN));
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[3], f.Zb1, f.dp, f.n_pad, (uint64_t)f.dp * 2, 64, MF_BN));
   MfParams prm{};
+  prm.Qb0 = (const uint32_t*)f.Zb0; prm.Qb1 = (const uint32_t*)f.Zb1;
   prm.zn = f.zn; prm.zlo = f.zlo; prm.zhi = f.zhi; prm.n = n; prm.n_tiles = (int)(f.n_pad / MF_BN); prm.rb_start = block_row_start; prm.rb_stride = block_row_stride;
   prm.fs = f.fs; prm.list = f.list; prm.list_counts = f.list_counts; prm.list_cap = f.list_cap; prm.err_flag = f.err_flag;
   const int64_t row_blocks = f.n_pad / MF_BM;

@@ -2,7 +2,5 @@
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q --tb=short -p no:cacheprovider -k "fast_median" 2>&1 | tail -3
-for m in coop thread; do
-NSVGD_MEDIAN_EXACT=$m timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ab_$m.log 2>&1; echo "$m exit $?"
-grep '^{' gpurun_out/ab_$m.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['breakdown_ms_per_step']['median_exact_list_kernel'], d['breakdown_ms_per_step']['median_op'], d['result'])"
-done
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ab.log 2>&1; echo "exit $?"
+grep '^{' gpurun_out/ab.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['breakdown_ms_per_step'], d['result'])"
