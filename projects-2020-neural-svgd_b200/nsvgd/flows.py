@@ -23,8 +23,10 @@ def svgd_flow(key,
               bandwidth=1.,
               compute_metrics=None,
               catch_exceptions: bool = True,
-              device="cuda"):
-    """Same arguments, defaults and return value (kernel_gradient, particles, err) as flows.py:70-110."""
+              device="cuda",
+              cuda_graph: bool = False):
+    """Same arguments, defaults and return value (kernel_gradient, particles, err) as flows.py:70-110.
+    cuda_graph=True (extension): the steps are replayed from one captured CUDA graph (Particles.step_many)."""
     gen = torch.Generator(device="cpu")
     gen.manual_seed(int(key))
     target, proposal = setup.get()
@@ -46,6 +48,16 @@ def svgd_flow(key,
                                       optimizer=particle_optimizer,
                                       compute_metrics=compute_metrics,
                                       device=device)
+    if cuda_graph:
+        try:
+            svgd_particles.step_many(n_steps, None)
+        except Exception as err:
+            if catch_exceptions:
+                warnings.warn("caught error!")
+                return kernel_gradient, svgd_particles, err
+            raise
+        svgd_particles.done()
+        return kernel_gradient, svgd_particles, None
     for _ in range(n_steps):
         try:
             svgd_particles.step(None)
