@@ -44,6 +44,19 @@ def test_workspace_query_and_argument_validation():
         _lib.check(_lib.ERR_UNSUPPORTED)
 
 
+def test_p2p_entry_points_validate_the_communicator():
+    """peer-memory all-reduces (csrc/p2p.cuh): bad rank/world/blocks are rejected before any CUDA call"""
+    lib = _lib.load()
+    assert lib.nsvgd_p2p_block_bytes() == 1024 + 2 * 8192 * 8
+    blocks = (C.c_void_p * 2)(None, None)
+    assert lib.nsvgd_p2p_allreduce(None, 0, 2, blocks, None, 4, 0) == _lib.ERR_INVALID        # null peer blocks
+    assert b"communicator" in lib.nsvgd_last_error()
+    assert lib.nsvgd_p2p_allreduce(None, 3, 2, blocks, None, 4, 0) == _lib.ERR_INVALID        # rank >= world
+    assert lib.nsvgd_p2p_allreduce(None, 0, 99, blocks, None, 4, 0) == _lib.ERR_INVALID       # world > 16
+    assert lib.nsvgd_p2p_median_advance(None, 0, 2, blocks, None, None, 0) == _lib.ERR_INVALID
+    assert lib.nsvgd_p2p_apply_update_f32(None, 0, 2, blocks, None, None, 1, 1, 1, 1, None, 0.1, 1, 0.5, None, None) == _lib.ERR_INVALID
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_no_cpu_fallback():
     x = torch.randn(8, 2)
