@@ -58,10 +58,21 @@ class RBFKernel:
         if normalize:
             raise NotImplementedError("normalize=True is not on the SVGD hot path")
 
+    def is_ard(self):
+        """a (d,) bandwidth vector (kernels.py:52-65 with `bandwidth` of shape (d,)): SURVEY 8f N3"""
+        return self.bandwidth.ndim == 1 and self.bandwidth.numel() > 1
+
+    def ard_scale(self, device):
+        """per-coordinate length scales h_a: k(x, y) = exp(-sum_a (x_a - y_a)^2 / (2 h_a^2)).  The engine then runs on
+        the rescaled cloud x' = x / h with unit bandwidth (stein.py / metrics.py do the three elementwise ops)."""
+        b = self.bandwidth.to(device=device, dtype=torch.float32)
+        return b if self.squared else torch.sqrt(b)
+
     def h(self):
         """effective bandwidth h with k = exp(-r^2/(2 h^2))"""
-        if self.bandwidth.ndim != 0 and self.bandwidth.numel() != 1:
-            raise NotImplementedError("vector (ARD) bandwidths are not on the SVGD hot path (SURVEY 8f N3)")
+        if self.is_ard():
+            raise NotImplementedError("this entry point needs a scalar bandwidth; vector (ARD) bandwidths are supported by "
+                                      "stein.get_phistar / phistar / phistar_i and metrics.get_mmd (SURVEY 8f N3)")
         b = self.bandwidth.reshape(())
         return b if self.squared else torch.sqrt(b)
 

@@ -16,6 +16,11 @@ def get_mmd(kernel=None):
     kernel = kernels.get_rbf_kernel(1.) if kernel is None else kernel
     if not getattr(kernel, "is_rbf", False):
         raise NotImplementedError("get_mmd: only RBF / funnel kernels dispatch to the CUDA engine")
+    if not kernel.funnel and kernel.is_ard():
+        def mmd_ard(xs, ys):                      # vector bandwidth: unit-bandwidth engine call on x / h
+            sc = kernel.ard_scale(xs.device)
+            return engine.mmd((xs / sc).contiguous(), (ys / sc).contiguous(), 1.0).to(xs.dtype)
+        return mmd_ard
     h = float(kernel.h())
 
     def mmd(xs, ys):

@@ -40,9 +40,16 @@ class KernelGradient:
 
     def _bandwidth(self, inducing_particles):
         # truthiness test as in models.py:657/680: None or 0 -> median heuristic
-        if isinstance(self.bandwidth, torch.Tensor):
+        if isinstance(self.bandwidth, torch.Tensor) or self._ard():
             return self.bandwidth
         return self.bandwidth if self.bandwidth else kernels.median_heuristic(inducing_particles)
+
+    def _ard(self):
+        """a (d,) bandwidth vector: served by stein.get_phistar (unscaled field); the fused scaled step needs a scalar"""
+        b = self.bandwidth
+        if b is None or isinstance(b, (int, float)):
+            return False
+        return torch.as_tensor(b).squeeze().ndim == 1 and torch.as_tensor(b).numel() > 1
 
     def get_field(self, inducing_particles, batch=None):
         """return -phistar                                                 models.py:654-660"""
@@ -60,6 +67,8 @@ class KernelGradient:
         bandwidth = self._bandwidth(inducing_particles)
         kernel = self.kernel(bandwidth)
         phi = stein.get_phistar(kernel, target_logp, inducing_particles)
+        if phi.ard:
+            raise NotImplementedError("scaled=True needs the closed-form KSD, which is built for a scalar bandwidth")
         vals, stats = engine.phistar(inducing_particles, inducing_particles, phi.scores, phi.h,
                                      Sq=phi.scores, stats=True)
         ksd = stats[0] / stats[2]
@@ -176,7 +185,7 @@ class Particles:
         """Updates particles in the direction given by self.gradient      models.py:143-167
         Returns: particles (updated), optimizer_state (updated), grad_aux dict."""
         owner = getattr(self.gradient, "__self__", None)
-        if isinstance(owner, KernelGradient) and self.optimizer_str == "sgd":
+        if isinstance(owner, KernelGradient) and self.optimizer_str == "sgd" and not owner._ard():
             particles = particles.clone()
             grads, grad_aux = owner.step_sgd(particles, params, self.learning_rate)
             return particles, optimizer_state, grad_aux
@@ -219,7 +228,8 @@ class Particles:
         The tracer (`compute_metrics`, every 10th step) runs eagerly between replays, as in `log()`.
         Falls back to the eager loop unless the plug-in is `KernelGradient` with the sgd optimizer on CUDA."""
         owner = getattr(self.gradient, "__self__", None)
-        if not (isinstance(owner, KernelGradient) and self.optimizer_str == "sgd" and self.particles.is_cuda and n_steps > 0):
+        if not (isinstance(owner, KernelGradient) and self.optimizer_str == "sgd" and self.particles.is_cuda and n_steps > 0
+                and not owner._ard()):
             for _ in range(n_steps):
                 self.step(params)
             return None

@@ -29,16 +29,35 @@ def _require_rbf(kernel, who):
     return kernel.h()
 
 
+def _phistar_any_bandwidth(kernel, who, Q, X, S, aux=False):
+    """phi* for a scalar bandwidth (one engine call) or a (d,) ARD bandwidth vector (kernels.py:52-65 with a vector):
+    with x' = x / h (elementwise) the kernel has unit bandwidth, the scores w.r.t. x' are s h, and
+    phi_a = phi'_a / h_a -- three elementwise ops around the same engine call."""
+    if getattr(kernel, "is_rbf", False) and not getattr(kernel, "funnel", False) and kernel.is_ard():
+        sc = kernel.ard_scale(X.device)
+        if sc.numel() != X.shape[1]:
+            raise ValueError(f"Bandwidth has shape {tuple(sc.shape)}.")
+        out = engine.phistar((Q / sc).contiguous(), (X / sc).contiguous(), (S * sc).contiguous(), 1.0, aux=aux)
+        if aux:
+            return out[0] / sc, out[1] / sc
+        return out / sc
+    h = _require_rbf(kernel, who)
+    return engine.phistar(Q, X, S, h, aux=aux)
+
+
 class PhiStar(BatchedFunction):
     """phi* as a function of one point; carries what the closed forms need."""
 
     def __init__(self, kernel, logp, samples, scores=None):
         self.kernel, self.logp, self.samples = kernel, logp, samples
-        self.h = _require_rbf(kernel, "get_phistar")
+        self.ard = bool(getattr(kernel, "is_rbf", False) and not getattr(kernel, "funnel", False) and kernel.is_ard())
+        self.h = None if self.ard else _require_rbf(kernel, "get_phistar")
         self.scores = score(logp, samples) if scores is None else scores
         super().__init__(self._phi_batch)
 
     def _phi_batch(self, xs):
+        if self.ard:
+            return _phistar_any_bandwidth(self.kernel, "get_phistar", xs, self.samples, self.scores)
         return engine.phistar(xs, self.samples, self.scores, self.h)
 
 
@@ -51,8 +70,7 @@ def phistar_i(xi, x, logp, kernel, aux=True):
     """stein.py:180-197"""
     if xi.ndim > 1:
         raise ValueError(f"Shape of xi must be (d,). Instead, received shape {tuple(xi.shape)}")
-    h = _require_rbf(kernel, "phistar_i")
-    out = engine.phistar(xi[None, :], x, score(logp, x), h, aux=aux)
+    out = _phistar_any_bandwidth(kernel, "phistar_i", xi[None, :], x, score(logp, x), aux=aux)
     if aux:
         return out[0][0], out[1][0]
     return out[0]
@@ -60,8 +78,7 @@ def phistar_i(xi, x, logp, kernel, aux=True):
 
 def phistar(particles, leaders, logp, kernel):
     """stein.py:206-222: (n,d) updates and (n,2,d) [drift, repulsion] aux; rectangular n x l."""
-    h = _require_rbf(kernel, "phistar")
-    return engine.phistar(particles, leaders, score(logp, leaders), h, aux=True)
+    return _phistar_any_bandwidth(kernel, "phistar", particles, leaders, score(logp, leaders), aux=True)
 
 
 def stein_discrepancy(xs, logp, f, aux=False):
@@ -71,6 +88,8 @@ def stein_discrepancy(xs, logp, f, aux=False):
     base = getattr(f, "base", None)
     if not isinstance(base, PhiStar):
         raise NotImplementedError("stein_discrepancy: f must come from stein.get_phistar")
+    if base.ard:
+        raise NotImplementedError("stein_discrepancy: the closed-form divergence is built for a scalar bandwidth")
     if aux:
         raise NotImplementedError("stein_discrepancy(aux=True) is not on the hot path")
     s_q = score(logp, xs)

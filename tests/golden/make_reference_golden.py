@@ -162,10 +162,52 @@ def worker(tag):
         print(tag, name, "h_median", float(out["h_median"]), "ksd_u", float(out["ksd_u_hfix"]), "mmd", float(out["mmd_rbf"]))
 
 
+def worker_ard(tag):
+    """vector (ARD) bandwidth: kernels.get_rbf_kernel(bandwidth of shape (d,)) through stein.phistar / get_phistar /
+    KernelGradient (unscaled) / metrics.get_mmd -> tests/golden/ref_ard_<tag>.npz"""
+    import collections
+    import collections.abc
+    import warnings
+    warnings.simplefilter("ignore", SyntaxWarning)
+    collections.Mapping = collections.abc.Mapping
+    sys.path[:0] = [os.path.join(HERE, "refshim"), REF]
+    sys.dont_write_bytecode = True
+    import numpy as onp
+    import torch
+    import jax.numpy as jnp
+    from jax import vmap, grad
+    from nvgd.src import kernels, stein, metrics, models
+    fdt = jnp.float32
+    T = lambda a: torch.as_tensor(onp.asarray(a)).to(fdt)
+    N = lambda t: t.detach().numpy() if isinstance(t, torch.Tensor) else onp.asarray(t)
+    name, n, d, m, seed, kind, hfix = CASES[1]                      # gauss_n64_d5
+    X, Y, mean, prec = inputs(n, d, m, seed, kind)
+    mean_t, prec_t = T(mean), T(prec)
+    logp = lambda x: -0.5 * jnp.dot(x - mean_t, jnp.dot(prec_t, x - mean_t))
+    bw = onp.array([0.6, 1.1, 0.8, 1.7, 0.9], dtype=onp.float64)
+    Xt, Yt = T(X), T(Y)
+    k = kernels.get_rbf_kernel(T(bw))
+    out = {"X": X, "Y": Y, "bandwidth": bw, "Sx": N(vmap(grad(logp))(Xt))}
+    out["K"] = N(vmap(vmap(k, (0, None)), (None, 0))(Xt, Yt))
+    phi, aux = stein.phistar(Xt, Xt, logp, k)
+    out["phi"], out["aux"] = N(phi), N(aux)
+    phi_r, aux_r = stein.phistar(Yt, Xt, logp, k)
+    out["phi_rect"], out["aux_rect"] = N(phi_r), N(aux_r)
+    out["phi_closure"] = N(vmap(stein.get_phistar(k, logp, Xt))(Xt))
+    out["mmd"] = N(metrics.get_mmd(k)(Xt, Yt))
+    # (models.KernelGradient cannot take the vector: `self.bandwidth if self.bandwidth else ...` (models.py:657) raises on
+    #  an array with more than one element, in JAX as under the stand-in)
+    onp.savez_compressed(os.path.join(HERE, f"ref_ard_{tag}.npz"), **out)
+    print(tag, "ard", float(onp.abs(out["phi"]).max()), float(out["mmd"]))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 2 and sys.argv[2] == "ard":
+        worker_ard(sys.argv[1])
+    elif len(sys.argv) > 1:
         worker(sys.argv[1])
     else:
         for tag, widen in (("f32", "0"), ("f64", "1")):
             env = dict(os.environ, REFSHIM_WIDEN=widen, PYTHONDONTWRITEBYTECODE="1")
             subprocess.run([sys.executable, os.path.abspath(__file__), tag], check=True, env=env)
+            subprocess.run([sys.executable, os.path.abspath(__file__), tag, "ard"], check=True, env=env)

@@ -157,3 +157,32 @@ def test_svgd_flow_vs_reference_execution(name):
     assert _rel(parts.particles - X0.cuda(), r["flow4_X"] - r["X"].astype(np.float64)) < RTOL
     mmd0 = parts.rundata["mmd"][0]
     assert float(mmd0[1]) == pytest.approx(float(r["flow4_mmd0"]), abs=1e-5)
+
+
+def test_ard_bandwidth_vs_reference_execution():
+    """N3: vector (ARD) bandwidth through stein.phistar / get_phistar / phistar_i and metrics.get_mmd"""
+    from nsvgd import kernels, stein, metrics, models, vmap
+    r = dict(np.load(os.path.join(GOLDEN_DIR, "ref_ard_f64.npz")))
+    logp = _logp("gauss_n64_d5")
+    X = torch.tensor(r["X"], device="cuda")
+    Y = torch.tensor(r["Y"], device="cuda")
+    k = kernels.get_rbf_kernel(torch.tensor(r["bandwidth"], dtype=torch.float32))
+    assert float(k(X[0].cpu(), Y[1].cpu())) == pytest.approx(float(r["K"][1, 0]), rel=1e-5)
+    phi, aux = stein.phistar(X, X, logp, k)
+    assert _rel(phi, r["phi"]) < RTOL and _rel(aux, r["aux"]) < RTOL
+    phi_r, aux_r = stein.phistar(Y, X, logp, k)
+    assert _rel(phi_r, r["phi_rect"]) < RTOL and _rel(aux_r, r["aux_rect"]) < RTOL
+    f = stein.get_phistar(k, logp, X)
+    assert _rel(vmap(f)(X), r["phi_closure"]) < RTOL
+    assert _rel(f(X[3]), r["phi_closure"][3]) < RTOL
+    one, _ = stein.phistar_i(X[7], X, logp, k)
+    assert _rel(one, r["phi"][7]) < RTOL
+    assert float(metrics.get_mmd(k)(X, Y)) == pytest.approx(float(r["mmd"]), abs=1e-5)
+    with pytest.raises(NotImplementedError):
+        stein.stein_discrepancy(X, logp, f)
+    with pytest.raises(NotImplementedError):
+        stein.ksd_squared_u(X, logp, k)
+    # the plug-in (an extension: the reference's KernelGradient raises on a bandwidth vector, models.py:657)
+    kg = models.KernelGradient(target_logp=logp, bandwidth=torch.tensor(r["bandwidth"], dtype=torch.float32), scaled=False)
+    g = kg.gradient(None, X)
+    assert _rel(g, -r["phi"]) < RTOL

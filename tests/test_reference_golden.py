@@ -127,3 +127,18 @@ def test_particle_steps_vs_reference_execution(name):
     for i in range(4):
         X, _, _, _ = so.svgd_step_sgd(X, _oracle_score(name, X), 1e-1, bandwidth=1.0, scaled=True, lambda_reg=0.5)
     assert _rel(X, r["flow4_X"]) < 1e-6
+
+
+def test_ard_bandwidth_rescaling_vs_reference_execution():
+    """N3: kernels.get_rbf_kernel with a (d,) bandwidth vector, executed by the reference (stein.phistar, get_phistar,
+    metrics.get_mmd).  The product serves it by rescaling x' = x/h, s' = s h, phi = phi'/h around a unit-bandwidth engine
+    call; this pins that identity (oracle on the rescaled cloud == the reference with the vector)."""
+    r = dict(np.load(os.path.join(GOLDEN_DIR, "ref_ard_f64.npz")))
+    X, Y, S, bw = r["X"].astype(np.float64), r["Y"].astype(np.float64), r["Sx"].astype(np.float64), r["bandwidth"]
+    phi, aux = so.phistar(X / bw, X / bw, S * bw, 1.0, aux=True)
+    assert _rel(phi / bw, r["phi"]) < 1e-12 and _rel(aux / bw, r["aux"]) < 1e-12
+    assert _rel(phi / bw, r["phi_closure"]) < 1e-12
+    phi_r, aux_r = so.phistar(Y / bw, X / bw, S * bw, 1.0, aux=True)
+    assert _rel(phi_r / bw, r["phi_rect"]) < 1e-12 and _rel(aux_r / bw, r["aux_rect"]) < 1e-12
+    assert so.mmd(X / bw, Y / bw, 1.0) == pytest.approx(float(r["mmd"]), abs=1e-13)
+    assert _rel(so.kernel_matrix(Y / bw, X / bw, 1.0), r["K"]) < 1e-12
