@@ -81,6 +81,42 @@ def phistar(particles, leaders, logp, kernel):
     return _phistar_any_bandwidth(kernel, "phistar", particles, leaders, score(logp, leaders), aux=True)
 
 
+def phistar_u(followers, leaders, logp, kernel):
+    """stein.py:225-270: followers get the V-statistic over the leaders, leaders the U-statistic (their own
+    k(x_i, x_i) term left out, divisor l-1).  Returns (l+m, d) updates for concat(leaders, followers) and (l+m, 2, d) aux.
+    Closed form: one rectangular engine call, then for the leader rows phi_U = (l phi_V - s_i) / (l - 1) because the
+    diagonal term is k(x_i,x_i) s_i + grad k = s_i.  The reference zeroes the diagonal of the phi matrix only — its aux
+    keeps the diagonal terms and is merely divided by l-1 (stein.py:263-269); reproduced as is."""
+    if getattr(kernel, "is_ard", lambda: False)():
+        raise NotImplementedError("phistar_u: scalar bandwidth only")
+    particles = torch.cat([leaders, followers], dim=0)
+    s_lead = score(logp, leaders)
+    phi, aux = _phistar_any_bandwidth(kernel, "phistar_u", particles, leaders, s_lead, aux=True)
+    l = leaders.shape[0]
+    phi = phi.clone(); aux = aux.clone()
+    phi[:l] = (l * phi[:l] - s_lead) / (l - 1)
+    aux[:l] = aux[:l] * (l / (l - 1))
+    return phi, aux
+
+
+def ksd_squared_l(samples, logp, k, return_stddev=False):
+    """stein.py:353-380: the linear-time estimator mean_i u_p(x_i, y_i) over the two halves of `samples` (an odd count
+    drops the last sample).  O(n d): plain elementwise device ops, no pair engine involved."""
+    h = _require_rbf(k, "ksd_squared_l")
+    n = samples.shape[0] - (samples.shape[0] % 2)
+    xs, ys = samples[: n // 2], samples[n // 2: n]
+    sx, sy = score(logp, xs), score(logp, ys)
+    h2 = (h * h) if isinstance(h, torch.Tensor) else float(h) ** 2
+    diff = xs - ys
+    r2 = torch.sum(diff * diff, dim=1)
+    kk = torch.exp(-r2 / (2 * h2))
+    d = samples.shape[1]
+    outs = kk * (torch.sum(sx * sy, dim=1) + torch.sum((sx - sy) * diff, dim=1) / h2 + d / h2 - r2 / (h2 * h2))
+    if return_stddev:
+        return torch.mean(outs), torch.std(outs, unbiased=True) / xs.shape[0]
+    return torch.mean(outs)
+
+
 def stein_discrepancy(xs, logp, f, aux=False):
     """stein.py:99-106 for a witness f built from get_phistar (optionally through
     utils.negative / utils.mul): mean_i[ s_i . f(x_i) + div f(x_i) ] in closed form.

@@ -197,8 +197,15 @@ def worker_ard(tag):
     out["mmd"] = N(metrics.get_mmd(k)(Xt, Yt))
     # (models.KernelGradient cannot take the vector: `self.bandwidth if self.bandwidth else ...` (models.py:657) raises on
     #  an array with more than one element, in JAX as under the stand-in)
+    # leader / follower U-statistic (stein.phistar_u, stein.py:225-270), scalar bandwidth
+    l_ = 24
+    ku = kernels.get_rbf_kernel(hfix)
+    phi_u, aux_u = stein.phistar_u(Xt[l_:], Xt[:l_], logp, ku)       # followers, leaders
+    out["u_leaders"] = onp.int64(l_)
+    out["u_h"] = onp.float64(hfix)
+    out["phi_u"], out["aux_u"] = N(phi_u), N(aux_u)
     onp.savez_compressed(os.path.join(HERE, f"ref_ard_{tag}.npz"), **out)
-    print(tag, "ard", float(onp.abs(out["phi"]).max()), float(out["mmd"]))
+    print(tag, "ard", float(onp.abs(out["phi"]).max()), float(out["mmd"]), "phistar_u", out["phi_u"].shape)
 
 
 if __name__ == "__main__":

@@ -186,3 +186,25 @@ def test_ard_bandwidth_vs_reference_execution():
     kg = models.KernelGradient(target_logp=logp, bandwidth=torch.tensor(r["bandwidth"], dtype=torch.float32), scaled=False)
     g = kg.gradient(None, X)
     assert _rel(g, -r["phi"]) < RTOL
+
+
+def test_phistar_u_and_linear_ksd():
+    """N3: leader/follower U-statistic (stein.phistar_u) vs the reference's execution; linear-time KSD vs the oracle's u_p"""
+    from nsvgd import kernels, stein
+    from oracle import svgd_oracle as so
+    r = dict(np.load(os.path.join(GOLDEN_DIR, "ref_ard_f64.npz")))
+    logp = _logp("gauss_n64_d5")
+    X = torch.tensor(r["X"], device="cuda")
+    l, h = int(r["u_leaders"]), float(r["u_h"])
+    k = kernels.get_rbf_kernel(h)
+    phi_u, aux_u = stein.phistar_u(X[l:], X[:l], logp, k)
+    assert _rel(phi_u, r["phi_u"]) < RTOL and _rel(aux_u, r["aux_u"]) < RTOL
+    S = r["Sx"].astype(np.float64)
+    Xn = r["X"].astype(np.float64)
+    for n_use in (64, 63):
+        half = n_use // 2
+        M = so.ksd_matrix(Xn[:half], S[:half], Xn[half:2 * half], S[half:2 * half], h)
+        want = float(np.mean(np.diag(M)))
+        got, sd = stein.ksd_squared_l(X[:n_use], logp, k, return_stddev=True)
+        assert float(got) == pytest.approx(want, rel=1e-4, abs=1e-6)
+        assert float(sd) == pytest.approx(float(np.std(np.diag(M), ddof=1) / half), rel=1e-3)

@@ -142,3 +142,15 @@ def test_ard_bandwidth_rescaling_vs_reference_execution():
     assert _rel(phi_r / bw, r["phi_rect"]) < 1e-12 and _rel(aux_r / bw, r["aux_rect"]) < 1e-12
     assert so.mmd(X / bw, Y / bw, 1.0) == pytest.approx(float(r["mmd"]), abs=1e-13)
     assert _rel(so.kernel_matrix(Y / bw, X / bw, 1.0), r["K"]) < 1e-12
+
+
+def test_phistar_u_closed_form_vs_reference_execution():
+    """stein.phistar_u (stein.py:225-270): leaders' rows are (l phi_V - s_i)/(l-1); the reference's aux keeps its diagonal
+    terms and is only divided by l-1 — both reproduced by the closed form the product uses."""
+    r = dict(np.load(os.path.join(GOLDEN_DIR, "ref_ard_f64.npz")))
+    X, S = r["X"].astype(np.float64), r["Sx"].astype(np.float64)
+    l, h = int(r["u_leaders"]), float(r["u_h"])
+    phi, aux = so.phistar(X, X[:l], S[:l], h, aux=True)
+    phi[:l] = (l * phi[:l] - S[:l]) / (l - 1)
+    aux[:l] = aux[:l] * (l / (l - 1))
+    assert _rel(phi, r["phi_u"]) < 1e-12 and _rel(aux, r["aux_u"]) < 1e-12
