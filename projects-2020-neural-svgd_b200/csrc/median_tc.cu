@@ -679,12 +679,13 @@ __global__ void __launch_bounds__(256, 2) exact_list_kernel(const float* __restr
 // own two rows) is bound by the L1 tag stage: every LDG.128 of a warp touches 32 different lines and each line is looked up
 // 8 times (ncu: l1tex throughput 85 %, L2 26 %, issue 12 %; profiles/r01_ncu_exact_final.txt).  Here a warp takes 32 pairs
 // and moves their 64 rows through shared memory one 128-byte column slice at a time: 8 lanes read one line of one row
-// (one lookup per line, 16 loads in flight per lane), the slice is parked in two padded 32 x 32 tiles, and lane p then
-// adds pair p's 32 terms of the slice in the DEFINED sequential order (same arithmetic, bit-identical results).
+// (one lookup per line, 16 loads in flight per lane); the loading lane holds both rows of its pair for its 4 coordinates,
+// so it parks the squared differences (last coordinate weighted) in ONE padded 32 x 32 tile, and lane p then adds pair p's
+// 32 terms of the slice in the DEFINED sequential order (same arithmetic, bit-identical results).
 // Requires d % 4 == 0, ldp % 4 == 0, 16-byte aligned rows, d <= 128.
 constexpr int XL_STRIDE = 36;                         // floats per tile row: 32 + 4 pad -> conflict-free LDS.128 / STS.128
 constexpr int XL_TILE = 32 * XL_STRIDE;
-constexpr int XL_SMEM = 8 * 2 * XL_TILE * (int)sizeof(float);
+constexpr int XL_SMEM = 8 * XL_TILE * (int)sizeof(float);
 __global__ void __launch_bounds__(256, 2) exact_list_coop_kernel(const float* __restrict__ P, int d, int64_t ldp, float w_last,
                                                                  FastMedState* fs, const unsigned long long* __restrict__ list,
                                                                  const uint32_t* __restrict__ list_counts, uint32_t list_cap,
@@ -697,8 +698,7 @@ __global__ void __launch_bounds__(256, 2) exact_list_coop_kernel(const float* __
   const float Lv = fs->L, Uv = fs->U;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int r = lane >> 3, q = lane & 7;              // cooperative loads: 8 lanes per row, 4 rows per instruction
-  float* tA = xl_smem + w * 2 * XL_TILE;
-  float* tB = tA + XL_TILE;
+  float* tA = xl_smem + w * XL_TILE;
   const int nslices = (d + 31) >> 5;
   const int last_group = (d >> 2) - 1;                // the float4 group that holds the weighted coordinate d-1
   uint32_t below = 0;
@@ -717,10 +717,11 @@ __global__ void __launch_bounds__(256, 2) exact_list_coop_kernel(const float* __
         ia[u] = __shfl_sync(0xffffffffu, i, 4 * u + r);
         jb[u] = __shfl_sync(0xffffffffu, j, 4 * u + r);
       }
-      float acc = 0.f, last_diff = 0.f;
+      float acc = 0.f;
       for (int sl = 0; sl < nslices; ++sl) {
         const int col = 32 * sl + 4 * q;
         const bool inb = col < d;
+        const bool wgt = (col >> 2) == last_group;     // this lane's float4 ends with the weighted coordinate d-1
         float4 va[8], vb[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -728,27 +729,27 @@ __global__ void __launch_bounds__(256, 2) exact_list_coop_kernel(const float* __
           vb[u] = inb ? __ldg(reinterpret_cast<const float4*>(P + (int64_t)jb[u] * ldp + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncwarp();                                  // the previous slice has been consumed
+        // the loading lane holds both rows of its pair for these 4 coordinates: park the squared differences (the last
+        // coordinate already weighted: w * (diff * diff), as the defined order prescribes) -- one tile instead of two
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          *reinterpret_cast<float4*>(tA + (4 * u + r) * XL_STRIDE + 4 * q) = va[u];
-          *reinterpret_cast<float4*>(tB + (4 * u + r) * XL_STRIDE + 4 * q) = vb[u];
+          const float d0 = va[u].x - vb[u].x, d1 = va[u].y - vb[u].y, d2 = va[u].z - vb[u].z, d3 = va[u].w - vb[u].w;
+          float t3 = __fmul_rn(d3, d3);
+          if (wgt) t3 = __fmul_rn(w_last, t3);
+          *reinterpret_cast<float4*>(tA + (4 * u + r) * XL_STRIDE + 4 * q) =
+              make_float4(__fmul_rn(d0, d0), __fmul_rn(d1, d1), __fmul_rn(d2, d2), t3);
         }
         __syncwarp();
         const int kmax = min(8, (d - 32 * sl) >> 2);
         for (int k = 0; k < kmax; ++k) {
-          const float4 a4 = *reinterpret_cast<const float4*>(tA + lane * XL_STRIDE + 4 * k);
-          const float4 b4 = *reinterpret_cast<const float4*>(tB + lane * XL_STRIDE + 4 * k);
-          const float d0 = a4.x - b4.x, d1 = a4.y - b4.y, d2 = a4.z - b4.z, d3 = a4.w - b4.w;
-          acc = __fadd_rn(acc, __fmul_rn(d0, d0));
-          acc = __fadd_rn(acc, __fmul_rn(d1, d1));
-          acc = __fadd_rn(acc, __fmul_rn(d2, d2));
-          if (8 * sl + k != last_group) acc = __fadd_rn(acc, __fmul_rn(d3, d3));
-          else last_diff = d3;
+          const float4 t4 = *reinterpret_cast<const float4*>(tA + lane * XL_STRIDE + 4 * k);
+          acc = __fadd_rn(acc, t4.x);
+          acc = __fadd_rn(acc, t4.y);
+          acc = __fadd_rn(acc, t4.z);
+          acc = __fadd_rn(acc, t4.w);                  // for the last group this is acc + w (diff diff): the final add
         }
       }
-      float tl = __fmul_rn(last_diff, last_diff);
-      tl = __fmul_rn(w_last, tl);
-      const float dv = __fadd_rn(acc, tl);
+      const float dv = acc;
       bool is_cand = false;
       if (t < count) {
         if (dv != dv) any_nan = true;
