@@ -208,8 +208,57 @@ def worker_ard(tag):
     print(tag, "ard", float(onp.abs(out["phi"]).max()), float(out["mmd"]), "phistar_u", out["phi_u"].shape)
 
 
+def worker_cfg1(tag, n_steps=1000):
+    """BASELINE configs[0]: SVGD on the 2-D funnel, n = 100, median-heuristic bandwidth, scaled field, sgd lr = 5e-2,
+    MMD tracers every 10 steps (funnel_mmd_comparison.py:33,79) -- a LONG run of the reference's own Particles /
+    KernelGradient / tracer code -> tests/golden/ref_cfg1_<tag>.npz (snapshots every 50 steps, bandwidth and MMD traces)."""
+    import collections
+    import collections.abc
+    import warnings
+    warnings.simplefilter("ignore", SyntaxWarning)
+    collections.Mapping = collections.abc.Mapping
+    sys.path[:0] = [os.path.join(HERE, "refshim"), REF]
+    sys.dont_write_bytecode = True
+    import numpy as onp
+    import torch
+    import jax
+    import jax.numpy as jnp
+    from nvgd.src import metrics, models
+    fdt = jnp.float32
+    T = lambda a: torch.as_tensor(onp.asarray(a)).to(fdt)
+    N = lambda t: t.detach().numpy() if isinstance(t, torch.Tensor) else onp.asarray(t)
+
+    def funnel_logp(x):
+        xs, y = x[:-1], x[-1]
+        return -y ** 2 / 18.0 - 0.5 * xs.shape[0] * y - 0.5 * jnp.exp(-y) * jnp.sum(xs ** 2)
+    rng = onp.random.default_rng(2020)
+    X0 = rng.standard_normal((100, 2)).astype(onp.float32)
+    yy = rng.standard_normal((100, 1)) * 3.0
+    target = onp.concatenate([rng.standard_normal((100, 1)) * onp.exp(yy / 2), yy], axis=1).astype(onp.float32)
+    kg = models.KernelGradient(target_logp=funnel_logp, bandwidth=None, scaled=True, lambda_reg=0.5)
+    p = models.Particles(key=jax.random.PRNGKey(0), gradient=kg.gradient, init_samples=T(X0), learning_rate=5e-2,
+                         optimizer="sgd", compute_metrics=metrics.get_funnel_tracer(T(target)))
+    snaps = {0: N(p.particles).copy()}
+    for k in range(1, n_steps + 1):
+        p.step(None)
+        if k % 50 == 0:
+            snaps[k] = N(p.particles).copy()
+    out = {"X0": X0, "target": target, "lr": onp.float64(5e-2), "n_steps": onp.int64(n_steps),
+           "snap_steps": onp.asarray(sorted(snaps)), "snaps": onp.stack([snaps[k] for k in sorted(snaps)]),
+           "h": onp.asarray([N(b) for b in p.rundata["bandwidth"]]),
+           "gnorm": onp.asarray([N(b) for b in p.rundata["global_grad_norm"]]),
+           "mmd_steps": onp.asarray([st for st, _ in p.rundata["rbf_mmd"]]),
+           "rbf_mmd": onp.asarray([N(v) for _, v in p.rundata["rbf_mmd"]]),
+           "funnel_mmd": onp.asarray([N(v) for _, v in p.rundata["funnel_mmd"]])}
+    onp.savez_compressed(os.path.join(HERE, f"ref_cfg1_{tag}.npz"), **out)
+    print(tag, "cfg1", n_steps, "steps; h", float(out["h"][0]), "->", float(out["h"][-1]), "funnel mmd", float(out["funnel_mmd"][0]),
+          "->", float(out["funnel_mmd"][-1]))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 2 and sys.argv[2] == "ard":
+    if len(sys.argv) > 2 and sys.argv[2] == "cfg1":
+        worker_cfg1(sys.argv[1])
+    elif len(sys.argv) > 2 and sys.argv[2] == "ard":
         worker_ard(sys.argv[1])
     elif len(sys.argv) > 1:
         worker(sys.argv[1])
@@ -218,3 +267,4 @@ if __name__ == "__main__":
             env = dict(os.environ, REFSHIM_WIDEN=widen, PYTHONDONTWRITEBYTECODE="1")
             subprocess.run([sys.executable, os.path.abspath(__file__), tag], check=True, env=env)
             subprocess.run([sys.executable, os.path.abspath(__file__), tag, "ard"], check=True, env=env)
+            subprocess.run([sys.executable, os.path.abspath(__file__), tag, "cfg1"], check=True, env=env)
