@@ -208,3 +208,33 @@ def test_phistar_u_and_linear_ksd():
         got, sd = stein.ksd_squared_l(X[:n_use], logp, k, return_stddev=True)
         assert float(got) == pytest.approx(want, rel=1e-4, abs=1e-6)
         assert float(sd) == pytest.approx(float(np.std(np.diag(M), ddof=1) / half), rel=1e-3)
+
+
+def test_cfg1_thousand_steps_vs_reference_execution():
+    """BASELINE configs[0] on the GPU: 2-D funnel, n = 100, median bandwidth, scaled sgd, 1000 graph-replayed steps
+    (Particles.step_many) vs 1000 steps of the reference's own loop (tests/golden/ref_cfg1_f64.npz).  First 20 steps
+    tight; beyond that the map amplifies rounding (the reference's float32 and float64 runs differ by 1-3 %), so the long
+    horizon is compared through bandwidth, moments and the MMD tracers (tests/test_reference_golden.py has the CPU twin)."""
+    from nsvgd import distributions, models, metrics
+    r = dict(np.load(os.path.join(GOLDEN_DIR, "ref_cfg1_f64.npz")))
+    tgt = distributions.Funnel(2)
+    target = torch.tensor(r["target"], device="cuda")
+    kg = models.KernelGradient(target_logp=tgt.logpdf, bandwidth=None, scaled=True, lambda_reg=0.5)
+    p = models.Particles(key=0, gradient=kg.gradient, init_samples=torch.tensor(r["X0"]), learning_rate=float(r["lr"]),
+                         optimizer="sgd", compute_metrics=metrics.get_funnel_tracer(target))
+    p.step_many(int(r["n_steps"]), None)
+    hs = np.asarray([float(h) for h in p.rundata["bandwidth"]])
+    gn = np.asarray([float(g) for g in p.rundata["global_grad_norm"]])
+    np.testing.assert_allclose(hs[:20], r["h"][:20], rtol=1e-5)
+    np.testing.assert_allclose(gn[:20], r["gnorm"][:20], rtol=1e-4)
+    X = p.particles.double().cpu().numpy()
+    ref_end = r["snaps"][-1]
+    assert hs[-1] == pytest.approx(float(r["h"][-1]), rel=0.02)
+    np.testing.assert_allclose(X.mean(0), ref_end.mean(0), atol=0.03)
+    np.testing.assert_allclose(X.std(0), ref_end.std(0), rtol=0.03)
+    steps = [s for s, _ in p.rundata["rbf_mmd"]]
+    assert steps == r["mmd_steps"].tolist()
+    assert float(p.rundata["rbf_mmd"][0][1]) == pytest.approx(float(r["rbf_mmd"][0]), abs=1e-5)
+    assert float(p.rundata["funnel_mmd"][0][1]) == pytest.approx(float(r["funnel_mmd"][0]), abs=1e-5)
+    assert float(p.rundata["rbf_mmd"][-1][1]) == pytest.approx(float(r["rbf_mmd"][-1]), abs=2e-3)
+    assert float(p.rundata["funnel_mmd"][-1][1]) == pytest.approx(float(r["funnel_mmd"][-1]), abs=2e-3)
