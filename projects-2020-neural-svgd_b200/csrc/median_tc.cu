@@ -878,7 +878,7 @@ int median_fast_sample(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   NSVGD_CUDA(cudaMemsetAsync(f.cand_counts, 0, sizeof(uint32_t) * MF_NSEG * MF_CSTRIDE, st));
   // weighted last coordinate scaled by sqrt(w) AFTER centring
   NSVGD_PROPAGATE(launch_tc_prep(st, P, nullptr, n, dz, ldp, f.n_pad, f.dp, f.mu, sqrtf(w_last), f.Zb0, f.Zb1, nullptr,
-                                 nullptr, f.zn, nullptr, nullptr));
+                                 nullptr, f.zn, nullptr, nullptr, nullptr));
   filter_vectors_kernel<<<(unsigned)std::min<int64_t>(ceil_div(f.n_pad, 256), 1024), 256, 0, st>>>(f.zn, f.n_pad, f.zlo, f.zhi);
   NSVGD_LAUNCH_CHECK();
   constexpr int WX_SMEM = WX_WARPS * 32 * WX_STRIDE * (int)sizeof(float);

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
                                                       __nv_bfloat16* __restrict__ Xb0, __nv_bfloat16* __restrict__ Xb1,
                                                       __nv_bfloat16* __restrict__ Vt0, __nv_bfloat16* __restrict__ Vt1,
                                                       float* __restrict__ xn, float* __restrict__ cv,
-                                                      const float* __restrict__ h_combine) {
+                                                      const float* __restrict__ h_combine, uint32_t* __restrict__ xn_max_bits) {
   // h_combine != null: COMBINED form, one transposed block W^T = (S - Xc/h^2)^T in rows [0, dp) of Vt
   // (phi_i = (1/n)[(K W)_i + rowsum_i qc_i / h^2]: the second GEMM has N = dp instead of 2 dp columns)
   __shared__ float T[64][129];   // one half (S or Xc) of the block, fp32
@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
         if (lane == 0) {
           xn[row] = rv ? acc_n : 1e30f;   // padded row: k underflows to 0, and 0 * finite stays 0
           if (cv) cv[row] = rv ? acc_c : 0.f;
+          if (xn_max_bits && rv) atomicMax(xn_max_bits, __float_as_uint(acc_n));   // >= 0: uint order = float order; NaN is largest
         }
       }
     }
@@ -146,10 +147,10 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
 
 int launch_tc_prep(cudaStream_t st, const float* X, const float* S, int64_t n, int64_t d, int64_t ldx, int64_t rows_pad,
                    int dp, const float* mu, float last_scale, void* Xb0, void* Xb1, void* Vt0, void* Vt1, float* xn,
-                   float* cv, const float* h_combine) {
+                   float* cv, const float* h_combine, uint32_t* xn_max_bits) {
   tc_prep_kernel<<<(unsigned)(rows_pad / 64), 256, 0, st>>>(X, S, n, d, ldx, rows_pad, dp, mu, last_scale,
                                                             (__nv_bfloat16*)Xb0, (__nv_bfloat16*)Xb1, (__nv_bfloat16*)Vt0,
-                                                            (__nv_bfloat16*)Vt1, xn, cv, h_combine);
+                                                            (__nv_bfloat16*)Vt1, xn, cv, h_combine, xn_max_bits);
   NSVGD_LAUNCH_CHECK();
   return NSVGD_OK;
 }
@@ -163,6 +164,8 @@ struct TcParams {
   int64_t m_pad;
   int tiles_total, tiles_per_split;
   uint32_t* err_flag;
+  const uint32_t* xn_max_bits;    // max over particles and queries of |xc|^2 (float bits), written by tc_prep_kernel
+  float gram_tau;                 // ONE Gram pass when max|xc|^2 / h^2 <= gram_tau (0: always three)
   int dbg;                        // NSVGD_TC_DEBUG timing experiments: 1 = no MMAs issued, 2 = pair math skipped (results invalid)
 };
 
@@ -330,6 +333,16 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
       constexpr uint32_t idesc_pv = umma_idesc_bf16(TC_BM, VC);
       const uint32_t sX_a = smem_u32(sX), sV_a = smem_u32(sV);
       int vcount = 0;
+      // ADAPTIVE GRAM PRECISION.  delta k / k = delta g / h^2 and a single bf16 piece per operand gives
+      // |delta g| <= 2^-8 |q||x|: for wide kernels (max|xc|^2 / h^2 <= gram_tau = 0.5) one pass b0 b0' keeps phi* within
+      // 1e-5 of float64 (measured 1.3e-6 at cfg4's ratio 0.07, 3.9e-5 at ratio 2.2: profiles/r01_passcount_study.txt), so
+      // the two cross passes are skipped -- a third of the kernel's MMA flops.  Tight kernels keep all three.
+      int npass = 3;
+      if (p.gram_tau > 0.f) {
+        const float hh = *p.h_dev;
+        const float ratio = __uint_as_float(*p.xn_max_bits) / (hh * hh);
+        if (ratio <= p.gram_tau) npass = 1;          // false for NaN
+      }
       mbar_wait(q_full, 0, watch, 0x300);
       tc_fence_after();
       auto issue_gram = [&](int t) {
@@ -345,6 +358,7 @@ phi_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ 
           if (!(p.dbg & 1))
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
+            if (pass >= npass) break;
             const int pa = pass == 2 ? 1 : 0;     // Q piece: b0, b0, b1   (A operand, in TMEM)
             const int pb = pass == 1 ? 1 : 0;     // X piece: b0, b1, b0   (B operand, shared memory)
 #pragma unroll
@@ -680,11 +694,12 @@ int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dr
 
   NSVGD_PROPAGATE(launch_colmean(st, a.X, a.n, a.d, a.ldx, mpart, mu));
   NSVGD_CUDA(cudaMemsetAsync(err_flag, 0, 16, st));
+  uint32_t* xn_max_bits = err_flag + 1;      // zeroed with the error flag just above
   NSVGD_PROPAGATE(launch_tc_prep(st, a.X, a.S, a.n, a.d, a.ldx, pl.n_pad, dp, mu, 1.f, Xb0, Xb1, Vt0, Vt1, xn, cv,
-                                 combined ? a.h_dev : nullptr));
+                                 combined ? a.h_dev : nullptr, xn_max_bits));
   if (!pl.q_is_x)
     NSVGD_PROPAGATE(launch_tc_prep(st, a.Q, nullptr, a.m, a.d, a.ldq, pl.m_pad, dp, mu, 1.f, Qb0, Qb1, nullptr, nullptr, qn,
-                                   nullptr, nullptr));
+                                   nullptr, nullptr, xn_max_bits));
   CUtensorMap maps[6];
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[2], Xb0, dp, pl.n_pad, (uint64_t)dp * 2, 64, TC_BN));
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&maps[3], Xb1, dp, pl.n_pad, (uint64_t)dp * 2, 64, TC_BN));
@@ -694,6 +709,9 @@ int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dr
   prm.Qb0 = (const uint32_t*)Qb0; prm.Qb1 = (const uint32_t*)Qb1; prm.xn = xn; prm.cv = cv; prm.qn = qn; prm.h_dev = a.h_dev; prm.O = O; prm.scal = scal; prm.m_pad = pl.m_pad;
   prm.tiles_total = pl.tiles_total; prm.tiles_per_split = pl.tiles_per_split; prm.err_flag = err_flag;
   if (const char* env = getenv("NSVGD_TC_DEBUG")) prm.dbg = atoi(env);
+  prm.xn_max_bits = xn_max_bits;
+  prm.gram_tau = 0.5f;
+  if (const char* env = getenv("NSVGD_TC_GRAM_TAU")) prm.gram_tau = (float)atof(env);      // 0 -> always three Gram passes
   if (dp == 64) NSVGD_PROPAGATE(launch_tc<64>(st, pl, maps, prm, combined));
   else NSVGD_PROPAGATE(launch_tc<128>(st, pl, maps, prm, combined));
 
