@@ -60,3 +60,47 @@ if __name__ == "__main__":
             err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
             row = np.max(np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1))
             print(f"   {gp} Gram pass(es): rel Frobenius error {err:.2e}, max row error {row:.2e}")
+
+
+def phi_emulated_pw(X, S, h, variant):
+    """second-GEMM variants with ONE Gram pass: 'full' p0w0+p0w1+p1w0, 'no_p1' p0w0+p0w1, 'no_w1' p0w0+p1w0, 'single' p0w0"""
+    n, d = X.shape
+    mu = X.mean(0, dtype=np.float64).astype(np.float32)
+    Xc = (X - mu).astype(np.float32)
+    W = (S - Xc / np.float32(h * h)).astype(np.float32)
+    x0, _ = split(Xc)
+    w0, w1 = split(W)
+    G = x0 @ x0.T
+    xn = (Xc * Xc).sum(1)
+    cs = np.float32(0.72134752044448170368 / (h * h))
+    K = np.exp2((2 * cs * G - cs * xn[:, None] - cs * xn[None, :]).astype(np.float32))
+    p0, p1 = split(K)
+    if variant == "full":
+        M, Kq = p0 @ w0 + p0 @ w1 + p1 @ w0, p0 + p1
+    elif variant == "no_p1":
+        M, Kq = p0 @ w0 + p0 @ w1, p0          # rowsum must use the same quantised k
+    elif variant == "no_w1":
+        M, Kq = p0 @ w0 + p1 @ w0, p0 + p1
+    else:
+        M, Kq = p0 @ w0, p0
+    return (M + Kq.sum(1, keepdims=True) * Xc / np.float32(h * h)) / n
+
+
+def study_pw():
+    n, d = 4096, 128
+    X, S = so.gaussian_diag_workload(n, d, seed=0)
+    S = (S * 0.02).astype(np.float32)
+    S_coh = np.tile(S[:1] * 5 + 0.3, (n, 1)).astype(np.float32)          # coherent scores: every particle pushes the same way
+    print("\nsecond GEMM (P.W) variants, one Gram pass:")
+    for sname, SS in (("cfg4 scores", S), ("coherent scores", S_coh)):
+        for h in (51.85, 9.5):
+            ref = so.phistar(X, X, SS, h)
+            out = []
+            for v in ("full", "no_p1", "no_w1", "single"):
+                got = phi_emulated_pw(X, SS, h, v)
+                out.append(f"{v} {np.linalg.norm(got - ref) / np.linalg.norm(ref):.1e}")
+            print(f"   {sname}, h = {h}: " + ", ".join(out))
+
+
+if __name__ == "__main__":
+    study_pw()
