@@ -386,7 +386,7 @@ def main():
     roofline = None
     gram_passes = 3
     try:        # the kernel's device-side rule (phi_tc.cu: adaptive Gram precision), re-evaluated on the host for the report
-        tau = float(os.environ.get("NSVGD_TC_GRAM_TAU", "0.5"))
+        tau = float(os.environ.get("NSVGD_TC_GRAM_TAU", "0.1"))
         xc2max = float(((Xh - Xh.mean(0)) ** 2).sum(1).max())
         if tau > 0 and np.isfinite(h_val) and h_val > 0 and xc2max / (h_val * h_val) <= tau:
             gram_passes = 1
@@ -403,7 +403,7 @@ def main():
                     "gram_passes": gram_passes,
                     "note": "achieved = algorithmic 6*m*n*d flop (SURVEY 8d) / CUDA-event time of the kernel; the kernel executes "
                             "(2*gram_passes + 6)*m*n*d MMA flop (COMBINED form: second GEMM against W = S - Xc/h^2, N = d, bf16 "
-                            "2-piece split, 3 passes; Gram: 1 pass when max|xc|^2/h^2 <= 0.5, else 3) = executed_mma_frac of the "
+                            "2-piece split, 3 passes; Gram: 1 pass when max|xc|^2/h^2 <= 0.1, else 3) = executed_mma_frac of the "
                             "peak; traffic = ncu DRAM bytes per launch (algorithmic 3*n*d*4 = 100.7 MB); peak = " + pk["source"]
                             + ("" if graphed is None else "; kernel events from an un-graphed pass after the graph-replayed timed region")}
     cpu_baseline = None

@@ -100,7 +100,7 @@ PATH_CASES = [
     ("simt", 1000, 3, 1.3), ("simt", 333, 1, 0.7), ("simt", 257, 8, 2.0), ("simt", 300, 16, 3.0), ("simt", 130, 31, 4.0),
     ("generic", 700, 50, 5.0), ("generic", 300, 3, 1.3), ("generic", 129, 200, 12.0), ("generic", 64, 1030, 30.0),
     ("tc", 2048, 128, 8.0), ("tc", 1500, 100, 7.0), ("tc", 1024, 64, 5.5), ("tc", 1111, 50, 5.0), ("tc", 4096, 128, 3.0),
-    ("tc", 2048, 128, 30.0), ("tc", 1500, 100, 40.0),      # wide kernels: max|xc|^2/h^2 <= 0.5 -> ONE Gram pass (adaptive precision)
+    ("tc", 2048, 128, 30.0), ("tc", 1500, 100, 40.0),      # wide kernels around the adaptive-precision threshold (max|xc|^2/h^2 = 0.21 / 0.09; <= 0.1 -> ONE Gram pass)
     ("large", 1500, 200, 12.0), ("large", 1100, 515, 20.0), ("large", 4500, 130, 9.0),
 ]
 
