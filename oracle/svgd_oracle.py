@@ -381,3 +381,46 @@ def phistar_f32_blocked(Q, X, S, h, block=2048):
         rs = K.sum(1, keepdims=True)
         out[s:s + block] = (KV[:, :d] + (rs * q - KV[:, d:]) / h2) / F32(n)
     return out
+
+
+# --------------------------------------------------------------------------
+# fp64 blocked evaluation of phi* and the KSD / l2 statistics at BASELINE sizes
+# (n = 65536): torch CPU on all cores, row-blocked so that memory stays at
+# O(block * n).  Same formulas as phistar() / div_phistar() above
+# (stein.py:180-203, 99-106; utils.py:483-487; models.py:677-689).
+# --------------------------------------------------------------------------
+def phistar_stats_f64_blocked(X, S, h, block=512, rows=None, lambda_reg=0.5):
+    """Returns dict(phi=(n,d) fp64 [or only the requested `rows`], ksd, l2, alpha).
+    ksd / l2 are means over ALL n query rows, so every block is evaluated; `rows`
+    only limits what is kept of phi."""
+    import torch
+    torch.set_num_threads(max(1, __import__("os").cpu_count() or 1))
+    Xt = torch.as_tensor(np.asarray(X, np.float64)); St = torch.as_tensor(np.asarray(S, np.float64))
+    n, d = Xt.shape
+    h2 = float(h) ** 2
+    xn = (Xt * Xt).sum(1)
+    c = (St * Xt).sum(1)
+    V = torch.cat([St, Xt, torch.ones(n, 1, dtype=torch.float64), c[:, None]], dim=1)      # K @ [S | X | 1 | c]
+    keep = None if rows is None else np.asarray(rows)
+    phi_keep = np.empty((n if keep is None else len(keep), d))
+    pos = None if keep is None else {int(r): i for i, r in enumerate(keep)}
+    t_sum, l_sum = 0.0, 0.0
+    for s in range(0, n, block):
+        q = Xt[s:s + block]
+        r2 = (xn[s:s + block, None] + xn[None, :] - 2.0 * (q @ Xt.T)).clamp_(min=0.0)
+        K = torch.exp(r2 * (-0.5 / h2))
+        KV = K @ V
+        KS, KX, rs, Kc = KV[:, :d], KV[:, d:2 * d], KV[:, 2 * d], KV[:, 2 * d + 1]
+        phi = (KS + (rs[:, None] * q - KX) / h2) / n
+        b = (K * r2).sum(1)
+        div = ((Kc - (q * KS).sum(1)) / h2 + (d / h2) * rs - b / h2 ** 2) / n
+        t_sum += float(((St[s:s + block] * phi).sum(1) + div).sum())
+        l_sum += float((phi * phi).sum())
+        if keep is None:
+            phi_keep[s:s + block] = phi.numpy()
+        else:
+            for r in range(s, min(s + block, n)):
+                if r in pos:
+                    phi_keep[pos[r]] = phi[r - s].numpy()
+    ksd, l2 = t_sum / n, l_sum / n
+    return {"phi": phi_keep, "ksd": ksd, "l2": l2, "alpha": ksd / (2 * lambda_reg * l2)}

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -24,13 +25,26 @@ void set_error(const char* fmt, ...) {
 }
 
 int device_sm_count() {
-  static int cached = 0;
-  if (cached) return cached;
+  static std::atomic<int> cached[64];          // per device ordinal
   int dev = 0, sms = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (int c = cached[dev].load(std::memory_order_relaxed)) return c;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
-  cached = sms;
-  return cached;
+  cached[dev].store(sms, std::memory_order_relaxed);
+  return sms;
+}
+
+int ensure_dyn_smem(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::map<const void*, uint64_t> done;   // kernel -> bit mask of devices already configured
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  std::lock_guard<std::mutex> lk(mu);
+  uint64_t& mask = done[kernel];
+  if (mask & (1ull << dev)) return NSVGD_OK;
+  NSVGD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  mask |= 1ull << dev;
+  return NSVGD_OK;
 }
 
 // ---- optional event timing of the dominant kernels (off by default; not graph-capturable when on)

@@ -70,6 +70,9 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
 int device_sm_count();
+// cudaFuncAttributeMaxDynamicSharedMemorySize, once per (kernel, device): the attribute is per device, so a second GPU
+// in the same process (JAX, multi-device torch) needs its own call
+int ensure_dyn_smem(const void* kernel, int bytes);
 void prof_begin(int tag, cudaStream_t st);
 void prof_end(int tag, cudaStream_t st);
 
@@ -121,8 +124,11 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 //   GRAMW form : O[split][m_pad x ldo] = K W partial, W = S - Xc/h^2 (one block: the second GEMM is half as wide);
 //                scal[...] = {rowsum, kc, b, kg = sum_j k g_ij = qc_i.(K Xc)_i};
 //                phi_i = (1/n)[(K W)_i + rowsum_i qc_i/h^2],  qc_i.(K S)_i = qc_i.(K W)_i + kg_i/h^2
+//   GRAMW2 form: O[split][m_pad x ldo] = K [W | 1 | c | 0..] partial (ldo = dpad + 16): rowsum and kc are columns dpad, dpad + 1;
+//                scal[parts][m_pad x 2] = {b, kg}
 struct EpilogueArgs {
-  int form;               // 0 = DIRECT, 1 = GRAM, 2 = GRAMW
+  int form;               // 0 = DIRECT, 1 = GRAM, 2 = GRAMW, 3 = GRAMW2 (rowsum / K c in columns dpad, dpad + 1 of O; scal = {b, kg})
+  const uint32_t* err_flag;   // tensor-core paths: non-zero when a kernel aborted on its watchdog -> phi and stats are NaN
   const float* KS;        // DIRECT: m x d (ld = d)
   const float* R;         // DIRECT
   const float* O;         // GRAM: nsplit x m_pad x ldo

@@ -843,11 +843,7 @@ __global__ void fast_commit_kernel(const FastMedState* fs, const SelectState* cs
 template <int DP>
 static int launch_filter(cudaStream_t st, const CUtensorMap* maps, const MfParams& prm, int64_t row_blocks) {
   using L = MfSmem<DP>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NSVGD_CUDA(cudaFuncSetAttribute(median_filter_tc_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-    attr_set = true;
-  }
+  NSVGD_PROPAGATE(ensure_dyn_smem((const void*)median_filter_tc_kernel<DP>, L::DYN_BYTES));
   const int64_t my_blocks = prm.rb_start < row_blocks ? ceil_div(row_blocks - prm.rb_start, prm.rb_stride) : 0;
   if (my_blocks == 0) return NSVGD_OK;
   const unsigned chunks = (unsigned)ceil_div(prm.n_tiles, MF_CHUNK);
@@ -877,17 +873,13 @@ int median_fast_sample(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   NSVGD_CUDA(cudaMemsetAsync(f.list_counts, 0, sizeof(uint32_t) * MF_NSEG * MF_CSTRIDE, st));
   NSVGD_CUDA(cudaMemsetAsync(f.cand_counts, 0, sizeof(uint32_t) * MF_NSEG * MF_CSTRIDE, st));
   // weighted last coordinate scaled by sqrt(w) AFTER centring
-  NSVGD_PROPAGATE(launch_tc_prep(st, P, nullptr, n, dz, ldp, f.n_pad, f.dp, f.mu, sqrtf(w_last), f.Zb0, f.Zb1, nullptr,
-                                 nullptr, f.zn, nullptr, nullptr, nullptr));
+  NSVGD_PROPAGATE(launch_tc_prep(st, P, nullptr, n, dz, ldp, f.n_pad, f.dp, f.mu, sqrtf(w_last), f.Zb0, f.Zb1, nullptr, nullptr,
+                                 nullptr, 0, f.zn, nullptr, nullptr, nullptr));
   filter_vectors_kernel<<<(unsigned)std::min<int64_t>(ceil_div(f.n_pad, 256), 1024), 256, 0, st>>>(f.zn, f.n_pad, f.zlo, f.zhi);
   NSVGD_LAUNCH_CHECK();
   constexpr int WX_SMEM = WX_WARPS * 32 * WX_STRIDE * (int)sizeof(float);
-  static bool wx_attr = false;
-  if (!wx_attr) {
-    NSVGD_CUDA(cudaFuncSetAttribute(sample_pairs_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WX_SMEM));
-    NSVGD_CUDA(cudaFuncSetAttribute(exact_list_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WX_SMEM));
-    wx_attr = true;
-  }
+  NSVGD_PROPAGATE(ensure_dyn_smem((const void*)sample_pairs_warp_kernel, WX_SMEM));
+  NSVGD_PROPAGATE(ensure_dyn_smem((const void*)exact_list_warp_kernel, WX_SMEM));
   const uint32_t per = MF_SAMPLES / (uint32_t)nparts;
   const uint32_t s_begin = per * (uint32_t)part, s_end = s_begin + per;
   prof_begin(4, st);
@@ -959,11 +951,7 @@ int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   // gather re-uses rows through L1 and beats the warp-cooperative variant here (1.85 vs 2.5 ms at cfg4)
   const char* xl_env = getenv("NSVGD_MEDIAN_EXACT");        // "thread": the one-thread-per-pair kernel (A/B measurements)
   if (vec && dz % 4 == 0 && !(xl_env && xl_env[0] == 't')) {
-    static bool xl_attr = false;
-    if (!xl_attr) {
-      NSVGD_CUDA(cudaFuncSetAttribute(exact_list_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XL_SMEM));
-      xl_attr = true;
-    }
+    NSVGD_PROPAGATE(ensure_dyn_smem((const void*)exact_list_coop_kernel, XL_SMEM));
     exact_list_coop_kernel<<<dim3((unsigned)std::max(1, sms * 8 / MF_NSEG), MF_NSEG), 256, XL_SMEM, st>>>(
         P, (int)dz, ldp, w_last, f.fs, f.list, f.list_counts, f.list_cap, f.cand, f.cand_counts, f.cand_cap, main_state);
   } else if (vec) {

@@ -123,7 +123,7 @@ int median_fast(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t 
 // phi_tc.cu: centre + bf16 2-piece split (+ optional transposed [S|Xc] pieces); last_scale multiplies the
 // centred last coordinate (literal median mode)
 int launch_tc_prep(cudaStream_t st, const float* X, const float* S, int64_t n, int64_t d, int64_t ldx, int64_t rows_pad,
-                   int dp, const float* mu, float last_scale, void* Xb0, void* Xb1, void* Vt0, void* Vt1, float* xn,
-                   float* cv, const float* h_combine, uint32_t* xn_max_bits);
+                   int dp, const float* mu, float last_scale, void* Xb0, void* Xb1, void* Xh, void* Vt0, void* Vt1,
+                   int vt_extra, float* xn, float* cv, const float* h_combine, uint32_t* max_bits);
 
 }  // namespace nsvgd

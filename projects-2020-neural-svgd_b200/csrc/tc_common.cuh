@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "common.cuh"
+
 namespace nsvgd {
 namespace tc {
 
@@ -129,6 +131,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : NS_O4(v, 0) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : NS_O4(v, 0), NS_O4(v, 4)
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
                ::NS_I4(v, 0), NS_I4(v, 4), "r"(taddr)
@@ -158,6 +169,11 @@ __device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t by
 // both K-major (bits 15,16 = 0), N >> 3 in [17,23), M >> 4 in [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// same with fp16 operands (a_format = b_format = 0): 11-bit significands, used by the single-pass Gram of phi_tcw.cu
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T   (one elected thread)
@@ -190,12 +206,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
+// pack two floats into f16x2 (round to nearest even): low 16 bits = a, high 16 bits = b
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 __device__ __forceinline__ float bf16lo_to_float(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf16hi_to_float(uint32_t p) { return __uint_as_float(p & 0xFFFF0000u); }
 
 }  // namespace tc
 
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed)
+// (16-bit elements: the same map serves bf16 and fp16 tiles -- TMA only moves the bytes)
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                       uint32_t box_inner, uint32_t box_outer);
 

@@ -21,12 +21,24 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const EpilogueArgs a) {
   const float h = *a.h_dev;
   const float inv_h2 = 1.f / (h * h);
   const float inv_n = 1.f / (float)a.n;
+  // a tensor-core kernel that aborted on its mbarrier watchdog leaves partial sums behind: never turn them into a
+  // normal-looking phi / step -- NaN out, like any other invalid input
+  const bool poisoned = a.err_flag && *a.err_flag != 0u;
   double t_row = 0.0, l_row = 0.0;
   if (row < a.m) {
     float rowsum = 0.f, aval = 0.f, bval = 0.f, kg = 0.f;
     if (a.form == 0) {
       const float4 sc = *reinterpret_cast<const float4*>(&a.scal[row * 4]);
       rowsum = sc.x; aval = sc.y; bval = sc.z;
+    } else if (a.form == 3) {
+      for (int s = 0; s < a.nsplit; ++s) {
+        const float* o = a.O + ((int64_t)s * a.m_pad + row) * a.ldo + a.dpad;
+        rowsum += o[0]; aval += o[1];                              // (K 1)_i and (K c)_i: columns of the second GEMM
+      }
+      for (int s = 0; s < a.scal_parts; ++s) {
+        const float2 sc = *reinterpret_cast<const float2*>(&a.scal[((int64_t)s * a.m_pad + row) * 2]);
+        bval += sc.x; kg += sc.y;
+      }
     } else {
       const int parts = a.scal_parts > 0 ? a.scal_parts : a.nsplit;
       for (int s = 0; s < parts; ++s) {
@@ -40,7 +52,7 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const EpilogueArgs a) {
       if (a.form == 0) {
         ks = a.KS[row * a.d + c];
         rr = a.R[row * a.d + c];
-      } else if (a.form == 2) {
+      } else if (a.form >= 2) {
         float kw = 0.f;
         for (int s = 0; s < a.nsplit; ++s) kw += a.O[((int64_t)s * a.m_pad + row) * a.ldo + c];
         const float qc = a.Q[row * a.ldq + c] - a.mu[c];
@@ -75,10 +87,14 @@ __global__ void __launch_bounds__(256) epilogue_kernel(const EpilogueArgs a) {
     }
     sphi = warp_sum(sphi); l2 = warp_sum(l2);
     if (a.form == 1) { qks = warp_sum(qks); aval = aval - qks; }   // a_i = (K c)_i - qc_i.(K S)_i
-    if (a.form == 2) { qks = warp_sum(qks); aval = aval - fmaf(kg, inv_h2, qks); }   // qc.(K S) = qc.(K W) + kg/h^2
+    if (a.form >= 2) { qks = warp_sum(qks); aval = aval - fmaf(kg, inv_h2, qks); }   // qc.(K S) = qc.(K W) + kg/h^2
     const float div = (aval * inv_h2 + (float)a.d * inv_h2 * rowsum - bval * inv_h2 * inv_h2) * inv_n;
     t_row = (double)sphi + (double)div;
     l_row = (double)l2;
+    if (poisoned) {
+      for (int64_t c = lane; c < a.d; c += 32) a.phi[row * a.ldphi + c] = nanf("");
+      t_row = l_row = (double)nanf("");
+    }
   }
   if (a.stats_dev) {
     if (lane == 0) { sh_t[w] = t_row; sh_l[w] = l_row; }
@@ -103,16 +119,28 @@ __global__ void __launch_bounds__(256) epilogue_gram4_kernel(const EpilogueArgs 
   const float h = *a.h_dev;
   const float inv_h2 = 1.f / (h * h);
   const float inv_n = 1.f / (float)a.n;
+  const bool poisoned = a.err_flag && *a.err_flag != 0u;
   double t_row = 0.0, l_row = 0.0;
   if (row < a.m) {
     float rowsum = 0.f, aval = 0.f, bval = 0.f, kg = 0.f;
     const int parts = a.scal_parts > 0 ? a.scal_parts : a.nsplit;
-    for (int s = lane; s < parts; s += 32) {
-      const float4 sc = *reinterpret_cast<const float4*>(&a.scal[((int64_t)s * a.m_pad + row) * 4]);
-      rowsum += sc.x; aval += sc.y; bval += sc.z; kg += sc.w;
+    if (a.form == 3) {
+      for (int s = lane; s < a.nsplit; s += 32) {
+        const float2 rc = *reinterpret_cast<const float2*>(a.O + ((int64_t)s * a.m_pad + row) * a.ldo + a.dpad);
+        rowsum += rc.x; aval += rc.y;                              // (K 1)_i and (K c)_i: columns of the second GEMM
+      }
+      for (int s = lane; s < parts; s += 32) {
+        const float2 sc = *reinterpret_cast<const float2*>(&a.scal[((int64_t)s * a.m_pad + row) * 2]);
+        bval += sc.x; kg += sc.y;
+      }
+    } else {
+      for (int s = lane; s < parts; s += 32) {
+        const float4 sc = *reinterpret_cast<const float4*>(&a.scal[((int64_t)s * a.m_pad + row) * 4]);
+        rowsum += sc.x; aval += sc.y; bval += sc.z; kg += sc.w;
+      }
     }
     rowsum = warp_sum(rowsum); aval = warp_sum(aval); bval = warp_sum(bval); kg = warp_sum(kg);
-    const bool gramw = a.form == 2;
+    const bool gramw = a.form >= 2;
     float sphi = 0.f, l2 = 0.f, qks = 0.f;
     for (int64_t c = 4 * lane; c < a.d; c += 128) {
       float4 ks = make_float4(0.f, 0.f, 0.f, 0.f), kx = ks;
@@ -156,6 +184,10 @@ __global__ void __launch_bounds__(256) epilogue_gram4_kernel(const EpilogueArgs 
     const float div = (aval * inv_h2 + (float)a.d * inv_h2 * rowsum - bval * inv_h2 * inv_h2) * inv_n;
     t_row = (double)sphi + (double)div;
     l_row = (double)l2;
+    if (poisoned) {
+      for (int64_t c = lane; c < a.d; c += 32) a.phi[row * a.ldphi + c] = nanf("");
+      t_row = l_row = (double)nanf("");
+    }
   }
   if (a.stats_dev) {
     if (lane == 0) { sh_t[w] = t_row; sh_l[w] = l_row; }
