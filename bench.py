@@ -9,14 +9,15 @@ i.e. what models.Particles.step does for KernelGradient(bandwidth=None, scaled=T
     python bench.py --gpus N --steps K --warmup W            # our CUDA path (torchrun for N > 1)
     python bench.py --impl reference ...                      # CPU arm (the oracle port: JAX is not installable)
 
-Prints ONE JSON line on rank 0.  Timing: CUDA events on the launching stream, barrier +
-synchronize on both sides, max over ranks; particles move every step and an L2-sized buffer is
-rewritten between steps (config.l2_flush).
+Prints ONE JSON line on rank 0.  Timing: CUDA events on the launching stream, barrier + synchronize on both sides,
+max over ranks; particles move every step and an L2-sized buffer is rewritten between steps (config.l2_flush).
+Both arms print the same `config` object.  The headline run uses the literal median mode (what kernels.py:169
+executes); `offdiag_mode` holds a second, shorter run with the docstring's off-diagonal median (a 13x tighter bandwidth:
+three bf16-split Gram passes instead of one fp16 pass).
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -31,6 +32,12 @@ import torch  # noqa: E402
 
 METRIC = "svgd_pairwise_interactions_per_s"
 UNIT = "n^2*d/s"
+LR, LAMBDA_REG = 1e-3, 0.5
+
+# Exact median-heuristic bandwidths of workload(n, d, seed=0), as produced by the CUDA select (bit-identical between
+# the tensor-core filtered select and the 3-pass SIMT select: tests/test_gpu_fullsize.py).  The CPU arm uses the SAME
+# bandwidth as the GPU arm; computing it on the CPU (2.1e9 pair distances) is out of reach and is stated as excluded.
+KNOWN_BANDWIDTH = {(65536, 128, "literal"): 51.85246658325195, (65536, 128, "offdiag"): 3.3723738193511963}
 
 
 def parse():
@@ -44,9 +51,10 @@ def parse():
     ap.add_argument("--path", default="auto")
     ap.add_argument("--median-mode", default="literal", choices=["literal", "offdiag", "full"])
     ap.add_argument("--bandwidth", type=float, default=0.0, help="> 0: fixed bandwidth (skip the median heuristic)")
-    ap.add_argument("--cpu-rows", type=int, default=2048, help="query rows of the bounded CPU sample")
+    ap.add_argument("--cpu-rows", type=int, default=8192, help="query rows of the bounded CPU sample (per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-offdiag", action="store_true", help="skip the secondary off-diagonal-median run")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step as one CUDA graph (auto: when row-sharded, where host issue time limits the step)")
     return ap.parse_args()
@@ -60,65 +68,96 @@ def workload(n, d, seed=0):
     return X, (S * np.float32(0.02)).astype(np.float32)
 
 
-class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+def config_of(args, world):
+    """identical in both arms (ours / reference): the driver compares it"""
+    return {"workload": f"svgd_step n={args.n} d={args.d} (BASELINE configs[3])", "n": args.n, "d": args.d,
+            "bandwidth": (f"median heuristic ({args.median_mode}) every step" if args.bandwidth <= 0 else f"fixed {args.bandwidth}"),
+            "scaled": True, "optimizer": "sgd", "lr": LR, "lambda_reg": LAMBDA_REG,
+            "parallelism": f"row-sharded x{world}", "l2_flush": "192 MiB fill between steps (GPU arm)"}
 
-    def __init__(self, gpu_index=0):
-        self.lines, self.proc, self.gpu = [], None, gpu_index
+
+class ClockSampler:
+    """SM clock, power and clock-event (throttle) reasons DURING the timed region, sampled through NVML every 5 ms
+    (nvidia-smi -lms cannot go below ~100 ms: the row-sharded timed regions are 30-70 ms long)."""
+    BITS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
+
+    def __init__(self, device_index=0, period_s=0.005):
+        self.samples, self.period, self.stop_flag, self.thread, self.h, self.err = [], period_s, False, None, None, None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            except Exception:
+                uuid = None
+            if uuid:
+                try:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+                except Exception:
+                    self.h = None
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:          # NVML unavailable: say so in the record
+            self.err = str(e)[:120]
+
+    def _reasons(self):
+        nv = self.nv
+        for name in ("nvmlDeviceGetCurrentClocksEventReasons", "nvmlDeviceGetCurrentClocksThrottleReasons"):
+            fn = getattr(nv, name, None)
+            if fn is not None:
+                try:
+                    return int(fn(self.h))
+                except Exception:
+                    continue
+        return 0
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.samples.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                     nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0, self._reasons()))
+            except Exception as e:
+                self.err = str(e)[:120]
+                return
+            time.sleep(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        if self.h is None:
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, power, reasons = [], [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples" + (f": {self.err}" if self.err else "")]}
+        sm = [s[0] for s in self.samples]
+        bits = 0
+        for s in self.samples:
+            bits |= s[2]
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": self.max_mhz,
+                "power_w_max": float(max(s[1] for s in self.samples)), "samples": len(sm), "period_ms": 1e3 * self.period,
+                "source": "NVML", "reasons": sorted(v for k, v in self.BITS.items() if bits & k)}
 
 
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         p = json.load(open(path))
-        return {"bf16_tflops": p.get("bf16_tflops_sustained", p.get("bf16_tflops")), "hbm_gbs": p.get("hbm_gbs"),
-                "source": "MEASURED_PEAKS.json (sustained bf16: kernel timed inside a long step)"}
-    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+        return {"burst": p.get("bf16_tflops"), "sustained": p.get("bf16_tflops_sustained", p.get("bf16_tflops")),
+                "hbm_gbs": p.get("hbm_gbs"), "source": "MEASURED_PEAKS.json"}
+    return {"burst": 1650.0, "sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 def ncu_traffic(n, d, m_local):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
-    (profiles/phi_tc_traffic.json); only valid for the configuration it was captured on."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture of
+    the SHIPPED kernel (profiles/phi_tc_traffic.json); only valid for the configuration it was captured on."""
     path = os.path.join(ROOT, "profiles", "phi_tc_traffic.json")
     if n == 65536 and d == 128 and m_local == n and os.path.exists(path):
         t = json.load(open(path))
@@ -126,34 +165,69 @@ def ncu_traffic(n, d, m_local):
     return None
 
 
-def cpu_port_rate(X, S, h, rows, repeats=1):
-    """The oracle's fp32 blocked port (sgemm Gram -> exp -> sgemm) on all host cores for `rows` query
-    rows against all n particles.  Returns (n^2*d-units per second, seconds, cores)."""
-    from oracle.svgd_oracle import phistar_f32_blocked
+def host_gram_passes(Xh, h):
+    """the kernel's device-side rule (phi_tc.cu::tcw_onepass), re-evaluated on the host for the report: ONE fp16 Gram pass
+    iff the rigorous bound (2 N R + R^2) / h^2 on |delta ln k| is <= gram_eps, N = max|xc|, R = max|xc - fp16(xc)|."""
+    try:
+        eps = float(os.environ.get("NSVGD_TC_GRAM_EPS", "5e-5"))
+        if not (eps > 0 and np.isfinite(h) and h > 0):
+            return 3, None
+        xc = (Xh - Xh.astype(np.float64).mean(0).astype(np.float32)).astype(np.float32)
+        with np.errstate(over="ignore"):
+            f = xc.astype(np.float16).astype(np.float32)
+        f[np.abs(f) < 6.103515625e-05] = 0.0
+        nmax = float(np.sqrt((xc.astype(np.float64) ** 2).sum(1).max()))
+        r2 = float((((xc - f).astype(np.float64)) ** 2).sum(1).max())
+        bound = (2.0 * nmax * np.sqrt(r2) + r2) / (h * h)
+        return (1 if bound <= eps else 3), bound
+    except Exception:
+        return 3, None
+
+
+def cpu_port_rate(X, S, h, rows, threads=None):
+    """The oracle's fp32 blocked port (sgemm Gram -> exp -> sgemm) on torch CPU with every host core, for `rows` query
+    rows against all n particles.  Returns (n^2*d-units per second, seconds, threads)."""
+    from oracle.svgd_oracle import phistar_f32_blocked_torch
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)          # torchrun exports OMP_NUM_THREADS=1: undo it for the CPU arm
     n, d = X.shape
     rows = min(rows, n)
-    best = float("inf")
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        phistar_f32_blocked(X[:rows], X, S, h, block=1024)
-        best = min(best, time.perf_counter() - t0)
-    return rows * n * d / best, best, os.cpu_count()
+    Xt, St = torch.as_tensor(X), torch.as_tensor(S)
+    t0 = time.perf_counter()
+    phistar_f32_blocked_torch(Xt[:rows], Xt, St, h, block=1024)
+    dt = time.perf_counter() - t0
+    return rows * n * d / dt, dt, torch.get_num_threads()
+
+
+def cpu_bandwidth(args, X):
+    """the bandwidth the CPU arm uses: the GPU arm's exact value for this workload (median selection itself is excluded
+    from the CPU arm: 2.1e9 pair distances)"""
+    if args.bandwidth > 0:
+        return args.bandwidth, "fixed"
+    key = (args.n, args.d, args.median_mode)
+    if key in KNOWN_BANDWIDTH:
+        return KNOWN_BANDWIDTH[key], "exact value of the GPU arm's median select for this workload (bench.KNOWN_BANDWIDTH)"
+    from oracle.svgd_oracle import median_heuristic
+    sub = X[: min(args.n, 2048)]
+    return float(median_heuristic(sub, args.median_mode)), "oracle median of the first 2048 particles"
 
 
 def run_reference(args):
-    """--impl reference: the reference's own implementation cannot be installed (JAX/jaxlib/haiku/optax
-    absent, no network), so this arm times the CPU restatement (oracle port) on the host cores, each
-    step a bounded sample (cpu-rows query rows x all n particles) of the same workload."""
+    """--impl reference: the reference's own implementation cannot be installed (JAX/jaxlib/haiku/optax absent, no
+    network), so this arm times the CPU restatement (oracle port) on ALL host cores, each step a bounded sample
+    (cpu-rows query rows x all n particles) of the same workload at the same bandwidth as the GPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     X, S = workload(args.n, args.d)
-    h = 6.0 if args.bandwidth <= 0 else args.bandwidth     # the exact CPU median at n=65536 is out of reach; phi-only sample
+    h, h_src = cpu_bandwidth(args, X)
+    threads = os.cpu_count() or 1
     for _ in range(max(args.warmup, 1)):
-        cpu_port_rate(X, S, h, min(args.cpu_rows, 512))
+        cpu_port_rate(X, S, h, min(args.cpu_rows, 1024), threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_port_rate(X, S, h, args.cpu_rows)
+        cpu_port_rate(X, S, h, args.cpu_rows, threads)
     dt = time.perf_counter() - t0
     rows = min(args.cpu_rows, args.n)
     value = args.steps * rows * args.n * args.d / dt
@@ -173,14 +247,15 @@ def run_reference(args):
                       "what": "oracle/structural.py get_field_scaled (vmap/grad/jacfwd mirror of stein.py + models.py:677-689), torch CPU"}
     except Exception as e:      # informational only
         structural = {"error": str(e)[:200]}
+    sample = (f"{rows} query rows x {args.n} particles per step, phi* only at h={h:.6g} ({h_src}); the median selection is "
+              f"EXCLUDED from the CPU arm; torch CPU fp32 (MKL sgemm + vectorised exp), {threads} threads")
     out = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"svgd_step n={args.n} d={args.d} (BASELINE configs[3])", "n": args.n, "d": args.d,
-                   "note": "reference JAX unavailable in image; CPU restatement (oracle port), phi* only, bounded sample"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                         "sample": f"{rows} query rows x {args.n} particles per step (phi* only, fixed h={h}), numpy/BLAS fp32"},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(args, world),
+        "arm": {"note": "reference JAX unavailable in image (jax/jaxlib/haiku/optax absent, no network): CPU restatement "
+                        "(oracle port) on all host cores, bounded sample per step", "bandwidth_used": h},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "structural_restatement": structural,
     }
@@ -194,7 +269,7 @@ def main():
 
     import torch.distributed as dist
     from nsvgd import _lib, engine
-    from nsvgd.parallel import ShardedSVGD, row_partition
+    from nsvgd.parallel import GraphedStep, ShardedSVGD, row_partition
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -205,101 +280,135 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n, d, K, W = args.n, args.d, args.steps, args.warmup
-    lr, lam = 1e-3, 0.5
+    lr, lam = LR, LAMBDA_REG
     fixed_h = args.bandwidth if args.bandwidth > 0 else None
 
     Xh, Sh = workload(n, d)
     r0, r1 = row_partition(n, world, rank)
+    m_local = r1 - r0
     X0 = torch.tensor(Xh[r0:r1], device=dev)
     S_loc = torch.tensor(Sh[r0:r1], device=dev)
     X_loc = X0.clone()
-    sharded = ShardedSVGD(n, d, median_mode=args.median_mode) if world > 1 else None
     flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-
     use_graph = args.graph == "on" or (args.graph == "auto" and world > 1)
-    graphed = None
-    launches_per_replay = 0
-
-    def one_step():
-        if graphed is not None:
-            return graphed.replay()
-        if world > 1:
-            h, aux, _ = sharded.step(X_loc, S_loc, lr, scaled=True, lambda_reg=lam, bandwidth=fixed_h)
-        else:
-            h = fixed_h if fixed_h else engine.median_heuristic(X_loc, args.median_mode)
-            aux, _ = engine.svgd_step_sgd(X_loc, S_loc, h, lr, scaled=True, lambda_reg=lam, path=args.path)
-        return h, aux
+    pk = peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    if use_graph:
-        l0 = _lib.launch_count()
-        if world > 1:
-            graphed = sharded.capture(X_loc, S_loc, lr, scaled=True, lambda_reg=lam, bandwidth=fixed_h)
-        else:
-            from nsvgd.parallel import GraphedStep
-            one_step(); torch.cuda.synchronize()
-            g_ = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_):
-                h_, aux_ = one_step()
-            graphed = GraphedStep(g_, h_, aux_)
-        launches_per_replay = (_lib.launch_count() - l0) // 2       # warm-up pass + captured pass
+    def run_mode(mode, K, W, want_clocks):
+        """W warm-up + K timed steps of the full SVGD step with the median in `mode`.  Returns a dict."""
+        sharded = ShardedSVGD(n, d, median_mode=mode) if world > 1 else None
         X_loc.copy_(X0)
-    for _ in range(W):
-        flush.fill_(1)
-        one_step()
-    barrier()
+        state = {"graphed": None}
 
-    # ---- timed region: K steps, device events, L2 flushed between steps (flush excluded by events) ----
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    _lib.profile_enable(graphed is None)      # library-side events cannot be recorded inside a replayed graph
-    launches0 = _lib.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    barrier()
-    t_wall0 = time.perf_counter()
-    for i in range(K):
-        flush.fill_(i & 1)
-        ev[i][0].record()
-        h, aux = one_step()
-        ev[i][1].record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = _lib.launch_count() - launches0 if graphed is None else launches_per_replay * K
-    clocks = sampler.stop() if rank == 0 else None
-    step_ms = sum(a.elapsed_time(b) for a, b in ev)
-    h_val = float(h) if not isinstance(h, torch.Tensor) else float(h.item())
-    aux_host = aux.cpu().numpy()
-    if graphed is not None:
-        # per-kernel breakdown / roofline: a second, un-graphed pass of min(K, 5) steps with the library-side
-        # CUDA events on (not part of `value`; says so in roofline.note)
-        g_keep, graphed = graphed, None
-        _lib.profile_enable(True)
-        KP = max(1, min(K, 5))
-        for i in range(KP):
-            flush.fill_(i & 1)
+        def one_step():
+            if state["graphed"] is not None:
+                return state["graphed"].replay()
+            if world > 1:
+                h, aux, _ = sharded.step(X_loc, S_loc, lr, scaled=True, lambda_reg=lam, bandwidth=fixed_h)
+            else:
+                h = fixed_h if fixed_h else engine.median_heuristic(X_loc, mode)
+                aux, _ = engine.svgd_step_sgd(X_loc, S_loc, h, lr, scaled=True, lambda_reg=lam, path=args.path)
+            return h, aux
+
+        launches_per_replay = 0
+        if use_graph:
+            l0 = _lib.launch_count()
+            if world > 1:
+                state["graphed"] = sharded.capture(X_loc, S_loc, lr, scaled=True, lambda_reg=lam, bandwidth=fixed_h)
+            else:
+                one_step(); torch.cuda.synchronize()
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_):
+                    h_, aux_ = one_step()
+                state["graphed"] = GraphedStep(g_, h_, aux_)
+            launches_per_replay = (_lib.launch_count() - l0) // 2       # warm-up pass + captured pass
+            X_loc.copy_(X0)
+        for _ in range(W):
+            flush.fill_(1)
             one_step()
         barrier()
-        graphed = g_keep
-    else:
-        KP = K
-    phi_main_ms, phi_main_cnt = _lib.profile_read(0)
-    hist_ms, hist_cnt = _lib.profile_read(1)
-    phi_op_ms, _ = _lib.profile_read(2)
-    med_op_ms, _ = _lib.profile_read(3)
-    med_sample_ms, _ = _lib.profile_read(4)
-    med_exact_ms, _ = _lib.profile_read(5)
-    med_filter_ms, _ = _lib.profile_read(6)
-    _lib.profile_enable(False)
-    t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+        sampler = ClockSampler(local_rank) if (want_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+        graphed = state["graphed"]
+        _lib.profile_enable(graphed is None)      # library-side events cannot be recorded inside a replayed graph
+        launches0 = _lib.launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        barrier()
+        t_wall0 = time.perf_counter()
+        for i in range(K):
+            flush.fill_(i & 1)
+            ev[i][0].record()
+            h, aux = one_step()
+            ev[i][1].record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        launches = _lib.launch_count() - launches0 if graphed is None else launches_per_replay * K
+        clocks = sampler.stop() if sampler else None
+        step_ms = sum(a.elapsed_time(b) for a, b in ev)
+        h_val = float(h) if not isinstance(h, torch.Tensor) else float(h.item())
+        aux_host = aux.cpu().numpy()
+        if graphed is not None:
+            # per-kernel breakdown / roofline: a second, un-graphed pass of min(K, 5) steps with the library-side
+            # CUDA events on (not part of `value`; says so in the notes)
+            state["graphed"] = None
+            _lib.profile_enable(True)
+            KP = max(1, min(K, 5))
+            for i in range(KP):
+                flush.fill_(i & 1)
+                one_step()
+            barrier()
+            state["graphed"] = graphed
+        else:
+            KP = K
+        prof = {tag: _lib.profile_read(tag) for tag in range(7)}
+        _lib.profile_enable(False)
+        t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        return {"one_step": one_step, "state": state, "sharded": sharded, "total_ms": total_ms, "K": K, "KP": KP, "prof": prof,
+                "h": h_val, "aux": aux_host, "launches": int(launches), "clocks": clocks, "t_wall": t_wall, "graphed": graphed}
+
+    def kernel_roofline(res, mode):
+        ms, cnt = res["prof"][0]
+        if not cnt:
+            return None
+        avg_ms = ms / cnt
+        gram_passes, bound = host_gram_passes(Xh, res["h"]) if d > 32 else (0, None)
+        flop = 6.0 * m_local * n * d            # algorithmic: Gram 2 m n d + K [S|X] 4 m n d   (SURVEY 8d)
+        achieved = flop / (avg_ms * 1e-3) / 1e12
+        timed_s = res["total_ms"] * 1e-3
+        use_burst = timed_s < 1.0               # a kernel timed alone / in a short region holds burst clocks (VERDICT r1)
+        peak = pk["burst"] if use_burst else pk["sustained"]
+        exec_units = (2 * gram_passes + 6 * (d + 16.0) / d) if d > 32 else 6.0      # N = d + 16 columns in the second GEMM
+        return {"bound": "tensor", "kernel": "phi_tcw_kernel" if d > 32 else "phi_smalld_kernel", "achieved": achieved,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "frac_burst": achieved / pk["burst"],
+                "frac_sustained": achieved / pk["sustained"], "peak_kind": "burst" if use_burst else "sustained",
+                "traffic": ncu_traffic(n, d, m_local) if mode == "literal" else None, "avg_kernel_ms": avg_ms, "launches": cnt,
+                "gram_passes": gram_passes, "gram_error_bound": bound,
+                "executed_mma_frac_burst": exec_units / 6.0 * achieved / pk["burst"],
+                "note": "achieved = algorithmic 6*m*n*d flop (SURVEY 8d) / CUDA-event time of the kernel; the kernel executes "
+                        "(2*gram_passes + 6*(d+16)/d)*m*n*d MMA flop (second GEMM against [S - Xc/h^2 | 1 | c], bf16 2-piece split, "
+                        "3 passes; Gram: ONE fp16 pass when the rigorous bound (2NR+R^2)/h^2 <= 5e-5, else three bf16-split passes); "
+                        "peak = " + pk["source"] + (" burst (timed region %.2f s < 1 s)" % timed_s if use_burst else " sustained")
+                        + ("" if res["graphed"] is None else "; kernel events from an un-graphed pass after the graph-replayed timed region")}
+
+    def step_roofline(res):
+        ms = res["total_ms"] / res["K"]
+        flop = 7.0 * float(n) * n * d / world          # per GPU: phi* 6 + one upper-triangular Gram for the median (SURVEY 8d)
+        ach = flop / (ms * 1e-3) / 1e12
+        return {"achieved": ach, "unit": "TFLOP/s per GPU", "peak": pk["burst"], "frac_burst": ach / pk["burst"],
+                "frac_sustained": ach / pk["sustained"], "what": "algorithmic 7*n^2*d/N flop per GPU / ms_per_step"}
+
+    res = run_mode(args.median_mode, K, W, want_clocks=True)
+    total_ms = res["total_ms"]
     value = K * float(n) * n * d / (total_ms * 1e-3)
+    one_step, graphed, sharded = res["one_step"], res["graphed"], res["sharded"]
 
     # ---- e2e: the reference-facing call with HOST buffers, copies inside the timed region -------------
     e2e = None
@@ -344,7 +453,7 @@ def main():
                 d2h_done.record(d2h)
         e2e_step()
         barrier()
-        KE = max(2, min(K, 5))
+        KE = max(2, min(K, 10))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(KE):
@@ -356,19 +465,39 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": KE * float(n) * n * d / (float(te.item()) * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(2 * (r1 - r0) * d * 4), "d2h_bytes_per_step": int((r1 - r0) * d * 4 + 64),
+               "h2d_bytes_per_step": int(2 * m_local * d * 4), "d2h_bytes_per_step": int(m_local * d * 4 + 64),
                "steps": KE, "api": "nsvgd.engine.median_heuristic + svgd_step_sgd (C ABI nsvgd_median_h_f32 / nsvgd_step_sgd_f32), pinned host buffers"}
+
+    # ---- secondary: the docstring's off-diagonal median (north-star intent; three Gram passes) ---------------
+    offdiag = None
+    if not args.no_offdiag and not fixed_h and args.median_mode != "offdiag":
+        if res["state"]["graphed"] is not None:
+            res["state"]["graphed"] = None
+            torch.cuda.synchronize()
+        K2 = max(3, min(K, 10))
+        r2 = run_mode("offdiag", K2, 3, want_clocks=False)
+        rf = kernel_roofline(r2, "offdiag") if rank == 0 else None
+        offdiag = {"median_mode": "offdiag", "steps": K2, "ms_per_step": r2["total_ms"] / K2,
+                   "value": K2 * float(n) * n * d / (r2["total_ms"] * 1e-3), "unit": UNIT,
+                   "result": {"h": r2["h"], "ksd": float(r2["aux"][0]), "l2": float(r2["aux"][1]), "alpha": float(r2["aux"][2])},
+                   "phi_main_kernel_ms": (r2["prof"][0][0] / r2["prof"][0][1]) if r2["prof"][0][1] else None,
+                   "median_op_ms": r2["prof"][3][0] / r2["KP"],
+                   "roofline": rf, "roofline_step": step_roofline(r2)}
+        if r2["state"]["graphed"] is not None:
+            r2["state"]["graphed"] = None
+        res_graph_live = False
+    else:
+        res_graph_live = graphed is not None
 
     def shutdown():
         """A CUDA graph that captured NCCL kernels must be released before the communicator goes away, and
         destroy_process_group() was observed to hang after graph replays (torch 2.11 / NCCL 2.28): synchronise,
         drop the graph, barrier, and leave without tearing the communicator down."""
-        nonlocal graphed
         if world == 1:
             return
         torch.cuda.synchronize()
-        if graphed is not None:
-            graphed = None
+        if use_graph:
+            res["state"]["graphed"] = None
             torch.cuda.synchronize()
             dist.barrier()
             torch.cuda.synchronize()
@@ -380,60 +509,41 @@ def main():
         shutdown()
         return
 
-    # ---- roofline of the dominant kernel (phi* main kernel) --------------------------------------------
-    pk = peaks()
-    m_local = r1 - r0
-    roofline = None
-    gram_passes = 3
-    try:        # the kernel's device-side rule (phi_tc.cu: adaptive Gram precision), re-evaluated on the host for the report
-        tau = float(os.environ.get("NSVGD_TC_GRAM_TAU", "0.1"))
-        xc2max = float(((Xh - Xh.mean(0)) ** 2).sum(1).max())
-        if tau > 0 and np.isfinite(h_val) and h_val > 0 and xc2max / (h_val * h_val) <= tau:
-            gram_passes = 1
-    except Exception:
-        pass
-    if phi_main_cnt:
-        avg_ms = phi_main_ms / phi_main_cnt
-        flop = 6.0 * m_local * n * d            # algorithmic: Gram 2 m n d + K [S|X] 4 m n d   
-        achieved = flop / (avg_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "phi_tc_kernel" if d > 32 else "phi_smalld_kernel",
-                    "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-                    "traffic": ncu_traffic(n, d, m_local), "avg_kernel_ms": avg_ms, "launches": phi_main_cnt,
-                    "executed_mma_frac": (2 * gram_passes + 6) / 6.0 * achieved / pk["bf16_tflops"],
-                    "gram_passes": gram_passes,
-                    "note": "achieved = algorithmic 6*m*n*d flop (SURVEY 8d) / CUDA-event time of the kernel; the kernel executes "
-                            "(2*gram_passes + 6)*m*n*d MMA flop (COMBINED form: second GEMM against W = S - Xc/h^2, N = d, bf16 "
-                            "2-piece split, 3 passes; Gram: 1 pass when max|xc|^2/h^2 <= 0.1, else 3) = executed_mma_frac of the "
-                            "peak; traffic = ncu DRAM bytes per launch (algorithmic 3*n*d*4 = 100.7 MB); peak = " + pk["source"]
-                            + ("" if graphed is None else "; kernel events from an un-graphed pass after the graph-replayed timed region")}
+    roofline = kernel_roofline(res, args.median_mode)
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, secs, cores = cpu_port_rate(Xh, Sh, h_val if np.isfinite(h_val) and h_val > 0 else 6.0, args.cpu_rows)
+        h_cpu = res["h"] if np.isfinite(res["h"]) and res["h"] > 0 else 6.0
+        rate, secs, cores = cpu_port_rate(Xh, Sh, h_cpu, args.cpu_rows)      # warm-up (thread pool, MKL)
+        reps, tot_rows, tot_s = 0, 0, 0.0
+        while tot_s < 8.0 and reps < 8:                                        # bounded: ~10 s of CPU work
+            rate, secs, cores = cpu_port_rate(Xh, Sh, h_cpu, args.cpu_rows)
+            reps += 1; tot_rows += min(args.cpu_rows, n); tot_s += secs
+        rate = tot_rows * float(n) * d / tot_s
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{min(args.cpu_rows, n)} query rows x {n} particles, phi* only (no median), numpy/BLAS fp32, {secs:.2f} s; "
+                        "sample": f"{reps} x {min(args.cpu_rows, n)} query rows x {n} particles at h={h_cpu:.6g} (the GPU arm's), phi* only "
+                                  f"(median selection EXCLUDED), torch CPU fp32 (MKL sgemm + vectorised exp), {cores} threads, {tot_s:.2f} s; "
                                   "reference JAX not installable in this image"}
+    KP = res["KP"]
+    prof = res["prof"]
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32 (bf16x2-split tensor-core MMAs, fp32 accumulate)" if d > 32 else "f32",
-        "data": "synthetic",
-        "config": {"workload": f"svgd_step n={n} d={d} (BASELINE configs[3])", "n": n, "d": d, "rows_per_gpu": m_local,
-                   "bandwidth": "median heuristic (%s) every step" % args.median_mode if not fixed_h else f"fixed {fixed_h}",
-                   "scaled": True, "optimizer": "sgd", "parallelism": f"row-sharded x{world}", "l2_flush": "192 MiB fill between steps",
-                   "path": args.path,
-                   "small_allreduces": ("peer memory over NVLink, fused into the consumer kernels (csrc/p2p.cuh)"
-                                        if (sharded is not None and sharded.comm is not None) else ("nccl" if world > 1 else "none")),
-                   "launch": "one CUDA graph replay per step (collectives captured)" if graphed is not None else "eager (C-ABI calls per op)"},
-        "breakdown_ms_per_step": {"median_op": med_op_ms / KP, "median_tc_filter_kernel": med_filter_ms / KP,
-                                  "median_sample_kernel": med_sample_ms / KP, "median_exact_list_kernel": med_exact_ms / KP,
-                                  "median_simt_hist_kernels": hist_ms / KP, "phi_op": phi_op_ms / KP,
-                                  "phi_main_kernel": phi_main_ms / KP,
+        "dtype": "f32 (tensor-core MMAs on bf16x2-split / fp16 operands, fp32 accumulate)" if d > 32 else "f32",
+        "data": "synthetic", "config": config_of(args, world),
+        "arm": {"rows_per_gpu": m_local, "path": args.path,
+                "small_allreduces": ("peer memory over NVLink, fused into the consumer kernels (csrc/p2p.cuh)"
+                                     if (sharded is not None and sharded.comm is not None) else ("nccl" if world > 1 else "none")),
+                "launch": "one CUDA graph replay per step (collectives captured)" if graphed is not None else "eager (C-ABI calls per op)"},
+        "breakdown_ms_per_step": {"median_op": prof[3][0] / KP, "median_tc_filter_kernel": prof[6][0] / KP,
+                                  "median_sample_kernel": prof[4][0] / KP, "median_exact_list_kernel": prof[5][0] / KP,
+                                  "median_simt_hist_kernels": prof[1][0] / KP, "phi_op": prof[2][0] / KP,
+                                  "phi_main_kernel": prof[0][0] / KP,
                                   "source": "library-side CUDA events, " + ("the timed region" if graphed is None else
                                             f"a separate un-graphed pass of {KP} steps after the timed region")},
-        "phi_only_value": (KP * float(m_local) * n * d / (phi_op_ms * 1e-3)) if phi_op_ms else None,
-        "result": {"h": h_val, "ksd": float(aux_host[0]), "l2": float(aux_host[1]), "alpha": float(aux_host[2])},
-        "wall_s": t_wall, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-        "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "phi_only_value": (KP * float(m_local) * n * d / (prof[2][0] * 1e-3)) if prof[2][0] else None,
+        "result": {"h": res["h"], "ksd": float(res["aux"][0]), "l2": float(res["aux"][1]), "alpha": float(res["aux"][2])},
+        "wall_s": res["t_wall"], "gpu_launches": res["launches"], "clocks": res["clocks"], "roofline": roofline,
+        "roofline_step": step_roofline(res), "offdiag_mode": offdiag, "cpu_baseline": cpu_baseline, "e2e": e2e,
     }
     print(json.dumps(out), flush=True)
     shutdown()

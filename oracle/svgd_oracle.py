@@ -424,3 +424,27 @@ def phistar_stats_f64_blocked(X, S, h, block=512, rows=None, lambda_reg=0.5):
                     phi_keep[pos[r]] = phi[r - s].numpy()
     ksd, l2 = t_sum / n, l_sum / n
     return {"phi": phi_keep, "ksd": ksd, "l2": l2, "alpha": ksd / (2 * lambda_reg * l2)}
+
+
+def phistar_f32_blocked_torch(Q, X, S, h, block=2048):
+    """The same fp32 Gram-trick port as phistar_f32_blocked, on torch CPU so that exp and the GEMMs use every host core
+    (NumPy's exp is single-threaded).  bench.py's CPU arm; inputs are torch float32 CPU tensors or arrays."""
+    import torch
+    Q = torch.as_tensor(Q, dtype=torch.float32); X = torch.as_tensor(X, dtype=torch.float32)
+    S = torch.as_tensor(S, dtype=torch.float32)
+    n, d = X.shape
+    h2 = float(h) ** 2
+    mu = X.double().mean(0).float()
+    Xc = X - mu
+    xn = (Xc * Xc).sum(1)
+    V = torch.cat([S, Xc], dim=1)
+    out = torch.empty_like(Q)
+    for s in range(0, Q.shape[0], block):
+        q = Q[s:s + block] - mu
+        qn = (q * q).sum(1)
+        r2 = torch.addmm(qn[:, None] + xn[None, :], q, Xc.T, alpha=-2.0).clamp_(min=0.0)
+        K = r2.mul_(-0.5 / h2).exp_()
+        KV = K @ V
+        rs = K.sum(1, keepdim=True)
+        out[s:s + block] = (KV[:, :d] + (rs * q - KV[:, d:]) / h2) / n
+    return out
