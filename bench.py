@@ -365,7 +365,7 @@ def main():
             state["graphed"] = graphed
         else:
             KP = K
-        prof = {tag: _lib.profile_read(tag) for tag in range(7)}
+        prof = {tag: _lib.profile_read(tag) for tag in range(15)}
         _lib.profile_enable(False)
         t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -536,7 +536,10 @@ def main():
                 "launch": "one CUDA graph replay per step (collectives captured)" if graphed is not None else "eager (C-ABI calls per op)"},
         "breakdown_ms_per_step": {"median_op": prof[3][0] / KP, "median_tc_filter_kernel": prof[6][0] / KP,
                                   "median_sample_kernel": prof[4][0] / KP, "median_exact_list_kernel": prof[5][0] / KP,
-                                  "median_simt_hist_kernels": prof[1][0] / KP, "phi_op": prof[2][0] / KP,
+                                  "median_prepare": prof[12][0] / KP, "median_prep_kernels": prof[8][0] / KP,
+                                  "median_bracket_select": prof[9][0] / KP, "median_resolve_candidate_select": prof[10][0] / KP,
+                                  "median_fallback_passes_(early_exit)": prof[11][0] / KP,
+                                  "phi_prep": prof[13][0] / KP, "phi_epilogue": prof[14][0] / KP, "phi_op": prof[2][0] / KP,
                                   "phi_main_kernel": prof[0][0] / KP,
                                   "source": "library-side CUDA events, " + ("the timed region" if graphed is None else
                                             f"a separate un-graphed pass of {KP} steps after the timed region")},

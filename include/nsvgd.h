@@ -158,6 +158,13 @@ int nsvgd_p2p_timeout_flag(const void* own_block, int* flag_out);
 int nsvgd_p2p_allreduce(void* stream, int rank, int world, void* const* blocks, void* buf, int64_t nwords, int is_f64);
 /* = all-reduce(hist) + nsvgd_median_advance */
 int nsvgd_p2p_median_advance(void* stream, int rank, int world, void* const* blocks, void* state_dev, uint64_t* hist_dev, int pass);
+/* The whole tensor-core filtered select for one rank of a row-sharded group in ONE call: sample slice `rank` of `world`,
+ * fused 3-pass bracket select (histograms summed across ranks inside the kernel), filter over the 128-row blocks
+ * rank, rank + world, ..., exact evaluation, pack + resolve, fused candidate select, conditional SIMT fallback.  Leaves the
+ * resolved order statistics in state_dev (then nsvgd_median_finish).  world = 1: the single-GPU path. */
+int nsvgd_p2p_median_fast_run(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last, int mode,
+                              int rank, int world, void* const* blocks, void* state_dev, uint64_t* hist_dev, void* ws,
+                              size_t ws_bytes);
 /* = all-reduce(reduce_dev[4]) + nsvgd_median_fast_resolve */
 int nsvgd_p2p_median_fast_resolve(void* stream, int rank, int world, void* const* blocks, void* state_dev, void* ws,
                                   size_t ws_bytes, int64_t n, int64_t dz, int64_t* reduce_dev);

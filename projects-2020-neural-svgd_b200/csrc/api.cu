@@ -50,7 +50,7 @@ int ensure_dyn_smem(const void* kernel, int bytes) {
 // ---- optional event timing of the dominant kernels (off by default; not graph-capturable when on)
 struct ProfSlot { cudaEvent_t a, b; };
 static bool g_prof_on = false;
-static std::vector<ProfSlot> g_prof[8];
+static std::vector<ProfSlot> g_prof[16];
 static std::mutex g_prof_mu;
 
 void prof_begin(int tag, cudaStream_t st) {
@@ -126,7 +126,7 @@ extern "C" int nsvgd_profile_enable(int on) {
 }
 
 extern "C" int nsvgd_profile_read(int tag, double* total_ms, int* count) {
-  NSVGD_REQUIRE(tag >= 0 && tag < 8 && total_ms && count, NSVGD_ERR_INVALID, "profile_read: bad arguments");
+  NSVGD_REQUIRE(tag >= 0 && tag < 16 && total_ms && count, NSVGD_ERR_INVALID, "profile_read: bad arguments");
   std::lock_guard<std::mutex> lk(g_prof_mu);
   double tot = 0.0; int c = 0;
   for (auto& s : g_prof[tag]) {

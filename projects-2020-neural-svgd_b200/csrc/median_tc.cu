@@ -50,7 +50,16 @@ static uint32_t cand_capacity(int64_t n) {
   return (uint32_t)std::min<double>(P / 96.0 + (double)(1 << 22), 4.0e9);
 }
 
+// scratch of one fused 3-pass select (fused_select_kernel): one global histogram per pass + the grid-wide hand-shake
+struct FusedSelScratch {
+  unsigned long long hist[NSVGD_SELECT_PASSES][2 * NSVGD_SELECT_BINS];
+  uint32_t done[4];      // CTAs that have flushed their histogram of pass p
+  uint32_t flag[4];      // set by the last CTA of pass p once the select state has advanced
+};
+
 struct FastWs {
+  FusedSelScratch* sel;  // [2]: bracket select, candidate select (inside the zero block)
+  char* zero_block; size_t zero_bytes;
   FastMedState* fs; SelectState* bracket; SelectState* cand_state;
   float* mu; double* mpart; __nv_bfloat16* Zb0; __nv_bfloat16* Zb1; float* zn; float* zlo; float* zhi; float* Ds;
   unsigned long long* list; float* cand; uint32_t* err_flag;
@@ -76,9 +85,15 @@ static size_t fast_layout(int64_t n, int64_t dz, WsCarver& w, FastWs* o) {
   f.Ds = w.take<float>(MF_SAMPLES);
   f.list = w.take<unsigned long long>((size_t)f.list_cap * MF_NSEG);
   f.cand = w.take<float>((size_t)f.cand_cap * MF_NSEG);
+  // one contiguous block that a single memset clears per call: error flag, list counters, select scratch
+  w.off = (w.off + 1023) / 1024 * 1024;
+  const size_t z0 = w.off;
   f.err_flag = w.take<uint32_t>(64);   // [0] error flag; bytes 64.. = the single-GPU reduce block
   f.list_counts = w.take<uint32_t>(MF_NSEG * MF_CSTRIDE);
   f.cand_counts = w.take<uint32_t>(MF_NSEG * MF_CSTRIDE);
+  f.sel = w.take<FusedSelScratch>(2);
+  f.zero_block = w.dry ? nullptr : w.base + z0;
+  f.zero_bytes = w.off - z0;
   if (o) *o = f;
   return w.off;
 }
@@ -278,15 +293,6 @@ __global__ void filter_vectors_kernel(const float* __restrict__ zn, int64_t n_pa
     const float z = zn[t];
     zlo[t] = -z * (1.f + MF_KAPPA);
     zhi[t] = -z * (1.f - MF_KAPPA);
-  }
-}
-
-__global__ void bracket_set_kernel(FastMedState* fs, const SelectState* bracket, int l_is_zero, int u_is_inf) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    fs->below = 0ull; fs->list_count = 0u; fs->cand_count = 0u; fs->overflow = 0u; fs->fallback = 0u;
-    fs->L = l_is_zero ? 0.f : bracket->value[0];
-    fs->U = u_is_inf ? __uint_as_float(0x7f800000u) : bracket->value[1];
-    fs->u_is_inf = (uint32_t)u_is_inf; fs->pad = 0u;
   }
 }
 
@@ -803,15 +809,18 @@ __global__ void fast_resolve_kernel(FastMedState* fs, const SelectState* main_st
 // row-sharded: the all-reduce of {below, candidates, bad, listed} over peer memory fused into the resolve step
 __global__ void __launch_bounds__(64) fast_resolve_p2p_kernel(const P2PComm c, FastMedState* fs, const SelectState* main_state,
                                                               SelectState* cs, long long* red) {
-  p2p_allreduce_cta(c, reinterpret_cast<unsigned long long*>(red), 4, false);
-  if (threadIdx.x == 0) fast_resolve_body(fs, main_state, cs, red);
+  const bool ok = p2p_allreduce_cta(c, reinterpret_cast<unsigned long long*>(red), 4, false);
+  if (threadIdx.x == 0) {
+    if (!ok) const_cast<SelectState*>(main_state)->nan_flag = 1u;       // late peer -> h = NaN on this rank
+    fast_resolve_body(fs, main_state, cs, red);
+  }
 }
 
 // row-sharded: ONE kernel per radix pass = all-reduce of [candidate histogram | fallback histogram] over peer memory
 // + the candidate-select decision + (only when the fallback flag is set) the SIMT-select decision
 __global__ void __launch_bounds__(1024) fast_advance2_p2p_kernel(const P2PComm c, const FastMedState* fs, SelectState* cand_state,
                                                                  SelectState* main_state, unsigned long long* hist, int pass) {
-  p2p_allreduce_cta(c, hist, 4 * NSVGD_SELECT_BINS, false);
+  if (!p2p_allreduce_cta(c, hist, 4 * NSVGD_SELECT_BINS, false) && threadIdx.x == 0) main_state->nan_flag = 1u;
   select_advance_body(cand_state, hist, pass);
   if (fs->fallback) select_advance_body(main_state, hist + 2 * NSVGD_SELECT_BINS, pass);
 }
@@ -833,11 +842,176 @@ __device__ __forceinline__ void fast_resolve_body(FastMedState* fs, const Select
   fs->fallback = fb;
 }
 
+// pack + (peer-memory all-reduce when row-sharded) + resolve in one launch
+__device__ __forceinline__ void fast_pack_body(FastMedState* fs, const uint32_t* list_counts, uint32_t list_cap, uint32_t* cand_counts,
+                                               uint32_t cand_cap, const uint32_t* err_flag, long long* red) {
+  long long bad = *err_flag != 0u ? 1 : 0;
+  unsigned long long ncand = 0ull, nlist = 0ull;
+  for (int sgm = 0; sgm < MF_NSEG; ++sgm) {
+    const uint32_t lc = list_counts[sgm * MF_CSTRIDE], cc = cand_counts[sgm * MF_CSTRIDE];
+    if (lc > list_cap || cc > cand_cap) bad = 1;                   // a list overflowed (massive ties)
+    if (cc > cand_cap) cand_counts[sgm * MF_CSTRIDE] = cand_cap;
+    ncand += min(cc, cand_cap); nlist += lc;
+  }
+  fs->list_count = (uint32_t)min(nlist, 0xFFFFFFFFull);
+  fs->cand_count = (uint32_t)min(ncand, 0xFFFFFFFFull);
+  red[0] = (long long)fs->below; red[1] = (long long)ncand; red[2] = bad; red[3] = (long long)nlist;
+}
+
+__global__ void __launch_bounds__(64) fast_pack_resolve_kernel(const P2PComm c, int world, FastMedState* fs, const uint32_t* list_counts,
+                                                               uint32_t list_cap, uint32_t* cand_counts, uint32_t cand_cap,
+                                                               const uint32_t* err_flag, SelectState* main_state, SelectState* cs,
+                                                               long long* red) {
+  if (threadIdx.x == 0) fast_pack_body(fs, list_counts, list_cap, cand_counts, cand_cap, err_flag, red);
+  __syncthreads();
+  bool ok = true;
+  if (world > 1) ok = p2p_allreduce_cta(c, reinterpret_cast<unsigned long long*>(red), 4, false);
+  if (threadIdx.x == 0) {
+    if (!ok) main_state->nan_flag = 1u;
+    fast_resolve_body(fs, main_state, cs, red);
+  }
+}
+
 __global__ void fast_commit_kernel(const FastMedState* fs, const SelectState* cs, SelectState* main_state) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (fs->fallback) return;     // the conditional SIMT passes will resolve main_state instead
   for (int t = 0; t < 2; ++t) main_state->value[t] = main_state->is_zero[t] ? 0.f : cs->value[t];
   main_state->done = 1;
+}
+
+// ---------------------------------------------------------------------------- fused 3-pass radix select over a value buffer
+// ONE launch resolves both target order statistics of a buffer (the sampled distances -> bracket, the exact candidates ->
+// result) instead of 3 x (memset + histogram + advance): per pass every CTA histograms its share in shared memory
+// (with a warp-uniform fast path: the distances of one cloud share their leading radix digits, plain shared-memory atomics
+// serialised on one or two bins -- 35 us per pass over 4M values), adds it to the pass's global histogram, and the LAST CTA to finish
+// (atomic ticket) takes the select decision -- after summing the histogram over the ranks through peer memory when
+// row-sharded -- and releases a flag the other CTAs of the (co-resident, <= #SM) grid wait for.
+// final_mode: 1 -> publish the bracket [L, U] (bracket_set), 2 -> commit the resolved values to the main select state.
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256) fused_select_kernel(const float* __restrict__ vals, const uint32_t* __restrict__ counts_dev,
+                                                           int count_stride, int nseg, uint32_t seg_cap, uint32_t v_begin,
+                                                           uint32_t v_end, SelectState* state, FusedSelScratch* sc, const P2PComm c,
+                                                           int world, int final_mode, FastMedState* fs, SelectState* main_state,
+                                                           int l_is_zero, int u_is_inf) {
+  __shared__ unsigned int hist_s[2 * NSVGD_SELECT_BINS];
+  __shared__ uint32_t s_last;
+  const int lane = threadIdx.x & 31;
+  for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
+    for (int t = threadIdx.x; t < 2 * NSVGD_SELECT_BINS; t += 256) hist_s[t] = 0u;
+    __syncthreads();
+    const uint32_t mask = *(volatile uint32_t*)&state->mask;
+    const uint32_t p0 = *(volatile uint32_t*)&state->prefix[0], p1 = *(volatile uint32_t*)&state->prefix[1];
+    const int shift = pass_shift(pass);
+    const unsigned int binmask = (unsigned int)pass_bins(pass) - 1u;
+    // segmented buffers: the CTAs are dealt out over the segments (CTA b works on segments b % G, b % G + G, ... with its
+    // G-group peers, G = min(nseg, grid)) so that every CTA has work whatever the segment sizes
+    const uint32_t G = min((uint32_t)nseg, gridDim.x);
+    const uint32_t peers_n = (gridDim.x - (blockIdx.x % G) + G - 1u) / G;      // CTAs that share my segments
+    const uint32_t my_idx = blockIdx.x / G;
+    for (int sgm = (int)(blockIdx.x % G); sgm < nseg; sgm += (int)G) {
+      const uint32_t begin = counts_dev ? 0u : v_begin;
+      const uint32_t end = counts_dev ? min(counts_dev[sgm * count_stride], seg_cap) : v_end;
+      const float* v0 = vals + (size_t)sgm * seg_cap;
+      // a warp takes 128 consecutive values per trip: four independent coalesced loads in flight per lane, then four
+      // warp-aggregated histogram updates (warp-uniform trip count: the match needs the whole warp)
+      for (uint32_t base = begin + (my_idx * 8u + (threadIdx.x >> 5)) * 128u; base < end; base += peers_n * 8u * 128u) {
+        unsigned int bits4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t t = base + lane + 32u * u;
+          bits4[u] = t < end ? __float_as_uint(v0[t]) : 0x7fc00000u;      // out of range -> NaN pattern -> ignored
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned int bits = bits4[u];
+          const bool ok = (bits & 0x7fffffffu) <= 0x7f800000u;             // NaNs are reported by the producers of the buffer
+          const unsigned int bin = (bits >> shift) & binmask;
+          const bool m0 = ok && (bits & mask) == p0;
+          const bool m1 = ok && (bits & mask) == p1;
+          const unsigned int key = (m0 || m1) ? (bin | (m0 ? 0x1000u : 0u) | (m1 ? 0x2000u : 0u)) : 0x80000000u;
+          // uniform fast path: the whole warp in one bin (the leading radix digits of one cloud's distances; plain
+          // shared-memory atomics serialised on one or two bins here) -> ONE atomic; otherwise the lanes are spread out
+          const unsigned int key0 = __shfl_sync(0xffffffffu, key, 0);
+          if (__all_sync(0xffffffffu, key == key0)) {
+            if (lane == 0 && (m0 || m1)) {
+              if (m0) atomicAdd(&hist_s[bin], 32u);
+              if (m1) atomicAdd(&hist_s[NSVGD_SELECT_BINS + bin], 32u);
+            }
+          } else {
+            if (m0) atomicAdd(&hist_s[bin], 1u);
+            if (m1) atomicAdd(&hist_s[NSVGD_SELECT_BINS + bin], 1u);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * NSVGD_SELECT_BINS; t += 256) {
+      const unsigned int v = hist_s[t];
+      if (v) atomicAdd(&sc->hist[pass][t], (unsigned long long)v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&sc->done[pass], 1u) == gridDim.x - 1u) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      if (world > 1 && !p2p_allreduce_cta(c, sc->hist[pass], 2 * NSVGD_SELECT_BINS, false) && threadIdx.x == 0)
+        (main_state ? main_state : state)->nan_flag = 1u;            // late peer -> h = NaN instead of a partial sum
+      // stage the summed histogram in shared memory (independent coalesced loads) before the scan: 64 dependent L2 round
+      // trips per lane cost ~20 us per pass otherwise
+      unsigned long long* hist64 = reinterpret_cast<unsigned long long*>(hist_s);     // 2 x 2048 u32 -> reuse as 2048 u64 per target
+      for (int w2 = 0; w2 < 2; ++w2) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < NSVGD_SELECT_BINS; t += 256) hist64[t] = sc->hist[pass][w2 * NSVGD_SELECT_BINS + t];
+        __syncthreads();
+        select_advance_one(state, hist64, pass, w2);
+      }
+      select_advance_commit(state, pass);
+      if (pass == NSVGD_SELECT_PASSES - 1 && threadIdx.x == 0) {
+        if (final_mode == 1) {             // bracket [L, U] for the tensor-core filter
+          fs->below = 0ull; fs->list_count = 0u; fs->cand_count = 0u; fs->overflow = 0u; fs->fallback = 0u;
+          fs->L = l_is_zero ? 0.f : state->value[0];
+          fs->U = u_is_inf ? __uint_as_float(0x7f800000u) : state->value[1];
+          fs->u_is_inf = (uint32_t)u_is_inf; fs->pad = 0u;
+        } else if (final_mode == 2 && !fs->fallback) {   // candidates resolved: commit (else the conditional SIMT passes do)
+          for (int t = 0; t < 2; ++t) main_state->value[t] = main_state->is_zero[t] ? 0.f : state->value[t];
+          main_state->done = 1;
+        }
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) st_release_gpu_u32(&sc->flag[pass], 1u);
+    } else if (pass + 1 < NSVGD_SELECT_PASSES) {
+      if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire_gpu_u32(&sc->flag[pass]) == 0u) {
+          if (clock64() - t0 > 8000000000ll) { (main_state ? main_state : state)->nan_flag = 1u; break; }   // never hang
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+static int launch_fused_select(cudaStream_t st, const float* vals, const uint32_t* counts_dev, int count_stride, int nseg,
+                               uint32_t seg_cap, uint32_t v_begin, uint32_t v_end, SelectState* state, FusedSelScratch* sc,
+                               const P2PComm* comm, int final_mode, FastMedState* fs, SelectState* main_state, int l_is_zero,
+                               int u_is_inf) {
+  P2PComm c{};
+  if (comm) c = *comm; else { c.rank = 0; c.world = 1; }
+  // co-resident by construction: four 256-thread CTAs (16 KB of shared memory each) per SM
+  fused_select_kernel<<<device_sm_count() * 4, 256, 0, st>>>(vals, counts_dev, count_stride, nseg, seg_cap, v_begin, v_end, state, sc,
+                                                         c, c.world, final_mode, fs, main_state, l_is_zero, u_is_inf);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
 }
 
 template <int DP>
@@ -868,15 +1042,15 @@ int median_fast_sample(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   fast_layout(n, dz, w, &f);
   NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "median_fast: workspace too small (%zu < %zu)", ws_bytes, w.off);
   const int sms = device_sm_count();
+  prof_begin(8, st);
   NSVGD_PROPAGATE(launch_colmean(st, P, n, dz, ldp, f.mpart, f.mu));
-  NSVGD_CUDA(cudaMemsetAsync(f.err_flag, 0, 16, st));
-  NSVGD_CUDA(cudaMemsetAsync(f.list_counts, 0, sizeof(uint32_t) * MF_NSEG * MF_CSTRIDE, st));
-  NSVGD_CUDA(cudaMemsetAsync(f.cand_counts, 0, sizeof(uint32_t) * MF_NSEG * MF_CSTRIDE, st));
+  NSVGD_CUDA(cudaMemsetAsync(f.zero_block, 0, f.zero_bytes, st));   // error flag, list / candidate counters, select scratch
   // weighted last coordinate scaled by sqrt(w) AFTER centring
   NSVGD_PROPAGATE(launch_tc_prep(st, P, nullptr, n, dz, ldp, f.n_pad, f.dp, f.mu, sqrtf(w_last), f.Zb0, f.Zb1, nullptr, nullptr,
                                  nullptr, 0, f.zn, nullptr, nullptr, nullptr));
   filter_vectors_kernel<<<(unsigned)std::min<int64_t>(ceil_div(f.n_pad, 256), 1024), 256, 0, st>>>(f.zn, f.n_pad, f.zlo, f.zhi);
   NSVGD_LAUNCH_CHECK();
+  prof_end(8, st);
   constexpr int WX_SMEM = WX_WARPS * 32 * WX_STRIDE * (int)sizeof(float);
   NSVGD_PROPAGATE(ensure_dyn_smem((const void*)sample_pairs_warp_kernel, WX_SMEM));
   NSVGD_PROPAGATE(ensure_dyn_smem((const void*)exact_list_warp_kernel, WX_SMEM));
@@ -899,9 +1073,12 @@ int median_fast_sample(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
 }
 
 // stage 1 (all MF_SAMPLES sampled distances present in the workspace): bracket, filter, exact list, summary
+// comm != null: row-sharded over peer memory -- the bracket select runs over THIS rank's sample slice [s_begin, s_end) and
+// sums the histograms across ranks inside the kernel; red (the local summary) is then written by the resolve kernel.
 int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, long long r_lo,
                        long long r_hi, int64_t block_row_start, int64_t block_row_stride, SelectState* main_state,
-                       uint64_t* hist, void* ws, size_t ws_bytes, long long* red) {
+                       uint64_t* hist, void* ws, size_t ws_bytes, long long* red, const P2PComm* comm, uint32_t s_begin,
+                       uint32_t s_end) {
   NSVGD_REQUIRE(median_fast_supported(n, dz), NSVGD_ERR_UNSUPPORTED, "median_fast: unsupported shape");
   NSVGD_REQUIRE(r_lo >= 0 && r_hi >= r_lo, NSVGD_ERR_UNSUPPORTED, "median_fast: needs genuine pair ranks");
   WsCarver w(ws, ws_bytes);
@@ -918,18 +1095,19 @@ int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   const double ns = (double)MF_SAMPLES;
   const double p_lo = ((double)r_lo + 0.5) / Ppairs, p_hi = ((double)r_hi + 0.5) / Ppairs;
   const double sig_lo = sqrt(ns * p_lo * (1.0 - p_lo)), sig_hi = sqrt(ns * p_hi * (1.0 - p_hi));
-  long long a = (long long)floor(p_lo * ns - 6.0 * sig_lo - 16.0);
-  long long b = (long long)ceil(p_hi * ns + 6.0 * sig_hi + 16.0);
+  // 5 sigma + slack on either side: a miss (probability ~6e-7 per step) only costs the device-side fallback to the SIMT
+  // select (still exact); the bracket is 17 % narrower than at 6 sigma and so is the list of pairs to re-evaluate
+  long long a = (long long)floor(p_lo * ns - 5.0 * sig_lo - 16.0);
+  long long b = (long long)ceil(p_hi * ns + 5.0 * sig_hi + 16.0);
   const int l_is_zero = a < 0, u_is_inf = b >= (long long)MF_SAMPLES;
   if (a < 0) a = 0;
   if (b >= (long long)MF_SAMPLES) b = (long long)MF_SAMPLES - 1;
+  (void)hist;
+  prof_begin(9, st);
   NSVGD_PROPAGATE(launch_select_init(st, f.bracket, a, b, 1.f));
-  for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
-    NSVGD_PROPAGATE(launch_buffer_hist(st, f.Ds, nullptr, 0, 1, 0, MF_SAMPLES, f.bracket, pass, hist, nullptr));
-    NSVGD_PROPAGATE(launch_select_advance(st, f.bracket, hist, pass, nullptr));
-  }
-  bracket_set_kernel<<<1, 32, 0, st>>>(f.fs, f.bracket, l_is_zero, u_is_inf);
-  NSVGD_LAUNCH_CHECK();
+  NSVGD_PROPAGATE(launch_fused_select(st, f.Ds, nullptr, 0, 1, 0, s_begin, s_end, f.bracket, &f.sel[0], comm, 1, f.fs, nullptr,
+                                      l_is_zero, u_is_inf));
+  prof_end(9, st);
 
   // --- 2. tensor-core filter over the upper triangle (128-row blocks strided across ranks)
   CUtensorMap maps[4];
@@ -963,8 +1141,10 @@ int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   }
   prof_end(5, st);
   NSVGD_LAUNCH_CHECK();
-  fast_pack_kernel<<<1, 32, 0, st>>>(f.fs, f.list_counts, f.list_cap, f.cand_counts, f.cand_cap, f.err_flag, red);
-  NSVGD_LAUNCH_CHECK();
+  if (red) {       // staged use with an external all-reduce of the summary in between
+    fast_pack_kernel<<<1, 32, 0, st>>>(f.fs, f.list_counts, f.list_cap, f.cand_counts, f.cand_cap, f.err_flag, red);
+    NSVGD_LAUNCH_CHECK();
+  }
   return NSVGD_OK;
 }
 
@@ -1011,30 +1191,48 @@ const uint32_t* median_fast_fallback_flag(void* ws, size_t ws_bytes, int64_t n, 
   return &f.fs->fallback;
 }
 
-// single-GPU composition of the stages
+// the whole filtered select for one rank: comm == null -> single GPU; else row-sharded over peer memory (128-row blocks
+// rank, rank + world, ... of the filter; sample slice rank of world; every exchange fused into its consumer kernel).
+// 13 launches + 1 memset (+ 9 early-exit launches of the conditional SIMT fallback) instead of ~45.
+int median_fast_run(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, long long r_lo,
+                    long long r_hi, const P2PComm* comm, SelectState* main_state, uint64_t* hist, void* ws, size_t ws_bytes) {
+  FastWs f;
+  NSVGD_PROPAGATE(fast_ws(n, dz, ws, ws_bytes, &f));
+  long long* red = (long long*)(f.err_flag) + 8;      // err_flag block is 256 bytes, 16 used
+  const int rank = comm ? comm->rank : 0, world = comm ? comm->world : 1;
+  const bool slice = comm && MF_SAMPLES % (uint32_t)world == 0 && (MF_SAMPLES / (uint32_t)world) % 32 == 0;
+  const uint32_t per = slice ? MF_SAMPLES / (uint32_t)world : MF_SAMPLES;
+  const uint32_t s_begin = slice ? per * (uint32_t)rank : 0u, s_end = s_begin + per;
+  NSVGD_PROPAGATE(median_fast_sample(st, P, n, dz, ldp, w_last, slice ? rank : 0, slice ? world : 1, ws, ws_bytes, nullptr, nullptr));
+  // (an unsliceable world size: every rank samples everything and contributes 1/world-th... not needed: world | 2^22 in practice)
+  NSVGD_REQUIRE(!comm || slice, NSVGD_ERR_UNSUPPORTED, "median_fast_run: world size %d does not divide the sample count", world);
+  NSVGD_PROPAGATE(median_fast_stage1(st, P, n, dz, ldp, w_last, r_lo, r_hi, rank, world, main_state, hist, ws, ws_bytes, nullptr,
+                                     comm, s_begin, s_end));
+  P2PComm c{};
+  if (comm) c = *comm; else { c.rank = 0; c.world = 1; }
+  prof_begin(10, st);
+  fast_pack_resolve_kernel<<<1, 64, 0, st>>>(c, world, f.fs, f.list_counts, f.list_cap, f.cand_counts, f.cand_cap, f.err_flag,
+                                             main_state, f.cand_state, red);
+  NSVGD_LAUNCH_CHECK();
+  NSVGD_PROPAGATE(launch_fused_select(st, f.cand, f.cand_counts, MF_CSTRIDE, MF_NSEG, f.cand_cap, 0u, 0u, f.cand_state, &f.sel[1], comm,
+                                      2, f.fs, main_state, 0, 0));
+  prof_end(10, st);
+  prof_begin(11, st);
+  // conditional fallback: the SIMT 3-pass select; kernels return at once unless fs->fallback is set (identical on all ranks)
+  for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
+    NSVGD_PROPAGATE(launch_pair_hist(st, P, n, dz, ldp, w_last, rank, world, main_state, pass, hist, &f.fs->fallback));
+    if (comm) NSVGD_PROPAGATE(launch_select_advance_p2p(st, *comm, main_state, hist, pass, &f.fs->fallback));
+    else NSVGD_PROPAGATE(launch_select_advance(st, main_state, hist, pass, &f.fs->fallback));
+  }
+  prof_end(11, st);
+  return NSVGD_OK;
+}
+
 int median_fast(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, long long r_lo,
                 long long r_hi, int64_t tile_row_start, int64_t tile_row_stride, SelectState* main_state, uint64_t* hist,
                 void* ws, size_t ws_bytes) {
-  // red lives at the tail of the workspace region reserved by median_fast_workspace()
-  FastWs f;
-  NSVGD_PROPAGATE(fast_ws(n, dz, ws, ws_bytes, &f));
-  long long* red = (long long*)(f.err_flag) + 8;      // err_flag block is 256-byte aligned, 16 bytes used
-  NSVGD_PROPAGATE(median_fast_sample(st, P, n, dz, ldp, w_last, 0, 1, ws, ws_bytes, nullptr, nullptr));
-  NSVGD_PROPAGATE(median_fast_stage1(st, P, n, dz, ldp, w_last, r_lo, r_hi, tile_row_start, tile_row_stride, main_state, hist,
-                                     ws, ws_bytes, red));
-  NSVGD_PROPAGATE(median_fast_resolve(st, main_state, ws, ws_bytes, n, dz, red));
-  for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
-    NSVGD_PROPAGATE(median_fast_cand_hist(st, ws, ws_bytes, n, dz, pass, hist));
-    NSVGD_PROPAGATE(median_fast_cand_advance(st, ws, ws_bytes, n, dz, hist, pass));
-  }
-  NSVGD_PROPAGATE(median_fast_commit(st, main_state, ws, ws_bytes, n, dz));
-  // conditional fallback: the SIMT 3-pass select; kernels return at once unless fs->fallback is set
-  for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
-    NSVGD_PROPAGATE(launch_pair_hist(st, P, n, dz, ldp, w_last, tile_row_start, tile_row_stride, main_state, pass, hist,
-                                     &f.fs->fallback));
-    NSVGD_PROPAGATE(launch_select_advance(st, main_state, hist, pass, &f.fs->fallback));
-  }
-  return NSVGD_OK;
+  (void)tile_row_start; (void)tile_row_stride;
+  return median_fast_run(st, P, n, dz, ldp, w_last, r_lo, r_hi, nullptr, main_state, hist, ws, ws_bytes);
 }
 
 }  // namespace nsvgd
@@ -1067,8 +1265,21 @@ extern "C" int nsvgd_median_fast_stage1(void* stream, const float* Z, int64_t n,
   long long r_lo, r_hi;
   median_ranks_host(n, mode, &r_lo, &r_hi);
   return median_fast_stage1((cudaStream_t)stream, Z, n, dz, ldz, w_last, r_lo, r_hi, block_row_start, block_row_stride,
-                            (SelectState*)state_dev, hist_dev, ws, ws_bytes, (long long*)reduce_dev);
+                            (SelectState*)state_dev, hist_dev, ws, ws_bytes, (long long*)reduce_dev, nullptr, 0u, MF_SAMPLES);
 }
+extern "C" int nsvgd_p2p_median_fast_run(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last, int mode,
+                                         int rank, int world, void* const* blocks, void* state_dev, uint64_t* hist_dev, void* ws,
+                                         size_t ws_bytes) {
+  NSVGD_REQUIRE(Z && state_dev && hist_dev && ws, NSVGD_ERR_INVALID, "p2p_median_fast_run: null pointer");
+  NSVGD_REQUIRE(mode >= 0 && mode <= 2, NSVGD_ERR_INVALID, "p2p_median_fast_run: bad mode %d", mode);
+  P2PComm c;
+  NSVGD_REQUIRE(p2p_make_comm(&c, rank, world, blocks), NSVGD_ERR_INVALID, "p2p_median_fast_run: bad communicator");
+  long long r_lo, r_hi;
+  median_ranks_host(n, mode, &r_lo, &r_hi);
+  return median_fast_run((cudaStream_t)stream, Z, n, dz, ldz, w_last, r_lo, r_hi, world > 1 ? &c : nullptr, (SelectState*)state_dev,
+                         hist_dev, ws, ws_bytes);
+}
+
 extern "C" int nsvgd_median_fast_resolve(void* stream, void* state_dev, void* ws, size_t ws_bytes, int64_t n, int64_t dz,
                                          const int64_t* reduce_dev) {
   NSVGD_REQUIRE(state_dev && reduce_dev, NSVGD_ERR_INVALID, "median_fast_resolve: null pointer");

@@ -47,7 +47,10 @@ __device__ __forceinline__ unsigned long long p2p_ld_relaxed_sys(const unsigned 
 
 // In-place sum of buf[0..nwords) over all ranks; ALL threads of ONE CTA must call it (blockDim.x >= world).
 // f64 = false: unsigned 64-bit integer adds; true: double adds in rank order.
-__device__ __forceinline__ void p2p_allreduce_cta(const P2PComm& c, unsigned long long* buf, int nwords, bool f64) {
+// Returns false (on every thread) when a peer did not arrive within the watchdog time: the block's timeout flag is set
+// and buf is POISONED (NaN doubles / all-ones integers) so that the consumer cannot turn a partial sum into a
+// normal-looking bandwidth or step; the callers additionally raise their own NaN flags.
+__device__ __forceinline__ bool p2p_allreduce_cta(const P2PComm& c, unsigned long long* buf, int nwords, bool f64) {
   unsigned char* me = c.blk[c.rank];
   uint32_t* my_flags = reinterpret_cast<uint32_t*>(me);
   volatile uint32_t* epoch_p = reinterpret_cast<volatile uint32_t*>(me + 64);
@@ -57,14 +60,21 @@ __device__ __forceinline__ void p2p_allreduce_cta(const P2PComm& c, unsigned lon
   for (int i = threadIdx.x; i < nwords; i += blockDim.x) my_slot[i] = buf[i];
   __threadfence_system();
   __syncthreads();
+  int late = 0;
   if ((int)threadIdx.x < c.world) {
     p2p_st_release_sys(reinterpret_cast<uint32_t*>(c.blk[threadIdx.x]) + c.rank, epoch);      // publish to peer
     const long long t0 = clock64();
     while ((int32_t)(p2p_ld_acquire_sys(my_flags + threadIdx.x) - epoch) < 0) {               // wait for peer
-      if (clock64() - t0 > 4000000000ll) { *reinterpret_cast<volatile uint32_t*>(me + 68) = 1u; break; }
+      if (clock64() - t0 > 4000000000ll) { *reinterpret_cast<volatile uint32_t*>(me + 68) = 1u; late = 1; break; }
     }
   }
-  __syncthreads();
+  const bool timed_out = __syncthreads_or(late) != 0;
+  if (timed_out) {
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) buf[i] = f64 ? 0x7ff8000000000000ull : ~0ull;
+    __syncthreads();
+    if (threadIdx.x == 0) *epoch_p = epoch;
+    return false;
+  }
   for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
     if (f64) {
       double acc = 0.0;
@@ -81,6 +91,7 @@ __device__ __forceinline__ void p2p_allreduce_cta(const P2PComm& c, unsigned lon
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) *epoch_p = epoch;
+  return true;
 }
 #endif
 

@@ -328,8 +328,9 @@ __global__ void __launch_bounds__(1024) select_advance_kernel(SelectState* s, co
 
 // row-sharded SIMT select: all-reduce of the histogram over peer memory fused into the decision kernel
 __global__ void __launch_bounds__(1024) select_advance_p2p_kernel(const P2PComm c, SelectState* s, unsigned long long* hist,
-                                                                  int pass) {
-  p2p_allreduce_cta(c, hist, 2 * NSVGD_SELECT_BINS, false);
+                                                                  int pass, const uint32_t* run_flag) {
+  if (run_flag && *run_flag == 0u) return;       // the flag is identical on every rank (it derives from all-reduced counts)
+  if (!p2p_allreduce_cta(c, hist, 2 * NSVGD_SELECT_BINS, false) && threadIdx.x == 0) s->nan_flag = 1u;   // late peer -> h = NaN
   select_advance_body(s, hist, pass);
 }
 
@@ -401,8 +402,8 @@ int launch_select_advance(cudaStream_t st, SelectState* s, const uint64_t* hist,
   return NSVGD_OK;
 }
 
-int launch_select_advance_p2p(cudaStream_t st, const P2PComm& c, SelectState* s, uint64_t* hist, int pass) {
-  select_advance_p2p_kernel<<<1, 1024, 0, st>>>(c, s, (unsigned long long*)hist, pass);
+int launch_select_advance_p2p(cudaStream_t st, const P2PComm& c, SelectState* s, uint64_t* hist, int pass, const uint32_t* run_flag) {
+  select_advance_p2p_kernel<<<1, 1024, 0, st>>>(c, s, (unsigned long long*)hist, pass, run_flag);
   NSVGD_LAUNCH_CHECK();
   return NSVGD_OK;
 }
@@ -422,9 +423,7 @@ int launch_pair_hist(cudaStream_t st, const float* Z, int64_t n, int64_t dz, int
   const int64_t target = (int64_t)device_sm_count() * 8;
   const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(tiles, 32));
   const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(rows, ceil_div(target, gx)));
-  prof_begin(1, st);
   pair_tile_kernel<MODE_HIST><<<dim3(gx, gy), 256, 0, st>>>(a);
-  prof_end(1, st);
   NSVGD_LAUNCH_CHECK();
   return NSVGD_OK;
 }
@@ -495,7 +494,7 @@ extern "C" int nsvgd_p2p_median_advance(void* stream, int rank, int world, void*
   NSVGD_REQUIRE(p2p_make_comm(&c, rank, world, blocks), NSVGD_ERR_INVALID, "p2p_median_advance: bad communicator");
   NSVGD_REQUIRE(state_dev && hist_dev, NSVGD_ERR_INVALID, "p2p_median_advance: null pointer");
   NSVGD_REQUIRE(pass >= 0 && pass < NSVGD_SELECT_PASSES, NSVGD_ERR_INVALID, "p2p_median_advance: bad pass %d", pass);
-  return launch_select_advance_p2p((cudaStream_t)stream, c, (SelectState*)state_dev, hist_dev, pass);
+  return launch_select_advance_p2p((cudaStream_t)stream, c, (SelectState*)state_dev, hist_dev, pass, nullptr);
 }
 
 extern "C" int nsvgd_median_finish(void* stream, const void* state_dev, int64_t n, float* h_dev) {
@@ -547,7 +546,9 @@ extern "C" int nsvgd_median_h_f32(void* stream, const float* X, int64_t n, int64
   NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "median_h: workspace too small (%zu < %zu)", ws_bytes, w.off);
   int64_t dz; float w_last;
   prof_begin(3, st);
+  prof_begin(12, st);
   NSVGD_PROPAGATE(nsvgd_median_prepare(stream, X, n, d, ldx, mode, Z, &dz, &w_last, state));
+  prof_end(12, st);
   const float* P = mode == NSVGD_MEDIAN_LITERAL ? Z : X;
   const int64_t ldp = mode == NSVGD_MEDIAN_LITERAL ? dz : ldx;
   const char* env = getenv("NSVGD_MEDIAN_FAST");

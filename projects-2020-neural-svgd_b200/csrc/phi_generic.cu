@@ -44,8 +44,16 @@ __global__ void __launch_bounds__(256) colmean_final_kernel(const double* __rest
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * 32 + lane;
   double s = 0.0;
-  if (c < d)
-    for (int64_t b = w; b < blocks; b += 8) s += part[b * d + c];
+  if (c < d) {
+    // four independent partial sums: the loop is a chain of L2 round trips otherwise (32 us for 1024 partials)
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int64_t b = w;
+    for (; b + 24 < blocks; b += 32) {
+      s0 += part[b * d + c]; s1 += part[(b + 8) * d + c]; s2 += part[(b + 16) * d + c]; s3 += part[(b + 24) * d + c];
+    }
+    for (; b < blocks; b += 8) s0 += part[b * d + c];
+    s = (s0 + s1) + (s2 + s3);
+  }
   sh[w][lane] = s;
   __syncthreads();
   if (w == 0 && c < d) {

@@ -1221,6 +1221,7 @@ int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dr
   if (dry) return NSVGD_OK;
   NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "phi_tc: workspace too small (%zu < %zu)", ws_bytes, w.off);
 
+  prof_begin(13, st);
   NSVGD_PROPAGATE(launch_colmean(st, a.X, a.n, a.d, a.ldx, mpart, mu));
   NSVGD_CUDA(cudaMemsetAsync(err_flag, 0, 16, st));
   uint32_t* max_bits = err_flag + 1;      // [1] max |xc|^2, [2] max fp16 residual^2: zeroed with the error flag just above
@@ -1229,6 +1230,7 @@ int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dr
   if (!pl.q_is_x)
     NSVGD_PROPAGATE(launch_tc_prep(st, a.Q, nullptr, a.m, a.d, a.ldq, pl.m_pad, dp, mu, 1.f, Qb0, Qb1, use_w ? Qh : nullptr,
                                    nullptr, nullptr, 0, qn, nullptr, nullptr, max_bits));
+  prof_end(13, st);
   EpilogueArgs e{};
   if (use_w) {
     CUtensorMap maps[5];
@@ -1273,7 +1275,10 @@ int phi_tc(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dr
   e.m_pad = pl.m_pad; e.ldo = vc; e.dpad = dp; e.mu = mu;
   e.Q = a.Q; e.ldq = a.ldq; e.Sq = a.Sq; e.m = a.m; e.n = a.n; e.d = a.d; e.h_dev = a.h_dev;
   e.phi = a.phi; e.ldphi = a.ldphi; e.aux = a.aux; e.stats_dev = a.stats_dev; e.partials = partials;
-  return launch_epilogue(st, e);
+  prof_begin(14, st);
+  const int rc = launch_epilogue(st, e);
+  prof_end(14, st);
+  return rc;
 }
 
 // ---------------------------------------------------------------------------- bring-up probes

@@ -32,48 +32,63 @@ struct FastMedState {
 __device__ __forceinline__ int pass_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
 __device__ __forceinline__ int pass_bins(int pass) { return pass == 2 ? 1024 : 2048; }
 
-// One radix-select decision (both target ranks) from a histogram: warp t (t = 0,1) resolves target t.  Shared by the
-// plain advance kernel and the kernels that first all-reduce the histogram over peer memory (p2p.cuh).
+// One radix-select decision from a histogram.  select_advance_one: warp 0 of the CTA resolves target `w` from hh[0..bins)
+// (global or shared memory) and parks the result; select_advance_commit publishes both.  select_advance_body = the two
+// targets from one global histogram [2][NSVGD_SELECT_BINS] (warp t resolves target t).  Shared by the plain advance kernel,
+// the fused select and the kernels that first all-reduce the histogram over peer memory (p2p.cuh).
 // Call from ALL threads of a CTA with blockDim.x >= 64.
-__device__ __forceinline__ void select_advance_body(SelectState* s, const unsigned long long* hist, int pass) {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ uint32_t new_prefix[2];
-  __shared__ unsigned long long new_rank[2];
+__device__ __forceinline__ void select_scan_warp(const SelectState* s, const unsigned long long* hh, int pass, int w, int lane,
+                                                 uint32_t* new_prefix, unsigned long long* new_rank) {
   const int nb = pass == 2 ? 1024 : 2048;
   const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
-  if (w < 2) {
-    const unsigned long long* hh = hist + (size_t)w * NSVGD_SELECT_BINS;
-    const unsigned long long target = s->rank[w];
-    const int per = nb / 32;
-    unsigned long long lsum = 0;
-    for (int b = 0; b < per; ++b) lsum += hh[lane * per + b];
-    unsigned long long incl = lsum;   // inclusive scan over lanes
+  const unsigned long long target = s->rank[w];
+  const int per = nb / 32;
+  unsigned long long lsum = 0;
+  for (int b = 0; b < per; ++b) lsum += hh[lane * per + b];
+  unsigned long long incl = lsum;   // inclusive scan over lanes
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const unsigned long long excl = incl - lsum;
-    const bool mine = target >= excl && target < incl;
-    const unsigned int ball = __ballot_sync(0xffffffffu, mine);
-    if (ball == 0u) {  // rank beyond the population (cannot happen for valid ranks)
-      if (lane == 0) { new_prefix[w] = s->prefix[w]; new_rank[w] = target; }
-    } else if (lane == (__ffs(ball) - 1)) {
-      unsigned long long cum = excl;
-      int b = 0;
-      for (; b < per; ++b) {
-        const unsigned long long c = hh[lane * per + b];
-        if (target < cum + c) break;
-        cum += c;
-      }
-      new_prefix[w] = s->prefix[w] | ((uint32_t)(lane * per + b) << shift);
-      new_rank[w] = target - cum;
-    }
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
   }
+  const unsigned long long excl = incl - lsum;
+  const bool mine = target >= excl && target < incl;
+  const unsigned int ball = __ballot_sync(0xffffffffu, mine);
+  if (ball == 0u) {  // rank beyond the population (cannot happen for valid ranks)
+    if (lane == 0) { new_prefix[w] = s->prefix[w]; new_rank[w] = target; }
+  } else if (lane == (__ffs(ball) - 1)) {
+    unsigned long long cum = excl;
+    int b = 0;
+    for (; b < per; ++b) {
+      const unsigned long long c = hh[lane * per + b];
+      if (target < cum + c) break;
+      cum += c;
+    }
+    new_prefix[w] = s->prefix[w] | ((uint32_t)(lane * per + b) << shift);
+    new_rank[w] = target - cum;
+  }
+}
+
+struct SelectScratch { uint32_t new_prefix[2]; unsigned long long new_rank[2]; };
+__device__ __forceinline__ SelectScratch* select_scratch() {
+  __shared__ SelectScratch sc;
+  return &sc;
+}
+
+__device__ __forceinline__ void select_advance_one(const SelectState* s, const unsigned long long* hh, int pass, int w) {
+  SelectScratch* sc = select_scratch();
+  if ((threadIdx.x >> 5) == 0) select_scan_warp(s, hh, pass, w, threadIdx.x & 31, sc->new_prefix, sc->new_rank);
+  __syncthreads();
+}
+
+__device__ __forceinline__ void select_advance_commit(SelectState* s, int pass) {
+  SelectScratch* sc = select_scratch();
+  const int nb = pass == 2 ? 1024 : 2048;
+  const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
   __syncthreads();
   if (threadIdx.x == 0) {
-    s->prefix[0] = new_prefix[0]; s->prefix[1] = new_prefix[1];
-    s->rank[0] = new_rank[0]; s->rank[1] = new_rank[1];
+    s->prefix[0] = sc->new_prefix[0]; s->prefix[1] = sc->new_prefix[1];
+    s->rank[0] = sc->new_rank[0]; s->rank[1] = sc->new_rank[1];
     s->mask |= ((uint32_t)(nb - 1)) << shift;
     if (pass == NSVGD_SELECT_PASSES - 1) {
       s->value[0] = s->is_zero[0] ? 0.f : __uint_as_float(s->prefix[0]);
@@ -82,6 +97,13 @@ __device__ __forceinline__ void select_advance_body(SelectState* s, const unsign
     }
   }
   __syncthreads();
+}
+
+__device__ __forceinline__ void select_advance_body(SelectState* s, const unsigned long long* hist, int pass) {
+  SelectScratch* sc = select_scratch();
+  const int w = threadIdx.x >> 5;
+  if (w < 2) select_scan_warp(s, hist + (size_t)w * NSVGD_SELECT_BINS, pass, w, threadIdx.x & 31, sc->new_prefix, sc->new_rank);
+  select_advance_commit(s, pass);
 }
 
 // DEFINED-ORDER fp32 squared distance of one pair (oracle/svgd_oracle.py::pair_sqdist_f32):
@@ -106,7 +128,7 @@ int launch_buffer_hist(cudaStream_t st, const float* vals, const uint32_t* count
                        uint32_t seg_cap, uint32_t count_host, const SelectState* state, int pass, uint64_t* hist,
                        const uint32_t* run_flag);
 int launch_select_advance(cudaStream_t st, SelectState* s, const uint64_t* hist, int pass, const uint32_t* run_flag);
-int launch_select_advance_p2p(cudaStream_t st, const P2PComm& c, SelectState* s, uint64_t* hist, int pass);
+int launch_select_advance_p2p(cudaStream_t st, const P2PComm& c, SelectState* s, uint64_t* hist, int pass, const uint32_t* run_flag);
 int launch_pair_hist(cudaStream_t st, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last,
                      int64_t tile_row_start, int64_t tile_row_stride, const SelectState* state, int pass,
                      uint64_t* hist, const uint32_t* run_flag);

@@ -240,7 +240,7 @@ __global__ void step_aux_kernel(const double* __restrict__ stats, int scaled, fl
 // rank) over peer memory fused into the kernel that turns them into the step scaling
 __global__ void __launch_bounds__(64) step_aux_p2p_kernel(const P2PComm c, double* stats, int scaled, float lambda_reg, float lr,
                                                           double* aux) {
-  p2p_allreduce_cta(c, reinterpret_cast<unsigned long long*>(stats), 4, true);
+  p2p_allreduce_cta(c, reinterpret_cast<unsigned long long*>(stats), 4, true);   // late peer: stats poisoned with NaN -> alpha, X NaN
   if (threadIdx.x == 0) step_aux_body(stats, scaled, lambda_reg, lr, aux);
 }
 

@@ -36,7 +36,7 @@ SYMBOLS = [
     "nsvgd_tc_probe_gram", "nsvgd_tc_probe_pv",
     "nsvgd_p2p_block_bytes", "nsvgd_p2p_alloc", "nsvgd_p2p_open", "nsvgd_p2p_close", "nsvgd_p2p_free",
     "nsvgd_p2p_timeout_flag", "nsvgd_p2p_allreduce", "nsvgd_p2p_median_advance", "nsvgd_p2p_median_fast_resolve",
-    "nsvgd_p2p_median_fast_advance2", "nsvgd_p2p_apply_update_f32",
+    "nsvgd_p2p_median_fast_advance2", "nsvgd_p2p_median_fast_run", "nsvgd_p2p_apply_update_f32",
 ]
 
 
@@ -98,6 +98,7 @@ def load():
     lib.nsvgd_p2p_median_advance.argtypes = [vp, i32, i32, pvp, vp, vp, i32]
     lib.nsvgd_p2p_median_fast_resolve.argtypes = [vp, i32, i32, pvp, vp, vp, sz, i64, i64, vp]
     lib.nsvgd_p2p_median_fast_advance2.argtypes = [vp, i32, i32, pvp, vp, vp, sz, i64, i64, vp, i32]
+    lib.nsvgd_p2p_median_fast_run.argtypes = [vp, vp, i64, i64, i64, f32, i32, i32, i32, pvp, vp, vp, vp, sz]
     lib.nsvgd_p2p_apply_update_f32.argtypes = [vp, i32, i32, pvp, vp, vp, i64, i64, i64, i64, vp, f32, i32, f32, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)

@@ -291,6 +291,13 @@ class MedianSelect:
         check(load().nsvgd_p2p_median_fast_advance2(stream_ptr(self.x.device), comm.rank, comm.world, comm.blocks, ptr(self.state),
                                                     ptr(ws), ws.numel(), self.n, self.dz, ptr(self.hist_all), p))
 
+    def p2p_fast_run(self, comm):
+        """the whole filtered select of this rank in one C call (fused selects, every exchange inside its consumer kernel)"""
+        ws = self._fws()
+        check(load().nsvgd_p2p_median_fast_run(stream_ptr(self.x.device), ptr(self.P), self.n, self.dz, ld(self.P), self.w_last,
+                                               _lib.MEDIAN_MODES[self.mode], comm.rank, comm.world, comm.blocks, ptr(self.state),
+                                               ptr(self.hist), ptr(ws), ws.numel()))
+
     def p2p_advance(self, comm, p: int):
         check(load().nsvgd_p2p_median_advance(stream_ptr(self.x.device), comm.rank, comm.world, comm.blocks, ptr(self.state),
                                               ptr(self.hist), p))

@@ -81,6 +81,12 @@ class ShardedSVGD:
     def median_heuristic(self, X_all: torch.Tensor) -> torch.Tensor:
         sel = self.engine.MedianSelect(X_all, self.median_mode)
         sum_ = dict(op=dist.ReduceOp.SUM, group=self.group)
+        if getattr(sel, "fast_supported", False) and self.comm is not None and hasattr(sel, "p2p_fast_run") \
+                and (1 << 22) % self.world == 0 and ((1 << 22) // self.world) % 32 == 0:
+            # one C call: sample slice, fused bracket select, filter, exact list, resolve, fused candidate select; every
+            # exchange (4 histogram sums, the counts) happens inside its consumer kernel over NVLink peer memory
+            sel.p2p_fast_run(self.comm)
+            return sel.finish()
         if getattr(sel, "fast_supported", False):
             # tensor-core filtered select: the bracket is identical on every rank (deterministic sample of
             # the gathered particles); counts and candidate histograms are all-reduced between the stages.

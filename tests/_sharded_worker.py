@@ -1,4 +1,4 @@
-"""2-rank NCCL check: the row-sharded step reproduces the single-GPU step (h bit-identical, X to 1e-6)."""
+"""Worker of tests/test_sharded_gpu.py (torchrun, NCCL, one rank per GPU): 2-rank NCCL check: the row-sharded step reproduces the single-GPU step (h bit-identical, X to 1e-6)."""
 import os, sys
 import numpy as np, torch, torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

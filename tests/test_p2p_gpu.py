@@ -1,6 +1,6 @@
 """GPU: the peer-memory all-reduces that row-sharded runs fuse into their consumer kernels (csrc/p2p.cuh), exercised by
 TWO PROCESSES that share one GPU: cudaIpc maps each process's block into the other, the flags / epochs / slot
-alternation are the real protocol.  (The multi-GPU form is scripts/check_sharded.py under torchrun + NCCL.)"""
+alternation are the real protocol.  (The multi-GPU form is tests/_sharded_worker.py under torchrun + NCCL.)"""
 import os
 import socket
 import subprocess
