@@ -965,16 +965,12 @@ __global__ void __launch_bounds__(256) fused_select_kernel(const float* __restri
       __threadfence();
       if (world > 1 && !p2p_allreduce_cta(c, sc->hist[pass], 2 * NSVGD_SELECT_BINS, false) && threadIdx.x == 0)
         (main_state ? main_state : state)->nan_flag = 1u;            // late peer -> h = NaN instead of a partial sum
-      // stage the summed histogram in shared memory (independent coalesced loads) before the scan: 64 dependent L2 round
-      // trips per lane cost ~20 us per pass otherwise
-      unsigned long long* hist64 = reinterpret_cast<unsigned long long*>(hist_s);     // 2 x 2048 u32 -> reuse as 2048 u64 per target
-      for (int w2 = 0; w2 < 2; ++w2) {
-        __syncthreads();
-        for (int t = threadIdx.x; t < NSVGD_SELECT_BINS; t += 256) hist64[t] = sc->hist[pass][w2 * NSVGD_SELECT_BINS + t];
-        __syncthreads();
-        select_advance_one(state, hist64, pass, w2);
-      }
-      select_advance_commit(state, pass);
+      // stage the summed histogram in shared memory (independent coalesced loads; the counts of a value buffer fit 32 bits)
+      // before the scan: 64 dependent L2 round trips per lane cost ~20 us per pass otherwise
+      __syncthreads();
+      for (int t = threadIdx.x; t < 2 * NSVGD_SELECT_BINS; t += 256) hist_s[t] = (unsigned int)sc->hist[pass][t];
+      __syncthreads();
+      select_advance_smem32(state, hist_s, pass);
       if (pass == NSVGD_SELECT_PASSES - 1 && threadIdx.x == 0) {
         if (final_mode == 1) {             // bracket [L, U] for the tensor-core filter
           fs->below = 0ull; fs->list_count = 0u; fs->cand_count = 0u; fs->overflow = 0u; fs->fallback = 0u;

@@ -38,28 +38,26 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
   }
 }
 
-__global__ void __launch_bounds__(256) colmean_final_kernel(const double* __restrict__ part, int64_t blocks, int64_t n,
-                                                            int64_t d, float* __restrict__ mu) {
-  __shared__ double sh[8][33];
+__global__ void __launch_bounds__(1024) colmean_final_kernel(const double* __restrict__ part, int64_t blocks, int64_t n,
+                                                             int64_t d, float* __restrict__ mu) {
+  // 32 warps per 32 columns: each lane's chain of (dependent) L2 round trips is blocks / 32 long
+  __shared__ double sh[32][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * 32 + lane;
   double s = 0.0;
   if (c < d) {
-    // four independent partial sums: the loop is a chain of L2 round trips otherwise (32 us for 1024 partials)
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    double s0 = 0.0, s1 = 0.0;
     int64_t b = w;
-    for (; b + 24 < blocks; b += 32) {
-      s0 += part[b * d + c]; s1 += part[(b + 8) * d + c]; s2 += part[(b + 16) * d + c]; s3 += part[(b + 24) * d + c];
-    }
-    for (; b < blocks; b += 8) s0 += part[b * d + c];
-    s = (s0 + s1) + (s2 + s3);
+    for (; b + 32 < blocks; b += 64) { s0 += part[b * d + c]; s1 += part[(b + 32) * d + c]; }
+    for (; b < blocks; b += 32) s0 += part[b * d + c];
+    s = s0 + s1;
   }
   sh[w][lane] = s;
   __syncthreads();
   if (w == 0 && c < d) {
     double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sh[i][lane];
+    for (int i = 0; i < 32; ++i) t += sh[i][lane];
     mu[c] = (float)(t / (double)n);
   }
 }
@@ -68,7 +66,7 @@ int launch_colmean(cudaStream_t st, const float* X, int64_t n, int64_t d, int64_
   const int64_t blocks = ceil_div(n, MEAN_ROWS);
   colsum_partial_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, n, d, ldx, part);
   NSVGD_LAUNCH_CHECK();
-  colmean_final_kernel<<<(unsigned)ceil_div(d, 32), 256, 0, st>>>(part, blocks, n, d, mu);
+  colmean_final_kernel<<<(unsigned)ceil_div(d, 32), 1024, 0, st>>>(part, blocks, n, d, mu);
   NSVGD_LAUNCH_CHECK();
   return NSVGD_OK;
 }

@@ -77,7 +77,7 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
 // COMBINED form (h_combine != null): one transposed block W^T = (S - Xc/h^2)^T in rows [0, dp) of Vt
 // (phi_i = (1/n)[(K W)_i + rowsum_i qc_i / h^2]: the second GEMM has N = dp instead of 2 dp columns); with
 // vt_extra = 16 the rows [dp, dp + 16) hold {1, c_j, 0, ...}: rowsum_i = (K 1)_i and (K c)_i come out of the same MMAs.
-__global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ X, const float* __restrict__ S,
+__global__ void __launch_bounds__(256, 2) tc_prep_kernel(const float* __restrict__ X, const float* __restrict__ S,
                                                       int64_t n, int64_t d, int64_t ldx, int64_t rows_pad, int dp,
                                                       const float* __restrict__ mu, float last_scale,
                                                       __nv_bfloat16* __restrict__ Xb0, __nv_bfloat16* __restrict__ Xb1,
@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
                                                       const float* __restrict__ h_combine, uint32_t* __restrict__ max_bits) {
   __shared__ float T[64][129];   // one half (S or Xc) of the block, fp32
   __shared__ float cvs[64], ones[64];
+  __shared__ unsigned int smax[2];          // per-CTA maxima: 65536 x 2 same-address global atomics cost ~90 us otherwise
+  if (threadIdx.x < 2) smax[threadIdx.x] = 0u;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t r0 = (int64_t)blockIdx.x * 64;
   const bool combine = h_combine != nullptr;
@@ -95,12 +97,48 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
   for (int half = 0; half < 2; ++half) {      // 0: Xc (also writes Xb, xn, cv), 1: S
     if (half == 1 && (!Vt0 || combine)) break;
     __syncthreads();
-    for (int rr = w; rr < 64; rr += 8) {
+    // Each warp owns 8 consecutive rows.  ALL of their loads are issued before any arithmetic (one DRAM round trip per
+    // warp instead of eight: the row-at-a-time form was latency-bound, ~110 us for 155 MB of traffic at n = 65536).
+    const int npair = dp >> 6;                         // column pairs per lane: 1 (dp = 64) or 2 (dp = 128)
+    const bool vec2 = ((ldx & 1) == 0) && ((((uintptr_t)X) & 7) == 0) && (!S || (((uintptr_t)S) & 7) == 0);
+#pragma unroll 1
+    for (int batch = 0; batch < 2; ++batch) {          // two batches of 4 rows: 32 loads in flight per lane, <= 128 registers
+    float xv[4][2][2], sv[4][2][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t row = r0 + w * 8 + batch * 4 + q;
+      const bool rv = row < n;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c0 = 2 * lane + 64 * u;
+        xv[q][u][0] = xv[q][u][1] = sv[q][u][0] = sv[q][u][1] = 0.f;
+        if (u < npair && rv) {
+          const float* src = (half == 0 ? X : S) + row * ldx + c0;
+          if (vec2 && c0 + 1 < d) {
+            const float2 t = *reinterpret_cast<const float2*>(src);
+            xv[q][u][0] = t.x; xv[q][u][1] = t.y;
+            if (half == 0 && S) { const float2 t2 = *reinterpret_cast<const float2*>(S + row * ldx + c0); sv[q][u][0] = t2.x; sv[q][u][1] = t2.y; }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              if (c0 + e < d) {
+                xv[q][u][e] = src[e];
+                if (half == 0 && S) sv[q][u][e] = S[row * ldx + c0 + e];
+              }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int rr = w * 8 + batch * 4 + q;
       const int64_t row = r0 + rr;
       const bool rv = row < n;
       float acc_n = 0.f, acc_c = 0.f, acc_r = 0.f;
-      // two adjacent columns per lane: packed bf16x2 (4-byte) stores, 128 bytes per warp store
-      for (int c0 = 2 * lane; c0 < dp; c0 += 64) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u >= npair) break;
+        const int c0 = 2 * lane + 64 * u;
         float v2[2] = {0.f, 0.f}, t2[2] = {0.f, 0.f};
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -108,16 +146,16 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
           float v = 0.f, tv = 0.f;
           if (rv && c < d) {
             if (half == 0) {
-              v = X[row * ldx + c] - mu[c];
+              v = xv[q][u][e] - mu[c];
               if (c == d - 1) v *= last_scale;
               acc_n = fmaf(v, v, acc_n);
               if (S) {
-                const float sv = S[row * ldx + c];
-                acc_c = fmaf(sv, v, acc_c);
-                if (combine) tv = fmaf(-v, inv_h2, sv);
+                const float s_ = sv[q][u][e];
+                acc_c = fmaf(s_, v, acc_c);
+                if (combine) tv = fmaf(-v, inv_h2, s_);
               }
             } else {
-              v = S[row * ldx + c];
+              v = xv[q][u][e];
             }
           }
           v2[e] = v; t2[e] = combine ? tv : v;
@@ -147,13 +185,15 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
           if (cv) cv[row] = rv ? acc_c : 0.f;
           cvs[rr] = rv ? acc_c : 0.f; ones[rr] = rv ? 1.f : 0.f;
           if (max_bits && rv) {
-            atomicMax(&max_bits[0], __float_as_uint(acc_n));   // >= 0: uint order = float order; NaN is largest
-            if (Xh) atomicMax(&max_bits[1], __float_as_uint(acc_r));
+            atomicMax(&smax[0], __float_as_uint(acc_n));       // >= 0: uint order = float order; NaN is largest
+            if (Xh) atomicMax(&smax[1], __float_as_uint(acc_r));
           }
         }
       }
     }
+    }
     __syncthreads();
+    if (half == 0 && max_bits && threadIdx.x < 2 && smax[threadIdx.x]) atomicMax(&max_bits[threadIdx.x], smax[threadIdx.x]);
     if (Vt0) {
       // transposed write: warp handles one coordinate c at a time, lane -> rows (2 lane, 2 lane + 1)
       const int64_t vrow0 = (half == 0 && !combine) ? dp : 0;   // Xc^T goes to rows [dp, 2dp), S^T (or W^T) to [0, dp)

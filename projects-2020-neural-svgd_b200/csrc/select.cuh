@@ -37,7 +37,8 @@ __device__ __forceinline__ int pass_bins(int pass) { return pass == 2 ? 1024 : 2
 // targets from one global histogram [2][NSVGD_SELECT_BINS] (warp t resolves target t).  Shared by the plain advance kernel,
 // the fused select and the kernels that first all-reduce the histogram over peer memory (p2p.cuh).
 // Call from ALL threads of a CTA with blockDim.x >= 64.
-__device__ __forceinline__ void select_scan_warp(const SelectState* s, const unsigned long long* hh, int pass, int w, int lane,
+template <typename HT>
+__device__ __forceinline__ void select_scan_warp(const SelectState* s, const HT* hh, int pass, int w, int lane,
                                                  uint32_t* new_prefix, unsigned long long* new_rank) {
   const int nb = pass == 2 ? 1024 : 2048;
   const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
@@ -75,11 +76,8 @@ __device__ __forceinline__ SelectScratch* select_scratch() {
   return &sc;
 }
 
-__device__ __forceinline__ void select_advance_one(const SelectState* s, const unsigned long long* hh, int pass, int w) {
-  SelectScratch* sc = select_scratch();
-  if ((threadIdx.x >> 5) == 0) select_scan_warp(s, hh, pass, w, threadIdx.x & 31, sc->new_prefix, sc->new_rank);
-  __syncthreads();
-}
+// both targets from a shared-memory histogram of 32-bit counts [2][NSVGD_SELECT_BINS] (warp t resolves target t)
+__device__ __forceinline__ void select_advance_smem32(SelectState* s, const uint32_t* hist32, int pass);
 
 __device__ __forceinline__ void select_advance_commit(SelectState* s, int pass) {
   SelectScratch* sc = select_scratch();
@@ -97,6 +95,13 @@ __device__ __forceinline__ void select_advance_commit(SelectState* s, int pass) 
     }
   }
   __syncthreads();
+}
+
+__device__ __forceinline__ void select_advance_smem32(SelectState* s, const uint32_t* hist32, int pass) {
+  SelectScratch* sc = select_scratch();
+  const int w = threadIdx.x >> 5;
+  if (w < 2) select_scan_warp(s, hist32 + (size_t)w * NSVGD_SELECT_BINS, pass, w, threadIdx.x & 31, sc->new_prefix, sc->new_rank);
+  select_advance_commit(s, pass);
 }
 
 __device__ __forceinline__ void select_advance_body(SelectState* s, const unsigned long long* hist, int pass) {

@@ -124,31 +124,64 @@ class PeerComm:
     through cudaIpc handles that are exchanged with one all-gather of the process group."""
 
     def __init__(self, group=None):
+        """The handshake runs in phases that cannot diverge: EVERY rank runs the same sequence of collectives (gather the
+        handles -- None on a local failure --, try the opens, gather an ok flag, barrier); failures are caught locally and
+        reported through the gathered status, so either all ranks get a communicator or all ranks raise."""
         import torch.distributed as dist
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         lib = load()
-        own = C.c_void_p()
+        self.own, self.peers, self.blocks, err = None, [], None, None
         handle = (C.c_ubyte * 64)()
-        check(lib.nsvgd_p2p_alloc(C.byref(own), handle))            # zero-filled and synchronised
-        self.own = own.value
+        try:
+            own = C.c_void_p()
+            check(lib.nsvgd_p2p_alloc(C.byref(own), handle))            # zero-filled and synchronised
+            self.own = own.value
+        except Exception as e:          # cudaIpc not permitted, out of memory, ...
+            err = e
         # handles travel as python objects: works on every backend (nccl, gloo) and also orders every rank's zero-fill
         # before any peer can write a flag
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle), group=group)
-        allh = b"".join(handles)
-        self.peers = []
-        ptrs = (C.c_void_p * self.world)()
-        for r in range(self.world):
-            if r == self.rank:
-                ptrs[r] = self.own
-                continue
-            pp = C.c_void_p()
-            buf = (C.c_ubyte * 64).from_buffer_copy(allh[64 * r: 64 * r + 64])
-            check(lib.nsvgd_p2p_open(buf, C.byref(pp)))
-            ptrs[r] = pp.value
-            self.peers.append(pp.value)
-        self.blocks = ptrs
+        dist.all_gather_object(handles, bytes(handle) if err is None else None, group=group)
+        if err is None and any(h is None for h in handles):
+            err = RuntimeError("a peer could not allocate its block")
+        if err is None:
+            try:
+                ptrs = (C.c_void_p * self.world)()
+                for r in range(self.world):
+                    if r == self.rank:
+                        ptrs[r] = self.own
+                        continue
+                    pp = C.c_void_p()
+                    buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                    check(lib.nsvgd_p2p_open(buf, C.byref(pp)))
+                    ptrs[r] = pp.value
+                    self.peers.append(pp.value)
+                self.blocks = ptrs
+            except Exception as e:      # no peer access between these devices, ...
+                err = e
+        oks = [None] * self.world
+        dist.all_gather_object(oks, 1 if err is None else 0, group=group)
         dist.barrier(group=group)
+        if min(oks) == 0:
+            self.close()
+            raise RuntimeError(f"peer-memory communicator unavailable on rank(s) {[r for r, o in enumerate(oks) if not o]}"
+                               + (f": {err}" if err is not None else ""))
+
+    def close(self):
+        """unmap the peers' blocks and free the own one (idempotent; also run by the destructor)"""
+        lib = load()
+        for p in getattr(self, "peers", []):
+            lib.nsvgd_p2p_close(p)
+        self.peers = []
+        if getattr(self, "own", None):
+            lib.nsvgd_p2p_free(self.own)
+        self.own, self.blocks = None, None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def timed_out(self) -> bool:
         flag = C.c_int(0)

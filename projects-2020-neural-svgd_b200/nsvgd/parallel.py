@@ -41,6 +41,7 @@ class ShardedSVGD:
         self.r0, self.r1 = row_partition(n, self.world, self.rank)
         self.max_rows = row_partition(n, self.world, 0)[1]
         self._buf = {}
+        self._side = None
         self.comm = None
         import os
         if p2p == "auto" and os.environ.get("NSVGD_P2P", "1") == "0":
@@ -57,6 +58,12 @@ class ShardedSVGD:
                 self.comm = None
                 if p2p == "on":
                     raise RuntimeError(f"peer-memory communicator unavailable: {err}")
+
+    def check_health(self):
+        """Host-side check of the peer-memory watchdog (synchronises): a peer that did not arrive within the time limit
+        has already turned h / alpha / the particles into NaN on the device (csrc/p2p.cuh); this raises on top of it."""
+        if self.comm is not None and self.comm.timed_out():
+            raise RuntimeError("a peer-memory all-reduce timed out: the results of the affected steps are NaN by construction")
 
     # ---- collectives -----------------------------------------------------------------------------
     def all_gather_rows(self, local: torch.Tensor, tag: str) -> torch.Tensor:
@@ -129,8 +136,20 @@ class ShardedSVGD:
     def step(self, X_local, S_local, lr, scaled=True, lambda_reg=0.5, bandwidth=None, want_grads=False):
         """Updates X_local in place.  Returns (h, step_aux, grads_local | None)."""
         X_all = self.all_gather_rows(X_local, "X")
-        S_all = self.all_gather_rows(S_local, "S")
-        h = bandwidth if bandwidth else self.median_heuristic(X_all)      # truthiness as in models.py:657
+        if bandwidth or not X_local.is_cuda:
+            S_all = self.all_gather_rows(S_local, "S")
+            h = bandwidth if bandwidth else self.median_heuristic(X_all)  # truthiness as in models.py:657
+        else:
+            # the scores are not needed before phi*: their all-gather rides on a side stream under the bandwidth
+            # selection (fork / join through events, so the pattern is also what a CUDA-graph capture records)
+            cur = torch.cuda.current_stream(X_local.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=X_local.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                S_all = self.all_gather_rows(S_local, "S")
+            h = self.median_heuristic(X_all)
+            cur.wait_stream(self._side)
         phi, stats = self.engine.phistar(X_local, X_all, S_all, h, Sq=S_local, stats=True)
         if self.comm is not None:
             step_aux, grads = self.engine.apply_update_p2p(self.comm, X_local, phi, stats, lr, scaled, lambda_reg,
