@@ -234,11 +234,55 @@ int nsvgd_ksum_f32(void* stream, const float* A, int64_t na, int64_t lda,
 int nsvgd_adam_update_f32(void* stream, float* X, const float* grads, float* m1, float* m2,
                           int64_t count, float lr, float b1, float b2, float eps, int64_t t);
 
-/* ---- tcgen05 bring-up probes (used by tests/test_tc_probe.py; not part of the drop-in API) */
-int nsvgd_tc_probe_gram(void* stream, const float* A /*128 x 128*/, const float* B /*64 x 128*/,
-                        float* G /*128 x 64*/, void* ws, size_t ws_bytes);
-int nsvgd_tc_probe_pv(void* stream, const float* P /*128 x 64*/, const float* V /*64 x 256*/,
-                      float* O /*128 x 256*/, void* ws, size_t ws_bytes);
+/* ---- vector (ARD) and full-matrix Gaussian kernels (kernels.py:52-65 with a (d,) bandwidth, kernels.py:83-88;
+ * nets.RBFKernel nets.py:24-49).  phi* and MMD run on the unit-bandwidth engine after a linear map of the
+ * particles (x' = x / h or x' = x Sigma^T; scores s' = s h or s Sigma^-1; phi = phi' / h or phi' Sigma): */
+int nsvgd_scale_cols_f32(void* stream, const float* X, int64_t n, int64_t d, int64_t ldx, const float* v, int invert,
+                         float* out, int64_t ldo);
+int nsvgd_matmul_f32(void* stream, const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, float* C,
+                     int64_t ldc, int64_t M, int64_t N, int64_t K, int accumulate);
+/* the KSD is not invariant under that map; closed form with per-coordinate weights inv_h2[a] = 1/h_a^2 (device, d floats) */
+int nsvgd_ksd_ard_f32(void* stream, const float* X, const float* Sx, int64_t n, int64_t ldx, const float* Y,
+                      const float* Sy, int64_t m, int64_t ldy, int64_t d, const float* inv_h2, float inv_h2_sum,
+                      int variant, double* out_dev, void* ws, size_t ws_bytes);
+
+/* linear-time KSD estimator (stein.py:353-380): mean_i u_p(x_i, x_{i + n/2}) over the two halves of the sample (an odd
+ * count drops the last one).  out_dev: 2 doubles {mean, std(ddof = 1) / (n/2)}; ws: >= (n/2) floats. */
+int nsvgd_ksd_linear_f32(void* stream, const float* X, const float* S, int64_t n, int64_t d, int64_t ld,
+                         const float* h_dev, double* out_dev, void* ws, size_t ws_bytes);
+
+/* ---- differentiable operators: backward rules -------------------------------------------------------
+ * The reference differentiates through its kernels and phi* with jax.grad / jacfwd (stein.py:99-106, 180-203; the
+ * kernel-learning notebooks differentiate the KSD w.r.t. the bandwidth).  These entry points are the closed-form
+ * backward rules a jax.custom_vjp (or torch.autograd.Function, nsvgd/autodiff.py) binds. */
+/* KSD (variant as nsvgd_ksd_f32) and d KSD / d h in one pass; out_dev, dh_dev: 1 double each */
+int nsvgd_ksd_dh_f32(void* stream, const float* X, const float* Sx, int64_t n, int64_t ldx, const float* Y,
+                     const float* Sy, int64_t m, int64_t ldy, int64_t d, const float* h_dev, int variant,
+                     double* out_dev, double* dh_dev, void* ws, size_t ws_bytes);
+/* cotangents of phi = phistar(Q; X, S, h) for an upstream cotangent G (m x d, leading dimension ldq like Q):
+ * dQ (m x d), dX (n x d), dS (n x d) (each may be NULL), dh_dev (1 double, may be NULL).  Q == X (the SVGD case): the
+ * caller adds dQ and dX.  Scratch: nsvgd_phi_vjp_workspace_bytes. */
+int nsvgd_phi_vjp_workspace_bytes(int64_t m, int64_t n, int64_t d, size_t* out_bytes);
+int nsvgd_phi_vjp_f32(void* stream, const float* Q, const float* G, int64_t m, int64_t ldq, const float* X, const float* S,
+                      int64_t n, int64_t ldx, int64_t d, const float* h_dev, float* dQ, int64_t lddq, float* dX, int64_t lddx,
+                      float* dS, int64_t ldds, double* dh_dev, void* ws, size_t ws_bytes);
+
+/* ---- grad log p (and optionally log p) of the reference's canonical targets, on the device ----------
+ * Replace vmap(grad(logp)) of stein.py:86-89 / models.py:662-675 for targets whose score has a closed form, so that a
+ * whole SVGD step is enqueued without the framework's autodiff.  S: n x d scores; logp: n values or NULL. */
+/* Neal's funnel (distributions.py:275-319): last coordinate y ~ N(0, 9), x_k | y ~ N(0, e^y) */
+int nsvgd_score_funnel_f32(void* stream, const float* X, int64_t n, int64_t d, int64_t ldx, float* S, int64_t lds,
+                           float* logp);
+/* N(mean, cov) (distributions.py:89-154, 627-639): prec = cov^-1 row-major d x d, or its diagonal (prec_is_diag);
+ * log_norm = -(d/2) log 2 pi - (1/2) log det cov */
+int nsvgd_score_gaussian_f32(void* stream, const float* X, int64_t n, int64_t d, int64_t ldx, const float* mean,
+                             const float* prec, int prec_is_diag, float log_norm, float* S, int64_t lds, float* logp);
+/* Bayesian logistic regression posterior (experiments/bayesian_logistic_regression.py:73-114, 169-190):
+ * params P[i] = [w (F), log alpha], d = F + 1; minibatch Xb (B x F, row-major), yb (B) in {0,1};
+ * log p = prior_logp(w, log alpha) + num_datapoints * SUM_batch log sigmoid(y' x.w)   (the reference's literal scaling) */
+int nsvgd_score_logreg_f32(void* stream, const float* P, int64_t n, int64_t d, int64_t ldp, const float* Xb, const float* yb,
+                           int64_t B, int64_t F, float num_datapoints, float a0, float b0, float* S, int64_t lds,
+                           float* logp);
 
 #ifdef __cplusplus
 }

@@ -164,3 +164,46 @@ def make_gaussian_logp(mean, precision):
         c = x - mean
         return -0.5 * torch.dot(c, precision @ c)
     return logp
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Line-for-line torch mirror of the logistic-regression target (experiments/bayesian_logistic_regression.py), fp64.
+# Differentiated with torch.func.grad it is the witness the closed-form scores of oracle/svgd_oracle.py
+# (and through them the CUDA kernel csrc/scores.cu) are pinned against (tests/test_scores.py).
+# ---------------------------------------------------------------------------------------------------------------
+def _gamma_logpdf(x, a, scale):
+    """scipy.stats.gamma.logpdf(x, a, scale=scale)"""
+    import math
+    return (a - 1) * torch.log(x) - x / scale - a * math.log(scale) - math.lgamma(a)
+
+
+def _norm_logpdf(x, scale):
+    """scipy.stats.norm.logpdf(x, scale=scale)"""
+    import math
+    return -0.5 * (x / scale) ** 2 - torch.log(scale) - 0.5 * math.log(2 * math.pi)
+
+
+def logreg_prior_logp(w, log_alpha, a0=1.0, b0=0.01):
+    """prior_logp, single-parameter branch                                                  :73-92"""
+    alpha = torch.exp(log_alpha)
+    logp_alpha = torch.sum(_gamma_logpdf(alpha, a0, scale=1 / b0))
+    logp_w = torch.sum(_norm_logpdf(w, scale=1 / torch.sqrt(alpha)))
+    return logp_alpha + logp_w
+
+
+def logreg_loglikelihood(y, x, w):
+    """loglikelihood: log p(y | x, w) = sum_i(logp(yi | xi, w))                             :103-114"""
+    y = ((y - 1 / 2) * 2)
+    logits = x @ w
+    prob_y = torch.special.expit(logits * y)
+    return torch.sum(torch.log(prob_y))
+
+
+def logreg_logp_literal(x, y, num_datapoints, a0=1.0, b0=0.01):
+    """get_minibatch_logp(x, y) -> logp(params), w.ndim == 1 branch                          :169-190"""
+    def logp(params):
+        w, log_alpha = params[:-1], params[-1]                       # unravel  :162-166
+        log_prior = logreg_prior_logp(w, log_alpha, a0, b0)
+        mean_loglikelihood = logreg_loglikelihood(y, x, w)
+        return log_prior + num_datapoints * mean_loglikelihood
+    return logp

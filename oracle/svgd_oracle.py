@@ -448,3 +448,59 @@ def phistar_f32_blocked_torch(Q, X, S, h, block=2048):
         rs = K.sum(1, keepdim=True)
         out[s:s + block] = (KV[:, :d] + (rs * q - KV[:, d:]) / h2) / n
     return out
+
+
+# --------------------------------------------------------------------------
+# N4  scores of the canonical targets (closed forms, fp64).  The logistic-
+# regression posterior restates experiments/bayesian_logistic_regression.py:
+#   prior_logp              :73-92    gamma.logpdf(alpha; a0, scale=1/b0) + sum norm.logpdf(w; scale=alpha^-1/2)
+#   loglikelihood           :103-114  SUM_i log expit(y'_i x_i.w),  y' = (y - 1/2) * 2
+#   get_minibatch_logp.logp :179-189  log_prior + num_datapoints * loglikelihood   (single-parameter branch: the
+#                                     plug-in differentiates one particle at a time, models.py:662-675 / stein.py:86-89)
+# params = ravel(w, log_alpha) = [w, log_alpha]  (:158-159); alpha = exp(log_alpha), no Jacobian term (:84-85).
+# oracle/structural.py::logreg_logp_literal is the line-for-line torch mirror these closed forms are pinned against.
+# --------------------------------------------------------------------------
+def logreg_logp(P, Xb, yb, num_datapoints, a0=1.0, b0=0.01):
+    P = np.asarray(P, np.float64); Xb = np.asarray(Xb, np.float64)
+    ys = (np.asarray(yb, np.float64) - 0.5) * 2.0
+    w, la = P[:, :-1], P[:, -1]
+    F = w.shape[1]
+    alpha = np.exp(la)
+    lg = (a0 - 1.0) * la - b0 * alpha + a0 * math.log(b0) - math.lgamma(a0)
+    lw = -0.5 * alpha * (w * w).sum(1) + 0.5 * F * la - 0.5 * F * math.log(2 * math.pi)
+    t = (w @ Xb.T) * ys[None, :]
+    ll = -(np.logaddexp(0.0, -t)).sum(1)                         # log expit(t) = -log(1 + e^-t)
+    return lg + lw + num_datapoints * ll
+
+
+def logreg_score(P, Xb, yb, num_datapoints, a0=1.0, b0=0.01):
+    P = np.asarray(P, np.float64); Xb = np.asarray(Xb, np.float64)
+    ys = (np.asarray(yb, np.float64) - 0.5) * 2.0
+    w, la = P[:, :-1], P[:, -1]
+    F = w.shape[1]
+    alpha = np.exp(la)
+    t = (w @ Xb.T) * ys[None, :]
+    g = num_datapoints * ys[None, :] * (1.0 / (1.0 + np.exp(t)))   # d/dz log expit(y' z) = y' expit(-y' z)
+    s_w = g @ Xb - w * alpha[:, None]
+    s_la = (a0 - 1.0) - b0 * alpha + 0.5 * F - 0.5 * alpha * (w * w).sum(1)
+    return np.concatenate([s_w, s_la[:, None]], axis=1)
+
+
+def gaussian_score(X, mean, cov):
+    """-(x - mean) cov^-1; cov a (d,) diagonal or (d,d) matrix        distributions.py:89-154"""
+    X = np.asarray(X, np.float64); mean = np.asarray(mean, np.float64); cov = np.asarray(cov, np.float64)
+    prec = np.diag(1.0 / cov) if cov.ndim == 1 else np.linalg.inv(cov)
+    return -(X - mean) @ prec
+
+
+def logreg_workload(n, F, B=128, seed=0, num_datapoints=418_000):
+    """cfg3-style synthetic stand-in for the covertype run (no dataset in the image): standardised features + intercept
+    column (:41), labels from a random ground-truth weight vector, particles from the prior (:66-71, a0=1, b0=0.01).
+    num_datapoints ~ the reference's len(x_train) = 0.8 * 0.9 * 581012."""
+    rng = np.random.default_rng(seed)
+    Xb = np.concatenate([rng.standard_normal((B, F - 1)), np.ones((B, 1))], axis=1).astype(F32)
+    w_true = rng.standard_normal(F) * 0.5
+    yb = (rng.random(B) < 1.0 / (1.0 + np.exp(-(Xb @ w_true)))).astype(F32)
+    alpha = rng.gamma(1.0, size=n) / 0.01
+    P = np.concatenate([rng.standard_normal((n, F)), np.log(alpha)[:, None]], axis=1).astype(F32)
+    return P, Xb, yb, float(num_datapoints)

@@ -36,14 +36,14 @@ int device_sm_count() {
 
 int ensure_dyn_smem(const void* kernel, int bytes) {
   static std::mutex mu;
-  static std::map<const void*, uint64_t> done;   // kernel -> bit mask of devices already configured
+  static std::map<std::pair<const void*, int>, int> done;   // (kernel, device) -> largest size configured so far
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
   std::lock_guard<std::mutex> lk(mu);
-  uint64_t& mask = done[kernel];
-  if (mask & (1ull << dev)) return NSVGD_OK;
+  int& cur = done[{kernel, dev}];
+  if (cur >= bytes) return NSVGD_OK;
   NSVGD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  mask |= 1ull << dev;
+  cur = bytes;
   return NSVGD_OK;
 }
 
@@ -212,7 +212,7 @@ extern "C" int nsvgd_workspace_bytes(int op, int64_t n, int64_t m, int64_t d, in
     case NSVGD_OP_MEDIAN: need = median_workspace(n, d); break;
     case NSVGD_OP_PHI: need = phi_need(m); break;
     case NSVGD_OP_STEP: need = phi_need(n) + (size_t)(n * d) * sizeof(float) + 1024; break;
-    case NSVGD_OP_KSD: need = (size_t)(tiles_n * std::max(tiles_n, tiles_m)) * sizeof(double) + 256; break;
+    case NSVGD_OP_KSD: need = 2 * (size_t)(tiles_n * std::max(tiles_n, tiles_m)) * sizeof(double) + 256; break;   // KSD + d/dh partials
     case NSVGD_OP_MMD: {
       const int64_t t = std::max(tiles_n, tiles_m);
       need = (size_t)(t * t) * sizeof(double) + (size_t)((n + m) * d) * sizeof(float) + 1024;

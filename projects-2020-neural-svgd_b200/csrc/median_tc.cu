@@ -52,7 +52,8 @@ static uint32_t cand_capacity(int64_t n) {
 
 // scratch of one fused 3-pass select (fused_select_kernel): one global histogram per pass + the grid-wide hand-shake
 struct FusedSelScratch {
-  unsigned long long hist[NSVGD_SELECT_PASSES][2 * NSVGD_SELECT_BINS];
+  uint32_t hist[NSVGD_SELECT_PASSES][2 * NSVGD_SELECT_BINS];   // 32-bit counts (a value buffer holds < 2^32 values over all ranks):
+                                                               // two counts per 64-bit word of the peer-memory exchange
   uint32_t done[4];      // CTAs that have flushed their histogram of pass p
   uint32_t flag[4];      // set by the last CTA of pass p once the select state has advanced
 };
@@ -820,7 +821,7 @@ __global__ void __launch_bounds__(64) fast_resolve_p2p_kernel(const P2PComm c, F
 // + the candidate-select decision + (only when the fallback flag is set) the SIMT-select decision
 __global__ void __launch_bounds__(1024) fast_advance2_p2p_kernel(const P2PComm c, const FastMedState* fs, SelectState* cand_state,
                                                                  SelectState* main_state, unsigned long long* hist, int pass) {
-  if (!p2p_allreduce_cta(c, hist, 4 * NSVGD_SELECT_BINS, false) && threadIdx.x == 0) main_state->nan_flag = 1u;
+  if (!p2p_allreduce_cta<1>(c, hist, 4 * NSVGD_SELECT_BINS, false) && threadIdx.x == 0) main_state->nan_flag = 1u;
   select_advance_body(cand_state, hist, pass);
   if (fs->fallback) select_advance_body(main_state, hist + 2 * NSVGD_SELECT_BINS, pass);
 }
@@ -896,7 +897,7 @@ __device__ __forceinline__ void st_release_gpu_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(256) fused_select_kernel(const float* __restrict__ vals, const uint32_t* __restrict__ counts_dev,
+__global__ void __launch_bounds__(256, 4) fused_select_kernel(const float* __restrict__ vals, const uint32_t* __restrict__ counts_dev,
                                                            int count_stride, int nseg, uint32_t seg_cap, uint32_t v_begin,
                                                            uint32_t v_end, SelectState* state, FusedSelScratch* sc, const P2PComm c,
                                                            int world, int final_mode, FastMedState* fs, SelectState* main_state,
@@ -955,7 +956,7 @@ __global__ void __launch_bounds__(256) fused_select_kernel(const float* __restri
     __syncthreads();
     for (int t = threadIdx.x; t < 2 * NSVGD_SELECT_BINS; t += 256) {
       const unsigned int v = hist_s[t];
-      if (v) atomicAdd(&sc->hist[pass][t], (unsigned long long)v);
+      if (v) atomicAdd(&sc->hist[pass][t], v);
     }
     __threadfence();
     __syncthreads();
@@ -963,12 +964,12 @@ __global__ void __launch_bounds__(256) fused_select_kernel(const float* __restri
     __syncthreads();
     if (s_last) {
       __threadfence();
-      if (world > 1 && !p2p_allreduce_cta(c, sc->hist[pass], 2 * NSVGD_SELECT_BINS, false) && threadIdx.x == 0)
+      if (world > 1 && !p2p_allreduce_cta(c, reinterpret_cast<unsigned long long*>(sc->hist[pass]), NSVGD_SELECT_BINS, false) && threadIdx.x == 0)
         (main_state ? main_state : state)->nan_flag = 1u;            // late peer -> h = NaN instead of a partial sum
       // stage the summed histogram in shared memory (independent coalesced loads; the counts of a value buffer fit 32 bits)
       // before the scan: 64 dependent L2 round trips per lane cost ~20 us per pass otherwise
       __syncthreads();
-      for (int t = threadIdx.x; t < 2 * NSVGD_SELECT_BINS; t += 256) hist_s[t] = (unsigned int)sc->hist[pass][t];
+      for (int t = threadIdx.x; t < 2 * NSVGD_SELECT_BINS; t += 256) hist_s[t] = sc->hist[pass][t];
       __syncthreads();
       select_advance_smem32(state, hist_s, pass);
       if (pass == NSVGD_SELECT_PASSES - 1 && threadIdx.x == 0) {
@@ -987,8 +988,14 @@ __global__ void __launch_bounds__(256) fused_select_kernel(const float* __restri
       if (threadIdx.x == 0) st_release_gpu_u32(&sc->flag[pass], 1u);
     } else if (pass + 1 < NSVGD_SELECT_PASSES) {
       if (threadIdx.x == 0) {
+        // back off between polls: ~600 CTAs re-reading one L2 line back to back slow down everything that shares the
+        // slice -- the last CTA's own loads and, when row-sharded, the peers' reads of this rank's slot (measured:
+        // 150 us per exchange at 8 GPUs without the back-off)
         const long long t0 = clock64();
+        unsigned int ns = 100u;
         while (ld_acquire_gpu_u32(&sc->flag[pass]) == 0u) {
+          __nanosleep(ns);
+          if (ns < 1600u) ns <<= 1;
           if (clock64() - t0 > 8000000000ll) { (main_state ? main_state : state)->nan_flag = 1u; break; }   // never hang
         }
       }
@@ -1003,8 +1010,16 @@ static int launch_fused_select(cudaStream_t st, const float* vals, const uint32_
                                int u_is_inf) {
   P2PComm c{};
   if (comm) c = *comm; else { c.rank = 0; c.world = 1; }
-  // co-resident by construction: four 256-thread CTAs (16 KB of shared memory each) per SM
-  fused_select_kernel<<<device_sm_count() * 4, 256, 0, st>>>(vals, counts_dev, count_stride, nseg, seg_cap, v_begin, v_end, state, sc,
+  // the grid MUST be co-resident (CTAs wait for each other): ask the occupancy calculator, at most four CTAs per SM
+  static std::atomic<int> per_sm_cached{0};
+  int per_sm = per_sm_cached.load();
+  if (!per_sm) {
+    NSVGD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_select_kernel, 256, 0));
+    NSVGD_REQUIRE(per_sm >= 1, NSVGD_ERR_CUDA, "fused_select_kernel does not fit on an SM");
+    per_sm = std::min(per_sm, 4);
+    per_sm_cached.store(per_sm);
+  }
+  fused_select_kernel<<<device_sm_count() * per_sm, 256, 0, st>>>(vals, counts_dev, count_stride, nseg, seg_cap, v_begin, v_end, state, sc,
                                                          c, c.world, final_mode, fs, main_state, l_is_zero, u_is_inf);
   NSVGD_LAUNCH_CHECK();
   return NSVGD_OK;

@@ -7,7 +7,7 @@
 namespace nsvgd {
 
 __global__ void __launch_bounds__(1024) p2p_allreduce_kernel(const P2PComm c, unsigned long long* buf, int nwords, int f64) {
-  p2p_allreduce_cta(c, buf, nwords, f64 != 0);
+  p2p_allreduce_cta<1>(c, buf, nwords, f64 != 0);
 }
 
 }  // namespace nsvgd

@@ -50,6 +50,7 @@ __device__ __forceinline__ unsigned long long p2p_ld_relaxed_sys(const unsigned 
 // Returns false (on every thread) when a peer did not arrive within the watchdog time: the block's timeout flag is set
 // and buf is POISONED (NaN doubles / all-ones integers) so that the consumer cannot turn a partial sum into a
 // normal-looking bandwidth or step; the callers additionally raise their own NaN flags.
+template <int BATCH = 4>
 __device__ __forceinline__ bool p2p_allreduce_cta(const P2PComm& c, unsigned long long* buf, int nwords, bool f64) {
   unsigned char* me = c.blk[c.rank];
   uint32_t* my_flags = reinterpret_cast<uint32_t*>(me);
@@ -75,17 +76,35 @@ __device__ __forceinline__ bool p2p_allreduce_cta(const P2PComm& c, unsigned lon
     if (threadIdx.x == 0) *epoch_p = epoch;
     return false;
   }
-  for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
-    if (f64) {
-      double acc = 0.0;
-      for (int r = 0; r < c.world; ++r)
-        acc += __longlong_as_double((long long)p2p_ld_relaxed_sys(reinterpret_cast<const unsigned long long*>(c.blk[r] + slot_off) + i));
-      buf[i] = (unsigned long long)__double_as_longlong(acc);
-    } else {
-      unsigned long long acc = 0ull;
-      for (int r = 0; r < c.world; ++r)
-        acc += p2p_ld_relaxed_sys(reinterpret_cast<const unsigned long long*>(c.blk[r] + slot_off) + i);
-      buf[i] = acc;
+  // All peer loads of up to BATCH words are issued BEFORE the first add: the asm statements keep their order, so
+  // `acc += load` per peer would wait for every NVLink round trip (~2 us) in turn -- 128 of them per thread for a
+  // 32 KB histogram on 8 ranks.
+  for (int i0 = threadIdx.x; i0 < nwords; i0 += BATCH * blockDim.x) {
+    unsigned long long v[BATCH][NSVGD_P2P_MAX_WORLD];
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) {
+      const int i = i0 + u * blockDim.x;
+#pragma unroll
+      for (int r = 0; r < NSVGD_P2P_MAX_WORLD; ++r)
+        v[u][r] = (i < nwords && r < c.world)
+                      ? p2p_ld_relaxed_sys(reinterpret_cast<const unsigned long long*>(c.blk[r] + slot_off) + i) : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i >= nwords) continue;
+      if (f64) {
+        double acc = 0.0;
+#pragma unroll
+        for (int r = 0; r < NSVGD_P2P_MAX_WORLD; ++r)
+          if (r < c.world) acc += __longlong_as_double((long long)v[u][r]);       // fixed rank order
+        buf[i] = (unsigned long long)__double_as_longlong(acc);
+      } else {
+        unsigned long long acc = 0ull;
+#pragma unroll
+        for (int r = 0; r < NSVGD_P2P_MAX_WORLD; ++r) acc += v[u][r];
+        buf[i] = acc;
+      }
     }
   }
   __threadfence();

@@ -22,7 +22,7 @@ constexpr int TILE = 64;
 constexpr int DK = 16;
 constexpr int LDS_ = TILE + 4;  // padded row of the transposed smem tiles (floats)
 
-enum PairMode { MODE_HIST = 0, MODE_KSUM = 1, MODE_KMAT = 2, MODE_KSD = 3 };
+enum PairMode { MODE_HIST = 0, MODE_KSUM = 1, MODE_KMAT = 2, MODE_KSD = 3, MODE_VJP = 4 };
 
 
 struct PairArgs {
@@ -38,8 +38,12 @@ struct PairArgs {
   const SelectState* state; int pass; unsigned long long* hist; const uint32_t* run_flag;
   // KSUM / KSD
   double* partials; float diag_weight;
-  // KMAT
+  float wsum;                            // KSD, ARD: sum_a 1/h_a^2 (host)
+  const float* wcoord;                   // KSD: per-coordinate weights 1/h_a^2 of an ARD bandwidth (null: scalar bandwidth)
+  double* partials_dh;                   // KSD / VJP: per-CTA partial sums of the derivative w.r.t. the bandwidth (or null)
+  // KMAT / VJP
   float* K; int64_t ldk;
+  float* C;                              // VJP: C_ij = k_ij (g_i.s_j + g_i.(q_i - x_j) / h^2), same layout as K
 };
 
 
@@ -51,8 +55,10 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(const PairArgs a) {
 
   __shared__ __align__(16) float As[DK][LDS_];
   __shared__ __align__(16) float Bs[DK][LDS_];
-  __shared__ __align__(16) float SAs[MODE == MODE_KSD ? DK : 1][LDS_];
-  __shared__ __align__(16) float SBs[MODE == MODE_KSD ? DK : 1][LDS_];
+  constexpr bool SCORES = (MODE == MODE_KSD || MODE == MODE_VJP);   // a second operand per side: scores (KSD) / cotangent and scores (VJP)
+  __shared__ __align__(16) float SAs[SCORES ? DK : 1][LDS_];
+  __shared__ __align__(16) float SBs[SCORES ? DK : 1][LDS_];
+  __shared__ float Ws[MODE == MODE_KSD ? DK : 1];      // ARD weights of the current coordinate chunk
   __shared__ unsigned int hist_s[MODE == MODE_HIST ? 2 * NSVGD_SELECT_BINS : 1];
   __shared__ double red_s[32];
 
@@ -74,14 +80,17 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(const PairArgs a) {
   const int64_t i0 = I * TILE, j0 = J * TILE;
 
   float acc[4][4];
-  float acc_ss[MODE == MODE_KSD ? 4 : 1][MODE == MODE_KSD ? 4 : 1];
-  float acc_sd[MODE == MODE_KSD ? 4 : 1][MODE == MODE_KSD ? 4 : 1];
+  float acc_ss[SCORES ? 4 : 1][SCORES ? 4 : 1];
+  float acc_sd[SCORES ? 4 : 1][SCORES ? 4 : 1];
+  float acc_q4[MODE == MODE_KSD ? 4 : 1][MODE == MODE_KSD ? 4 : 1];     // ARD: sum_a diff_a^2 / h_a^4
+  const bool ard = MODE == MODE_KSD && a.wcoord != nullptr;
 #pragma unroll
   for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
       acc[ii][jj] = 0.f;
-      if (MODE == MODE_KSD) { acc_ss[ii][jj] = 0.f; acc_sd[ii][jj] = 0.f; }
+      if (SCORES) { acc_ss[ii][jj] = 0.f; acc_sd[ii][jj] = 0.f; }
+      if (MODE == MODE_KSD) acc_q4[ii][jj] = 0.f;
     }
 
   // EXACT: the last coordinate is handled separately (weighted), main loop covers [0, d-1)
@@ -98,11 +107,12 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(const PairArgs a) {
       const int64_t gi = i0 + r, gj = j0 + r;
       As[lc][r] = (cv && gi < a.na) ? a.A[gi * a.lda + c] : 0.f;
       Bs[lc][r] = (cv && gj < a.nb) ? a.B[gj * a.ldb + c] : 0.f;
-      if (MODE == MODE_KSD) {
+      if (SCORES) {
         SAs[lc][r] = (cv && gi < a.na) ? a.SA[gi * a.lda + c] : 0.f;
         SBs[lc][r] = (cv && gj < a.nb) ? a.SB[gj * a.ldb + c] : 0.f;
       }
     }
+    if (MODE == MODE_KSD && threadIdx.x < DK) Ws[threadIdx.x] = (ard && c0 + threadIdx.x < dmain) ? a.wcoord[c0 + threadIdx.x] : 1.f;
     __syncthreads();
 #pragma unroll
     for (int c = 0; c < DK; ++c) {
@@ -111,7 +121,7 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(const PairArgs a) {
       const float ar[4] = {av.x, av.y, av.z, av.w};
       const float br[4] = {bv.x, bv.y, bv.z, bv.w};
       float sar[4], sbr[4];
-      if (MODE == MODE_KSD) {
+      if (SCORES) {
         const float4 sa = *reinterpret_cast<const float4*>(&SAs[c][ty * 4]);
         const float4 sb = *reinterpret_cast<const float4*>(&SBs[c][tx * 4]);
         sar[0] = sa.x; sar[1] = sa.y; sar[2] = sa.z; sar[3] = sa.w;
@@ -121,15 +131,21 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(const PairArgs a) {
       for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          const float diff = ar[ii] - br[jj];
+          float diff = ar[ii] - br[jj];
           if (EXACT) {
             acc[ii][jj] = __fadd_rn(acc[ii][jj], __fmul_rn(diff, diff));
+          } else if (MODE == MODE_KSD) {
+            // ARD: r'^2 = sum w diff^2, (s_x-s_y).(x-y)' = sum w (s_x-s_y) diff, sum w^2 diff^2; w = 1 for a scalar bandwidth
+            const float wd = Ws[c] * diff;
+            acc[ii][jj] = fmaf(wd, diff, acc[ii][jj]);
+            acc_q4[ii][jj] = fmaf(wd, wd, acc_q4[ii][jj]);
+            diff = wd;
           } else {
             acc[ii][jj] = fmaf(diff, diff, acc[ii][jj]);
           }
-          if (MODE == MODE_KSD) {
-            acc_ss[ii][jj] = fmaf(sar[ii], sbr[jj], acc_ss[ii][jj]);
-            acc_sd[ii][jj] = fmaf(sar[ii] - sbr[jj], diff, acc_sd[ii][jj]);
+          if (SCORES) {
+            acc_ss[ii][jj] = fmaf(sar[ii], sbr[jj], acc_ss[ii][jj]);                                    // s_x.s_y   | g_i.s_j
+            acc_sd[ii][jj] = fmaf(MODE == MODE_VJP ? sar[ii] : sar[ii] - sbr[jj], diff, acc_sd[ii][jj]);  // (s_x-s_y).(x-y) | g_i.(q_i-x_j)
           }
         }
     }
@@ -177,7 +193,7 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(const PairArgs a) {
     continue;
   }
 
-  const float h = a.h_dev ? *a.h_dev : a.h_host;
+  const float h = ard ? 1.f : (a.h_dev ? *a.h_dev : a.h_host);       // ARD: the weights carry the bandwidths
   const float inv_h2 = 1.f / (h * h);
   const float nc = -NSVGD_HALF_LOG2E * inv_h2;
 
@@ -195,8 +211,36 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(const PairArgs a) {
     return;
   }
 
+  if (MODE == MODE_VJP) {
+    // K_ij, C_ij = k_ij c_ij with c_ij = g_i.v_ij, v_ij = s_j + (q_i - x_j)/h^2; d/dh of sum_ij g_i.(k_ij v_ij):
+    // k r2/h^3 c - 2 k g_i.(q_i - x_j)/h^3
+    double ldh = 0.0;
+    const float inv_h3 = inv_h2 / h;
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const int64_t gi = i0 + ty * 4 + ii;
+      if (gi >= a.na) continue;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int64_t gj = j0 + tx * 4 + jj;
+        if (gj >= a.nb) continue;
+        const float r2 = acc[ii][jj];
+        const float k = ex2_approx(r2 * nc);
+        const float c = fmaf(acc_sd[ii][jj], inv_h2, acc_ss[ii][jj]);
+        a.K[gi * a.ldk + gj] = k;
+        a.C[gi * a.ldk + gj] = k * c;
+        ldh += (double)(k * inv_h3 * (r2 * c - 2.f * acc_sd[ii][jj]));
+      }
+    }
+    if (a.partials_dh) {
+      const double tot = block_sum(ldh, red_s);
+      if (threadIdx.x == 0) a.partials_dh[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
+    }
+    return;
+  }
+
   // KSUM / KSD: weighted block sum -> partials[block]
-  double local = 0.0;
+  double local = 0.0, local_dh = 0.0;
 #pragma unroll
   for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
@@ -210,12 +254,25 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(const PairArgs a) {
       float v = k;
       if (MODE == MODE_KSD) {
         const float r2 = acc[ii][jj];
-        v = k * (acc_ss[ii][jj] + acc_sd[ii][jj] * inv_h2 + (float)a.d * inv_h2 - r2 * inv_h2 * inv_h2);
+        // trace term: d/h^2 - r2/h^4, or sum_a 1/h_a^2 - sum_a diff_a^2/h_a^4 under an ARD bandwidth
+        const float u = ard ? acc_ss[ii][jj] + acc_sd[ii][jj] + a.wsum - acc_q4[ii][jj]
+                            : acc_ss[ii][jj] + acc_sd[ii][jj] * inv_h2 + (float)a.d * inv_h2 - r2 * inv_h2 * inv_h2;
+        v = k * u;
+        if (a.partials_dh) {
+          // d/dh [k u]: dk/dh = k r2/h^3;  du/dh = -2 (s_x-s_y).(x-y)/h^3 - 2 d/h^3 + 4 r2/h^5
+          const float inv_h3 = inv_h2 / h;
+          const float du = inv_h3 * (-2.f * acc_sd[ii][jj] - 2.f * (float)a.d + 4.f * r2 * inv_h2);
+          local_dh += (double)(wgt * k * (r2 * inv_h3 * u + du));
+        }
       }
       local += (double)(wgt * v);
     }
   const double tot = block_sum(local, red_s);
   if (threadIdx.x == 0) a.partials[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
+  if (MODE == MODE_KSD && a.partials_dh) {
+    const double tdh = block_sum(local_dh, red_s);
+    if (threadIdx.x == 0) a.partials_dh[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = tdh;
+  }
   }  // J
   }  // rr
   if (MODE == MODE_HIST) {
@@ -330,7 +387,7 @@ __global__ void __launch_bounds__(1024) select_advance_kernel(SelectState* s, co
 __global__ void __launch_bounds__(1024) select_advance_p2p_kernel(const P2PComm c, SelectState* s, unsigned long long* hist,
                                                                   int pass, const uint32_t* run_flag) {
   if (run_flag && *run_flag == 0u) return;       // the flag is identical on every rank (it derives from all-reduced counts)
-  if (!p2p_allreduce_cta(c, hist, 2 * NSVGD_SELECT_BINS, false) && threadIdx.x == 0) s->nan_flag = 1u;   // late peer -> h = NaN
+  if (!p2p_allreduce_cta<1>(c, hist, 2 * NSVGD_SELECT_BINS, false) && threadIdx.x == 0) s->nan_flag = 1u;   // late peer -> h = NaN
   select_advance_body(s, hist, pass);
 }
 
@@ -579,12 +636,10 @@ extern "C" int nsvgd_ksum_f32(void* stream, const float* A, int64_t na, int64_t 
                      symmetric ? 1.0 : 1.0, 0, ws, ws_bytes, false, nullptr);
 }
 
-// ------------------------------------------------------------------ KSD (stein.py:273-349)
-extern "C" int nsvgd_ksd_f32(void* stream, const float* X, const float* Sx, int64_t n, int64_t ldx, const float* Y,
-                             const float* Sy, int64_t m, int64_t ldy, int64_t d, const float* h_dev, int variant,
-                             double* out_dev, void* ws, size_t ws_bytes) {
-  cudaStream_t st = (cudaStream_t)stream;
-  NSVGD_REQUIRE(X && Sx && h_dev && out_dev, NSVGD_ERR_INVALID, "ksd: null pointer");
+static int ksd_impl(cudaStream_t st, const float* X, const float* Sx, int64_t n, int64_t ldx, const float* Y, const float* Sy,
+                    int64_t m, int64_t ldy, int64_t d, const float* h_dev, int variant, double* out_dev, double* dh_dev, void* ws,
+                    size_t ws_bytes, const float* wcoord = nullptr, float wsum = 0.f) {
+  NSVGD_REQUIRE(X && Sx && (h_dev || wcoord) && out_dev, NSVGD_ERR_INVALID, "ksd: null pointer");
   NSVGD_REQUIRE(variant >= 0 && variant <= 2, NSVGD_ERR_INVALID, "ksd: bad variant %d", variant);
   NSVGD_REQUIRE(n >= 1 && d >= 1 && ldx >= d, NSVGD_ERR_INVALID, "ksd: bad shape");
   const bool rect = variant == NSVGD_KSD_RECT;
@@ -597,15 +652,18 @@ extern "C" int nsvgd_ksd_f32(void* stream, const float* X, const float* Sx, int6
   dim3 g = tile_grid(n, m, 0, 1);
   const int64_t nblocks = (int64_t)g.x * g.y;
   WsCarver w(ws, ws_bytes);
-  double* partials = w.take<double>((size_t)nblocks);
+  double* partials = w.take<double>((size_t)nblocks * (dh_dev ? 2 : 1));
+  double* partials_dh = dh_dev ? partials + nblocks : nullptr;
   NSVGD_REQUIRE(ws && w.ok(), NSVGD_ERR_WORKSPACE, "ksd: workspace too small (%zu < %zu)", ws_bytes, w.off);
   NSVGD_REQUIRE(g.y <= 65535, NSVGD_ERR_INVALID, "ksd: too many row tiles");
   PairArgs a{};
   a.A = X; a.na = n; a.lda = ldx; a.B = Y; a.nb = m; a.ldb = ldy; a.SA = Sx; a.SB = Sy; a.d = d;
   a.symmetric = rect ? 0 : 1; a.tile_row_start = 0; a.tile_row_stride = 1; a.h_dev = h_dev;
-  a.partials = partials; a.diag_weight = variant == NSVGD_KSD_V ? 1.f : 0.f;
+  a.partials = partials; a.partials_dh = partials_dh; a.diag_weight = variant == NSVGD_KSD_V ? 1.f : 0.f;
+  a.wcoord = wcoord; a.wsum = wsum;
   if (!rect) {
-    zero_partials_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nblocks, 256), 1024), 256, 0, st>>>(partials, nblocks);
+    const int64_t nz = nblocks * (dh_dev ? 2 : 1);
+    zero_partials_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nz, 256), 1024), 256, 0, st>>>(partials, nz);
     NSVGD_LAUNCH_CHECK();
   }
   pair_tile_kernel<MODE_KSD><<<g, 256, 0, st>>>(a);
@@ -616,8 +674,53 @@ extern "C" int nsvgd_ksd_f32(void* stream, const float* X, const float* Sx, int6
   else scale = 1.0 / ((double)n * (double)n);
   reduce_partials_kernel<<<1, 1024, 0, st>>>(partials, nblocks, scale, 0, out_dev);
   NSVGD_LAUNCH_CHECK();
+  if (dh_dev) {
+    reduce_partials_kernel<<<1, 1024, 0, st>>>(partials_dh, nblocks, scale, 0, dh_dev);
+    NSVGD_LAUNCH_CHECK();
+  }
   return NSVGD_OK;
 }
+
+// ------------------------------------------------------------------ KSD (stein.py:273-349)
+extern "C" int nsvgd_ksd_f32(void* stream, const float* X, const float* Sx, int64_t n, int64_t ldx, const float* Y,
+                             const float* Sy, int64_t m, int64_t ldy, int64_t d, const float* h_dev, int variant,
+                             double* out_dev, void* ws, size_t ws_bytes) {
+  return ksd_impl((cudaStream_t)stream, X, Sx, n, ldx, Y, Sy, m, ldy, d, h_dev, variant, out_dev, nullptr, ws, ws_bytes);
+}
+
+// KSD and its derivative w.r.t. the bandwidth in one pass (the backward rule of the differentiable KSD)
+extern "C" int nsvgd_ksd_dh_f32(void* stream, const float* X, const float* Sx, int64_t n, int64_t ldx, const float* Y,
+                                const float* Sy, int64_t m, int64_t ldy, int64_t d, const float* h_dev, int variant,
+                                double* out_dev, double* dh_dev, void* ws, size_t ws_bytes) {
+  NSVGD_REQUIRE(dh_dev, NSVGD_ERR_INVALID, "ksd_dh: null dh pointer");
+  return ksd_impl((cudaStream_t)stream, X, Sx, n, ldx, Y, Sy, m, ldy, d, h_dev, variant, out_dev, dh_dev, ws, ws_bytes);
+}
+
+// KSD under a per-coordinate (ARD) bandwidth h_a (kernels.py:52-65 with a vector bandwidth):
+// u_p = k [ s_x.s_y + sum_a (s_x-s_y)_a (x-y)_a / h_a^2 + sum_a 1/h_a^2 - sum_a (x-y)_a^2 / h_a^4 ],  k = exp(-sum_a (x-y)_a^2 / (2 h_a^2)).
+// inv_h2: d weights 1/h_a^2 on the device; inv_h2_sum their sum (host).
+extern "C" int nsvgd_ksd_ard_f32(void* stream, const float* X, const float* Sx, int64_t n, int64_t ldx, const float* Y,
+                                 const float* Sy, int64_t m, int64_t ldy, int64_t d, const float* inv_h2, float inv_h2_sum,
+                                 int variant, double* out_dev, void* ws, size_t ws_bytes) {
+  NSVGD_REQUIRE(inv_h2, NSVGD_ERR_INVALID, "ksd_ard: null weights");
+  return ksd_impl((cudaStream_t)stream, X, Sx, n, ldx, Y, Sy, m, ldy, d, nullptr, variant, out_dev, nullptr, ws, ws_bytes, inv_h2,
+                  inv_h2_sum);
+}
+
+// K, C and the bandwidth-derivative partials of the phi* backward rule (vjp.cu)
+namespace nsvgd {
+int launch_pair_vjp(cudaStream_t st, const float* Q, const float* G, int64_t m, int64_t ldq, const float* X, const float* S,
+                    int64_t n, int64_t ldx, int64_t d, const float* h_dev, float* K, float* C, int64_t ldk, double* partials_dh) {
+  PairArgs a{};
+  a.A = Q; a.SA = G; a.na = m; a.lda = ldq; a.B = X; a.SB = S; a.nb = n; a.ldb = ldx; a.d = d;
+  a.tile_row_start = 0; a.tile_row_stride = 1; a.h_dev = h_dev; a.K = K; a.C = C; a.ldk = ldk; a.partials_dh = partials_dh;
+  dim3 g = tile_grid(m, n, 0, 1);
+  NSVGD_REQUIRE(g.y <= 65535, NSVGD_ERR_INVALID, "phi_vjp: too many row tiles (%u)", g.y);
+  pair_tile_kernel<MODE_VJP><<<g, 256, 0, st>>>(a);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+}  // namespace nsvgd
 
 // ------------------------------------------------------------------ MMD (metrics.py:88-127)
 namespace nsvgd {

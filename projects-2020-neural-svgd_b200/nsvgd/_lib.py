@@ -33,7 +33,8 @@ SYMBOLS = [
     "nsvgd_median_fast_cand_advance", "nsvgd_median_fast_commit", "nsvgd_median_fallback_hist",
     "nsvgd_median_fallback_advance", "nsvgd_phi_f32", "nsvgd_step_sgd_f32", "nsvgd_apply_update_f32",
     "nsvgd_ksd_f32", "nsvgd_mmd_f32", "nsvgd_ksum_f32", "nsvgd_adam_update_f32",
-    "nsvgd_tc_probe_gram", "nsvgd_tc_probe_pv",
+    "nsvgd_scale_cols_f32", "nsvgd_matmul_f32", "nsvgd_ksd_ard_f32", "nsvgd_ksd_linear_f32", "nsvgd_ksd_dh_f32", "nsvgd_phi_vjp_workspace_bytes", "nsvgd_phi_vjp_f32",
+    "nsvgd_score_funnel_f32", "nsvgd_score_gaussian_f32", "nsvgd_score_logreg_f32",
     "nsvgd_p2p_block_bytes", "nsvgd_p2p_alloc", "nsvgd_p2p_open", "nsvgd_p2p_close", "nsvgd_p2p_free",
     "nsvgd_p2p_timeout_flag", "nsvgd_p2p_allreduce", "nsvgd_p2p_median_advance", "nsvgd_p2p_median_fast_resolve",
     "nsvgd_p2p_median_fast_advance2", "nsvgd_p2p_median_fast_run", "nsvgd_p2p_apply_update_f32",
@@ -86,8 +87,16 @@ def load():
     lib.nsvgd_mmd_f32.argtypes = [vp, vp, i64, i64, vp, i64, i64, i64, f32, i32, vp, vp, sz]
     lib.nsvgd_ksum_f32.argtypes = [vp, vp, i64, i64, vp, i64, i64, i64, f32, i32, vp, vp, sz]
     lib.nsvgd_adam_update_f32.argtypes = [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, i64]
-    lib.nsvgd_tc_probe_gram.argtypes = [vp, vp, vp, vp, vp, sz]
-    lib.nsvgd_tc_probe_pv.argtypes = [vp, vp, vp, vp, vp, sz]
+    lib.nsvgd_scale_cols_f32.argtypes = [vp, vp, i64, i64, i64, vp, i32, vp, i64]
+    lib.nsvgd_matmul_f32.argtypes = [vp, vp, i64, i32, vp, i64, vp, i64, i64, i64, i64, i32]
+    lib.nsvgd_ksd_ard_f32.argtypes = [vp, vp, vp, i64, i64, vp, vp, i64, i64, i64, vp, f32, i32, vp, vp, sz]
+    lib.nsvgd_ksd_linear_f32.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, sz]
+    lib.nsvgd_ksd_dh_f32.argtypes = [vp, vp, vp, i64, i64, vp, vp, i64, i64, i64, vp, i32, vp, vp, vp, sz]
+    lib.nsvgd_phi_vjp_workspace_bytes.argtypes = [i64, i64, i64, C.POINTER(sz)]
+    lib.nsvgd_phi_vjp_f32.argtypes = [vp, vp, vp, i64, i64, vp, vp, i64, i64, i64, vp, vp, i64, vp, i64, vp, i64, vp, vp, sz]
+    lib.nsvgd_score_funnel_f32.argtypes = [vp, vp, i64, i64, i64, vp, i64, vp]
+    lib.nsvgd_score_gaussian_f32.argtypes = [vp, vp, i64, i64, i64, vp, vp, i32, f32, vp, i64, vp]
+    lib.nsvgd_score_logreg_f32.argtypes = [vp, vp, i64, i64, i64, vp, vp, i64, i64, f32, f32, f32, vp, i64, vp]
     pvp = C.POINTER(vp)
     lib.nsvgd_p2p_alloc.argtypes = [pvp, vp]
     lib.nsvgd_p2p_open.argtypes = [vp, pvp]

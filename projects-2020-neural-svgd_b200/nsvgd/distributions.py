@@ -1,6 +1,9 @@
 """Minimal targets/proposals for the harness (the reference's distributions.py is out of scope;
 it only has to hand the hot path a `logpdf`).  Each logpdf object is a callable on (d,) tensors
-(usable with torch.func.grad) and also exposes batched analytic `.score(X)` / `.batch_logp(X)`."""
+(usable with torch.func.grad) and also exposes batched analytic `.score(X)` / `.batch_logp(X)`.
+On CUDA tensors `.score` / `.batch_logp` run the device kernels of csrc/scores.cu: the step
+scores -> bandwidth -> phi* -> update is then enqueued without autodiff; CPU tensors (harness set-up, sampling)
+use the same closed forms in torch."""
 from __future__ import annotations
 
 import math
@@ -27,6 +30,9 @@ class Funnel:
             return -y ** 2 / 18.0 - 0.5 * (d - 1) * y - 0.5 * torch.exp(-y) * torch.sum(xs ** 2)
 
         def score(X):
+            if X.is_cuda:
+                from . import engine
+                return engine.score_funnel(X)
             xs, y = X[:, :-1], X[:, -1:]
             gx = -xs * torch.exp(-y)
             gy = -y / 9.0 - (d - 1) / 2.0 + 0.5 * torch.exp(-y) * torch.sum(xs * xs, dim=1, keepdim=True)
@@ -62,7 +68,15 @@ class Gaussian:
             c = x - mean_.to(x.device)
             return -0.5 * torch.dot(c, prec_.to(x.device) @ c)
 
+        dev_cache = {}
+
         def score(X):
+            if X.is_cuda:
+                from . import engine
+                if X.device not in dev_cache:
+                    dev_cache[X.device] = (mean_.to(X.device), prec_.to(X.device).contiguous())
+                m, p_ = dev_cache[X.device]
+                return engine.score_gaussian(X, m, p_)
             return -(X - mean_.to(X.device)) @ prec_.to(X.device).T
 
         def batch_logp(X):
@@ -87,3 +101,51 @@ class Setup:
 
 
 funnel = Setup(Funnel(2), Gaussian([-3.0, 0.0], [9.0, 9.0]))      # distributions.py:594-596
+
+
+
+class LogisticRegressionPosterior:
+    """The target of experiments/bayesian_logistic_regression.py: params = [w (F features incl. intercept), log alpha],
+    alpha ~ Gamma(a0, rate b0), w | alpha ~ N(0, 1/alpha), y | x, w ~ Bernoulli(sigmoid(x.w))   (:31, :73-114).
+    `get_minibatch_logp(x, y)` mirrors :169-190 -- including its literal scaling num_datapoints * SUM over the batch --
+    and returns a logp object that is callable on one (d,) parameter vector (torch.func.grad works on it) and exposes
+    the batched device-side `.score(P)` / `.batch_logp(P)` (nsvgd_score_logreg_f32)."""
+
+    def __init__(self, num_features, num_datapoints, a0=1.0, b0=0.01):
+        self.F, self.N, self.a0, self.b0 = int(num_features), float(num_datapoints), float(a0), float(b0)
+        self.d = self.F + 1
+
+    def sample_from_prior(self, num, key=None):
+        """ravel(*sample_from_prior) (:66-71, :209): alpha ~ Gamma(a0) / b0, w ~ N(0, I)"""
+        g = torch.distributions.Gamma(torch.tensor(self.a0), torch.tensor(1.0))
+        if key is not None:
+            torch.manual_seed(int(key) if not isinstance(key, torch.Generator) else key.initial_seed())
+        alpha = g.sample((num,)) / self.b0
+        w = torch.randn(num, self.F)
+        return torch.cat([w, torch.log(alpha)[:, None]], dim=1)
+
+    def get_minibatch_logp(self, x, y):
+        F, N, a0, b0 = self.F, self.N, self.a0, self.b0
+        x = torch.as_tensor(x, dtype=torch.float32)
+        y = torch.as_tensor(y, dtype=torch.float32)
+        if x.shape[0] != y.shape[0] or x.ndim <= y.ndim:
+            raise AssertionError("x, y must be minibatches of the same length")       # the asserts of :176-177
+
+        def logp(params):
+            w, la = params[:-1], params[-1]
+            alpha = torch.exp(la)
+            lg = (a0 - 1.0) * la - b0 * alpha + a0 * math.log(b0) - math.lgamma(a0)
+            lw = torch.sum(-0.5 * alpha * w * w + 0.5 * la - 0.5 * math.log(2 * math.pi))
+            ys = (y.to(params.device) - 0.5) * 2.0
+            ll = torch.sum(torch.nn.functional.logsigmoid(ys * (x.to(params.device) @ w)))
+            return lg + lw + N * ll
+
+        def score(P):
+            from . import engine
+            return engine.score_logreg(P, x.to(P.device), y.to(P.device), N, a0, b0)
+
+        def batch_logp(P):
+            from . import engine
+            return engine.score_logreg(P, x.to(P.device), y.to(P.device), N, a0, b0, want_logp=True)[1]
+
+        return _LogPdf(logp, score, batch_logp)

@@ -212,6 +212,55 @@ def ksd(X, Sx, h, variant="v", Y=None, Sy=None) -> torch.Tensor:
     return out[0]
 
 
+def scale_cols(X, v, invert=False):
+    """X * v or X / v per column on the device (the linear map of a vector bandwidth; csrc/vjp.cu)."""
+    X = require_cuda_f32(X, "X")
+    n, d = X.shape
+    v = v.to(device=X.device, dtype=torch.float32).contiguous()
+    out = torch.empty((n, d), dtype=torch.float32, device=X.device)
+    check(load().nsvgd_scale_cols_f32(stream_ptr(X.device), ptr(X), n, d, ld(X), ptr(v), int(bool(invert)), ptr(out), d))
+    return out
+
+
+def matmul(A, B):
+    """A @ B in fp32 through the library's SIMT GEMM (the d x d linear maps of a full-matrix Gaussian kernel)."""
+    A = require_cuda_f32(A, "A"); B = require_cuda_f32(B.to(A.device), "B").contiguous()
+    M, K = A.shape
+    N = B.shape[1]
+    out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    check(load().nsvgd_matmul_f32(stream_ptr(A.device), ptr(A), ld(A), 0, ptr(B), N, ptr(out), N, M, N, K, 0))
+    return out
+
+
+def ksd_ard(X, Sx, h_vec, variant="v", Y=None, Sy=None) -> torch.Tensor:
+    """KSD^2 under a per-coordinate bandwidth vector h_a (closed form, csrc/pair_engine.cu) -> 0-dim float64 tensor."""
+    X = require_cuda_f32(X, "X").contiguous(); Sx = require_cuda_f32(Sx, "Sx").contiguous()
+    n, d = X.shape
+    m = n
+    if variant == "rect":
+        Y = require_cuda_f32(Y, "Y").contiguous(); Sy = require_cuda_f32(Sy, "Sy").contiguous()
+        m = Y.shape[0]
+    w = (1.0 / (h_vec.to(device=X.device, dtype=torch.float32) ** 2)).contiguous()
+    if w.shape != (d,):
+        raise ValueError(f"Bandwidth has shape {tuple(h_vec.shape)}.")
+    out = torch.empty(1, dtype=torch.float64, device=X.device)
+    ws = workspace(workspace_bytes("ksd", n, m, d), X.device)
+    check(load().nsvgd_ksd_ard_f32(stream_ptr(X.device), ptr(X), ptr(Sx), n, d, ptr(Y), ptr(Sy), m, d, d, ptr(w), float(w.sum().item()),
+                                   _lib.KSD_VARIANTS[variant], ptr(out), ptr(ws), ws.numel()))
+    return out[0]
+
+
+def ksd_linear(X, S, h):
+    """linear-time KSD estimator (stein.py:353-380) -> float64[2] device tensor {mean, std(ddof=1) / (n/2)}."""
+    X = require_cuda_f32(X, "samples").contiguous(); S = require_cuda_f32(S, "scores").contiguous()
+    n, d = X.shape
+    h_dev = as_h_dev(h, X.device)
+    out = torch.empty(2, dtype=torch.float64, device=X.device)
+    ws = workspace(max(4 * (n // 2), 256), X.device)
+    check(load().nsvgd_ksd_linear_f32(stream_ptr(X.device), ptr(X), ptr(S), n, d, d, ptr(h_dev), ptr(out), ptr(ws), ws.numel()))
+    return out
+
+
 def mmd(X, Y, h=1.0, funnel=False) -> torch.Tensor:
     """MMD^2 (metrics.py:88-105) -> 0-dim float64 device tensor."""
     X = require_cuda_f32(X, "xs").contiguous(); Y = require_cuda_f32(Y, "ys").contiguous()
@@ -230,6 +279,49 @@ def adam_update(X, grads, m1, m2, lr, t, b1=0.9, b2=0.999, eps=1e-8):
     """optax.adam(lr) applied to the particles in place (utils.py:711-715)."""
     check(load().nsvgd_adam_update_f32(stream_ptr(X.device), ptr(X), ptr(grads), ptr(m1), ptr(m2), X.numel(),
                                        float(lr), float(b1), float(b2), float(eps), int(t)))
+
+
+# ---- device-side scores of the canonical targets (csrc/scores.cu; SURVEY 8f-N4) -----------------------------------
+def score_funnel(X, want_logp=False):
+    """grad log p (and log p) of Neal's funnel at every row of X (distributions.py:275-319)."""
+    X = require_cuda_f32(X, "X")
+    n, d = X.shape
+    S = torch.empty((n, d), dtype=torch.float32, device=X.device)
+    lp = torch.empty(n, dtype=torch.float32, device=X.device) if want_logp else None
+    check(load().nsvgd_score_funnel_f32(stream_ptr(X.device), ptr(X), n, d, ld(X), ptr(S), d, ptr(lp)))
+    return (S, lp) if want_logp else S
+
+
+def score_gaussian(X, mean, prec, log_norm=0.0, want_logp=False):
+    """grad log p (and log p) of N(mean, prec^-1); prec is a (d,d) precision matrix or its (d,) diagonal."""
+    X = require_cuda_f32(X, "X")
+    n, d = X.shape
+    mean = require_cuda_f32(mean.to(X.device), "mean", ndim=1).contiguous()
+    prec = prec.to(device=X.device, dtype=torch.float32).contiguous()
+    if prec.shape not in ((d,), (d, d)) or mean.shape != (d,):
+        raise ValueError(f"mean must be ({d},) and prec ({d},) or ({d},{d}); got {tuple(mean.shape)}, {tuple(prec.shape)}")
+    S = torch.empty((n, d), dtype=torch.float32, device=X.device)
+    lp = torch.empty(n, dtype=torch.float32, device=X.device) if want_logp else None
+    check(load().nsvgd_score_gaussian_f32(stream_ptr(X.device), ptr(X), n, d, ld(X), ptr(mean), ptr(prec), int(prec.ndim == 1),
+                                          float(log_norm), ptr(S), d, ptr(lp)))
+    return (S, lp) if want_logp else S
+
+
+def score_logreg(P, Xb, yb, num_datapoints, a0=1.0, b0=0.01, want_logp=False):
+    """grad log p (and log p) of the Bayesian logistic-regression posterior at the particles P = [w | log alpha]
+    for the minibatch (Xb, yb)  (experiments/bayesian_logistic_regression.py:73-114, 169-190)."""
+    P = require_cuda_f32(P, "params")
+    Xb = require_cuda_f32(Xb, "x").contiguous()
+    yb = require_cuda_f32(yb.to(torch.float32), "y", ndim=1).contiguous()
+    n, d = P.shape
+    B, F = Xb.shape
+    if yb.shape[0] != B:
+        raise ValueError("x and y must have the same number of data points")
+    S = torch.empty((n, d), dtype=torch.float32, device=P.device)
+    lp = torch.empty(n, dtype=torch.float32, device=P.device) if want_logp else None
+    check(load().nsvgd_score_logreg_f32(stream_ptr(P.device), ptr(P), n, d, ld(P), ptr(Xb), ptr(yb), B, F, float(num_datapoints),
+                                        float(a0), float(b0), ptr(S), d, ptr(lp)))
+    return (S, lp) if want_logp else S
 
 
 # ---- select building blocks for the row-sharded median (parallel.py) -------------------------------

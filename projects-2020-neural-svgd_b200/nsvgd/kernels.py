@@ -112,6 +112,46 @@ def get_funnel_kernel(bandwidth):
     return FunnelKernel(bandwidth)
 
 
+class FullGaussianKernel:
+    """kernels.py:83-88: k(x, y) = exp(-|Sigma (x - y)|^2 / 2) for a (d, d) matrix Sigma (the "full" parametrisation of
+    nets.RBFKernel, nets.py:44-48).  With x' = Sigma x it is the unit-bandwidth RBF kernel, so phi* and MMD dispatch to the
+    same engine after a linear map of particles and scores (stein.py / metrics.py); Sigma must be invertible for phi*."""
+    is_rbf = True
+    funnel = False
+    is_full = True
+
+    def __init__(self, sigma, dim=None):
+        sigma = torch.as_tensor(sigma, dtype=torch.float32)
+        if sigma.ndim != 2 or sigma.shape[0] != sigma.shape[1]:
+            raise ValueError(f"sigma needs to be a (d, d) matrix. Instead it has shape {tuple(sigma.shape)}")
+        if dim is not None and sigma.shape[0] != dim:
+            raise ValueError(f"sigma has shape {tuple(sigma.shape)}.")
+        self.sigma, self.dim = sigma, dim
+        self.bandwidth = torch.tensor(1.0)
+
+    def is_ard(self):
+        return False
+
+    def h(self):
+        raise NotImplementedError("this entry point needs a scalar bandwidth; the full-matrix Gaussian kernel is supported by "
+                                  "stein.get_phistar / phistar / phistar_i and metrics.get_mmd (SURVEY 8f N3)")
+
+    def __call__(self, x, y):
+        x, y = _check_xy(x, y, self.dim)
+        s = self.sigma.to(x.device) @ (x - y)
+        return torch.exp(-torch.sum(s * s) / 2)
+
+
+def get_multivariate_gaussian_kernel(sigma, dim=None):
+    """kernels.py:83-88"""
+    return FullGaussianKernel(sigma, dim)
+
+
+def get_rbf_kernel_logscaled(logh, normalize=False):
+    """kernels.py:77-81 (the reference passes `normalize` positionally into `squared`: reproduced -> squared=normalize)"""
+    return get_rbf_kernel(torch.exp(torch.as_tensor(logh, dtype=torch.float32)), normalize)
+
+
 def median_heuristic(x, mode=None):
     """kernels.py:160-172.  Returns a 0-dim float32 DEVICE tensor (no host sync).
     mode None -> engine.DEFAULT_MEDIAN_MODE ("literal": exactly what the reference executes)."""
@@ -128,4 +168,3 @@ def _unsupported(name):
 get_tophat_kernel = _unsupported("get_tophat_kernel")
 get_imq_kernel = _unsupported("get_imq_kernel")
 get_inverse_log_kernel = _unsupported("get_inverse_log_kernel")
-get_multivariate_gaussian_kernel = _unsupported("get_multivariate_gaussian_kernel")

@@ -16,10 +16,15 @@ def get_mmd(kernel=None):
     kernel = kernels.get_rbf_kernel(1.) if kernel is None else kernel
     if not getattr(kernel, "is_rbf", False):
         raise NotImplementedError("get_mmd: only RBF / funnel kernels dispatch to the CUDA engine")
+    if getattr(kernel, "is_full", False):
+        def mmd_full(xs, ys):                     # full-matrix Gaussian kernel: unit-bandwidth engine call on x Sigma^T
+            sig_t = kernel.sigma.to(device=xs.device, dtype=xs.dtype).T.contiguous()
+            return engine.mmd(engine.matmul(xs, sig_t), engine.matmul(ys, sig_t), 1.0).to(xs.dtype)
+        return mmd_full
     if not kernel.funnel and kernel.is_ard():
         def mmd_ard(xs, ys):                      # vector bandwidth: unit-bandwidth engine call on x / h
             sc = kernel.ard_scale(xs.device)
-            return engine.mmd((xs / sc).contiguous(), (ys / sc).contiguous(), 1.0).to(xs.dtype)
+            return engine.mmd(engine.scale_cols(xs, sc, True), engine.scale_cols(ys, sc, True), 1.0).to(xs.dtype)
         return mmd_ard
     h = float(kernel.h())
 

@@ -29,18 +29,39 @@ def _require_rbf(kernel, who):
     return kernel.h()
 
 
+def _is_full(kernel):
+    return bool(getattr(kernel, "is_full", False))
+
+
+def _is_ard(kernel):
+    return bool(getattr(kernel, "is_rbf", False) and not getattr(kernel, "funnel", False) and not _is_full(kernel) and kernel.is_ard())
+
+
 def _phistar_any_bandwidth(kernel, who, Q, X, S, aux=False):
-    """phi* for a scalar bandwidth (one engine call) or a (d,) ARD bandwidth vector (kernels.py:52-65 with a vector):
-    with x' = x / h (elementwise) the kernel has unit bandwidth, the scores w.r.t. x' are s h, and
-    phi_a = phi'_a / h_a -- three elementwise ops around the same engine call."""
-    if getattr(kernel, "is_rbf", False) and not getattr(kernel, "funnel", False) and kernel.is_ard():
+    """phi* for a scalar bandwidth (one engine call), a (d,) ARD bandwidth vector (kernels.py:52-65 with a vector) or a
+    full (d, d) matrix (kernels.py:83-88).  With x' = A x (A = diag(1/h) or Sigma) the kernel has unit bandwidth, the
+    scores w.r.t. x' are A^-T s, and phi = A^T phi': a linear map on the device (nsvgd_scale_cols_f32 / nsvgd_matmul_f32)
+    before and after the same engine call."""
+    if _is_ard(kernel):
         sc = kernel.ard_scale(X.device)
         if sc.numel() != X.shape[1]:
             raise ValueError(f"Bandwidth has shape {tuple(sc.shape)}.")
-        out = engine.phistar((Q / sc).contiguous(), (X / sc).contiguous(), (S * sc).contiguous(), 1.0, aux=aux)
+        out = engine.phistar(engine.scale_cols(Q, sc, True), engine.scale_cols(X, sc, True), engine.scale_cols(S, sc, False), 1.0, aux=aux)
         if aux:
-            return out[0] / sc, out[1] / sc
-        return out / sc
+            d = X.shape[1]
+            return engine.scale_cols(out[0], sc, True), engine.scale_cols(out[1].reshape(-1, d), sc, True).reshape(out[1].shape)
+        return engine.scale_cols(out, sc, True)
+    if _is_full(kernel):
+        sig = kernel.sigma.to(device=X.device, dtype=torch.float32)
+        if sig.shape[0] != X.shape[1]:
+            raise ValueError(f"sigma has shape {tuple(sig.shape)}.")
+        sig_t = sig.T.contiguous()
+        sig_inv = torch.linalg.inv(sig.double()).float().contiguous()       # d x d set-up on the caller's matrix
+        out = engine.phistar(engine.matmul(Q, sig_t), engine.matmul(X, sig_t), engine.matmul(S, sig_inv), 1.0, aux=aux)
+        if aux:
+            d = X.shape[1]
+            return engine.matmul(out[0], sig.contiguous()), engine.matmul(out[1].reshape(-1, d), sig.contiguous()).reshape(out[1].shape)
+        return engine.matmul(out, sig.contiguous())
     h = _require_rbf(kernel, who)
     return engine.phistar(Q, X, S, h, aux=aux)
 
@@ -50,7 +71,8 @@ class PhiStar(BatchedFunction):
 
     def __init__(self, kernel, logp, samples, scores=None):
         self.kernel, self.logp, self.samples = kernel, logp, samples
-        self.ard = bool(getattr(kernel, "is_rbf", False) and not getattr(kernel, "funnel", False) and kernel.is_ard())
+        self.ard = _is_ard(kernel) or _is_full(kernel)           # a non-scalar bandwidth: linear map around the engine
+        self.ard_vector = _is_ard(kernel)
         self.h = None if self.ard else _require_rbf(kernel, "get_phistar")
         self.scores = score(logp, samples) if scores is None else scores
         super().__init__(self._phi_batch)
@@ -101,20 +123,13 @@ def phistar_u(followers, leaders, logp, kernel):
 
 def ksd_squared_l(samples, logp, k, return_stddev=False):
     """stein.py:353-380: the linear-time estimator mean_i u_p(x_i, y_i) over the two halves of `samples` (an odd count
-    drops the last sample).  O(n d): plain elementwise device ops, no pair engine involved."""
+    drops the last sample).  One warp per pair on the device (nsvgd_ksd_linear_f32)."""
     h = _require_rbf(k, "ksd_squared_l")
     n = samples.shape[0] - (samples.shape[0] % 2)
-    xs, ys = samples[: n // 2], samples[n // 2: n]
-    sx, sy = score(logp, xs), score(logp, ys)
-    h2 = (h * h) if isinstance(h, torch.Tensor) else float(h) ** 2
-    diff = xs - ys
-    r2 = torch.sum(diff * diff, dim=1)
-    kk = torch.exp(-r2 / (2 * h2))
-    d = samples.shape[1]
-    outs = kk * (torch.sum(sx * sy, dim=1) + torch.sum((sx - sy) * diff, dim=1) / h2 + d / h2 - r2 / (h2 * h2))
+    out = engine.ksd_linear(samples[:n], score(logp, samples[:n]), h)
     if return_stddev:
-        return torch.mean(outs), torch.std(outs, unbiased=True) / xs.shape[0]
-    return torch.mean(outs)
+        return out[0].to(torch.float32), out[1].to(torch.float32)
+    return out[0].to(torch.float32)
 
 
 def stein_discrepancy(xs, logp, f, aux=False):
@@ -135,19 +150,39 @@ def stein_discrepancy(xs, logp, f, aux=False):
     return (val * scale).to(torch.float32) if isinstance(scale, torch.Tensor) else (val * scale).to(torch.float32)
 
 
+def _wants_grad(h):
+    return isinstance(h, torch.Tensor) and h.requires_grad and torch.is_grad_enabled()
+
+
 def ksd_squared(xs, ys, logp, k):
-    """stein.py:273-295"""
+    """stein.py:273-295.  Differentiable w.r.t. a bandwidth tensor that requires grad (autodiff.py); a (d,)
+    ARD bandwidth vector uses the per-coordinate closed form (nsvgd_ksd_ard_f32)."""
+    if _is_ard(k):
+        return engine.ksd_ard(xs, score(logp, xs), k.ard_scale(xs.device), "rect", ys, score(logp, ys)).to(torch.float32)
     h = _require_rbf(k, "ksd_squared")
+    if _wants_grad(h):
+        from . import autodiff
+        return autodiff.ksd_squared(xs, score(logp, xs), h, "rect", ys, score(logp, ys))
     return engine.ksd(xs, score(logp, xs), h, "rect", ys, score(logp, ys)).to(torch.float32)
 
 
 def ksd_squared_u(xs, logp, k):
     """stein.py:299-323"""
+    if _is_ard(k):
+        return engine.ksd_ard(xs, score(logp, xs), k.ard_scale(xs.device), "u").to(torch.float32)
     h = _require_rbf(k, "ksd_squared_u")
+    if _wants_grad(h):
+        from . import autodiff
+        return autodiff.ksd_squared(xs, score(logp, xs), h, "u")
     return engine.ksd(xs, score(logp, xs), h, "u").to(torch.float32)
 
 
 def ksd_squared_v(xs, logp, k, dummy_arg1=None, dummy_arg2=None):
     """stein.py:327-349"""
+    if _is_ard(k):
+        return engine.ksd_ard(xs, score(logp, xs), k.ard_scale(xs.device), "v").to(torch.float32)
     h = _require_rbf(k, "ksd_squared_v")
+    if _wants_grad(h):
+        from . import autodiff
+        return autodiff.ksd_squared(xs, score(logp, xs), h, "v")
     return engine.ksd(xs, score(logp, xs), h, "v").to(torch.float32)

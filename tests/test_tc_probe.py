@@ -7,13 +7,26 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def _probe_lib():
+    """the probes live in a TEST-ONLY library (libnsvgd_probe.so, include/nsvgd_probe.h), not in the product library"""
+    import ctypes as C
+    import os
+    from nsvgd import _lib
+    _lib.load()                               # libnsvgd.so first: the probe library links against it
+    lib = C.CDLL(os.path.join(os.path.dirname(_lib.LIB_PATH), "libnsvgd_probe.so"))
+    vp, sz = C.c_void_p, C.c_size_t
+    lib.nsvgd_tc_probe_gram.argtypes = [vp, vp, vp, vp, vp, sz]
+    lib.nsvgd_tc_probe_pv.argtypes = [vp, vp, vp, vp, vp, sz]
+    return lib
+
+
 def bf16_round(a):
     return torch.as_tensor(a, dtype=torch.float32).to(torch.bfloat16).to(torch.float32).numpy()
 
 
 def test_probe_gram():
     from nsvgd import _lib
-    lib = _lib.load()
+    lib = _probe_lib()
     rng = np.random.default_rng(0)
     A = rng.standard_normal((128, 128)).astype(np.float32)
     B = rng.standard_normal((64, 128)).astype(np.float32)
@@ -30,7 +43,7 @@ def test_probe_gram():
 
 def test_probe_pv():
     from nsvgd import _lib
-    lib = _lib.load()
+    lib = _probe_lib()
     rng = np.random.default_rng(1)
     P = rng.random((128, 64)).astype(np.float32)
     V = rng.standard_normal((64, 256)).astype(np.float32)
