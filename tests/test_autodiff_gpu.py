@@ -33,7 +33,7 @@ def test_ksd_gradient_wrt_bandwidth_vs_structural_autodiff(variant):
     Y = torch.randn(m, d, generator=g, dtype=torch.float64)
     prec = torch.tensor([0.5, 2.0, 1.0], dtype=torch.float64)
     logp = lambda x: -0.5 * torch.sum(prec * x * x)
-    score = lambda Z: -Z * prec
+    score = lambda Z: -Z * prec.to(Z.device, Z.dtype)
 
     def ksd_of_h(h):
         k = st.get_rbf_kernel(h)

@@ -180,8 +180,17 @@ def test_ard_bandwidth_vs_reference_execution():
     assert float(metrics.get_mmd(k)(X, Y)) == pytest.approx(float(r["mmd"]), abs=1e-5)
     with pytest.raises(NotImplementedError):
         stein.stein_discrepancy(X, logp, f)
-    with pytest.raises(NotImplementedError):
-        stein.ksd_squared_u(X, logp, k)
+    # the closed-form KSD under a vector bandwidth (round 2) against the structural mirror of stein.py
+    from oracle import structural as st
+    hv = torch.tensor(r["bandwidth"], dtype=torch.float64)
+    X64 = torch.tensor(r["X"], dtype=torch.float64)
+    (_, n_, d_, m_, seed_, kind_, _), = [c for c in CASES if c[0] == "gauss_n64_d5"]
+    _, _, mean_, prec_ = inputs(n_, d_, m_, seed_, kind_)
+    mean64, prec64 = torch.tensor(mean_, dtype=torch.float64), torch.tensor(prec_, dtype=torch.float64)
+    logp64 = lambda x: -0.5 * torch.dot(x - mean64, prec64 @ (x - mean64))
+    ref_u = float(st.ksd_squared_u(X64, logp64, st.get_rbf_kernel(hv)))
+    ref_v = float(st.ksd_squared_v(X64, logp64, st.get_rbf_kernel(hv)))
+    assert float(stein.ksd_squared_u(X, logp, k)) == pytest.approx(ref_u, abs=RTOL * abs(ref_v))
     # the plug-in (an extension: the reference's KernelGradient raises on a bandwidth vector, models.py:657)
     kg = models.KernelGradient(target_logp=logp, bandwidth=torch.tensor(r["bandwidth"], dtype=torch.float32), scaled=False)
     g = kg.gradient(None, X)

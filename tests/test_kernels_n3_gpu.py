@@ -35,7 +35,7 @@ def full_kernel64(sigma):
 
 
 def test_full_matrix_gaussian_kernel_phistar_and_mmd():
-    from nsvgd import kernels, metrics, stein
+    from nsvgd import kernels, metrics, stein, utils
     X, Y, logp64, logp32 = _setup()
     g = torch.Generator().manual_seed(3)
     sigma = torch.eye(4, dtype=torch.float64) * 0.7 + 0.2 * torch.randn(4, 4, generator=g, dtype=torch.float64)
@@ -43,7 +43,7 @@ def test_full_matrix_gaussian_kernel_phistar_and_mmd():
     k = kernels.get_multivariate_gaussian_kernel(sigma.float())
     assert float(k(X[0].float(), X[1].float())) == pytest.approx(float(k64(X[0], X[1])), rel=1e-5)
     ref = torch.func.vmap(st.get_phistar(k64, logp64, X))(Y)
-    got = stein.get_phistar(k, logp32, X.float().cuda())(Y.float().cuda())
+    got = utils.vmap(stein.get_phistar(k, logp32, X.float().cuda()))(Y.float().cuda())
     assert rel(got.cpu(), ref) < TOL
     ref_phi, ref_aux = st.phistar(Y, X, logp64, k64)
     phi, aux = stein.phistar(Y.float().cuda(), X.float().cuda(), logp32, k)
@@ -73,11 +73,11 @@ def test_ksd_under_an_ard_bandwidth(variant):
 
 
 def test_ard_phistar_through_device_maps_matches_structural():
-    from nsvgd import kernels, stein
+    from nsvgd import kernels, stein, utils
     X, Y, logp64, logp32 = _setup(n=70, d=5, seed=2)
     hvec = torch.tensor([0.8, 1.5, 2.2, 1.1, 0.6], dtype=torch.float64)
     ref = torch.func.vmap(st.get_phistar(st.get_rbf_kernel(hvec), logp64, X))(Y)
-    got = stein.get_phistar(kernels.get_rbf_kernel(hvec.float()), logp32, X.float().cuda())(Y.float().cuda())
+    got = utils.vmap(stein.get_phistar(kernels.get_rbf_kernel(hvec.float()), logp32, X.float().cuda()))(Y.float().cuda())
     assert rel(got.cpu(), ref) < TOL
 
 
@@ -85,7 +85,7 @@ def test_ard_phistar_through_device_maps_matches_structural():
 def test_learnable_rbf_kernel_module_dispatches_to_the_engine(param):
     """nets.RBFKernel (nets.py:24-49): the three parametrisations coincide at initialisation; after a parameter change the
     module's own evaluation and the engine's phi* under module.kernel() agree with the structural mirror"""
-    from nsvgd import nets, stein
+    from nsvgd import nets, stein, utils
     X, Y, logp64, logp32 = _setup(n=40, d=3, seed=4)
     mod = nets.RBFKernel(parametrization=param, dim=3)
     xy = torch.stack([X[0], X[1]]).float()
@@ -94,7 +94,6 @@ def test_learnable_rbf_kernel_module_dispatches_to_the_engine(param):
         for p in mod.parameters():
             p.add_(0.3 * torch.randn(p.shape, generator=torch.Generator().manual_seed(7)))
     k = mod.kernel()
-    k64 = lambda x, y: mod.double()(torch.stack([x, y])).detach() if False else None
     # float64 callable with the module's parameter values
     if param == "diagonal":
         b = mod.bandwidth.detach().double(); kc = lambda x, y: torch.exp(-torch.sum((x - y) ** 2 / b ** 2) / 2)
@@ -104,5 +103,5 @@ def test_learnable_rbf_kernel_module_dispatches_to_the_engine(param):
         kc = full_kernel64(mod.sigma.detach().double())
     assert float(mod(xy)) == pytest.approx(float(kc(X[0], X[1])), rel=1e-5)
     ref = torch.func.vmap(st.get_phistar(kc, logp64, X))(Y)
-    got = stein.get_phistar(k, logp32, X.float().cuda())(Y.float().cuda())
+    got = utils.vmap(stein.get_phistar(k, logp32, X.float().cuda()))(Y.float().cuda())
     assert rel(got.cpu(), ref) < TOL

@@ -144,6 +144,6 @@ def test_cfg3_logreg_n8192_step(F):
     ref = so.phistar_stats_f64_blocked(P, S, h, block=1024)
     g_ref = -ref["alpha"] * ref["phi"]
     assert rel(grads.cpu(), g_ref) < 2e-4
-    assert rel(Pd.cpu(), P.astype(np.float64) - 1e-6 * g_ref) < 1e-6
+    assert rel(Pd.cpu(), P.astype(np.float64) - 1e-6 * g_ref) < 1e-5      # |lr * grads| ~ |P| here: 2e-4 on the gradients -> ~2e-6
     assert np.isfinite(aux["logp"].cpu().numpy()).all()
     assert np.abs(aux["logp"].cpu().numpy() - so.logreg_logp(P, Xb, yb, N)).max() < 2e-5 * np.abs(so.logreg_logp(P, Xb, yb, N)).max()
