@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-offdiag", action="store_true", help="skip the secondary off-diagonal-median run")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the timings of the other BASELINE configs")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step as one CUDA graph (auto: when row-sharded, where host issue time limits the step)")
     return ap.parse_args()
@@ -210,6 +211,84 @@ def cpu_bandwidth(args, X):
     from oracle.svgd_oracle import median_heuristic
     sub = X[: min(args.n, 2048)]
     return float(median_heuristic(sub, args.median_mode)), "oracle median of the first 2048 particles"
+
+
+def secondary_workloads(dev):
+    """The other BASELINE configs as end-to-end steps on one GPU (parity for each is in tests/; these are timings only,
+    CUDA events, 3 warm-up + 10 timed steps each).  Reported under "secondary"; not part of `value`."""
+    from nsvgd import distributions, engine, kernels, metrics, models, stein
+    from oracle import svgd_oracle as so
+    out = {}
+
+    def timed(fn, steps=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps
+
+    try:    # configs[1]: 50-D correlated Gaussian, n = 2048, KSD_U + MMD tracked every step (device-side scores)
+        rng = np.random.default_rng(3)
+        d, n, m = 50, 2048, 500
+        Q, _ = np.linalg.qr(rng.standard_normal((d, d)))
+        cov = Q.T @ np.diag(np.logspace(-2, 0, d)) @ Q
+        tgt = distributions.Gaussian(np.zeros(d), cov)
+        X = torch.tensor(rng.standard_normal((n, d)).astype(np.float32), device=dev)
+        Y = torch.tensor((rng.standard_normal((m, d)) @ np.linalg.cholesky(cov).T).astype(np.float32), device=dev)
+        kg = models.KernelGradient(target_logp=tgt.logpdf, bandwidth=None, scaled=True, lambda_reg=0.5)
+        mmd = metrics.get_mmd(kernels.get_rbf_kernel(1.0))
+
+        def step2():
+            _, aux = kg.step_sgd(X, None, 1e-3)
+            stein.ksd_squared_u(X, tgt.logpdf, kernels.get_rbf_kernel(aux["bandwidth"]))
+            mmd(X, Y)
+        ms = timed(step2)
+        out["cfg2_gaussian_n2048_d50_ksdU_mmd_every_step"] = {"ms_per_step": ms, "n2d_per_s": n * n * d / (ms * 1e-3)}
+    except Exception as e:
+        out["cfg2_gaussian_n2048_d50_ksdU_mmd_every_step"] = {"error": str(e)[:200]}
+    for F in (54, 55):      # configs[2]: logistic regression posterior, d = 55 (BASELINE) / 56 (reference), n = 8192
+        try:
+            P, Xb, yb, N = so.logreg_workload(8192, F, B=128, seed=F)
+            tgt = distributions.LogisticRegressionPosterior(F, N)
+            kg = models.KernelGradient(get_target_logp=lambda batch: tgt.get_minibatch_logp(*batch), scaled=True)
+            Pd = torch.tensor(P, device=dev)
+            batch = (torch.tensor(Xb, device=dev), torch.tensor(yb, device=dev))
+            ms = timed(lambda: kg.step_sgd(Pd, batch, 1e-9))
+            out[f"cfg3_logreg_n8192_d{F + 1}"] = {"ms_per_step": ms, "n2d_per_s": 8192.0 * 8192 * (F + 1) / (ms * 1e-3)}
+        except Exception as e:
+            out[f"cfg3_logreg_n8192_d{F + 1}"] = {"error": str(e)[:200]}
+    try:    # configs[0]: 2-D funnel, n = 100, median bandwidth, scaled sgd, tracer every 10th step (graph-replayed loop)
+        tgt, prop = distributions.funnel.get()
+        g = torch.Generator().manual_seed(0)
+        kg = models.KernelGradient(target_logp=tgt.logpdf, bandwidth=None, scaled=True, lambda_reg=0.5)
+        parts = models.Particles(0, kg.gradient, prop.sample(100, g), learning_rate=5e-2, optimizer="sgd",
+                                 compute_metrics=metrics.get_funnel_tracer(tgt.sample(100, g).to(dev)))
+        parts.step_many(50)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        parts.step_many(1000)
+        torch.cuda.synchronize()
+        us = (time.perf_counter() - t0) * 1e3
+        out["cfg1_funnel_n100_d2_1000_steps"] = {"us_per_step": us, "steps_per_s": 1e6 / us}
+    except Exception as e:
+        out["cfg1_funnel_n100_d2_1000_steps"] = {"error": str(e)[:200]}
+    try:    # configs[4]: BNN weight space, d = 4096, n = 16384 (phi* + KSD/l2 statistics at a fixed bandwidth)
+        rng = np.random.default_rng(5)
+        n, d = 16384, 4096
+        X = torch.tensor((rng.standard_normal((n, d)) * 0.15).astype(np.float32), device=dev)
+        S = torch.tensor((rng.standard_normal((n, d)) * 0.5).astype(np.float32), device=dev)
+        h = float(np.sqrt(0.5 * 2 * d * 0.15 ** 2 / np.log(n + 1)))
+        ms = timed(lambda: engine.phistar(X, X, S, h, Sq=S, stats=True), steps=5, warm=2)
+        out["cfg5_bnn_n16384_d4096_phi"] = {"ms_per_call": ms, "n2d_per_s": float(n) * n * d / (ms * 1e-3),
+                                            "algorithmic_tflops": 6.0 * n * n * d / (ms * 1e-3) / 1e12}
+    except Exception as e:
+        out["cfg5_bnn_n16384_d4096_phi"] = {"error": str(e)[:200]}
+    return out
 
 
 def run_reference(args):
@@ -523,6 +602,12 @@ def main():
                         "sample": f"{reps} x {min(args.cpu_rows, n)} query rows x {n} particles at h={h_cpu:.6g} (the GPU arm's), phi* only "
                                   f"(median selection EXCLUDED), torch CPU fp32 (MKL sgemm + vectorised exp), {cores} threads, {tot_s:.2f} s; "
                                   "reference JAX not installable in this image"}
+    secondary = None
+    if world == 1 and not args.no_secondary and n == 65536 and d == 128:
+        try:
+            secondary = secondary_workloads(dev)
+        except Exception as e:      # informational only: never lose the headline line
+            secondary = {"error": str(e)[:200]}
     KP = res["KP"]
     prof = res["prof"]
     out = {
@@ -546,7 +631,7 @@ def main():
         "phi_only_value": (KP * float(m_local) * n * d / (prof[2][0] * 1e-3)) if prof[2][0] else None,
         "result": {"h": res["h"], "ksd": float(res["aux"][0]), "l2": float(res["aux"][1]), "alpha": float(res["aux"][2])},
         "wall_s": res["t_wall"], "gpu_launches": res["launches"], "clocks": res["clocks"], "roofline": roofline,
-        "roofline_step": step_roofline(res), "offdiag_mode": offdiag, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "roofline_step": step_roofline(res), "offdiag_mode": offdiag, "secondary": secondary, "cpu_baseline": cpu_baseline, "e2e": e2e,
     }
     print(json.dumps(out), flush=True)
     shutdown()

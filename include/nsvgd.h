@@ -234,6 +234,22 @@ int nsvgd_ksum_f32(void* stream, const float* A, int64_t na, int64_t lda,
 int nsvgd_adam_update_f32(void* stream, float* X, const float* grads, float* m1, float* m2,
                           int64_t count, float lr, float b1, float b2, float eps, int64_t t);
 
+/* ---- K complete SVGD steps in ONE launch for latency-bound sizes: one persistent CTA runs, per step,
+ * log -> [tracers every `cadence`-th step] -> device scores -> exact median bandwidth -> phi* + KSD/l2 -> scaled sgd update,
+ * i.e. models.Particles.step + log (models.py:143-197) for KernelGradient with optax.sgd, tracer cadence on the device.
+ * Limits: nsvgd_loop_small_supported(n, d) (n <= 1024, d <= 32, n * d <= 8192); target 0 = funnel, 1 = gaussian with
+ * tparams = [mean (d) | precision (d*d, or its diagonal if tparams_diag)].  h_fixed > 0 skips the median heuristic.
+ * Logs (each may be NULL): particles [K][n][d], mean / std [K][d], bandwidth [K], logp [K][n], grad norms [K],
+ * stats [K][3] = {ksd, l2, alpha}.  Tracer (Y != NULL): tracer_kind 1 = RBF MMD, 2 = RBF + funnel-kernel MMD
+ * (metrics.py:112-127) into mmd_out [.][2], mmd_step [.], *mmd_count (zeroed by the caller). */
+int nsvgd_loop_small_supported(int64_t n, int64_t d);
+int nsvgd_svgd_loop_small_f32(void* stream, float* X, int64_t n, int64_t d, int target, const float* tparams,
+                              int tparams_diag, float log_norm, int median_mode, float h_fixed, float lr, int scaled,
+                              float lambda_reg, int64_t K, int64_t step0, float* log_particles, float* log_mean,
+                              float* log_std, float* log_bandwidth, float* log_logp, float* log_gnorm,
+                              float* log_gnorm_post, double* log_stats, const float* Y, int64_t m, int cadence,
+                              int tracer_kind, float tracer_h, float* mmd_out, int64_t* mmd_step, int* mmd_count);
+
 /* ---- vector (ARD) and full-matrix Gaussian kernels (kernels.py:52-65 with a (d,) bandwidth, kernels.py:83-88;
  * nets.RBFKernel nets.py:24-49).  phi* and MMD run on the unit-bandwidth engine after a linear map of the
  * particles (x' = x / h or x' = x Sigma^T; scores s' = s h or s Sigma^-1; phi = phi' / h or phi' Sigma): */

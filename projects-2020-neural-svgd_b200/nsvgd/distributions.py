@@ -12,8 +12,11 @@ import torch
 
 
 class _LogPdf:
-    def __init__(self, logp, score, batch_logp):
+    def __init__(self, logp, score, batch_logp, device_spec=None):
         self._logp, self.score, self.batch_logp = logp, score, batch_logp
+        # (target id, parameter tensor | None, diagonal precision?, log normaliser): lets the persistent small-n loop
+        # (csrc/small_loop.cu) evaluate the scores inside the kernel
+        self.device_spec = device_spec
 
     def __call__(self, x):
         return self._logp(x)
@@ -25,9 +28,12 @@ class Funnel:
     def __init__(self, d):
         self.d = d
 
+        # normalised like the reference (stats.norm.logpdf(y, 0, 3) + multivariate_normal.logpdf(x, 0, e^y I), :311-319)
+        lognorm = -math.log(3.0) - 0.5 * d * math.log(2.0 * math.pi)
+
         def logp(x):
             xs, y = x[:-1], x[-1]
-            return -y ** 2 / 18.0 - 0.5 * (d - 1) * y - 0.5 * torch.exp(-y) * torch.sum(xs ** 2)
+            return -y ** 2 / 18.0 - 0.5 * (d - 1) * y - 0.5 * torch.exp(-y) * torch.sum(xs ** 2) + lognorm
 
         def score(X):
             if X.is_cuda:
@@ -40,9 +46,9 @@ class Funnel:
 
         def batch_logp(X):
             xs, y = X[:, :-1], X[:, -1]
-            return -y ** 2 / 18.0 - 0.5 * (d - 1) * y - 0.5 * torch.exp(-y) * torch.sum(xs ** 2, dim=1)
+            return -y ** 2 / 18.0 - 0.5 * (d - 1) * y - 0.5 * torch.exp(-y) * torch.sum(xs ** 2, dim=1) + lognorm
 
-        self.logpdf = _LogPdf(logp, score, batch_logp)
+        self.logpdf = _LogPdf(logp, score, batch_logp, device_spec=(0, None, 0, lognorm))
 
     def sample(self, n_samples, key=None):
         y = torch.randn(n_samples, 1, generator=key) * 3
@@ -63,10 +69,12 @@ class Gaussian:
         self.prec = torch.linalg.inv(self.cov.double()).float()
         self.chol = torch.linalg.cholesky(self.cov.double()).float()
         mean_, prec_ = self.mean, self.prec
+        # normalised like stats.multivariate_normal.logpdf (:148-150)
+        lognorm = float(-0.5 * (self.d * math.log(2.0 * math.pi) + torch.logdet(self.cov.double())))
 
         def logp(x):
             c = x - mean_.to(x.device)
-            return -0.5 * torch.dot(c, prec_.to(x.device) @ c)
+            return -0.5 * torch.dot(c, prec_.to(x.device) @ c) + lognorm
 
         dev_cache = {}
 
@@ -81,9 +89,10 @@ class Gaussian:
 
         def batch_logp(X):
             c = X - mean_.to(X.device)
-            return -0.5 * torch.sum(c * (c @ prec_.to(X.device).T), dim=1)
+            return -0.5 * torch.sum(c * (c @ prec_.to(X.device).T), dim=1) + lognorm
 
-        self.logpdf = _LogPdf(logp, score, batch_logp)
+        self.logpdf = _LogPdf(logp, score, batch_logp,
+                              device_spec=(1, torch.cat([mean_.reshape(-1), prec_.reshape(-1)]).contiguous(), 0, lognorm))
 
     def sample(self, n_samples, key=None):
         z = torch.randn(n_samples, self.d, generator=key)

@@ -39,6 +39,9 @@ def get_mmd_tracer(target_samples, kernel=None):
 
     def compute_mmd(particles):
         return {"mmd": mmd(particles, target_samples)}
+    k = kernels.get_rbf_kernel(1.) if kernel is None else kernel
+    if not getattr(k, "funnel", False) and not getattr(k, "is_full", False) and not k.is_ard():
+        compute_mmd.tracer_spec = (1, target_samples, float(k.h()), ("mmd",))          # device-side cadence (small_loop.cu)
     return compute_mmd
 
 
@@ -50,4 +53,5 @@ def get_funnel_tracer(target_samples):
     def compute_mmd(particles):
         return {"rbf_mmd": rbf_mmd(particles, target_samples),
                 "funnel_mmd": funnel_mmd(particles, target_samples)}
+    compute_mmd.tracer_spec = (2, target_samples, 1.0, ("rbf_mmd", "funnel_mmd"))
     return compute_mmd

@@ -237,6 +237,8 @@ class Particles:
         n, d = X.shape
         dev = X.device
         log_particles = self.d < 400                                   # models.py:189
+        if self._step_many_persistent(owner, n_steps, params, log_particles):
+            return None
         bufs = {"bandwidth": torch.empty(n_steps, device=dev), "logp": torch.empty((n_steps, n), device=dev),
                 "global_grad_norm": torch.empty(n_steps, device=dev),
                 "global_grad_norm_post_update": torch.empty(n_steps, device=dev)}
@@ -288,6 +290,67 @@ class Particles:
                           "global_grad_norm_post_update": bufs["global_grad_norm_post_update"][k]})
             metrics.append_to_log(self.rundata, entry)
         return None
+
+    def _step_many_persistent(self, owner, n_steps, params, log_particles):
+        """All `n_steps` steps in ONE kernel launch (csrc/small_loop.cu) when the problem is latency-bound
+        and everything the step needs lives on the device: n * d small, a target with device-side scores (funnel,
+        Gaussian), the default RBF kernel with a scalar or median bandwidth, tracers that are MMDs against fixed target
+        samples.  Returns False (nothing done) otherwise; `rundata` gets the same keys and order as the eager loop."""
+        import ctypes as C
+        import os
+        from . import _lib
+        if os.environ.get("NSVGD_SMALL_LOOP", "1") == "0":
+            return False
+        X = self.particles
+        n, d = X.shape
+        lib = _lib.load()
+        logp = owner.get_target_logp(params)
+        spec = getattr(logp, "device_spec", None)
+        tr = getattr(self.compute_metrics, "tracer_spec", None) if self.compute_metrics else None
+        bw = owner.bandwidth
+        if (spec is None or owner.kernel is not kernels.get_rbf_kernel or not lib.nsvgd_loop_small_supported(n, d)
+                or (self.compute_metrics and tr is None) or isinstance(bw, torch.Tensor) or (spec[0] == 0 and d < 2)):
+            return False
+        dev = X.device
+        K = int(n_steps)
+        f32 = dict(dtype=torch.float32, device=dev)
+        bufs = {"bandwidth": torch.empty(K, **f32), "logp": torch.empty((K, n), **f32), "global_grad_norm": torch.empty(K, **f32),
+                "global_grad_norm_post_update": torch.empty(K, **f32)}
+        if log_particles:
+            bufs.update({"particles": torch.empty((K, n, d), **f32), "mean": torch.empty((K, d), **f32), "std": torch.empty((K, d), **f32)})
+        tparams = spec[1].to(dev) if spec[1] is not None else None
+        first = self.step_counter
+        mmd_out = mmd_step = mmd_count = Y = None
+        if tr is not None:
+            slots = K // 10 + 2
+            Y = tr[1].to(device=dev, dtype=torch.float32).contiguous()
+            mmd_out = torch.zeros((slots, 2), **f32)
+            mmd_step = torch.zeros(slots, dtype=torch.int64, device=dev)
+            mmd_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        mode = _lib.MEDIAN_MODES[engine.DEFAULT_MEDIAN_MODE]
+        p = _lib.ptr
+        _lib.check(lib.nsvgd_svgd_loop_small_f32(
+            _lib.stream_ptr(dev), p(X), n, d, int(spec[0]), p(tparams), int(spec[2]), float(spec[3]), mode,
+            float(bw) if bw else 0.0, float(self.learning_rate), int(bool(owner.scaled)), float(owner.lambda_reg), K, first,
+            p(bufs.get("particles")), p(bufs.get("mean")), p(bufs.get("std")), p(bufs["bandwidth"]), p(bufs["logp"]),
+            p(bufs["global_grad_norm"]), p(bufs["global_grad_norm_post_update"]), 0, p(Y), 0 if Y is None else Y.shape[0], 10,
+            0 if tr is None else int(tr[0]), 1.0 if tr is None else float(tr[2]), p(mmd_out), p(mmd_step), p(mmd_count)))
+        self.step_counter += K
+        if tr is not None:
+            cnt = int(mmd_count.item())
+            steps = mmd_step[:cnt].tolist()
+            for i in range(cnt):
+                entry = {name: (steps[i], mmd_out[i, j].clone()) for j, name in enumerate(tr[3])}
+                metrics.append_to_log(self.rundata, entry)
+        for k in range(K):
+            entry = {}
+            if log_particles:
+                entry.update({"step": first + k, "particles": bufs["particles"][k], "mean": bufs["mean"][k], "std": bufs["std"][k]})
+            entry.update({"bandwidth": bufs["bandwidth"][k], "logp": bufs["logp"][k],
+                          "global_grad_norm": bufs["global_grad_norm"][k],
+                          "global_grad_norm_post_update": bufs["global_grad_norm_post_update"][k]})
+            metrics.append_to_log(self.rundata, entry)
+        return True
 
     def log(self, grad_aux=None):
         """models.py:178-185 (tracer cadence: every 10 steps)"""

@@ -91,10 +91,68 @@ def test_svgd_flow_runs_unchanged_and_improves_mmd():
     assert set(tr) == {"rbf_mmd", "funnel_mmd"}
 
 
-def test_step_many_cuda_graph_equals_eager_loop():
-    """cfg1 shape (funnel, n=100, d=2, median bandwidth, scaled sgd): 25 graph-replayed steps == 25 eager steps,
-    same rundata keys / values, tracer cadence included; and it is faster per step."""
+def test_step_many_persistent_kernel_tracks_eager_loop():
+    """N2: cfg1 shape (funnel, n=100, d=2, median bandwidth, scaled sgd, funnel tracer every 10th step).
+    ALL steps in one launch of the persistent kernel (csrc/small_loop.cu) against the eager loop: bandwidth bit-identical
+    while the particles still agree bitwise (step 0), trajectories to 1e-5 over 30 steps, tracer cadence and values,
+    rundata keys; and the per-step cost."""
     import time
+    from nsvgd import distributions, models, kernels, metrics
+    tgt = distributions.Funnel(2)
+    X0 = torch.randn(100, 2, generator=torch.Generator().manual_seed(7))
+    Y = tgt.sample(80, torch.Generator().manual_seed(8)).cuda()
+
+    def make(tracer=True):
+        kg = models.KernelGradient(target_logp=tgt.logpdf, kernel=kernels.get_rbf_kernel, bandwidth=None, scaled=True, lambda_reg=0.5)
+        return models.Particles(key=0, gradient=kg.gradient, init_samples=X0, learning_rate=5e-2, optimizer="sgd",
+                                compute_metrics=metrics.get_funnel_tracer(Y) if tracer else None)
+    eager, fused = make(), make()
+    for _ in range(30):
+        eager.step(None)
+    l0 = __import__("nsvgd")._lib.launch_count()
+    fused.step_many(30, None)
+    assert __import__("nsvgd")._lib.launch_count() - l0 == 1, "the whole loop must be ONE kernel launch"
+    assert fused.step_counter == 30 and set(eager.rundata) == set(fused.rundata)
+    hb_e = [float(v) for v in eager.rundata["bandwidth"]]; hb_f = [float(v) for v in fused.rundata["bandwidth"]]
+    assert np.float32(hb_e[0]).tobytes() == np.float32(hb_f[0]).tobytes()
+    np.testing.assert_allclose(hb_f, hb_e, rtol=1e-5)
+    for key, tol in (("particles", 1e-5), ("mean", 1e-5), ("std", 1e-5), ("logp", 2e-5), ("global_grad_norm", 1e-4),
+                     ("global_grad_norm_post_update", 1e-4)):
+        a = torch.stack([torch.as_tensor(v).float().cuda() for v in eager.rundata[key]])
+        b = torch.stack([torch.as_tensor(v).float().cuda() for v in fused.rundata[key]])
+        assert torch.allclose(a, b, rtol=tol, atol=tol), key
+    assert torch.allclose(eager.particles, fused.particles, rtol=1e-5, atol=1e-5)
+    for name in ("rbf_mmd", "funnel_mmd"):
+        assert [s for s, _ in eager.rundata[name]] == [s for s, _ in fused.rundata[name]] == [0, 10, 20]
+        for (_, a), (_, b) in zip(eager.rundata[name], fused.rundata[name]):
+            assert float(a) == pytest.approx(float(b), abs=2e-6)
+    fused.done()
+    # a Gaussian target, fixed bandwidth, no tracer, d = 5 (the DMAX = 8 instantiation)
+    g5 = distributions.Gaussian(torch.zeros(5), torch.tensor([0.5, 1.0, 2.0, 0.2, 1.5]))
+    X5 = torch.randn(300, 5, generator=torch.Generator().manual_seed(9))
+    def make5():
+        kg = models.KernelGradient(target_logp=g5.logpdf, bandwidth=1.3, scaled=True)
+        return models.Particles(key=0, gradient=kg.gradient, init_samples=X5, learning_rate=1e-2, optimizer="sgd")
+    e5, f5 = make5(), make5()
+    for _ in range(10):
+        e5.step(None)
+    f5.step_many(10, None)
+    assert torch.allclose(e5.particles, f5.particles, rtol=1e-5, atol=1e-5)
+    # per-step cost of 1000 steps in one launch
+    t = make()
+    t.step_many(20, None)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    t.step_many(1000, None)
+    torch.cuda.synchronize(); us = (time.perf_counter() - t0) * 1e3
+    print(f"cfg1: {us:.1f} us per step (1000 steps, one launch, tracers every 10th step, logs included)")
+    assert us < 100.0, us
+
+
+def test_step_many_cuda_graph_equals_eager_loop(monkeypatch):
+    """cfg1 shape (funnel, n=100, d=2, median bandwidth, scaled sgd): 25 graph-replayed steps == 25 eager steps,
+    same rundata keys / values, tracer cadence included (the path for sizes / targets the persistent kernel does not take)."""
+    import time
+    monkeypatch.setenv("NSVGD_SMALL_LOOP", "0")
     from nsvgd import distributions, models, kernels, metrics
     tgt = distributions.Funnel(2)
     X0 = torch.randn(100, 2, generator=torch.Generator().manual_seed(7))
