@@ -1,20 +1,23 @@
-// phi_large.cu — phi* for d > 128 (BNN weight space: d = 4096, n = 16384) on the tensor cores.
+// phi_large.cu — phi* for d > 128 (BNN weight space: d = 4096, n = 16384) on hand-written tcgen05 GEMM kernels.
 // [stein.py:180-222 + kernels.py:52-65; closed forms in SURVEY.md 8a; SURVEY 7.2-3: "d > 128 cannot keep the output
 //  resident in TMEM ... materialise K and run a plain GEMM"]
 //
-// With d in the thousands both contractions are plain GEMMs, so they go to the library (cuBLAS bf16 tensor-op GEMMs with
-// fp32 accumulation; the prompt's rule: cuBLAS for plain library GEMMs, hand-written kernels for the fused ops) and the
-// hand-written part is what sits between them:
+// With d in the thousands the 128 x d output block of the fused kernel (phi_tc.cu) no longer fits TMEM, so phi* becomes two
+// dense contractions with the pair function fused into the epilogue of the first.  Both run on ONE persistent, warp-
+// specialised kernel (`lg_gemm`): TMA (SWIZZLE_128B) -> shared-memory ring -> tcgen05.mma (bf16 pieces, fp32 accumulate in
+// TMEM, two accumulator buffers so the epilogue of tile t overlaps the MMAs of tile t + 1) -> tcgen05.ld epilogue:
 //   prep   : centre, split every operand into two bf16 pieces (x = b0 + b1, 2^-18 relative), |xc|^2, s.xc,
-//            W = S - Xc/h^2 (COMBINED form, phi_tc.cu)
-//   Gram   : G[mc x nk] = Qc Xc^T          3 GEMM passes  b0 b0' + b1 b0' + b0 b1'   (K = d)
-//   pair   : k = exp2(2c g - c|q|^2 - c|x|^2) -> two bf16 pieces of k, row statistics rowsum / sum k c_j / sum k r2 /
-//            sum k g (one CTA per row, fp32x2 math, block reduction)                    [pair_large_kernel]
-//   P.W    : O_s[mc x d] = P W               3 GEMM passes                              (K = nk <= 4096)
-//   epilogue (update.cu, GRAMW form) adds the column-chunk partials O_s in fp32 RN.
-// Column chunks of <= 4096 particles keep every tensor-core accumulation run at <= 768 MMAs, the same budget as the fused
-// kernel (TMEM accumulator truncation).  Scratch: G 64 MiB + P pieces 64 MiB per 4096 x 4096 chunk.
-#include <cublas_v2.h>
+//            W^T = (S - Xc/h^2)^T (COMBINED form, phi_tc.cu; transposed so that the particle index is the K dimension)
+//   launch 1 (EPI_PAIR)  : G tile = Qc Xc^T (K = d; b0 b0' + b1 b0' + b0 b1' accumulated in one run) and, straight from
+//            TMEM, k = exp2(2c g - c|q|^2 - c|x|^2) -> the two bf16 pieces of k (P, row-major: the A operand of launch 2)
+//            + the four row statistics rowsum / sum k c_j / sum k r2 / sum k g per 256-column tile.  G never reaches HBM.
+//   launch 2 (EPI_STORE) : O_s[m x d] = P W over the particles of chunk s (K = 4096: 768 accumulating MMAs, the TMEM
+//            truncation budget of DESIGN.md 4.1), one fp32 slab per chunk
+//   epilogue (update.cu, GRAMW form) adds the slabs and the per-tile statistics in fp32 RN.
+// Piece reuse: one pipeline stage holds A0, A1, B0, B1 of a 64-wide k-block and feeds all three passes (4 tile loads per
+// 3 MMA blocks instead of 6).  CTA pairs (cta_group::2, M = 256 across the two SMs of a TPC): each CTA stages only half
+// of the B tile, which takes the L2 -> shared-memory traffic from 96 to 64 KB per k-block and CTA -- below the L2
+// throughput cap at full tensor rate.  NSVGD_LARGE_CTAS=1 selects the single-CTA (M = 128) variant.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -26,25 +29,323 @@ namespace nsvgd {
 
 using namespace tc;
 
-constexpr int64_t LG_MC = 4096, LG_NK = 4096;
-constexpr size_t LG_CUBLAS_WS = 32ull << 20;
+constexpr int LG_BM = 128, LG_BN = 256, LG_BK = 64;
+constexpr int64_t LG_NK = 4096;          // particles per accumulation run of the second GEMM
+constexpr int LG_THREADS = 192;          // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr uint32_t LG_TMEM_COLS = 512;   // two 128 x 256 fp32 accumulators
+enum { LG_EPI_PAIR = 0, LG_EPI_STORE = 1 };
 
-// one warp per row: centred bf16 pieces, norms, c_j, and (when S is given) the pieces of W = S - Xc/h^2
+template <int CTAS>
+struct LgSmem {
+  static constexpr int A_TILE = LG_BM * LG_BK * 2;                 // 16 KB: 128 rows x 64 bf16
+  static constexpr int B_TILE = (LG_BN / CTAS) * LG_BK * 2;        // 32 KB, or 16 KB per CTA of a pair
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;            // A0 | A1 | B0 | B1
+  static constexpr int STAGES = CTAS == 1 ? 2 : 3;
+  static constexpr int OFF_BAR = STAGES * STAGE;
+  static constexpr int NBAR = 2 * STAGES + 4;
+  static constexpr int BYTES = OFF_BAR + NBAR * 8 + 16 + 1024;     // + slack for the 1024-byte alignment of the ring
+};
+
+struct LgParams {
+  int epi;
+  int tiles_m, tiles_n, nsplit, group_m;   // tiles_m in units of 128 * CTAS rows
+  int kb_total, kb_per_split;              // 64-wide k-blocks: all of them / per accumulation run
+  int m_rows;                              // valid rows of this launch
+  int64_t row_off;                         // first row of this launch within the whole problem
+  // EPI_PAIR
+  const float* qn; const float* xn; const float* cv; const float* h_dev;
+  __nv_bfloat16* P0; __nv_bfloat16* P1; int64_t ldp;
+  float* scal; int64_t scal_stride;        // scal[(tile_n * scal_stride + row_off + r) * 4]
+  // EPI_STORE
+  float* O; int64_t ldo; int64_t o_split_stride; int n_cols;
+  uint32_t* err_flag;
+};
+
+__device__ __forceinline__ void lg_decode(const LgParams& p, int u, int& mt, int& nt, int& s) {
+  const int per_split = p.tiles_m * p.tiles_n;
+  s = u / per_split;
+  int r = u - s * per_split;
+  const int band = p.group_m * p.tiles_n;      // bands of group_m row tiles: the tiles in flight share operands in L2
+  const int b = r / band;
+  r -= b * band;
+  const int gm = min(p.group_m, p.tiles_m - b * p.group_m);
+  nt = r / gm;
+  mt = b * p.group_m + (r - nt * gm);
+}
+
+template <int CTAS>
+__device__ __forceinline__ void lg_body(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmB0,
+                                        const CUtensorMap& tmB1, const LgParams& p) {
+  using L = LgSmem<CTAS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = (uint64_t*)(smem + L::OFF_BAR);
+  uint64_t* full = bars;                   // [STAGES] TMA -> MMA        (pair: the leader's are used by both CTAs)
+  uint64_t* empty = full + L::STAGES;      // [STAGES] MMA -> TMA        (pair: multicast commit)
+  uint64_t* tfull = empty + L::STAGES;     // [2] accumulator ready      (pair: multicast commit)
+  uint64_t* tempty = tfull + 2;            // [2] accumulator drained    (pair: both CTAs' epilogue warps arrive on the leader's)
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  volatile uint32_t* abort_s = tmem_slot + 1;
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const int unit = blockIdx.x / CTAS, nunits = gridDim.x / CTAS;
+  const int total = p.tiles_m * p.tiles_n * p.nsplit;
+  Watch watch{abort_s, p.err_flag};
+
+  if (threadIdx.x == 0) {
+    *abort_s = (*(volatile uint32_t*)p.err_flag) ? 1u : 0u;
+    for (int i = 0; i < L::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4 * CTAS); }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB0); tma_prefetch_desc(&tmB1);
+  }
+  if (warp == 1) {
+    if (CTAS == 2) { tmem_alloc_pair(tmem_slot, LG_TMEM_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, LG_TMEM_COLS); tmem_relinquish(); }
+  }
+  tc_fence_before();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer (both CTAs of a pair) ===============================
+    const bool leader = elect_one();
+    int si = 0;
+    uint32_t ph = 0;
+    for (int u = unit; u < total; u += nunits) {
+      if (*abort_s) break;
+      int mt, nt, s;
+      lg_decode(p, u, mt, nt, s);
+      const int row0 = (mt * CTAS + (int)rank) * LG_BM;
+      const int col0 = nt * LG_BN + (int)rank * (LG_BN / CTAS);
+      const int kb0 = s * p.kb_per_split;
+      const int nkb = min(p.kb_per_split, p.kb_total - kb0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty[si], ph ^ 1, watch, 0x500 + si);
+        if (leader) {
+          uint8_t* dst = smem + si * L::STAGE;
+          const int kc = (kb0 + kb) * LG_BK;
+          if (CTAS == 2) {
+            const uint32_t fb = mapa_u32(smem_u32(&full[si]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full[si], 2 * L::STAGE);
+            tma_load_2d_pair(dst, &tmA0, fb, kc, row0);
+            tma_load_2d_pair(dst + 2 * L::A_TILE, &tmB0, fb, kc, col0);
+            tma_load_2d_pair(dst + L::A_TILE, &tmA1, fb, kc, row0);
+            tma_load_2d_pair(dst + 2 * L::A_TILE + L::B_TILE, &tmB1, fb, kc, col0);
+          } else {
+            mbar_arrive_expect_tx(&full[si], L::STAGE);
+            tma_load_2d(dst, &tmA0, &full[si], kc, row0);
+            tma_load_2d(dst + 2 * L::A_TILE, &tmB0, &full[si], kc, col0);
+            tma_load_2d(dst + L::A_TILE, &tmA1, &full[si], kc, row0);
+            tma_load_2d(dst + 2 * L::A_TILE + L::B_TILE, &tmB1, &full[si], kc, col0);
+          }
+        }
+        __syncwarp();
+        if (++si == L::STAGES) { si = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (the leader CTA only) ===============================
+    if (rank == 0) {
+      const bool leader = elect_one();
+      const uint32_t idesc = umma_idesc_bf16(LG_BM * CTAS, LG_BN);
+      const uint32_t sbase = smem_u32(smem);
+      int si = 0, it = 0;
+      uint32_t ph = 0;
+      for (int u = unit; u < total; u += nunits, ++it) {
+        if (*abort_s) break;
+        int mt, nt, s;
+        lg_decode(p, u, mt, nt, s);
+        const int kb0 = s * p.kb_per_split;
+        const int nkb = min(p.kb_per_split, p.kb_total - kb0);
+        const int as = it & 1;
+        mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1, watch, 0x520 + as);     // both CTAs have drained this accumulator
+        tc_fence_after();
+        const uint32_t dcol = tmem + (uint32_t)as * LG_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[si], ph, watch, 0x540 + si);
+          tc_fence_after();
+          if (leader) {
+            const uint32_t st = sbase + si * L::STAGE;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint64_t ad = umma_desc_sw128(st + (pass == 1 ? L::A_TILE : 0));                       // A piece: b0, b1, b0
+              const uint64_t bd = umma_desc_sw128(st + 2 * L::A_TILE + (pass == 2 ? L::B_TILE : 0));       // B piece: b0, b0, b1
+#pragma unroll
+              for (int ks = 0; ks < LG_BK / 16; ++ks) {
+                const uint32_t acc = (kb | pass | ks) ? 1u : 0u;
+                if (CTAS == 2) umma_ss_pair(dcol, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 32), idesc, acc);
+                else umma_ss(dcol, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 32), idesc, acc);
+              }
+            }
+            if (CTAS == 2) umma_commit_pair(&empty[si]); else umma_commit(&empty[si]);
+          }
+          __syncwarp();
+          if (++si == L::STAGES) { si = 0; ph ^= 1; }
+        }
+        if (leader) { if (CTAS == 2) umma_commit_pair(&tfull[as]); else umma_commit(&tfull[as]); }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =============================== epilogue: one thread per accumulator row ===============================
+    const int q = warp & 3;                                    // the TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;
+    const uint32_t tempty_remote = CTAS == 2 ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u;
+    float cs = 0.f;
+    if (p.epi == LG_EPI_PAIR) { const float h = *p.h_dev; cs = NSVGD_HALF_LOG2E / (h * h); }
+    int it = 0;
+    for (int u = unit; u < total; u += nunits, ++it) {
+      if (*abort_s) break;
+      int mt, nt, s;
+      lg_decode(p, u, mt, nt, s);
+      const int as = it & 1;
+      const int grow = (mt * CTAS + (int)rank) * LG_BM + r;    // row of this launch
+      const bool valid = grow < p.m_rows;
+      const int col0 = nt * LG_BN;
+      mbar_wait(&tfull[as], (it >> 1) & 1, watch, 0x560 + as);
+      tc_fence_after();
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)as * LG_BN;
+      if (p.epi == LG_EPI_PAIR) {
+        const float ai = valid ? -cs * p.qn[p.row_off + grow] : 0.f;
+        const float cs2 = 2.f * cs;
+        float rowsum = 0.f, kc = 0.f, ke = 0.f, kg = 0.f;
+        __nv_bfloat16* p0 = p.P0 + (int64_t)grow * p.ldp + col0;
+        __nv_bfloat16* p1 = p.P1 + (int64_t)grow * p.ldp + col0;
+#pragma unroll 1
+        for (int c = 0; c < LG_BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_wait_ld();
+          if (c == LG_BN / 32 - 1) {           // the accumulator is in registers: hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(tempty_remote + as * 8); else mbar_arrive(&tempty[as]); }
+          }
+          uint32_t w0[16], w1[16];
+          const float4* xn4 = reinterpret_cast<const float4*>(p.xn + col0 + c * 32);
+          const float4* cv4 = reinterpret_cast<const float4*>(p.cv + col0 + c * 32);
+#pragma unroll
+          for (int e4 = 0; e4 < 8; ++e4) {
+            const float4 xs = __ldg(xn4 + e4), cc = __ldg(cv4 + e4);
+            const float xa[4] = {xs.x, xs.y, xs.z, xs.w}, ca[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {
+              const int e = e4 * 4 + e2 * 2;
+              const float g0 = __uint_as_float(v[e]), g1 = __uint_as_float(v[e + 1]);
+              const float ex0 = fmaf(xa[e2 * 2], -cs, fmaf(g0, cs2, ai));
+              const float ex1 = fmaf(xa[e2 * 2 + 1], -cs, fmaf(g1, cs2, ai));
+              const float k0 = ex2_approx(ex0), k1 = ex2_approx(ex1);
+              const uint32_t a0 = pack_bf16x2(k0, k1);
+              const float h0 = bf16lo_to_float(a0), h1 = bf16hi_to_float(a0);
+              const uint32_t a1 = pack_bf16x2(k0 - h0, k1 - h1);
+              w0[e >> 1] = a0; w1[e >> 1] = a1;
+              const float q0 = h0 + bf16lo_to_float(a1), q1 = h1 + bf16hi_to_float(a1);   // the quantised k launch 2 consumes
+              rowsum += q0 + q1;
+              kc = fmaf(q0, ca[e2 * 2], fmaf(q1, ca[e2 * 2 + 1], kc));
+              ke = fmaf(q0, ex0, fmaf(q1, ex1, ke));
+              kg = fmaf(q0, g0, fmaf(q1, g1, kg));
+            }
+          }
+          if (valid) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              *reinterpret_cast<uint4*>(p0 + c * 32 + x * 8) = make_uint4(w0[4 * x], w0[4 * x + 1], w0[4 * x + 2], w0[4 * x + 3]);
+              *reinterpret_cast<uint4*>(p1 + c * 32 + x * 8) = make_uint4(w1[4 * x], w1[4 * x + 1], w1[4 * x + 2], w1[4 * x + 3]);
+            }
+          }
+        }
+        if (valid)      // b = sum k r2 = -sum k e / cs
+          *reinterpret_cast<float4*>(p.scal + ((int64_t)nt * p.scal_stride + p.row_off + grow) * 4) = make_float4(rowsum, kc, -ke / cs, kg);
+      } else {
+        float* o = p.O + (int64_t)s * p.o_split_stride + (int64_t)grow * p.ldo + col0;
+#pragma unroll 1
+        for (int c = 0; c < LG_BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_wait_ld();
+          if (c == LG_BN / 32 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(tempty_remote + as * 8); else mbar_arrive(&tempty[as]); }
+          }
+          if (valid) {
+#pragma unroll
+            for (int x = 0; x < 8; ++x)
+              if (col0 + c * 32 + x * 4 < p.n_cols)
+                *reinterpret_cast<uint4*>(o + c * 32 + x * 4) = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    if (CTAS == 2) tmem_dealloc_pair(tmem, LG_TMEM_COLS); else tmem_dealloc(tmem, LG_TMEM_COLS);
+  }
+}
+
+__global__ void __launch_bounds__(LG_THREADS, 1)
+lg_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ LgParams p) {
+  lg_body<1>(tmA0, tmA1, tmB0, tmB1, p);
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LG_THREADS, 1)
+lg_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ LgParams p) {
+  lg_body<2>(tmA0, tmA1, tmB0, tmB1, p);
+}
+
+static int lg_ctas() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NSVGD_LARGE_CTAS"); v = (e && atoi(e) == 1) ? 1 : 2; }
+  return v;
+}
+
+// A pieces: rows x K (row stride lda elements); B pieces: cols x K
+static int lg_launch(cudaStream_t st, int ctas, const __nv_bfloat16* A0, const __nv_bfloat16* A1, int64_t a_rows, int64_t lda,
+                     const __nv_bfloat16* B0, const __nv_bfloat16* B1, int64_t b_rows, int64_t ldb, int64_t kdim, LgParams prm) {
+  CUtensorMap mA0, mA1, mB0, mB1;
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&mA0, A0, (uint64_t)kdim, (uint64_t)a_rows, (uint64_t)lda * 2, LG_BK, LG_BM));
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&mA1, A1, (uint64_t)kdim, (uint64_t)a_rows, (uint64_t)lda * 2, LG_BK, LG_BM));
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&mB0, B0, (uint64_t)kdim, (uint64_t)b_rows, (uint64_t)ldb * 2, LG_BK, (uint32_t)(LG_BN / ctas)));
+  NSVGD_PROPAGATE(make_tmap_bf16_2d(&mB1, B1, (uint64_t)kdim, (uint64_t)b_rows, (uint64_t)ldb * 2, LG_BK, (uint32_t)(LG_BN / ctas)));
+  prm.tiles_m = (int)ceil_div(prm.m_rows, LG_BM * ctas);
+  prm.group_m = ctas == 2 ? 4 : 8;
+  const int64_t total = (int64_t)prm.tiles_m * prm.tiles_n * prm.nsplit;
+  NSVGD_REQUIRE(total < (1ll << 31), NSVGD_ERR_INVALID, "phi_large: too many tiles");
+  const int units = (int)std::min<int64_t>(total, std::max(1, device_sm_count() / ctas));
+  if (ctas == 2) {
+    NSVGD_PROPAGATE(ensure_dyn_smem((const void*)lg_gemm_pair_kernel, LgSmem<2>::BYTES));
+    lg_gemm_pair_kernel<<<units * 2, LG_THREADS, LgSmem<2>::BYTES, st>>>(mA0, mA1, mB0, mB1, prm);
+  } else {
+    NSVGD_PROPAGATE(ensure_dyn_smem((const void*)lg_gemm_kernel, LgSmem<1>::BYTES));
+    lg_gemm_kernel<<<units, LG_THREADS, LgSmem<1>::BYTES, st>>>(mA0, mA1, mB0, mB1, prm);
+  }
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
+// one warp per row: centred bf16 pieces, |xc|^2 and c_j = s_j . xc_j; rows in [n, rows_pad) are zero particles with
+// |xc|^2 = 1e30, which makes their k underflow to exactly 0
 __global__ void __launch_bounds__(256) large_prep_kernel(const float* __restrict__ X, const float* __restrict__ S, int64_t n,
                                                          int64_t rows_pad, int64_t d, int64_t ldx, int64_t ldk,
-                                                         const float* __restrict__ mu, const float* __restrict__ h_dev,
-                                                         __nv_bfloat16* __restrict__ Xb0, __nv_bfloat16* __restrict__ Xb1,
-                                                         __nv_bfloat16* __restrict__ Wb0, __nv_bfloat16* __restrict__ Wb1,
-                                                         float* __restrict__ xn, float* __restrict__ cv) {
+                                                         const float* __restrict__ mu, __nv_bfloat16* __restrict__ Xb0,
+                                                         __nv_bfloat16* __restrict__ Xb1, float* __restrict__ xn,
+                                                         float* __restrict__ cv) {
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows_pad) return;
   const bool rv = row < n;
-  float inv_h2 = 0.f;
-  if (S) { const float h = *h_dev; inv_h2 = 1.f / (h * h); }
   float acc_n = 0.f, acc_c = 0.f;
   for (int64_t c0 = 2 * lane; c0 < ldk; c0 += 64) {
-    float v2[2] = {0.f, 0.f}, w2[2] = {0.f, 0.f};
+    float v2[2] = {0.f, 0.f};
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int64_t c = c0 + e;
@@ -52,115 +353,72 @@ __global__ void __launch_bounds__(256) large_prep_kernel(const float* __restrict
         const float v = X[row * ldx + c] - mu[c];
         acc_n = fmaf(v, v, acc_n);
         v2[e] = v;
-        if (S) {
-          const float sv = S[row * ldx + c];
-          acc_c = fmaf(sv, v, acc_c);
-          w2[e] = fmaf(-v, inv_h2, sv);
-        }
+        if (S) acc_c = fmaf(S[row * ldx + c], v, acc_c);
       }
     }
     const uint32_t p0 = pack_bf16x2(v2[0], v2[1]);
     const uint32_t p1 = pack_bf16x2(v2[0] - bf16lo_to_float(p0), v2[1] - bf16hi_to_float(p0));
     *reinterpret_cast<uint32_t*>(&Xb0[row * ldk + c0]) = p0;
     *reinterpret_cast<uint32_t*>(&Xb1[row * ldk + c0]) = p1;
-    if (S) {
-      const uint32_t q0 = pack_bf16x2(w2[0], w2[1]);
-      const uint32_t q1 = pack_bf16x2(w2[0] - bf16lo_to_float(q0), w2[1] - bf16hi_to_float(q0));
-      *reinterpret_cast<uint32_t*>(&Wb0[row * ldk + c0]) = q0;
-      *reinterpret_cast<uint32_t*>(&Wb1[row * ldk + c0]) = q1;
-    }
   }
   acc_n = warp_sum(acc_n); acc_c = warp_sum(acc_c);
   if (lane == 0) {
-    xn[row] = rv ? acc_n : 1e30f;     // padded particle: k underflows to 0
+    xn[row] = rv ? acc_n : 1e30f;
     if (cv) cv[row] = rv ? acc_c : 0.f;
   }
 }
 
-// one CTA per query row of the chunk: G row -> two bf16 pieces of k + the four row statistics of this column chunk
-__global__ void __launch_bounds__(256) pair_large_kernel(const float* __restrict__ G, int64_t nk, const float* __restrict__ xn,
-                                                         const float* __restrict__ cv, const float* __restrict__ qn,
-                                                         const float* __restrict__ h_dev, __nv_bfloat16* __restrict__ Pb0,
-                                                         __nv_bfloat16* __restrict__ Pb1, float* __restrict__ scal) {
-  __shared__ float sh[4][8];
-  const int64_t row = blockIdx.x;
+// W^T pieces, K-major for launch 2: Wt[c][j] = S[j][c] - (X[j][c] - mu[c]) / h^2 ; 64 particles x 32 coordinates per CTA
+__global__ void __launch_bounds__(256) large_wt_kernel(const float* __restrict__ X, const float* __restrict__ S, int64_t n,
+                                                       int64_t d, int64_t ldx, const float* __restrict__ mu,
+                                                       const float* __restrict__ h_dev, __nv_bfloat16* __restrict__ Wt0,
+                                                       __nv_bfloat16* __restrict__ Wt1, int64_t ldw) {
+  __shared__ float t[32][65];
   const float h = *h_dev;
-  const float cs = NSVGD_HALF_LOG2E / (h * h);
-  const float ai = -cs * qn[row];
-  const float* g = G + row * nk;
-  float rowsum = 0.f, kc = 0.f, ke = 0.f, kg = 0.f;
-  for (int64_t j = 2 * threadIdx.x; j < nk; j += 512) {          // nk is a multiple of 8: pairs never straddle the end
-    const float2 gg = *reinterpret_cast<const float2*>(g + j);
-    const float2 xs = *reinterpret_cast<const float2*>(xn + j);
-    const float2 cc = *reinterpret_cast<const float2*>(cv + j);
-    const float ex0 = fmaf(xs.x, -cs, fmaf(gg.x, 2.f * cs, ai));
-    const float ex1 = fmaf(xs.y, -cs, fmaf(gg.y, 2.f * cs, ai));
-    const float k0 = ex2_approx(ex0), k1 = ex2_approx(ex1);
-    const uint32_t a0 = pack_bf16x2(k0, k1);
-    const float h0 = bf16lo_to_float(a0), h1 = bf16hi_to_float(a0);
-    const uint32_t a1 = pack_bf16x2(k0 - h0, k1 - h1);
-    *reinterpret_cast<uint32_t*>(&Pb0[row * nk + j]) = a0;
-    *reinterpret_cast<uint32_t*>(&Pb1[row * nk + j]) = a1;
-    const float q0 = h0 + bf16lo_to_float(a1), q1 = h1 + bf16hi_to_float(a1);   // the quantised k the GEMM consumes
-    rowsum += q0 + q1;
-    kc = fmaf(q0, cc.x, fmaf(q1, cc.y, kc));
-    ke = fmaf(q0, ex0, fmaf(q1, ex1, ke));
-    kg = fmaf(q0, gg.x, fmaf(q1, gg.y, kg));
-  }
-  rowsum = warp_sum(rowsum); kc = warp_sum(kc); ke = warp_sum(ke); kg = warp_sum(kg);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) { sh[0][w] = rowsum; sh[1][w] = kc; sh[2][w] = ke; sh[3][w] = kg; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float r = 0.f, c = 0.f, e = 0.f, gsum = 0.f;
+  const float inv_h2 = 1.f / (h * h);
+  const int64_t j0 = (int64_t)blockIdx.x * 64, c0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c = c0 + tx;
+  const float m = c < d ? mu[c] : 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { r += sh[0][i]; c += sh[1][i]; e += sh[2][i]; gsum += sh[3][i]; }
-    *reinterpret_cast<float4*>(scal + row * 4) = make_float4(r, c, -e / cs, gsum);   // b = sum k r2 = -sum k e / cs
+  for (int jj = ty; jj < 64; jj += 8) {
+    const int64_t j = j0 + jj;
+    float w = 0.f;
+    if (j < n && c < d) w = fmaf(-(X[j * ldx + c] - m), inv_h2, S[j * ldx + c]);
+    t[tx][jj] = w;
   }
-}
-
-static cublasHandle_t large_handle() {
-  static cublasHandle_t handles[64] = {};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  if (!handles[dev]) {
-    if (cublasCreate(&handles[dev]) != CUBLAS_STATUS_SUCCESS) { handles[dev] = nullptr; return nullptr; }
+  __syncthreads();
+  const int cc = threadIdx.x >> 3, jj0 = (threadIdx.x & 7) * 8;
+  if (c0 + cc < d) {
+    uint32_t w0[4], w1[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = t[cc][jj0 + 2 * e], b = t[cc][jj0 + 2 * e + 1];
+      w0[e] = pack_bf16x2(a, b);
+      w1[e] = pack_bf16x2(a - bf16lo_to_float(w0[e]), b - bf16hi_to_float(w0[e]));
+    }
+    *reinterpret_cast<uint4*>(&Wt0[(c0 + cc) * ldw + j0 + jj0]) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+    *reinterpret_cast<uint4*>(&Wt1[(c0 + cc) * ldw + j0 + jj0]) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
   }
-  return handles[dev];
-}
-
-#define NSVGD_CUBLAS(expr)                                                                   \
-  do {                                                                                       \
-    cublasStatus_t s_ = (expr);                                                              \
-    NSVGD_REQUIRE(s_ == CUBLAS_STATUS_SUCCESS, NSVGD_ERR_CUDA, "cuBLAS status %d at %s:%d", (int)s_, __FILE__, __LINE__); \
-  } while (0)
-
-// C[rows_c x cols_c] (row-major, ldc) (+)= A[rows_c x k] B  with the row-major operands described in the file header
-static int gemm3(cublasHandle_t hd, cublasOperation_t opa, int m, int n, int k, const __nv_bfloat16* A0, const __nv_bfloat16* A1,
-                 int lda, const __nv_bfloat16* B0, const __nv_bfloat16* B1, int ldb, float* Cm, int ldc) {
-  const float one = 1.f, zero = 0.f;
-  const __nv_bfloat16* As[3] = {A0, A1, A0};
-  const __nv_bfloat16* Bs[3] = {B0, B0, B1};
-  for (int pass = 0; pass < 3; ++pass)
-    NSVGD_CUBLAS(cublasGemmEx(hd, opa, CUBLAS_OP_N, m, n, k, &one, As[pass], CUDA_R_16BF, lda, Bs[pass], CUDA_R_16BF, ldb,
-                              pass == 0 ? &zero : &one, Cm, CUDA_R_32F, ldc, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT_TENSOR_OP));
-  return NSVGD_OK;
 }
 
 int phi_large(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dry, size_t* need) {
+  const int ctas = lg_ctas();
   const int64_t ldk = round_up(a.d, 8);
-  const int64_t n_pad = round_up(a.n, 8);
+  const int64_t n_pad = round_up(a.n, LG_BN);
   const int64_t ldo = round_up(a.d, 4);
   const int nsplit = (int)ceil_div(n_pad, LG_NK);
-  const int64_t mc = std::min<int64_t>(LG_MC, a.m), nkc = std::min<int64_t>(LG_NK, n_pad);
+  const int tiles_nx = (int)(n_pad / LG_BN);                 // 256-particle column tiles of the Gram
   const bool q_is_x = (a.Q == a.X && a.m == a.n && a.ldq == a.ldx);
+  // query rows per pair of launches: the two pieces of P (rows x n_pad bf16 each) stay within 1 GiB
+  const int64_t mc = std::min<int64_t>(round_up(a.m, 256), std::max<int64_t>(256, ((1ll << 30) / (n_pad * 4)) / 256 * 256));
   WsCarver w(ws, ws_bytes, dry);
   float* mu = w.take<float>((size_t)a.d);
   double* mpart = w.take<double>((size_t)colmean_partials(a.n, a.d));
   __nv_bfloat16* Xb0 = w.take<__nv_bfloat16>((size_t)(n_pad * ldk));
   __nv_bfloat16* Xb1 = w.take<__nv_bfloat16>((size_t)(n_pad * ldk));
-  __nv_bfloat16* Wb0 = w.take<__nv_bfloat16>((size_t)(n_pad * ldk));
-  __nv_bfloat16* Wb1 = w.take<__nv_bfloat16>((size_t)(n_pad * ldk));
+  __nv_bfloat16* Wt0 = w.take<__nv_bfloat16>((size_t)(a.d * n_pad));
+  __nv_bfloat16* Wt1 = w.take<__nv_bfloat16>((size_t)(a.d * n_pad));
   float* xn = w.take<float>((size_t)n_pad);
   float* cv = w.take<float>((size_t)n_pad);
   __nv_bfloat16 *Qb0 = Xb0, *Qb1 = Xb1;
@@ -170,53 +428,53 @@ int phi_large(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool
     Qb1 = w.take<__nv_bfloat16>((size_t)(a.m * ldk));
     qn = w.take<float>((size_t)a.m);
   }
-  float* G = w.take<float>((size_t)(mc * nkc));
-  __nv_bfloat16* Pb0 = w.take<__nv_bfloat16>((size_t)(mc * nkc));
-  __nv_bfloat16* Pb1 = w.take<__nv_bfloat16>((size_t)(mc * nkc));
+  __nv_bfloat16* P0 = w.take<__nv_bfloat16>((size_t)(mc * n_pad));
+  __nv_bfloat16* P1 = w.take<__nv_bfloat16>((size_t)(mc * n_pad));
   float* O = w.take<float>((size_t)nsplit * a.m * ldo);
-  float* scal = w.take<float>((size_t)nsplit * a.m * 4);
+  float* scal = w.take<float>((size_t)tiles_nx * a.m * 4);
   double* partials = w.take<double>((size_t)(2 * epilogue_blocks(a.m)));
-  void* cws = w.take<char>(LG_CUBLAS_WS);
+  uint32_t* err_flag = w.take<uint32_t>(64);
   if (need) *need = w.off;
   if (dry) return NSVGD_OK;
   NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "phi_large: workspace too small (%zu < %zu)", ws_bytes, w.off);
   NSVGD_REQUIRE(!a.aux, NSVGD_ERR_UNSUPPORTED, "phi_large: the [drift, repulsion] aux output is served by the generic path");
   NSVGD_REQUIRE(n_pad < (1ll << 31) && a.m < (1ll << 31) && ldk < (1ll << 31), NSVGD_ERR_INVALID, "phi_large: shape too large");
-  cublasHandle_t hd = large_handle();
-  NSVGD_REQUIRE(hd, NSVGD_ERR_CUDA, "phi_large: cublasCreate failed");
-  NSVGD_CUBLAS(cublasSetStream(hd, st));
-  NSVGD_CUBLAS(cublasSetWorkspace(hd, cws, LG_CUBLAS_WS));
 
+  NSVGD_CUDA(cudaMemsetAsync(err_flag, 0, 64 * sizeof(uint32_t), st));
   NSVGD_PROPAGATE(launch_colmean(st, a.X, a.n, a.d, a.ldx, mpart, mu));
-  large_prep_kernel<<<(unsigned)ceil_div(n_pad * 32, 256), 256, 0, st>>>(a.X, a.S, a.n, n_pad, a.d, a.ldx, ldk, mu, a.h_dev, Xb0,
-                                                                        Xb1, Wb0, Wb1, xn, cv);
+  large_prep_kernel<<<(unsigned)ceil_div(n_pad * 32, 256), 256, 0, st>>>(a.X, a.S, a.n, n_pad, a.d, a.ldx, ldk, mu, Xb0, Xb1, xn, cv);
+  NSVGD_LAUNCH_CHECK();
+  large_wt_kernel<<<dim3((unsigned)(n_pad / 64), (unsigned)ceil_div(a.d, 32)), 256, 0, st>>>(a.X, a.S, a.n, a.d, a.ldx, mu, a.h_dev,
+                                                                                          Wt0, Wt1, n_pad);
   NSVGD_LAUNCH_CHECK();
   if (!q_is_x) {
-    large_prep_kernel<<<(unsigned)ceil_div(a.m * 32, 256), 256, 0, st>>>(a.Q, nullptr, a.m, a.m, a.d, a.ldq, ldk, mu, a.h_dev, Qb0,
-                                                                        Qb1, nullptr, nullptr, qn, nullptr);
+    large_prep_kernel<<<(unsigned)ceil_div(a.m * 32, 256), 256, 0, st>>>(a.Q, nullptr, a.m, a.m, a.d, a.ldq, ldk, mu, Qb0, Qb1, qn,
+                                                                        nullptr);
     NSVGD_LAUNCH_CHECK();
   }
   prof_begin(0, st);
-  for (int64_t i0 = 0; i0 < a.m; i0 += LG_MC) {
-    const int64_t mi = std::min<int64_t>(LG_MC, a.m - i0);
-    for (int s = 0; s < nsplit; ++s) {
-      const int64_t j0 = (int64_t)s * LG_NK;
-      const int64_t nk = std::min<int64_t>(LG_NK, n_pad - j0);
-      // G^T (nk x mi, col-major, ld nk) = Xc_chunk (row-major nk x d) . Qc_chunk^T
-      NSVGD_PROPAGATE(gemm3(hd, CUBLAS_OP_T, (int)nk, (int)mi, (int)ldk, Xb0 + j0 * ldk, Xb1 + j0 * ldk, (int)ldk, Qb0 + i0 * ldk,
-                            Qb1 + i0 * ldk, (int)ldk, G, (int)nk));
-      pair_large_kernel<<<(unsigned)mi, 256, 0, st>>>(G, nk, xn + j0, cv + j0, qn + i0, a.h_dev, Pb0, Pb1,
-                                                      scal + ((int64_t)s * a.m + i0) * 4);
-      NSVGD_LAUNCH_CHECK();
-      // O_s^T (d x mi, col-major, ld ldo) = W_chunk^T (row-major nk x d viewed col-major d x nk) . P^T (nk x mi)
-      NSVGD_PROPAGATE(gemm3(hd, CUBLAS_OP_N, (int)a.d, (int)mi, (int)nk, Wb0 + j0 * ldk, Wb1 + j0 * ldk, (int)ldk, Pb0, Pb1, (int)nk,
-                            O + ((int64_t)s * a.m + i0) * ldo, (int)ldo));
-    }
+  for (int64_t i0 = 0; i0 < a.m; i0 += mc) {
+    const int64_t mi = std::min<int64_t>(mc, a.m - i0);
+    LgParams g{};
+    g.epi = LG_EPI_PAIR; g.tiles_n = tiles_nx; g.nsplit = 1;
+    g.kb_total = g.kb_per_split = (int)ceil_div(ldk, LG_BK);
+    g.m_rows = (int)mi; g.row_off = i0;
+    g.qn = qn; g.xn = xn; g.cv = cv; g.h_dev = a.h_dev; g.P0 = P0; g.P1 = P1; g.ldp = n_pad; g.scal = scal; g.scal_stride = a.m;
+    g.err_flag = err_flag;
+    NSVGD_PROPAGATE(lg_launch(st, ctas, Qb0 + i0 * ldk, Qb1 + i0 * ldk, mi, ldk, Xb0, Xb1, n_pad, ldk, ldk, g));
+    LgParams o{};
+    o.epi = LG_EPI_STORE; o.tiles_n = (int)ceil_div(a.d, LG_BN); o.nsplit = nsplit;
+    o.kb_total = (int)(n_pad / LG_BK); o.kb_per_split = (int)(LG_NK / LG_BK);
+    o.m_rows = (int)mi; o.row_off = i0;
+    o.O = O + i0 * ldo; o.ldo = ldo; o.o_split_stride = a.m * ldo; o.n_cols = (int)ldo;
+    o.err_flag = err_flag;
+    NSVGD_PROPAGATE(lg_launch(st, ctas, P0, P1, mi, n_pad, Wt0, Wt1, a.d, n_pad, n_pad, o));
   }
   prof_end(0, st);
 
   EpilogueArgs e{};
-  e.form = 2; e.O = O; e.scal = scal; e.nsplit = nsplit; e.scal_parts = nsplit; e.m_pad = a.m; e.ldo = ldo; e.dpad = 0; e.mu = mu;
+  e.form = 2; e.err_flag = err_flag; e.O = O; e.scal = scal; e.nsplit = nsplit; e.scal_parts = tiles_nx; e.m_pad = a.m; e.ldo = ldo;
+  e.dpad = 0; e.mu = mu;
   e.Q = a.Q; e.ldq = a.ldq; e.Sq = a.Sq; e.m = a.m; e.n = a.n; e.d = a.d; e.h_dev = a.h_dev;
   e.phi = a.phi; e.ldphi = a.ldphi; e.aux = nullptr; e.stats_dev = a.stats_dev; e.partials = partials;
   return launch_epilogue(st, e);
