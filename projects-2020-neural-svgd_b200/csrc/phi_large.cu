@@ -43,25 +43,35 @@ struct LgSmem {
   static constexpr int STAGES = CTAS == 1 ? 2 : 3;
   static constexpr int OFF_BAR = STAGES * STAGE;
   static constexpr int NBAR = 2 * STAGES + 4;
-  static constexpr int BYTES = OFF_BAR + NBAR * 8 + 16 + 1024;     // + slack for the 1024-byte alignment of the ring
+  static constexpr int OFF_COL = OFF_BAR + 128;                    // float4 [4 warps][256 columns]: column statistics of mirrored tiles
+  static constexpr int BYTES = OFF_COL + 4 * LG_BN * 16 + 1024;    // + slack for the 1024-byte alignment of the ring
+  static_assert(NBAR * 8 + 16 <= 128, "barrier block");
 };
 
 struct LgParams {
   int epi;
   int tiles_m, tiles_n, nsplit, group_m;   // tiles_m in units of 128 * CTAS rows
+  int total;                               // work units (tiles x splits) of the launch
   int kb_total, kb_per_split;              // 64-wide k-blocks: all of them / per accumulation run
   int m_rows;                              // valid rows of this launch
   int64_t row_off;                         // first row of this launch within the whole problem
   // EPI_PAIR
   const float* qn; const float* xn; const float* cv; const float* h_dev;
   __nv_bfloat16* P0; __nv_bfloat16* P1; int64_t ldp;
-  float* scal; int64_t scal_stride;        // scal[(tile_n * scal_stride + row_off + r) * 4]
+  float* scal; int64_t scal_stride;        // scal[(slot * scal_stride + row_off + r) * 4]
+  int sym;                                 // Q == X: only tiles on or above the diagonal are computed; an off-diagonal tile also
+                                           // writes its transpose (P^T and the column statistics).  slot = 2 * tile_n for the row
+                                           // statistics, the 128-row block index of the tile's rows for the mirrored ones; else tile_n
+  int ctas;
+  int diag;                                // Q == X: entry (i, i) is the particle against itself -> g_ii = |xc_i|^2 exactly (k_ii = 1)
   // EPI_STORE
   float* O; int64_t ldo; int64_t o_split_stride; int n_cols;
   uint32_t* err_flag;
 };
 
+__device__ __forceinline__ void lg_decode_sym(const LgParams& p, int u, int& mt, int& nt);
 __device__ __forceinline__ void lg_decode(const LgParams& p, int u, int& mt, int& nt, int& s) {
+  if (p.sym) { s = 0; lg_decode_sym(p, u, mt, nt); return; }
   const int per_split = p.tiles_m * p.tiles_n;
   s = u / per_split;
   int r = u - s * per_split;
@@ -71,6 +81,53 @@ __device__ __forceinline__ void lg_decode(const LgParams& p, int u, int& mt, int
   const int gm = min(p.group_m, p.tiles_m - b * p.group_m);
   nt = r / gm;
   mt = b * p.group_m + (r - nt * gm);
+}
+
+// symmetric launch: row tile mt (128 * ctas rows) takes the column tiles nt >= (mt * ctas) / 2; bands of group_m row tiles,
+// column-major inside a band (same enumeration on the host: lg_sym_tiles)
+__host__ __device__ __forceinline__ int lg_sym_nmin(int mt, int ctas) { return (mt * ctas) >> 1; }
+__device__ __forceinline__ void lg_decode_sym(const LgParams& p, int u, int& mt, int& nt) {
+  int r0 = 0, gm = 0;
+  for (int b = 0;; ++b) {
+    r0 = b * p.group_m;
+    gm = min(p.group_m, p.tiles_m - r0);
+    int cnt = 0;
+    for (int i = 0; i < gm; ++i) cnt += p.tiles_n - lg_sym_nmin(r0 + i, p.ctas);
+    if (u < cnt || r0 + gm >= p.tiles_m) break;
+    u -= cnt;
+  }
+  nt = lg_sym_nmin(r0, p.ctas);
+  for (;;) {
+    const int rmax = p.ctas == 2 ? nt : 2 * nt + 1;          // last row tile that takes column tile nt
+    const int rows = min(gm, rmax - r0 + 1);
+    if (rows >= gm) break;
+    if (u < rows) { mt = r0 + u; return; }
+    u -= rows;
+    ++nt;
+  }
+  nt += u / gm;
+  mt = r0 + u % gm;
+}
+static int64_t lg_sym_tiles(int tiles_m, int tiles_n, int ctas) {
+  int64_t t = 0;
+  for (int mt = 0; mt < tiles_m; ++mt) t += tiles_n - lg_sym_nmin(mt, ctas);
+  return t;
+}
+
+// t[e] of lane l -> returns sum over the 32 lanes of t[l'] ... for column l: 31 shuffles instead of 32 x 5
+__device__ __forceinline__ float warp_transpose_sum32(float (&t)[32], int lane) {
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int half = 16 >> s;
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = up ? t[i + half] : t[i];
+      const float send = up ? t[i] : t[i + half];
+      t[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return t[0];
 }
 
 template <int CTAS>
@@ -90,7 +147,7 @@ __device__ __forceinline__ void lg_body(const CUtensorMap& tmA0, const CUtensorM
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
   const int unit = blockIdx.x / CTAS, nunits = gridDim.x / CTAS;
-  const int total = p.tiles_m * p.tiles_n * p.nsplit;
+  const int total = p.total;
   Watch watch{abort_s, p.err_flag};
 
   if (threadIdx.x == 0) {
@@ -196,6 +253,7 @@ __device__ __forceinline__ void lg_body(const CUtensorMap& tmA0, const CUtensorM
     const int q = warp & 3;                                    // the TMEM lane quarter this warp may read
     const int r = q * 32 + lane;
     const uint32_t tempty_remote = CTAS == 2 ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u;
+    float4* colbuf = reinterpret_cast<float4*>(smem + L::OFF_COL);
     float cs = 0.f;
     if (p.epi == LG_EPI_PAIR) { const float h = *p.h_dev; cs = NSVGD_HALF_LOG2E / (h * h); }
     int it = 0;
@@ -211,8 +269,12 @@ __device__ __forceinline__ void lg_body(const CUtensorMap& tmA0, const CUtensorM
       tc_fence_after();
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)as * LG_BN;
       if (p.epi == LG_EPI_PAIR) {
-        const float ai = valid ? -cs * p.qn[p.row_off + grow] : 0.f;
+        // sym: every row of the launch is a (possibly padded) particle, so qn is defined (1e30 for the padding: k = 0)
+        const float ai = (valid || p.sym) ? -cs * p.qn[p.row_off + grow] : 0.f;
         const float cs2 = 2.f * cs;
+        const int rb128 = mt * CTAS + (int)rank;                 // 128-row block of this CTA's rows
+        const bool mirror = p.sym && nt > (rb128 >> 1);          // off-diagonal tile: also emit its transpose
+        const float ci = mirror ? p.cv[grow] : 0.f;
         float rowsum = 0.f, kc = 0.f, ke = 0.f, kg = 0.f;
         __nv_bfloat16* p0 = p.P0 + (int64_t)grow * p.ldp + col0;
         __nv_bfloat16* p1 = p.P1 + (int64_t)grow * p.ldp + col0;
@@ -226,7 +288,16 @@ __device__ __forceinline__ void lg_body(const CUtensorMap& tmA0, const CUtensorM
             __syncwarp();
             if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(tempty_remote + as * 8); else mbar_arrive(&tempty[as]); }
           }
+          // The accumulator of a diagonal entry grows monotonically to |xc_i|^2 over 3 d / 16 MMAs and picks up the TMEM
+          // truncation bias (2^-25 per MMA): at d = 4096 that is 2e-3 in g_ii, i.e. k_ii = 1 - 2e-4 where the
+          // reference has exp(0) = 1.  The entry is known in closed form, so it is set, not computed.
+          if (p.diag && c * 32 == (int)(p.row_off + grow - lane) - col0) {
+            const uint32_t gii = __float_as_uint(p.qn[p.row_off + grow]);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) if (e == lane) v[e] = gii;
+          }
           uint32_t w0[16], w1[16];
+          float qv[32], qe[32];
           const float4* xn4 = reinterpret_cast<const float4*>(p.xn + col0 + c * 32);
           const float4* cv4 = reinterpret_cast<const float4*>(p.cv + col0 + c * 32);
 #pragma unroll
@@ -249,6 +320,8 @@ __device__ __forceinline__ void lg_body(const CUtensorMap& tmA0, const CUtensorM
               kc = fmaf(q0, ca[e2 * 2], fmaf(q1, ca[e2 * 2 + 1], kc));
               ke = fmaf(q0, ex0, fmaf(q1, ex1, ke));
               kg = fmaf(q0, g0, fmaf(q1, g1, kg));
+              qv[e] = q0; qv[e + 1] = q1;
+              qe[e] = q0 * ex0; qe[e + 1] = q1 * ex1;
             }
           }
           if (valid) {
@@ -258,9 +331,50 @@ __device__ __forceinline__ void lg_body(const CUtensorMap& tmA0, const CUtensorM
               *reinterpret_cast<uint4*>(p1 + c * 32 + x * 8) = make_uint4(w1[4 * x], w1[4 * x + 1], w1[4 * x + 2], w1[4 * x + 3]);
             }
           }
+          if (mirror) {
+            // k_ji = k_ij: the transposed tile of P (a warp writes 32 consecutive rows' entries of one column: 64 bytes)
+            // and the statistics of the rows j of the column block, summed over this CTA's 128 rows i
+            unsigned short* t0 = reinterpret_cast<unsigned short*>(p.P0) + (int64_t)(col0 + c * 32) * p.ldp + grow;
+            unsigned short* t1 = reinterpret_cast<unsigned short*>(p.P1) + (int64_t)(col0 + c * 32) * p.ldp + grow;
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              t0[(int64_t)e * p.ldp] = (unsigned short)(w0[e >> 1] & 0xFFFFu);
+              t0[(int64_t)(e + 1) * p.ldp] = (unsigned short)(w0[e >> 1] >> 16);
+              t1[(int64_t)e * p.ldp] = (unsigned short)(w1[e >> 1] & 0xFFFFu);
+              t1[(int64_t)(e + 1) * p.ldp] = (unsigned short)(w1[e >> 1] >> 16);
+            }
+            float t[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) t[e] = qv[e] * __uint_as_float(v[e]);
+            const float s_kg = warp_transpose_sum32(t, lane);
+            const float s_ke = warp_transpose_sum32(qe, lane);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) t[e] = qv[e] * ci;
+            const float s_kc = warp_transpose_sum32(t, lane);
+            const float s_rs = warp_transpose_sum32(qv, lane);
+            colbuf[q * LG_BN + c * 32 + lane] = make_float4(s_rs, s_kc, s_ke, s_kg);
+          }
         }
         if (valid)      // b = sum k r2 = -sum k e / cs
-          *reinterpret_cast<float4*>(p.scal + ((int64_t)nt * p.scal_stride + p.row_off + grow) * 4) = make_float4(rowsum, kc, -ke / cs, kg);
+          *reinterpret_cast<float4*>(p.scal + ((int64_t)(p.sym ? 2 * nt : nt) * p.scal_stride + p.row_off + grow) * 4) =
+              make_float4(rowsum, kc, -ke / cs, kg);
+        if (mirror) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+          for (int hcol = 0; hcol < 2; ++hcol) {
+            const int col = hcol * 128 + r;
+            float4 acc = colbuf[col];
+#pragma unroll
+            for (int wq = 1; wq < 4; ++wq) {
+              const float4 o = colbuf[wq * LG_BN + col];
+              acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+            }
+            if (col0 + col < p.m_rows)
+              *reinterpret_cast<float4*>(p.scal + ((int64_t)rb128 * p.scal_stride + col0 + col) * 4) =
+                  make_float4(acc.x, acc.y, -acc.z / cs, acc.w);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
       } else {
         float* o = p.O + (int64_t)s * p.o_split_stride + (int64_t)grow * p.ldo + col0;
 #pragma unroll 1
@@ -302,6 +416,11 @@ lg_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   lg_body<2>(tmA0, tmA1, tmB0, tmB1, p);
 }
 
+static bool lg_sym_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NSVGD_LARGE_SYM"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v != 0;
+}
 static int lg_ctas() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("NSVGD_LARGE_CTAS"); v = (e && atoi(e) == 1) ? 1 : 2; }
@@ -316,10 +435,12 @@ static int lg_launch(cudaStream_t st, int ctas, const __nv_bfloat16* A0, const _
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&mA1, A1, (uint64_t)kdim, (uint64_t)a_rows, (uint64_t)lda * 2, LG_BK, LG_BM));
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&mB0, B0, (uint64_t)kdim, (uint64_t)b_rows, (uint64_t)ldb * 2, LG_BK, (uint32_t)(LG_BN / ctas)));
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&mB1, B1, (uint64_t)kdim, (uint64_t)b_rows, (uint64_t)ldb * 2, LG_BK, (uint32_t)(LG_BN / ctas)));
-  prm.tiles_m = (int)ceil_div(prm.m_rows, LG_BM * ctas);
+  prm.tiles_m = (int)ceil_div(prm.sym ? a_rows : prm.m_rows, LG_BM * ctas);
   prm.group_m = ctas == 2 ? 4 : 8;
-  const int64_t total = (int64_t)prm.tiles_m * prm.tiles_n * prm.nsplit;
+  prm.ctas = ctas;
+  const int64_t total = prm.sym ? lg_sym_tiles(prm.tiles_m, prm.tiles_n, ctas) : (int64_t)prm.tiles_m * prm.tiles_n * prm.nsplit;
   NSVGD_REQUIRE(total < (1ll << 31), NSVGD_ERR_INVALID, "phi_large: too many tiles");
+  prm.total = (int)total;
   const int units = (int)std::min<int64_t>(total, std::max(1, device_sm_count() / ctas));
   if (ctas == 2) {
     NSVGD_PROPAGATE(ensure_dyn_smem((const void*)lg_gemm_pair_kernel, LgSmem<2>::BYTES));
@@ -410,8 +531,8 @@ int phi_large(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool
   const int nsplit = (int)ceil_div(n_pad, LG_NK);
   const int tiles_nx = (int)(n_pad / LG_BN);                 // 256-particle column tiles of the Gram
   const bool q_is_x = (a.Q == a.X && a.m == a.n && a.ldq == a.ldx);
-  // query rows per pair of launches: the two pieces of P (rows x n_pad bf16 each) stay within 1 GiB
-  const int64_t mc = std::min<int64_t>(round_up(a.m, 256), std::max<int64_t>(256, ((1ll << 30) / (n_pad * 4)) / 256 * 256));
+  // query rows per pair of launches: the two pieces of P (rows x n_pad bf16 each) stay within 4 GiB
+  const int64_t mc = std::min<int64_t>(round_up(a.m, 256), std::max<int64_t>(256, ((4ll << 30) / (n_pad * 4)) / 256 * 256));
   WsCarver w(ws, ws_bytes, dry);
   float* mu = w.take<float>((size_t)a.d);
   double* mpart = w.take<double>((size_t)colmean_partials(a.n, a.d));
@@ -431,7 +552,10 @@ int phi_large(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool
   __nv_bfloat16* P0 = w.take<__nv_bfloat16>((size_t)(mc * n_pad));
   __nv_bfloat16* P1 = w.take<__nv_bfloat16>((size_t)(mc * n_pad));
   float* O = w.take<float>((size_t)nsplit * a.m * ldo);
-  float* scal = w.take<float>((size_t)tiles_nx * a.m * 4);
+  // Q == X in one row chunk: the Gram / pair launch computes the tiles on or above the diagonal only and mirrors them
+  const bool sym = q_is_x && mc >= n_pad && lg_sym_enabled();
+  const int scal_parts = sym || dry ? 2 * tiles_nx : tiles_nx;
+  float* scal = w.take<float>((size_t)scal_parts * a.m * 4);
   double* partials = w.take<double>((size_t)(2 * epilogue_blocks(a.m)));
   uint32_t* err_flag = w.take<uint32_t>(64);
   if (need) *need = w.off;
@@ -456,12 +580,13 @@ int phi_large(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool
   for (int64_t i0 = 0; i0 < a.m; i0 += mc) {
     const int64_t mi = std::min<int64_t>(mc, a.m - i0);
     LgParams g{};
-    g.epi = LG_EPI_PAIR; g.tiles_n = tiles_nx; g.nsplit = 1;
+    g.epi = LG_EPI_PAIR; g.tiles_n = tiles_nx; g.nsplit = 1; g.sym = sym ? 1 : 0; g.diag = q_is_x ? 1 : 0;
     g.kb_total = g.kb_per_split = (int)ceil_div(ldk, LG_BK);
     g.m_rows = (int)mi; g.row_off = i0;
     g.qn = qn; g.xn = xn; g.cv = cv; g.h_dev = a.h_dev; g.P0 = P0; g.P1 = P1; g.ldp = n_pad; g.scal = scal; g.scal_stride = a.m;
     g.err_flag = err_flag;
-    NSVGD_PROPAGATE(lg_launch(st, ctas, Qb0 + i0 * ldk, Qb1 + i0 * ldk, mi, ldk, Xb0, Xb1, n_pad, ldk, ldk, g));
+    if (sym) NSVGD_CUDA(cudaMemsetAsync(scal, 0, (size_t)scal_parts * a.m * 4 * sizeof(float), st));   // slots no tile writes
+    NSVGD_PROPAGATE(lg_launch(st, ctas, Qb0 + i0 * ldk, Qb1 + i0 * ldk, sym ? n_pad : mi, ldk, Xb0, Xb1, n_pad, ldk, ldk, g));
     LgParams o{};
     o.epi = LG_EPI_STORE; o.tiles_n = (int)ceil_div(a.d, LG_BN); o.nsplit = nsplit;
     o.kb_total = (int)(n_pad / LG_BK); o.kb_per_split = (int)(LG_NK / LG_BK);
@@ -473,7 +598,7 @@ int phi_large(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool
   prof_end(0, st);
 
   EpilogueArgs e{};
-  e.form = 2; e.err_flag = err_flag; e.O = O; e.scal = scal; e.nsplit = nsplit; e.scal_parts = tiles_nx; e.m_pad = a.m; e.ldo = ldo;
+  e.form = 2; e.err_flag = err_flag; e.O = O; e.scal = scal; e.nsplit = nsplit; e.scal_parts = scal_parts; e.m_pad = a.m; e.ldo = ldo;
   e.dpad = 0; e.mu = mu;
   e.Q = a.Q; e.ldq = a.ldq; e.Sq = a.Sq; e.m = a.m; e.n = a.n; e.d = a.d; e.h_dev = a.h_dev;
   e.phi = a.phi; e.ldphi = a.ldphi; e.aux = nullptr; e.stats_dev = a.stats_dev; e.partials = partials;
