@@ -36,6 +36,8 @@ struct PairArgs {
   const float* h_dev; float h_host;      // bandwidth (device pointer wins)
   // HIST
   const SelectState* state; int pass; unsigned long long* hist; const uint32_t* run_flag;
+  float* dstore;                         // HIST, pass 0: also keep every distance (one 64 x 64 block per upper-triangular tile, +inf
+                                         // where i >= j) so that the later passes histogram the buffer instead of recomputing
   // KSUM / KSD
   double* partials; float diag_weight;
   float wsum;                            // KSD, ARD: sum_a 1/h_a^2 (host)
@@ -176,6 +178,19 @@ __global__ void __launch_bounds__(256) pair_tile_kernel(const PairArgs a) {
     const SelectState stt = *a.state;
     const int shift = pass_shift(a.pass);
     const unsigned int binmask = (unsigned int)pass_bins(a.pass) - 1u;
+    if (a.dstore) {      // tile t(I, J) of the row-major upper triangle (tile_row_start = 0, stride 1)
+      float* blk = a.dstore + (size_t)(I * tiles_j - I * (I - 1) / 2 + (J - I)) * (TILE * TILE);
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) {
+        float o[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int64_t gi = i0 + ty * 4 + ii, gj = j0 + tx * 4 + jj;
+          o[jj] = (gi < a.na && gj < a.nb && gi < gj) ? acc[ii][jj] : __int_as_float(0x7f800000);
+        }
+        *reinterpret_cast<float4*>(blk + (ty * 4 + ii) * TILE + tx * 4) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
@@ -467,9 +482,10 @@ int launch_select_advance_p2p(cudaStream_t st, const P2PComm& c, SelectState* s,
 
 int launch_pair_hist(cudaStream_t st, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last,
                      int64_t tile_row_start, int64_t tile_row_stride, const SelectState* state, int pass,
-                     uint64_t* hist, const uint32_t* run_flag) {
+                     uint64_t* hist, const uint32_t* run_flag, float* dstore) {
   NSVGD_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint64_t) * 2 * NSVGD_SELECT_BINS, st));
   PairArgs a{};
+  a.dstore = dstore;
   a.A = Z; a.na = n; a.lda = ldz; a.B = Z; a.nb = n; a.ldb = ldz; a.d = dz; a.w_last = w_last;
   a.symmetric = 1; a.tile_row_start = tile_row_start; a.tile_row_stride = tile_row_stride;
   a.state = state; a.pass = pass; a.hist = (unsigned long long*)hist; a.run_flag = run_flag;
@@ -536,7 +552,7 @@ extern "C" int nsvgd_median_hist_pass(void* stream, const float* Z, int64_t n, i
   NSVGD_REQUIRE(pass >= 0 && pass < NSVGD_SELECT_PASSES, NSVGD_ERR_INVALID, "median_hist_pass: bad pass %d", pass);
   NSVGD_REQUIRE(tile_row_stride >= 1 && tile_row_start >= 0, NSVGD_ERR_INVALID, "median_hist_pass: bad tile row partition");
   return launch_pair_hist((cudaStream_t)stream, Z, n, dz, ldz, w_last, tile_row_start, tile_row_stride,
-                          (const SelectState*)state_dev, pass, hist_dev, nullptr);
+                          (const SelectState*)state_dev, pass, hist_dev, nullptr, nullptr);
 }
 
 extern "C" int nsvgd_median_advance(void* stream, void* state_dev, const uint64_t* hist_dev, int pass) {
@@ -563,9 +579,22 @@ extern "C" int nsvgd_median_finish(void* stream, const void* state_dev, int64_t 
   return NSVGD_OK;
 }
 
-// workspace: [state | hist | Z (literal) | fast-path scratch]
+// Shapes the tensor-core filter does not take (dz > 128, or n < 8192) with enough coordinates that a distance costs more
+// than a 4-byte store and two 4-byte loads: ONE pass of the exact SIMT pair engine computes every distance, histograms the
+// first radix digit and keeps the values; the other two radix passes histogram the buffer (HBM-bound, < 1 % of a compute
+// pass at d = 4096).  The values are the same fp32 numbers, so the result is bit-identical to the 3-pass select.
+static int64_t median_store_values(int64_t n, int64_t dz) {
+  if (median_fast_supported(n, dz) || dz <= 32 || n < 256) return 0;
+  const int64_t t = ceil_div(n, TILE);
+  const int64_t vals = t * (t + 1) / 2 * (TILE * TILE);
+  const char* env = getenv("NSVGD_MEDIAN_STORE");
+  if (env && env[0] == '0') return 0;
+  return vals <= (1ll << 31) ? vals : 0;
+}
+
+// workspace: [state | hist | Z (literal) | fast-path scratch | stored distances]
 static void median_ws_layout(int64_t n, int64_t d, int mode, WsCarver& w, void** state, uint64_t** hist, float** Z,
-                             void** fast, size_t* fast_bytes) {
+                             void** fast, size_t* fast_bytes, float** dstore = nullptr) {
   *state = w.take<char>(NSVGD_SELECT_STATE_BYTES);
   *hist = w.take<uint64_t>(2 * NSVGD_SELECT_BINS);
   *Z = nullptr;
@@ -576,6 +605,9 @@ static void median_ws_layout(int64_t n, int64_t d, int mode, WsCarver& w, void**
     *fast_bytes = median_fast_workspace(n, dz);
     *fast = w.take<char>(*fast_bytes, 1024);
   }
+  const int64_t sv = median_store_values(n, dz);
+  float* ds = sv ? w.take<float>((size_t)sv, 1024) : nullptr;
+  if (dstore) *dstore = ds;
 }
 
 namespace nsvgd {
@@ -598,8 +630,8 @@ extern "C" int nsvgd_median_h_f32(void* stream, const float* X, int64_t n, int64
   NSVGD_REQUIRE(mode >= 0 && mode <= 2, NSVGD_ERR_INVALID, "median_h: bad mode %d", mode);
   cudaStream_t st = (cudaStream_t)stream;
   WsCarver w(ws, ws_bytes);
-  void* state; uint64_t* hist; float* Z; void* fast; size_t fast_bytes;
-  median_ws_layout(n, d, mode, w, &state, &hist, &Z, &fast, &fast_bytes);
+  void* state; uint64_t* hist; float* Z; void* fast; size_t fast_bytes; float* dstore;
+  median_ws_layout(n, d, mode, w, &state, &hist, &Z, &fast, &fast_bytes, &dstore);
   NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "median_h: workspace too small (%zu < %zu)", ws_bytes, w.off);
   int64_t dz; float w_last;
   prof_begin(3, st);
@@ -617,8 +649,13 @@ extern "C" int nsvgd_median_h_f32(void* stream, const float* X, int64_t n, int64
     median_ranks_host(n, mode, &r_lo, &r_hi);
     NSVGD_PROPAGATE(median_fast(st, P, n, dz, ldp, w_last, r_lo, r_hi, 0, 1, (SelectState*)state, hist, fast, fast_bytes));
   } else {
+    const int64_t sv = dstore ? median_store_values(n, dz) : 0;
     for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
-      NSVGD_PROPAGATE(launch_pair_hist(st, P, n, dz, ldp, w_last, 0, 1, (const SelectState*)state, pass, hist, nullptr));
+      if (sv && pass > 0)
+        NSVGD_PROPAGATE(launch_buffer_hist(st, dstore, nullptr, 0, 1, 0, (uint32_t)sv, (const SelectState*)state, pass, hist, nullptr));
+      else
+        NSVGD_PROPAGATE(launch_pair_hist(st, P, n, dz, ldp, w_last, 0, 1, (const SelectState*)state, pass, hist, nullptr,
+                                         sv ? dstore : nullptr));
       NSVGD_PROPAGATE(launch_select_advance(st, (SelectState*)state, hist, pass, nullptr));
     }
   }

@@ -63,7 +63,8 @@ struct LgParams {
                                            // writes its transpose (P^T and the column statistics).  slot = 2 * tile_n for the row
                                            // statistics, the 128-row block index of the tile's rows for the mirrored ones; else tile_n
   int ctas;
-  int diag;                                // Q == X: entry (i, i) is the particle against itself -> g_ii = |xc_i|^2 exactly (k_ii = 1)
+  int64_t diag_off;                        // >= 0: the query rows ARE the particles diag_off, diag_off + 1, ... (Q == X, or the row block of a
+                                           // row-sharded rank): entry (i, diag_off + i) is a particle against itself -> g = |xc_i|^2 exactly
   // EPI_STORE
   float* O; int64_t ldo; int64_t o_split_stride; int n_cols;
   uint32_t* err_flag;
@@ -291,10 +292,16 @@ __device__ __forceinline__ void lg_body(const CUtensorMap& tmA0, const CUtensorM
           // The accumulator of a diagonal entry grows monotonically to |xc_i|^2 over 3 d / 16 MMAs and picks up the TMEM
           // truncation bias (2^-25 per MMA): at d = 4096 that is 2e-3 in g_ii, i.e. k_ii = 1 - 2e-4 where the
           // reference has exp(0) = 1.  The entry is known in closed form, so it is set, not computed.
-          if (p.diag && c * 32 == (int)(p.row_off + grow - lane) - col0) {
-            const uint32_t gii = __float_as_uint(p.qn[p.row_off + grow]);
+          if (p.diag_off >= 0) {
+            const int64_t jd = p.diag_off + p.row_off + grow - col0 - c * 32;      // column of this row's own particle in the chunk
+            if (__any_sync(0xffffffffu, jd >= 0 && jd < 32)) {
+              const uint32_t gii = __float_as_uint((valid || p.sym) ? p.qn[p.row_off + grow] : 0.f);
+              const int jdi = (int)jd;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) if (e == lane) v[e] = gii;
+              for (int e = 0; e < 32; ++e)      // predicated selects on named registers (a plain `if (e == jdi) v[e] = ..` becomes a
+                                                // dynamically indexed local-memory array)
+                asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\tselp.b32 %0, %3, %0, p;\n\t}" : "+r"(v[e]) : "r"(jdi), "r"(e), "r"(gii));
+            }
           }
           uint32_t w0[16], w1[16];
           float qv[32], qe[32];
@@ -530,7 +537,12 @@ int phi_large(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool
   const int64_t ldo = round_up(a.d, 4);
   const int nsplit = (int)ceil_div(n_pad, LG_NK);
   const int tiles_nx = (int)(n_pad / LG_BN);                 // 256-particle column tiles of the Gram
-  const bool q_is_x = (a.Q == a.X && a.m == a.n && a.ldq == a.ldx);
+  // the queries are a row range of the particle array (the SVGD step: all of it; a row-sharded rank: its block of the
+  // gathered array): their pieces and norms are the particles', and the pairs (i, diag_off + i) are self pairs
+  int64_t diag_off = -1;
+  if (a.ldq == a.ldx && a.Q >= a.X && (a.Q - a.X) % a.ldx == 0 && (a.Q - a.X) / a.ldx + a.m <= a.n) diag_off = (a.Q - a.X) / a.ldx;
+  const bool q_in_x = diag_off >= 0;
+  const bool q_is_x = q_in_x && a.m == a.n;
   // query rows per pair of launches: the two pieces of P (rows x n_pad bf16 each) stay within 4 GiB
   const int64_t mc = std::min<int64_t>(round_up(a.m, 256), std::max<int64_t>(256, ((4ll << 30) / (n_pad * 4)) / 256 * 256));
   WsCarver w(ws, ws_bytes, dry);
@@ -544,7 +556,7 @@ int phi_large(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool
   float* cv = w.take<float>((size_t)n_pad);
   __nv_bfloat16 *Qb0 = Xb0, *Qb1 = Xb1;
   float* qn = xn;
-  if (!q_is_x || dry) {
+  if (!q_in_x || dry) {
     Qb0 = w.take<__nv_bfloat16>((size_t)(a.m * ldk));
     Qb1 = w.take<__nv_bfloat16>((size_t)(a.m * ldk));
     qn = w.take<float>((size_t)a.m);
@@ -571,7 +583,8 @@ int phi_large(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool
   large_wt_kernel<<<dim3((unsigned)(n_pad / 64), (unsigned)ceil_div(a.d, 32)), 256, 0, st>>>(a.X, a.S, a.n, a.d, a.ldx, mu, a.h_dev,
                                                                                           Wt0, Wt1, n_pad);
   NSVGD_LAUNCH_CHECK();
-  if (!q_is_x) {
+  if (q_in_x) { Qb0 = Xb0 + diag_off * ldk; Qb1 = Xb1 + diag_off * ldk; qn = xn + diag_off; }
+  else {
     large_prep_kernel<<<(unsigned)ceil_div(a.m * 32, 256), 256, 0, st>>>(a.Q, nullptr, a.m, a.m, a.d, a.ldq, ldk, mu, Qb0, Qb1, qn,
                                                                         nullptr);
     NSVGD_LAUNCH_CHECK();
@@ -580,7 +593,7 @@ int phi_large(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool
   for (int64_t i0 = 0; i0 < a.m; i0 += mc) {
     const int64_t mi = std::min<int64_t>(mc, a.m - i0);
     LgParams g{};
-    g.epi = LG_EPI_PAIR; g.tiles_n = tiles_nx; g.nsplit = 1; g.sym = sym ? 1 : 0; g.diag = q_is_x ? 1 : 0;
+    g.epi = LG_EPI_PAIR; g.tiles_n = tiles_nx; g.nsplit = 1; g.sym = sym ? 1 : 0; g.diag_off = diag_off;
     g.kb_total = g.kb_per_split = (int)ceil_div(ldk, LG_BK);
     g.m_rows = (int)mi; g.row_off = i0;
     g.qn = qn; g.xn = xn; g.cv = cv; g.h_dev = a.h_dev; g.P0 = P0; g.P1 = P1; g.ldp = n_pad; g.scal = scal; g.scal_stride = a.m;

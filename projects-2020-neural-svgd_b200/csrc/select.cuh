@@ -136,7 +136,7 @@ int launch_select_advance(cudaStream_t st, SelectState* s, const uint64_t* hist,
 int launch_select_advance_p2p(cudaStream_t st, const P2PComm& c, SelectState* s, uint64_t* hist, int pass, const uint32_t* run_flag);
 int launch_pair_hist(cudaStream_t st, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last,
                      int64_t tile_row_start, int64_t tile_row_stride, const SelectState* state, int pass,
-                     uint64_t* hist, const uint32_t* run_flag);
+                     uint64_t* hist, const uint32_t* run_flag, float* dstore = nullptr);
 void median_ranks_host(int64_t n, int mode, long long* r_lo, long long* r_hi);
 
 // median_tc.cu: tensor-core filtered exact median.  Returns NSVGD_ERR_UNSUPPORTED when the shape is

@@ -150,7 +150,10 @@ class ShardedSVGD:
                 S_all = self.all_gather_rows(S_local, "S")
             h = self.median_heuristic(X_all)
             cur.wait_stream(self._side)
-        phi, stats = self.engine.phistar(X_local, X_all, S_all, h, Sq=S_local, stats=True)
+        # the queries as a row range OF the gathered array: the d > 128 path then reuses the particles' operand pieces and
+        # knows which pairs are self pairs (csrc/phi_large.cu)
+        Xq = X_all[self.r0:self.r1] if X_all.is_cuda and X_all.shape[0] == self.n else X_local
+        phi, stats = self.engine.phistar(Xq, X_all, S_all, h, Sq=S_local, stats=True)
         if self.comm is not None:
             step_aux, grads = self.engine.apply_update_p2p(self.comm, X_local, phi, stats, lr, scaled, lambda_reg,
                                                            want_grads=want_grads)

@@ -54,3 +54,14 @@ ref = engine.phistar(X[:512].contiguous(), X, S, h, path="generic")
 got = engine.phistar(X[:512].contiguous(), X, S, h, path="large")
 print("cfg5 slice (512 rows) large(rect) vs large(square) rel_fro", float((got - phi[:512]).norm() / got.norm()),
       "generic vs float64", float((ref.double() - ref64).norm() / ref64.norm()), flush=True)
+
+# the exact median bandwidth at cfg5 (literal mode): one exact pass + two buffer passes vs three recomputing passes
+for env in (None, "0"):
+    if env is None: os.environ.pop("NSVGD_MEDIAN_STORE", None)
+    else: os.environ["NSVGD_MEDIAN_STORE"] = env
+    hh = engine.median_heuristic(X)
+    torch.cuda.synchronize()
+    a.record()
+    hh = engine.median_heuristic(X)
+    b.record(); torch.cuda.synchronize()
+    print(f"cfg5 median_heuristic (NSVGD_MEDIAN_STORE={env}): {a.elapsed_time(b):.2f} ms, h = {hh.item():.9g}", flush=True)

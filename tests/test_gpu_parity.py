@@ -53,6 +53,28 @@ def test_bandwidth_bit_exact_vs_oracle(n, d, seed, mode):
     assert np.float32(got).tobytes() == np.float32(want).tobytes(), (got, want)
 
 
+@pytest.mark.parametrize("n,d,seed", [(1000, 50, 6), (777, 128, 8), (1500, 200, 9), (700, 515, 10), (300, 1030, 11)])
+@pytest.mark.parametrize("mode", so.MEDIAN_MODES)
+def test_bandwidth_stored_distance_select(n, d, seed, mode, monkeypatch):
+    """shapes outside the tensor-core filter (d > 128 or n < 8192) with d > 32: ONE exact pass keeps the distances and the
+    later radix passes histogram the buffer -- bit-identical to the oracle and to the 3-pass recomputing select; NaN and
+    all-equal inputs behave the same."""
+    from nsvgd import engine
+    rng = np.random.default_rng(seed)
+    X = (rng.standard_normal((n, d)) * 0.9 + 0.3).astype(np.float32)
+    X[5] = X[2]
+    want = so.median_heuristic(X, mode)
+    got = engine.median_heuristic(dev(X), mode).cpu().numpy()[0]
+    monkeypatch.setenv("NSVGD_MEDIAN_STORE", "0")
+    three = engine.median_heuristic(dev(X), mode).cpu().numpy()[0]
+    monkeypatch.delenv("NSVGD_MEDIAN_STORE")
+    assert np.float32(got).tobytes() == np.float32(want).tobytes() == np.float32(three).tobytes(), (got, want, three)
+    if mode == "offdiag":
+        X[11, 2] = np.nan
+        assert np.isnan(engine.median_heuristic(dev(X), mode).item())
+        assert engine.median_heuristic(dev(np.ones((n, d), np.float32)), mode).item() == 0.0
+
+
 def test_bandwidth_nan_and_zero():
     from nsvgd import engine
     X = np.random.default_rng(0).standard_normal((70, 3)).astype(np.float32)
@@ -101,8 +123,60 @@ PATH_CASES = [
     ("generic", 700, 50, 5.0), ("generic", 300, 3, 1.3), ("generic", 129, 200, 12.0), ("generic", 64, 1030, 30.0),
     ("tc", 2048, 128, 8.0), ("tc", 1500, 100, 7.0), ("tc", 1024, 64, 5.5), ("tc", 1111, 50, 5.0), ("tc", 4096, 128, 3.0),
     ("tc", 2048, 128, 30.0), ("tc", 1500, 100, 40.0),      # wide kernels around the adaptive-precision threshold (max|xc|^2/h^2 = 0.21 / 0.09; <= 0.1 -> ONE Gram pass)
-    ("large", 1500, 200, 12.0), ("large", 1100, 515, 20.0), ("large", 4500, 130, 9.0),
+    ("large", 1500, 200, 12.0), ("large", 1100, 515, 20.0), ("large", 4500, 130, 9.0), ("large", 2100, 1000, 25.0),
 ]
+
+
+def test_large_path_bnn_regime_self_term_dominated():
+    """BASELINE configs[4] regime at a size the fp64 oracle finishes in seconds: d = 4096, weights ~ 0.15 N(0, 1), the
+    bandwidth of the median heuristic (h^2 ~ |x|^2 / ln n), so every off-diagonal k is ~ e^-7 and the self term k_ii = 1
+    carries half of each row.  The diagonal Gram entries accumulate monotonically over 768 MMAs and would pick up the TMEM
+    truncation bias (k_ii = 1 - 2e-4) -- the kernel sets them in closed form.  Square (symmetric tiles + mirrored
+    transposes, 5 column tiles) against the oracle, and the rectangular form on the same rows."""
+    from nsvgd import engine
+    rng = np.random.default_rng(11)
+    n, d = 1200, 4096
+    X = (rng.standard_normal((n, d)) * 0.15 + 0.01).astype(np.float32)
+    S = (rng.standard_normal((n, d)) * 0.5).astype(np.float32)
+    h = float(np.sqrt(0.5 * 2 * d * 0.15 ** 2 / np.log(n + 1)))
+    ref = so.phistar(X, X, S, h)
+    Xd, Sd = dev(X), dev(S)
+    phi, st = engine.phistar(Xd, Xd, Sd, h, Sq=Sd, stats=True, path="large")
+    assert rel_fro(phi.cpu(), ref) < 0.5 * TOL, rel_fro(phi.cpu(), ref)
+    assert max_row_rel(phi.cpu(), ref) < TOL
+    st = st.cpu().numpy()
+    assert st[0] / n == pytest.approx(so.stein_discrepancy_phistar(X, S, h), rel=TOL)
+    assert st[1] / n == pytest.approx(so.l2_norm_squared(ref), rel=TOL)
+    # the row block of a row-sharded rank: a row range OF the particle array (self pairs at column 300 + i)
+    blk = engine.phistar(Xd[300:811], Xd, Sd, h, path="large")
+    assert rel_fro(blk.cpu(), ref[300:811]) < 0.5 * TOL, rel_fro(blk.cpu(), ref[300:811])
+    Q = (rng.standard_normal((300, d)) * 0.15).astype(np.float32)
+    assert rel_fro(engine.phistar(dev(Q), Xd, Sd, h, path="large").cpu(), so.phistar(Q, X, S, h)) < TOL
+
+
+def test_large_path_variants_agree():
+    """the single-CTA (M = 128) kernel and the full-rectangle (non-mirrored) tile enumeration against the default
+    (CTA pairs, symmetric tiles); the switches are read once per process, hence the subprocesses."""
+    import os, subprocess, sys
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, 'projects-2020-neural-svgd_b200')\n"
+        "from nsvgd import engine\n"
+        "rng = np.random.default_rng(4)\n"
+        "X = torch.tensor((rng.standard_normal((2300, 700)) * 0.3 + 0.2).astype(np.float32)).cuda()\n"
+        "S = torch.tensor((rng.standard_normal((2300, 700)) * 0.5).astype(np.float32)).cuda()\n"
+        "phi, st = engine.phistar(X, X, S, 7.0, Sq=S, stats=True, path='large')\n"
+        "np.save(sys.argv[1], np.concatenate([phi.cpu().numpy().ravel(), st.cpu().numpy().astype(np.float32)]))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for i, env in enumerate(({}, {"NSVGD_LARGE_CTAS": "1"}, {"NSVGD_LARGE_SYM": "0"}, {"NSVGD_LARGE_CTAS": "1", "NSVGD_LARGE_SYM": "0"})):
+        out = f"/tmp/nsvgd_large_variant_{os.getpid()}_{i}.npy"
+        subprocess.run([sys.executable, "-c", code, out], check=True, cwd=root, env={**os.environ, **env}, timeout=300)
+        outs.append(np.load(out)); os.remove(out)
+    for o in outs[1:]:
+        assert not np.isnan(o).any()
+        assert rel_fro(o[:-4], outs[0][:-4]) < 2e-6
+        np.testing.assert_allclose(o[-4:], outs[0][-4:], rtol=2e-6)
 
 
 @pytest.mark.parametrize("path,n,d,h", PATH_CASES)
@@ -116,7 +190,7 @@ def test_phi_paths_vs_oracle(path, n, d, h):
     Q = (np.random.default_rng(1).standard_normal((m, d)) * 0.9 + 0.4).astype(np.float32)
     Xd, Sd, Qd = dev(X), dev(S), dev(Q)
     ref, ref_aux = so.phistar(X, X, S, h, aux=True)
-    if path == "large":       # cuBLAS path: COMBINED form only (the aux split of d > 128 is served by "generic")
+    if path == "large":       # hand-written tcgen05 GEMM pair (csrc/phi_large.cu): COMBINED form only (the aux split of d > 128 is served by "generic")
         with pytest.raises(NotImplementedError):
             engine.phistar(Xd, Xd, Sd, h, Sq=Sd, aux=True, stats=True, path=path)
         phi, stats = engine.phistar(Xd, Xd, Sd, h, Sq=Sd, stats=True, path=path)
