@@ -33,8 +33,7 @@ constexpr int MF_THREADS = 64 + 32 * MF_CLS_WARPS;
 constexpr int MF_NVEC = 4;                               // ring of per-tile |z_j|^2 vectors
 constexpr int MF_STAGE = 128;                            // per-warp staging buffer (uncertain pairs) in shared memory
 constexpr uint32_t MF_SAMPLES = 1u << 22;
-constexpr int MF_NSEG = 64;          // independent append segments (one atomic counter per 128-byte line)
-constexpr int MF_CSTRIDE = 32;       // counter stride in uint32
+// MF_NSEG (independent append segments, one atomic counter per 128-byte line) and MF_CSTRIDE (counter stride in uint32): select.cuh
 // error radius of the filter relative to |z_i|^2 + |z_j|^2: bf16 2-piece products 2^-15, norms 2^-17,
 // defined-order rounding of the exact value 2^-16, centring 2^-22  =>  < 2^-14.2; kappa = 2^-13.
 constexpr float MF_KAPPA = 1.220703125e-4f;
@@ -50,13 +49,7 @@ static uint32_t cand_capacity(int64_t n) {
   return (uint32_t)std::min<double>(P / 96.0 + (double)(1 << 22), 4.0e9);
 }
 
-// scratch of one fused 3-pass select (fused_select_kernel): one global histogram per pass + the grid-wide hand-shake
-struct FusedSelScratch {
-  uint32_t hist[NSVGD_SELECT_PASSES][2 * NSVGD_SELECT_BINS];   // 32-bit counts (a value buffer holds < 2^32 values over all ranks):
-                                                               // two counts per 64-bit word of the peer-memory exchange
-  uint32_t done[4];      // CTAs that have flushed their histogram of pass p
-  uint32_t flag[4];      // set by the last CTA of pass p once the select state has advanced
-};
+// FusedSelScratch (scratch of one fused 3-pass select): select.cuh
 
 struct FastWs {
   FusedSelScratch* sel;  // [2]: bracket select, candidate select (inside the zero block)
@@ -873,11 +866,26 @@ __global__ void __launch_bounds__(64) fast_pack_resolve_kernel(const P2PComm c, 
   }
 }
 
+// single-GPU pack + resolve for the large-d filter (median_large.cu)
+int launch_fast_pack_resolve(cudaStream_t st, FastMedState* fs, const uint32_t* list_counts, uint32_t list_cap, uint32_t* cand_counts,
+                             uint32_t cand_cap, const uint32_t* err_flag, SelectState* main_state, SelectState* cand_state,
+                             long long* red);
+
 __global__ void fast_commit_kernel(const FastMedState* fs, const SelectState* cs, SelectState* main_state) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (fs->fallback) return;     // the conditional SIMT passes will resolve main_state instead
   for (int t = 0; t < 2; ++t) main_state->value[t] = main_state->is_zero[t] ? 0.f : cs->value[t];
   main_state->done = 1;
+}
+
+int launch_fast_pack_resolve(cudaStream_t st, FastMedState* fs, const uint32_t* list_counts, uint32_t list_cap, uint32_t* cand_counts,
+                             uint32_t cand_cap, const uint32_t* err_flag, SelectState* main_state, SelectState* cand_state,
+                             long long* red) {
+  P2PComm c{};
+  c.rank = 0; c.world = 1;
+  fast_pack_resolve_kernel<<<1, 64, 0, st>>>(c, 1, fs, list_counts, list_cap, cand_counts, cand_cap, err_flag, main_state, cand_state, red);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
 }
 
 // ---------------------------------------------------------------------------- fused 3-pass radix select over a value buffer
@@ -1004,7 +1012,7 @@ __global__ void __launch_bounds__(256, 4) fused_select_kernel(const float* __res
   }
 }
 
-static int launch_fused_select(cudaStream_t st, const float* vals, const uint32_t* counts_dev, int count_stride, int nseg,
+int launch_fused_select(cudaStream_t st, const float* vals, const uint32_t* counts_dev, int count_stride, int nseg,
                                uint32_t seg_cap, uint32_t v_begin, uint32_t v_end, SelectState* state, FusedSelScratch* sc,
                                const P2PComm* comm, int final_mode, FastMedState* fs, SelectState* main_state, int l_is_zero,
                                int u_is_inf) {

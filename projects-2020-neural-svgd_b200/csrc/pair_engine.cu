@@ -584,7 +584,7 @@ extern "C" int nsvgd_median_finish(void* stream, const void* state_dev, int64_t 
 // first radix digit and keeps the values; the other two radix passes histogram the buffer (HBM-bound, < 1 % of a compute
 // pass at d = 4096).  The values are the same fp32 numbers, so the result is bit-identical to the 3-pass select.
 static int64_t median_store_values(int64_t n, int64_t dz) {
-  if (median_fast_supported(n, dz) || dz <= 32 || n < 256) return 0;
+  if (median_fast_supported(n, dz) || median_large_supported(n, dz) || dz <= 32 || n < 256) return 0;
   const int64_t t = ceil_div(n, TILE);
   const int64_t vals = t * (t + 1) / 2 * (TILE * TILE);
   const char* env = getenv("NSVGD_MEDIAN_STORE");
@@ -592,7 +592,7 @@ static int64_t median_store_values(int64_t n, int64_t dz) {
   return vals <= (1ll << 31) ? vals : 0;
 }
 
-// workspace: [state | hist | Z (literal) | fast-path scratch | stored distances]
+// workspace: [state | hist | Z (literal) | fast-path scratch (d <= 128: median_tc.cu, d > 128: median_large.cu) | stored distances]
 static void median_ws_layout(int64_t n, int64_t d, int mode, WsCarver& w, void** state, uint64_t** hist, float** Z,
                              void** fast, size_t* fast_bytes, float** dstore = nullptr) {
   *state = w.take<char>(NSVGD_SELECT_STATE_BYTES);
@@ -603,6 +603,9 @@ static void median_ws_layout(int64_t n, int64_t d, int mode, WsCarver& w, void**
   *fast = nullptr; *fast_bytes = 0;
   if (median_fast_supported(n, dz)) {
     *fast_bytes = median_fast_workspace(n, dz);
+    *fast = w.take<char>(*fast_bytes, 1024);
+  } else if (median_large_supported(n, dz)) {
+    *fast_bytes = median_large_workspace(n, dz);
     *fast = w.take<char>(*fast_bytes, 1024);
   }
   const int64_t sv = median_store_values(n, dz);
@@ -647,7 +650,16 @@ extern "C" int nsvgd_median_h_f32(void* stream, const float* X, int64_t n, int64
     // bracket misses (probability ~1e-9) or a candidate list overflows (massive ties)
     long long r_lo, r_hi;
     median_ranks_host(n, mode, &r_lo, &r_hi);
-    NSVGD_PROPAGATE(median_fast(st, P, n, dz, ldp, w_last, r_lo, r_hi, 0, 1, (SelectState*)state, hist, fast, fast_bytes));
+    const bool aligned = ldp % 4 == 0 && (((uintptr_t)P) & 15) == 0;
+    if (median_fast_supported(n, dz))
+      NSVGD_PROPAGATE(median_fast(st, P, n, dz, ldp, w_last, r_lo, r_hi, 0, 1, (SelectState*)state, hist, fast, fast_bytes));
+    else if (aligned)
+      NSVGD_PROPAGATE(median_large(st, P, n, dz, ldp, w_last, r_lo, r_hi, (SelectState*)state, hist, fast, fast_bytes));
+    else
+      for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {      // unaligned rows: the recomputing 3-pass select
+        NSVGD_PROPAGATE(launch_pair_hist(st, P, n, dz, ldp, w_last, 0, 1, (const SelectState*)state, pass, hist, nullptr));
+        NSVGD_PROPAGATE(launch_select_advance(st, (SelectState*)state, hist, pass, nullptr));
+      }
   } else {
     const int64_t sv = dstore ? median_store_values(n, dz) : 0;
     for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {

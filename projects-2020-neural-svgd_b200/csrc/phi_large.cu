@@ -23,6 +23,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "select.cuh"
 #include "tc_common.cuh"
 
 namespace nsvgd {
@@ -33,7 +34,7 @@ constexpr int LG_BM = 128, LG_BN = 256, LG_BK = 64;
 constexpr int64_t LG_NK = 4096;          // particles per accumulation run of the second GEMM
 constexpr int LG_THREADS = 192;          // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr uint32_t LG_TMEM_COLS = 512;   // two 128 x 256 fp32 accumulators
-enum { LG_EPI_PAIR = 0, LG_EPI_STORE = 1 };
+enum { LG_EPI_PAIR = 0, LG_EPI_STORE = 1, LG_EPI_CLASSIFY = 2 };
 
 template <int CTAS>
 struct LgSmem {
@@ -67,6 +68,10 @@ struct LgParams {
                                            // row-sharded rank): entry (i, diag_off + i) is a particle against itself -> g = |xc_i|^2 exactly
   // EPI_STORE
   float* O; int64_t ldo; int64_t o_split_stride; int n_cols;
+  // EPI_CLASSIFY (median filter for d > 128, median_large.cu): symmetric tiles, pairs i < j < n_valid; xn = |z|^2
+  FastMedState* fs;                        // bracket [L, U] (read), below (atomic), overflow -> err_flag
+  unsigned short* tlist; uint32_t* tcount; uint32_t tcap;   // per 128 x 256 CTA tile: the uncertain pairs as (row << 8 | column)
+  float kappa_g, kappa_d; int n_valid;
   uint32_t* err_flag;
 };
 
@@ -382,6 +387,60 @@ __device__ __forceinline__ void lg_body(const CUtensorMap& tmA0, const CUtensorM
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
+      } else if (p.epi == LG_EPI_CLASSIFY) {
+        // d~ = |z_i|^2 + |z_j|^2 - 2 g~ against the bracket with the rigorous radius eps = kg N2 + kd (d~ + kg N2), N2 = |z_i|^2 + |z_j|^2:
+        // certainly below L -> counted, certainly above U -> dropped, else listed for the defined-order evaluation
+        uint32_t* ucount = reinterpret_cast<uint32_t*>(smem + L::OFF_COL);
+        const int rb128 = mt * CTAS + (int)rank;
+        const size_t tile_id = (size_t)rb128 * p.tiles_n + nt;
+        unsigned short* tl = p.tlist + tile_id * p.tcap;
+        if (r == 0) *ucount = 0u;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const float Lv = p.fs->L, Uv = p.fs->U;
+        const float zi = p.xn[grow];
+        const float kt = p.kappa_g * (1.f + p.kappa_d);
+        uint32_t below = 0;
+#pragma unroll 1
+        for (int c = 0; c < LG_BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_wait_ld();
+          if (c == LG_BN / 32 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(tempty_remote + as * 8); else mbar_arrive(&tempty[as]); }
+          }
+          const float4* xn4 = reinterpret_cast<const float4*>(p.xn + col0 + c * 32);
+#pragma unroll
+          for (int e4 = 0; e4 < 8; ++e4) {
+            const float4 xs = __ldg(xn4 + e4);
+            const float xa[4] = {xs.x, xs.y, xs.z, xs.w};
+#pragma unroll
+            for (int e1 = 0; e1 < 4; ++e1) {
+              const int e = e4 * 4 + e1;
+              const int gj = col0 + c * 32 + e;
+              const float n2 = zi + xa[e1];
+              const float dt = fmaf(-2.f, __uint_as_float(v[e]), n2);
+              const float eps = fmaf(p.kappa_d, dt, kt * n2);
+              const bool ok = grow < gj && gj < p.n_valid;
+              const bool is_below = dt + eps < Lv;
+              const bool is_above = dt - eps > Uv;
+              if (ok && is_below) ++below;
+              if (ok && !is_below && !is_above) {
+                const uint32_t pos = atomicAdd(ucount, 1u);
+                if (pos < p.tcap) tl[pos] = (unsigned short)((r << 8) | (c * 32 + e));
+              }
+            }
+          }
+        }
+        below = __reduce_add_sync(0xffffffffu, below);
+        if (lane == 0 && below) atomicAdd(&p.fs->below, (unsigned long long)below);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (r == 0) {
+          const uint32_t cnt = *ucount;
+          p.tcount[tile_id] = min(cnt, p.tcap);
+          if (cnt > p.tcap) atomicExch(p.err_flag, 0x40000000u);      // list overflow (massive ties): the exact SIMT select takes over
+        }
       } else {
         float* o = p.O + (int64_t)s * p.o_split_stride + (int64_t)grow * p.ldo + col0;
 #pragma unroll 1
@@ -459,6 +518,21 @@ static int lg_launch(cudaStream_t st, int ctas, const __nv_bfloat16* A0, const _
   NSVGD_LAUNCH_CHECK();
   return NSVGD_OK;
 }
+
+// median filter for d > 128 (median_large.cu): one symmetric Gram launch with the classify epilogue
+int lg_launch_classify(cudaStream_t st, const void* Zb0, const void* Zb1, int64_t n, int64_t n_pad, int64_t ldk, const float* zn,
+                       FastMedState* fs, unsigned short* tlist, uint32_t* tcount, uint32_t tcap, float kappa_g, float kappa_d,
+                       uint32_t* err_flag) {
+  LgParams g{};
+  g.epi = LG_EPI_CLASSIFY; g.tiles_n = (int)(n_pad / LG_BN); g.nsplit = 1; g.sym = 1; g.diag_off = -1;
+  g.kb_total = g.kb_per_split = (int)ceil_div(ldk, LG_BK);
+  g.m_rows = (int)n_pad; g.row_off = 0;
+  g.xn = zn; g.fs = fs; g.tlist = tlist; g.tcount = tcount; g.tcap = tcap; g.kappa_g = kappa_g; g.kappa_d = kappa_d; g.n_valid = (int)n;
+  g.err_flag = err_flag;
+  return lg_launch(st, lg_ctas(), (const __nv_bfloat16*)Zb0, (const __nv_bfloat16*)Zb1, n_pad, ldk, (const __nv_bfloat16*)Zb0,
+                   (const __nv_bfloat16*)Zb1, n_pad, ldk, ldk, g);
+}
+int lg_tile_rows() { return LG_BM; }
 
 // one warp per row: centred bf16 pieces, |xc|^2 and c_j = s_j . xc_j; rows in [n, rows_pad) are zero particles with
 // |xc|^2 = 1e30, which makes their k underflow to exactly 0

@@ -147,6 +147,33 @@ int median_fast(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t 
                 long long r_hi, int64_t tile_row_start, int64_t tile_row_stride, SelectState* main_state, uint64_t* hist,
                 void* ws, size_t ws_bytes);
 
+// shared by the two filtered selects (median_tc.cu, median_large.cu)
+constexpr int MF_NSEG = 64;          // independent append segments (one atomic counter per 128-byte line)
+constexpr int MF_CSTRIDE = 32;       // counter stride in uint32
+// scratch of one fused 3-pass select (fused_select_kernel): one global histogram per pass + the grid-wide hand-shake
+struct FusedSelScratch {
+  uint32_t hist[NSVGD_SELECT_PASSES][2 * NSVGD_SELECT_BINS];   // 32-bit counts (a value buffer holds < 2^32 values over all ranks):
+                                                               // two counts per 64-bit word of the peer-memory exchange
+  uint32_t done[4];      // CTAs that have flushed their histogram of pass p
+  uint32_t flag[4];      // set by the last CTA of pass p once the select state has advanced
+};
+int launch_fused_select(cudaStream_t st, const float* vals, const uint32_t* counts_dev, int count_stride, int nseg,
+                        uint32_t seg_cap, uint32_t v_begin, uint32_t v_end, SelectState* state, FusedSelScratch* sc,
+                        const P2PComm* comm, int final_mode, FastMedState* fs, SelectState* main_state, int l_is_zero,
+                        int u_is_inf);
+int launch_fast_pack_resolve(cudaStream_t st, FastMedState* fs, const uint32_t* list_counts, uint32_t list_cap, uint32_t* cand_counts,
+                             uint32_t cand_cap, const uint32_t* err_flag, SelectState* main_state, SelectState* cand_state,
+                             long long* red);
+
+// median_large.cu: the tensor-core filtered exact median for d > 128 (single GPU); phi_large.cu: its Gram + classify launch
+bool median_large_supported(int64_t n, int64_t dz);
+size_t median_large_workspace(int64_t n, int64_t dz);
+int median_large(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, long long r_lo, long long r_hi,
+                 SelectState* main_state, uint64_t* hist, void* ws, size_t ws_bytes);
+int lg_launch_classify(cudaStream_t st, const void* Zb0, const void* Zb1, int64_t n, int64_t n_pad, int64_t ldk, const float* zn,
+                       FastMedState* fs, unsigned short* tlist, uint32_t* tcount, uint32_t tcap, float kappa_g, float kappa_d,
+                       uint32_t* err_flag);
+
 // phi_tc.cu: centre + bf16 2-piece split (+ optional transposed [S|Xc] pieces); last_scale multiplies the
 // centred last coordinate (literal median mode)
 int launch_tc_prep(cudaStream_t st, const float* X, const float* S, int64_t n, int64_t d, int64_t ldx, int64_t rows_pad,

@@ -56,12 +56,21 @@ print("cfg5 slice (512 rows) large(rect) vs large(square) rel_fro", float((got -
       "generic vs float64", float((ref.double() - ref64).norm() / ref64.norm()), flush=True)
 
 # the exact median bandwidth at cfg5 (literal mode): one exact pass + two buffer passes vs three recomputing passes
-for env in (None, "0"):
-    if env is None: os.environ.pop("NSVGD_MEDIAN_STORE", None)
-    else: os.environ["NSVGD_MEDIAN_STORE"] = env
-    hh = engine.median_heuristic(X)
-    torch.cuda.synchronize()
-    a.record()
-    hh = engine.median_heuristic(X)
-    b.record(); torch.cuda.synchronize()
-    print(f"cfg5 median_heuristic (NSVGD_MEDIAN_STORE={env}): {a.elapsed_time(b):.2f} ms, h = {hh.item():.9g}", flush=True)
+from nsvgd import _lib
+for name, env in (("tensor-core filter", {}), ("one exact pass + stored distances", {"NSVGD_MEDIAN_LARGE": "0"}),
+                  ("three exact passes", {"NSVGD_MEDIAN_LARGE": "0", "NSVGD_MEDIAN_STORE": "0"})):
+    for k in ("NSVGD_MEDIAN_LARGE", "NSVGD_MEDIAN_STORE"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    for mode in ("literal", "offdiag"):
+        hh = engine.median_heuristic(X, mode)
+        torch.cuda.synchronize()
+        _lib.load().nsvgd_profile_enable(1)
+        a.record()
+        hh = engine.median_heuristic(X, mode)
+        b.record(); torch.cuda.synchronize()
+        ph = {nm: round(_lib.profile_read(tag)[0], 3) for nm, tag in (("prep", 8), ("sample", 4), ("bracket", 9), ("filter", 6), ("exact", 5),
+                                                                    ("resolve", 10), ("fallback", 11))}
+        _lib.load().nsvgd_profile_enable(0)
+        print(f"cfg5 median_heuristic [{name}] {mode}: {a.elapsed_time(b):.2f} ms, h = {hh.item():.9g}  phases(ms) {ph}", flush=True)
+

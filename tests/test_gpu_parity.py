@@ -75,6 +75,38 @@ def test_bandwidth_stored_distance_select(n, d, seed, mode, monkeypatch):
         assert engine.median_heuristic(dev(np.ones((n, d), np.float32)), mode).item() == 0.0
 
 
+@pytest.mark.parametrize("n,d,kind", [(2048, 132, "gauss"), (2500, 300, "gauss"), (3000, 1028, "gauss"), (2304, 512, "clusters"),
+                                      (2100, 256, "ties"), (2200, 640, "bnn")])
+@pytest.mark.parametrize("mode", so.MEDIAN_MODES)
+def test_bandwidth_large_d_filtered_select(n, d, kind, mode, monkeypatch):
+    """d > 128, n >= 2048: the tensor-core filtered select of csrc/median_large.cu (symmetric CTA-pair Gram with the classify
+    epilogue, per-tile lists, tile-wise defined-order evaluation) is bit-identical to the exact SIMT select -- on a Gaussian
+    cloud, on tight clusters (most pairs near, large positive Gram entries), on integer-valued coordinates (massive ties:
+    the lists overflow and the device-side fallback takes over) and in the BNN weight regime."""
+    from nsvgd import engine
+    rng = np.random.default_rng(n + d)
+    if kind == "gauss":
+        X = (rng.standard_normal((n, d)) * 0.9 + 0.3).astype(np.float32)
+    elif kind == "clusters":
+        centres = rng.standard_normal((3, d)) * 2.0
+        X = (centres[rng.integers(0, 3, n)] + rng.standard_normal((n, d)) * 0.01).astype(np.float32)
+    elif kind == "ties":
+        X = rng.integers(0, 2, (n, d)).astype(np.float32)
+    else:
+        X = (rng.standard_normal((n, d)) * 0.15).astype(np.float32)
+    X[5] = X[2]
+    got = engine.median_heuristic(dev(X), mode).cpu().numpy()[0]
+    monkeypatch.setenv("NSVGD_MEDIAN_LARGE", "0")
+    want = engine.median_heuristic(dev(X), mode).cpu().numpy()[0]
+    monkeypatch.delenv("NSVGD_MEDIAN_LARGE")
+    assert np.float32(got).tobytes() == np.float32(want).tobytes(), (got, want)
+    if (n, d) == (2048, 132):
+        assert np.float32(got).tobytes() == np.float32(so.median_heuristic(X, mode)).tobytes()
+    if mode == "offdiag" and kind == "gauss":
+        Xn = X.copy(); Xn[11, 2] = np.nan
+        assert np.isnan(engine.median_heuristic(dev(Xn), mode).item())
+
+
 def test_bandwidth_nan_and_zero():
     from nsvgd import engine
     X = np.random.default_rng(0).standard_normal((70, 3)).astype(np.float32)
