@@ -284,8 +284,11 @@ def secondary_workloads(dev):
         S = torch.tensor((rng.standard_normal((n, d)) * 0.5).astype(np.float32), device=dev)
         h = float(np.sqrt(0.5 * 2 * d * 0.15 ** 2 / np.log(n + 1)))
         ms = timed(lambda: engine.phistar(X, X, S, h, Sq=S, stats=True), steps=5, warm=2)
+        ms_med = timed(lambda: engine.median_heuristic(X), steps=3, warm=1)      # exact median bandwidth, literal mode (large-d filter)
         out["cfg5_bnn_n16384_d4096_phi"] = {"ms_per_call": ms, "n2d_per_s": float(n) * n * d / (ms * 1e-3),
-                                            "algorithmic_tflops": 6.0 * n * n * d / (ms * 1e-3) / 1e12}
+                                            "algorithmic_tflops": 6.0 * n * n * d / (ms * 1e-3) / 1e12,
+                                            "median_bandwidth_ms": ms_med, "step_ms": ms + ms_med,
+                                            "step_n2d_per_s": float(n) * n * d / ((ms + ms_med) * 1e-3)}
     except Exception as e:
         out["cfg5_bnn_n16384_d4096_phi"] = {"error": str(e)[:200]}
     return out

@@ -120,6 +120,11 @@ int nsvgd_median_finish(void* stream, const void* state_dev, int64_t n, float* h
  *   nsvgd_median_finish.
  * `ws` is a scratch region of nsvgd_median_fast_workspace_bytes() that must stay untouched between stages. */
 int nsvgd_median_fast_supported(int64_t n, int64_t dz);
+/* d > 128 (csrc/median_large.cu): nsvgd_median_h_f32 runs the tensor-core filtered exact select on ONE GPU (symmetric CTA-pair
+ * Gram with a classify epilogue, per-tile lists, tile-wise defined-order evaluation; 9 ms at n = 16384, d = 4096 vs 191 ms for
+ * the 3-pass SIMT select).  Row-sharded callers run it redundantly on the gathered array: the result is an exact order
+ * statistic, hence identical on every rank. */
+int nsvgd_median_large_supported(int64_t n, int64_t dz);
 int nsvgd_median_fast_workspace_bytes(int64_t n, int64_t dz, size_t* out_bytes);
 int nsvgd_median_fast_sample(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last,
                              int64_t part, int64_t nparts, void* ws, size_t ws_bytes, size_t* samples_offset_bytes,

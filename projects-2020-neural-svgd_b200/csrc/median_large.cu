@@ -358,3 +358,6 @@ int median_large(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t
 }
 
 }  // namespace nsvgd
+
+// the row-sharded host logic asks whether every rank should simply run the filtered select on the gathered array
+extern "C" int nsvgd_median_large_supported(int64_t n, int64_t dz) { return nsvgd::median_large_supported(n, dz) ? 1 : 0; }
