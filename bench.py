@@ -499,31 +499,47 @@ def main():
         out_host = torch.empty_like(Xp).pin_memory()
         aux_hostbuf = torch.empty(8, dtype=torch.float64).pin_memory()
 
-        side = torch.cuda.Stream(device=dev)
+        up = torch.cuda.Stream(device=dev)
         d2h = torch.cuda.Stream(device=dev)
-        s_ready, snap_ready, d2h_done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        snap_ready, d2h_done = torch.cuda.Event(), torch.cuda.Event()
         out_dev = torch.empty_like(X_loc)
         aux_dev = torch.empty(8, dtype=torch.float64, device=dev)
         d2h_done.record()
+        # Inputs are double-buffered: the host->device copy of step t + 1 (X and S, pinned host memory -> staging buffers, its own
+        # stream) runs under the compute of step t, like the device->host copy of the logged particles; every copy is inside the
+        # timed region (K uploads, K downloads for K steps) and each step consumes exactly the bytes uploaded for it.
+        stage = [(torch.empty_like(X_loc), torch.empty_like(S_loc)) for _ in range(2)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        freed = [torch.cuda.Event(), torch.cuda.Event()]
+        for ev in freed:
+            ev.record()
+        tick = [0]
+
+        def upload(i):
+            with torch.cuda.stream(up):
+                up.wait_event(freed[i])
+                stage[i][0].copy_(Xp, non_blocking=True)
+                stage[i][1].copy_(Sp, non_blocking=True)
+                ready[i].record(up)
+        upload(0)
 
         def e2e_step():
-            X_loc.copy_(Xp, non_blocking=True)
+            i = tick[0] & 1
+            tick[0] += 1
+            upload(i ^ 1)                                    # prefetch the next step's inputs
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ready[i])
+            X_loc.copy_(stage[i][0], non_blocking=True)      # device-to-device into the step's (graph-captured) buffers
+            S_loc.copy_(stage[i][1], non_blocking=True)
+            freed[i].record(cur)
             if world == 1 and graphed is None and not fixed_h:
-                # the scores are not needed before phi*: their copy rides under the bandwidth selection
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    S_loc.copy_(Sp, non_blocking=True)
-                    s_ready.record()
                 h_ = engine.median_heuristic(X_loc, args.median_mode)
-                torch.cuda.current_stream().wait_event(s_ready)
                 a, _ = engine.svgd_step_sgd(X_loc, S_loc, h_, lr, scaled=True, lambda_reg=lam, path=args.path)
             else:
-                S_loc.copy_(Sp, non_blocking=True)
                 _, a = one_step()
             # the reference logs the particle array every step (models.py:187-197): snapshot on the device, then the
             # device->host copy rides on its own stream under the next step's work (PCIe is full duplex); the timed
             # region ends only after the last copy has landed
-            cur = torch.cuda.current_stream()
             cur.wait_event(d2h_done)                         # the previous snapshot has left the device
             out_dev.copy_(X_loc, non_blocking=True)
             aux_dev.copy_(a, non_blocking=True)
@@ -541,6 +557,7 @@ def main():
         for _ in range(KE):
             e2e_step()
         torch.cuda.current_stream().wait_stream(d2h)         # every device->host copy is inside the timed region
+        torch.cuda.current_stream().wait_stream(up)          # ... and so is the (prefetched) upload issued by the last step
         e1.record()
         barrier()
         te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -548,7 +565,8 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": KE * float(n) * n * d / (float(te.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(2 * m_local * d * 4), "d2h_bytes_per_step": int(m_local * d * 4 + 64),
-               "steps": KE, "api": "nsvgd.engine.median_heuristic + svgd_step_sgd (C ABI nsvgd_median_h_f32 / nsvgd_step_sgd_f32), pinned host buffers"}
+               "steps": KE, "api": "nsvgd.engine.median_heuristic + svgd_step_sgd (C ABI nsvgd_median_h_f32 / nsvgd_step_sgd_f32), pinned host buffers; "
+                      "uploads double-buffered (the copy for step t+1 overlaps step t), downloads on their own stream"}
 
     # ---- secondary: the docstring's off-diagonal median (north-star intent; three Gram passes) ---------------
     offdiag = None
