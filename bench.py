@@ -521,22 +521,36 @@ def main():
                 stage[i][0].copy_(Xp, non_blocking=True)
                 stage[i][1].copy_(Sp, non_blocking=True)
                 ready[i].record(up)
-        upload(0)
+        # Row-sharded runs keep the upload in front of the step: at 8 ranks the prefetch stream next to the GRAPH-replayed step stalls
+        # for seconds (measured e2e 3.4e11, wherever the prefetch is issued; fine at N <= 4 and fine with eager launches: 2.65e14
+        # at N = 8 against 2.50e14 for graph + serial uploads) -- a graph-replay / copy-stream interaction that is not understood yet.
+        # NSVGD_BENCH_PREFETCH=1|late re-enables it for experiments.
+        prefetch = world == 1 or os.environ.get("NSVGD_BENCH_PREFETCH", "0") != "0"
+        late = os.environ.get("NSVGD_BENCH_PREFETCH", "0") == "late"      # experiment: issue the prefetch after the step's launch
+        if prefetch:
+            upload(0)
 
         def e2e_step():
-            i = tick[0] & 1
-            tick[0] += 1
-            upload(i ^ 1)                                    # prefetch the next step's inputs
             cur = torch.cuda.current_stream()
-            cur.wait_event(ready[i])
-            X_loc.copy_(stage[i][0], non_blocking=True)      # device-to-device into the step's (graph-captured) buffers
-            S_loc.copy_(stage[i][1], non_blocking=True)
-            freed[i].record(cur)
+            if prefetch:
+                i = tick[0] & 1
+                tick[0] += 1
+                if not late:
+                    upload(i ^ 1)                                # prefetch the next step's inputs
+                cur.wait_event(ready[i])
+                X_loc.copy_(stage[i][0], non_blocking=True)      # device-to-device into the step's buffers
+                S_loc.copy_(stage[i][1], non_blocking=True)
+                freed[i].record(cur)
+            else:
+                X_loc.copy_(Xp, non_blocking=True)
+                S_loc.copy_(Sp, non_blocking=True)
             if world == 1 and graphed is None and not fixed_h:
                 h_ = engine.median_heuristic(X_loc, args.median_mode)
                 a, _ = engine.svgd_step_sgd(X_loc, S_loc, h_, lr, scaled=True, lambda_reg=lam, path=args.path)
             else:
                 _, a = one_step()
+            if prefetch and late:
+                upload(i ^ 1)
             # the reference logs the particle array every step (models.py:187-197): snapshot on the device, then the
             # device->host copy rides on its own stream under the next step's work (PCIe is full duplex); the timed
             # region ends only after the last copy has landed
@@ -566,7 +580,8 @@ def main():
         e2e = {"value": KE * float(n) * n * d / (float(te.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(2 * m_local * d * 4), "d2h_bytes_per_step": int(m_local * d * 4 + 64),
                "steps": KE, "api": "nsvgd.engine.median_heuristic + svgd_step_sgd (C ABI nsvgd_median_h_f32 / nsvgd_step_sgd_f32), pinned host buffers; "
-                      "uploads double-buffered (the copy for step t+1 overlaps step t), downloads on their own stream"}
+                      + ("uploads double-buffered (the copy for step t+1 overlaps step t)" if world == 1 else "uploads in front of each step")
+                      + ", downloads on their own stream"}
 
     # ---- secondary: the docstring's off-diagonal median (north-star intent; three Gram passes) ---------------
     offdiag = None
