@@ -3,7 +3,7 @@
 // The reference keeps its JAX-facing signatures (kernels.median_heuristic, stein.get_phistar, ...)
 // and dispatches into libnsvgd.so through these handlers (INTEGRATION.md shows the Python side).
 // The XLA FFI headers (xla/ffi/api/ffi.h, shipped inside jaxlib) are NOT present in this image, so
-// the file is compile-guarded: `make ffi XLA_INCLUDE=$(python -c "import jax.ffi; print(jax.ffi.include_dir())")`
+// THIS FILE HAS NEVER BEEN THROUGH A COMPILER (rounds 1 and 2 alike); it is compile-guarded: `make ffi XLA_INCLUDE=$(python -c "import jax.ffi; print(jax.ffi.include_dir())")`
 // builds nsvgd/libnsvgd_ffi.so where jaxlib exists.  Nothing here computes: every handler forwards
 // device pointers, the XLA stream and an XLA scratch allocation to the C ABI.
 #if __has_include("xla/ffi/api/ffi.h")
@@ -36,23 +36,27 @@ static ffi::Error MedianImpl(cudaStream_t stream, ffi::ScratchAllocator scratch,
 }
 
 // phi[i] = phi*(q_i) for all rows of q (vmap of stein.get_phistar folded into ONE call)      stein.py:180-203
+// Attributes: want_aux = 1 -> the [drift, repulsion] split of stein.phistar is written (slower [S | Xc] form; d > 128 then runs
+// the generic path), 0 -> `aux` is a 1-element dummy result and the COMBINED form runs; want_stats = 1 -> `sq` holds the scores
+// AT THE QUERIES (an explicit argument: equal row counts do not make q the same points as x) and `stats` is written.
 static ffi::Error PhiImpl(cudaStream_t stream, ffi::ScratchAllocator scratch, ffi::Buffer<ffi::F32> q,
-                          ffi::Buffer<ffi::F32> x, ffi::Buffer<ffi::F32> s, ffi::Buffer<ffi::F32> h, int32_t path,
-                          ffi::ResultBuffer<ffi::F32> phi, ffi::ResultBuffer<ffi::F32> aux,
-                          ffi::ResultBuffer<ffi::F64> stats) {
+                          ffi::Buffer<ffi::F32> x, ffi::Buffer<ffi::F32> s, ffi::Buffer<ffi::F32> sq, ffi::Buffer<ffi::F32> h,
+                          int32_t path, int32_t want_aux, int32_t want_stats, ffi::ResultBuffer<ffi::F32> phi,
+                          ffi::ResultBuffer<ffi::F32> aux, ffi::ResultBuffer<ffi::F64> stats) {
   const auto qd = q.dimensions(), xd = x.dimensions();
   if (qd.size() != 2 || xd.size() != 2 || qd[1] != xd[1])
     return ffi::Error(ffi::ErrorCode::kInvalidArgument, "phistar: q (m,d) and x (n,d) must share d");
   const int64_t m = qd[0], n = xd[0], d = xd[1];
+  if (want_stats && (sq.dimensions().size() != 2 || sq.dimensions()[0] != m || sq.dimensions()[1] != d))
+    return ffi::Error(ffi::ErrorCode::kInvalidArgument, "phistar: want_stats needs sq of the shape of q");
   size_t bytes = 0;
   if (int st = nsvgd_workspace_bytes(NSVGD_OP_PHI, n, m, d, path, &bytes)) return status_to_error(st);
   auto ws = scratch.Allocate(bytes);
   if (!ws.has_value()) return ffi::Error(ffi::ErrorCode::kResourceExhausted, "phistar: scratch allocation failed");
-  // stats need the scores at the queries; on the SVGD step q is x, so s doubles as Sq
-  const float* sq = (m == n) ? s.typed_data() : nullptr;
-  return status_to_error(nsvgd_phi_f32(stream, q.typed_data(), sq, m, d, x.typed_data(), s.typed_data(), n, d, d,
-                                       h.typed_data(), phi->typed_data(), d, aux->typed_data(),
-                                       sq ? stats->typed_data() : nullptr, path, *ws, bytes));
+  return status_to_error(nsvgd_phi_f32(stream, q.typed_data(), want_stats ? sq.typed_data() : nullptr, m, d, x.typed_data(),
+                                       s.typed_data(), n, d, d, h.typed_data(), phi->typed_data(), d,
+                                       want_aux ? aux->typed_data() : nullptr, want_stats ? stats->typed_data() : nullptr, path,
+                                       *ws, bytes));
 }
 
 // one fused sgd step (models.py:143-167 with KernelGradient, models.py:654-689); x is donated (input_output_aliases)
@@ -66,8 +70,9 @@ static ffi::Error StepImpl(cudaStream_t stream, ffi::ScratchAllocator scratch, f
   if (int st = nsvgd_workspace_bytes(NSVGD_OP_STEP, n, n, d, path, &bytes)) return status_to_error(st);
   auto ws = scratch.Allocate(bytes);
   if (!ws.has_value()) return ffi::Error(ffi::ErrorCode::kResourceExhausted, "step: scratch allocation failed");
-  if (x_out->typed_data() != x.typed_data())
-    cudaMemcpyAsync(x_out->typed_data(), x.typed_data(), sizeof(float) * n * d, cudaMemcpyDeviceToDevice, stream);
+  if (x_out->typed_data() != x.typed_data() &&
+      cudaMemcpyAsync(x_out->typed_data(), x.typed_data(), sizeof(float) * n * d, cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+    return ffi::Error(ffi::ErrorCode::kInternal, "step: copying the particles into the output buffer failed");
   return status_to_error(nsvgd_step_sgd_f32(stream, x_out->typed_data(), s.typed_data(), n, d, d, h.typed_data(), lr, scaled,
                                             lambda_reg, grads->typed_data(), step_aux->typed_data(), path, *ws, bytes));
 }
@@ -101,7 +106,8 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(nsvgd_ffi_median, MedianImpl,
 XLA_FFI_DEFINE_HANDLER_SYMBOL(nsvgd_ffi_phi, PhiImpl,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>().Ctx<ffi::ScratchAllocator>()
                                   .Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>()
-                                  .Arg<ffi::Buffer<ffi::F32>>().Attr<int32_t>("path")
+                                  .Arg<ffi::Buffer<ffi::F32>>().Arg<ffi::Buffer<ffi::F32>>().Attr<int32_t>("path")
+                                  .Attr<int32_t>("want_aux").Attr<int32_t>("want_stats")
                                   .Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F32>>().Ret<ffi::Buffer<ffi::F64>>(),
                               {xla::ffi::Traits::kCmdBufferCompatible});
 XLA_FFI_DEFINE_HANDLER_SYMBOL(nsvgd_ffi_step, StepImpl,
