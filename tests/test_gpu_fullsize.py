@@ -126,3 +126,42 @@ def test_adversarial_coherent_residuals(e, ratio):
     st = stats.cpu().numpy()
     assert st[1] / n == pytest.approx(ref["l2"], rel=2 * TOL)
     assert st[0] / n == pytest.approx(ref["ksd"], rel=2 * TOL, abs=2 * TOL * abs(ref["l2"]) ** 0.5)
+
+
+def test_fullsize_cfg5_bnn_step_pieces():
+    """BASELINE configs[4] at full size (n = 16384, d = 4096, weights ~ 0.15 N(0, 1), the bench's `secondary` cloud), the
+    d > 128 kernels of csrc/phi_large.cu and csrc/median_large.cu:
+      (a) the tensor-core filtered median == one exact SIMT pass + stored distances, bit for bit (literal and offdiag);
+      (b) phi* with the KSD / l2 statistics at the median-heuristic-sized bandwidth (self term = half of every row) against
+          float64 on 384 query rows (torch on the GPU: the closed form of stein.py:180-222 with the RBF kernel), and the
+          block form a row-sharded rank uses (queries = a row range of the particle array)."""
+    from nsvgd import engine
+    n, d = 16384, 4096
+    rng = np.random.default_rng(5)
+    X = torch.tensor((rng.standard_normal((n, d)) * 0.15).astype(np.float32)).cuda()
+    S = torch.tensor((rng.standard_normal((n, d)) * 0.5).astype(np.float32)).cuda()
+    for mode in ("literal", "offdiag"):
+        fast = engine.median_heuristic(X, mode).item()
+        os.environ["NSVGD_MEDIAN_LARGE"] = "0"
+        try:
+            slow = engine.median_heuristic(X, mode).item()
+        finally:
+            del os.environ["NSVGD_MEDIAN_LARGE"]
+        assert np.float32(fast).tobytes() == np.float32(slow).tobytes(), (mode, fast, slow)
+    h = float(np.sqrt(0.5 * 2 * d * 0.15 ** 2 / np.log(n + 1)))
+    phi, stats = engine.phistar(X, X, S, h, Sq=S, stats=True)
+    rows = torch.arange(1000, 1384, device="cuda")
+    Xd, Sd = X.double(), S.double()
+    Qd = Xd[rows]
+    d2 = (Qd * Qd).sum(1)[:, None] + (Xd * Xd).sum(1)[None, :] - 2.0 * Qd @ Xd.T
+    K = torch.exp(-d2.clamp_min(0) / (2 * h * h))
+    K[torch.arange(len(rows)), rows] = 1.0
+    ref = ((K @ Sd + (K.sum(1)[:, None] * Qd - K @ Xd) / (h * h)) / n).cpu().numpy()
+    got = phi[rows].cpu().numpy()
+    assert rel_fro(got, ref) < 0.5 * TOL, rel_fro(got, ref)
+    assert max_row_rel(got, ref) < TOL, max_row_rel(got, ref)
+    blk = engine.phistar(X[1000:1384], X, S, h).cpu().numpy()
+    assert rel_fro(blk, ref) < 0.5 * TOL, rel_fro(blk, ref)
+    assert np.isfinite(stats.cpu().numpy()).all() and stats[2].item() == n
+    # l2 statistic = sum_i |phi_i|^2 over ALL rows, consistent with the phi the kernel returned
+    assert stats[1].item() == pytest.approx(float((phi.double() ** 2).sum().item()), rel=1e-5)

@@ -11,6 +11,7 @@ from conftest import GOLDEN_CASES
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-4
+ROW_TOL = 2 * TOL      # worst single row (relative to max(|row|, 1e-3 max|row|)); round 1 allowed 10 x TOL here
 
 
 def dev(a):
@@ -125,7 +126,7 @@ def test_phi_ksd_against_golden(golden, name, tag):
     h = float(g[f"h_{tag}"])
     phi, aux, stats = engine.phistar(X, X, Sx, h, Sq=Sx, aux=True, stats=True)
     assert rel_fro(phi.cpu(), g[f"phi_{tag}"]) < TOL
-    assert max_row_rel(phi.cpu(), g[f"phi_{tag}"]) < 10 * TOL
+    assert max_row_rel(phi.cpu(), g[f"phi_{tag}"]) < ROW_TOL, max_row_rel(phi.cpu(), g[f"phi_{tag}"])
     assert rel_fro(aux.cpu(), g[f"aux_{tag}"]) < TOL
     assert rel_fro(engine.phistar(Y, X, Sx, h).cpu(), g[f"phi_rect_{tag}"]) < TOL
     stats = stats.cpu().numpy()
@@ -230,7 +231,7 @@ def test_phi_paths_vs_oracle(path, n, d, h):
     else:
         phi, aux, stats = engine.phistar(Xd, Xd, Sd, h, Sq=Sd, aux=True, stats=True, path=path)
     assert rel_fro(phi.cpu(), ref) < TOL, rel_fro(phi.cpu(), ref)
-    assert max_row_rel(phi.cpu(), ref) < 10 * TOL
+    assert max_row_rel(phi.cpu(), ref) < ROW_TOL, max_row_rel(phi.cpu(), ref)
     assert rel_fro(aux.cpu(), ref_aux) < TOL
     st = stats.cpu().numpy()
     sd_ref = so.stein_discrepancy_phistar(X, S, h)
@@ -241,7 +242,7 @@ def test_phi_paths_vs_oracle(path, n, d, h):
     # without the aux output the tensor-core path runs its COMBINED form (second GEMM against W = S - Xc/h^2);
     # the KSD statistic is then recovered from qc.(K W) + sum_j k g_ij / h^2: square and rectangular
     phi2, st2 = engine.phistar(Xd, Xd, Sd, h, Sq=Sd, stats=True, path=path)
-    assert rel_fro(phi2.cpu(), ref) < TOL and max_row_rel(phi2.cpu(), ref) < 10 * TOL
+    assert rel_fro(phi2.cpu(), ref) < TOL and max_row_rel(phi2.cpu(), ref) < ROW_TOL, max_row_rel(phi2.cpu(), ref)
     st2 = st2.cpu().numpy()
     assert st2[0] / n == pytest.approx(sd_ref, rel=2 * TOL, abs=2 * TOL * abs(so.l2_norm_squared(ref)) ** 0.5)
     assert st2[1] / n == pytest.approx(so.l2_norm_squared(ref), rel=2 * TOL)
@@ -306,7 +307,7 @@ def test_full_size_rows_sampled_against_oracle():
     rows = np.random.default_rng(0).choice(n, 48, replace=False)
     ref = so.phistar(X[rows], X, S, h)
     assert rel_fro(phi[rows].cpu(), ref) < TOL
-    assert max_row_rel(phi[rows].cpu(), ref) < 10 * TOL
+    assert max_row_rel(phi[rows].cpu(), ref) < ROW_TOL, max_row_rel(phi[rows].cpu(), ref)
     perm = torch.randperm(n, device="cuda")
     phi_p = engine.phistar(Xd[perm].contiguous(), Xd[perm].contiguous(), Sd[perm].contiguous(), h)
     assert rel_fro(phi_p.cpu(), phi[perm].cpu()) < 2e-5
