@@ -32,7 +32,8 @@ constexpr int ML_TR = 128, ML_TC = 256;        // the CTA tile of the filter
 constexpr int ML_XT = 512;                     // threads of the exact-tile kernel
 constexpr int ML_XP = 4;                       // pairs per thread and round
 constexpr int ML_XSTRIDE = 36;                 // floats per row slice in shared memory (32 + 4: 16-byte aligned rows)
-constexpr int ML_XSMEM = 512 * ML_XSTRIDE * (int)sizeof(float);
+constexpr int ML_XROWS_BYTES = 512 * ML_XSTRIDE * (int)sizeof(float);
+constexpr int ML_XSMEM = ML_XROWS_BYTES + 2 * (int)ML_TCAP * (int)sizeof(unsigned short);      // row slices + the tile's row-sorted pair list
 
 bool median_large_supported(int64_t n, int64_t dz) {
   const char* env = getenv("NSVGD_MEDIAN_LARGE");
@@ -194,8 +195,9 @@ __global__ void __launch_bounds__(ML_XT, 2) ml_exact_tiles_kernel(const float* _
                                                                   const uint32_t* __restrict__ tcount, int tiles_n,
                                                                   float* __restrict__ cand, uint32_t* cand_counts, uint32_t cand_cap,
                                                                   SelectState* main_state) {
-  extern __shared__ __align__(16) float xs[];        // [512 rows][ML_XSTRIDE]
+  extern __shared__ __align__(16) float xs[];        // [512 rows][ML_XSTRIDE] | sorted pair list
   __shared__ unsigned int sh_below;
+  __shared__ uint32_t row_hist[257];
   const int I = blockIdx.y, J = blockIdx.x;
   if (J < I) return;
   const uint32_t c0 = tcount[(size_t)(2 * I) * tiles_n + J], c1 = tcount[(size_t)(2 * I + 1) * tiles_n + J];
@@ -212,17 +214,51 @@ __global__ void __launch_bounds__(ML_XT, 2) ml_exact_tiles_kernel(const float* _
   const int nslices = (d + 31) >> 5;
   const int last_group = (d >> 2) - 1;
   const int lrow = threadIdx.x >> 3, lq = threadIdx.x & 7;      // loads: 8 threads per row slice, 64 rows per pass
+  // The filter appends the pairs of a tile in arbitrary order.  Counting sort by row (key = row << 8 | column, row in [0, 256)):
+  // consecutive lanes then hold pairs of the SAME row, whose slice reads broadcast -- the kernel is bound by shared-memory
+  // wavefronts (ncu: 80 % of peak, 41 % bank conflicts with random row pairs).  Measured at cfg5: 5.94 -> 5.33 ms.  Two
+  // bank-aware orders of the column side (round-robin over the classes c mod 8 inside a row; 8 class queues interleaved slot by
+  // slot) were measured too and did not help (5.7 / 5.9 ms): kept simple.
+  unsigned short* sorted = reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(xs) + ML_XROWS_BYTES);
+  for (int t = threadIdx.x; t < 257; t += ML_XT) row_hist[t] = 0u;
+  __syncthreads();
+  for (uint32_t t = threadIdx.x; t < total; t += ML_XT) {
+    const unsigned short e = t < c0 ? l0[t] : l1[t - c0];
+    atomicAdd(&row_hist[(t < c0 ? 0 : 128) + (e >> 8) + 1], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {                 // exclusive prefix over the 256 rows: 8 per lane + a warp scan
+    uint32_t loc[8], sum = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { loc[u] = row_hist[1 + threadIdx.x * 8 + u]; sum += loc[u]; }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    uint32_t run = inc - sum;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { row_hist[1 + threadIdx.x * 8 + u] = run; run += loc[u]; }
+  }
+  __syncthreads();
+  for (uint32_t t = threadIdx.x; t < total; t += ML_XT) {
+    const unsigned short e = t < c0 ? l0[t] : l1[t - c0];
+    const uint32_t row = (t < c0 ? 0u : 128u) + (uint32_t)(e >> 8);
+    const uint32_t pos = atomicAdd(&row_hist[1 + row], 1u);
+    sorted[pos] = (unsigned short)((row << 8) | (e & 255u));
+  }
+  __syncthreads();
+  const uint32_t nwork = total;
   uint32_t below = 0;
   bool any_nan = false;
-  for (uint32_t base = 0; base < total; base += ML_XT * ML_XP) {
+  for (uint32_t base = 0; base < nwork; base += ML_XT * ML_XP) {
     int ra[ML_XP], rb[ML_XP];
     float acc[ML_XP];
+    bool live[ML_XP];
 #pragma unroll
     for (int k = 0; k < ML_XP; ++k) {
       const uint32_t t = base + threadIdx.x + ML_XT * k;
-      const uint32_t tc = min(t, total - 1u);                   // idle slots shadow the last pair
-      const unsigned short e = tc < c0 ? l0[tc] : l1[tc - c0];
-      ra[k] = (tc < c0 ? 0 : 128) + (e >> 8);
+      live[k] = t < nwork;
+      const unsigned short e = sorted[min(t, nwork - 1u)];                    // idle slots shadow the last pair
+      ra[k] = e >> 8;
       rb[k] = 256 + (e & 255);
       acc[k] = 0.f;
     }
@@ -262,7 +298,7 @@ __global__ void __launch_bounds__(ML_XT, 2) ml_exact_tiles_kernel(const float* _
       const uint32_t t = base + threadIdx.x + ML_XT * k;
       const float dv = acc[k];
       bool is_cand = false;
-      if (t < total) {
+      if (live[k]) {
         if (dv != dv) any_nan = true;
         else if (dv < Lv) ++below;
         else if (dv <= Uv) is_cand = true;
@@ -327,8 +363,11 @@ int median_large(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t
 
   // --- filter: symmetric Gram + classify
   const int T = 3 * (int)ceil_div(dz, 16);
-  const float kappa_g = 3.0517578125e-5f + 1.5f * (float)T * 2.384185791015625e-7f;     // 2^-15 + 1.5 T 2^-22
-  const float kappa_d = (float)(dz + 4) * 5.9604644775390625e-8f * 1.0001f;              // (d + 4) 2^-24
+  // NSVGD_MEDIAN_LARGE_KAPPA_SCALE (tests only): shrink both radii to measure how much margin the bound has on a given cloud
+  float kscale = 1.f;
+  if (const char* ks = getenv("NSVGD_MEDIAN_LARGE_KAPPA_SCALE")) kscale = (float)atof(ks);
+  const float kappa_g = kscale * (3.0517578125e-5f + 1.5f * (float)T * 2.384185791015625e-7f);     // 2^-15 + 1.5 T 2^-22
+  const float kappa_d = kscale * ((float)(dz + 4) * 5.9604644775390625e-8f * 1.0001f);              // (d + 4) 2^-24
   prof_begin(6, st);
   NSVGD_PROPAGATE(lg_launch_classify(st, f.Zb0, f.Zb1, n, f.n_pad, f.ldk, f.zn, f.fs, f.tlist, f.tcount, ML_TCAP, kappa_g, kappa_d, f.err_flag));
   prof_end(6, st);

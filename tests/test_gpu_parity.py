@@ -108,6 +108,29 @@ def test_bandwidth_large_d_filtered_select(n, d, kind, mode, monkeypatch):
         assert np.isnan(engine.median_heuristic(dev(Xn), mode).item())
 
 
+@pytest.mark.parametrize("n,d,kind", [(2500, 300, "gauss"), (2200, 640, "bnn"), (2304, 512, "clusters"), (2048, 4096, "bnn")])
+def test_bandwidth_large_d_filter_radius_has_margin(n, d, kind, monkeypatch):
+    """How conservative is the error radius of the large-d filter?  The classification is only trusted because the radius
+    bounds the tensor-core Gram error (assumed <= 4 ulp of the largest partial sum per MMA, csrc/median_large.cu); with BOTH
+    radii shrunk 8-fold the select must still return the identical bits on these clouds -- i.e. the actual error is at least
+    8 x below the bound (a shrunk radius that misclassified a pair near the target rank would shift the order statistic)."""
+    from nsvgd import engine
+    rng = np.random.default_rng(n + d)
+    if kind == "gauss":
+        X = (rng.standard_normal((n, d)) * 0.9 + 0.3).astype(np.float32)
+    elif kind == "clusters":
+        centres = rng.standard_normal((3, d)) * 2.0
+        X = (centres[rng.integers(0, 3, n)] + rng.standard_normal((n, d)) * 0.01).astype(np.float32)
+    else:
+        X = (rng.standard_normal((n, d)) * 0.15).astype(np.float32)
+    for mode in ("literal", "offdiag"):
+        want = engine.median_heuristic(dev(X), mode).cpu().numpy()[0]
+        monkeypatch.setenv("NSVGD_MEDIAN_LARGE_KAPPA_SCALE", "0.125")
+        got = engine.median_heuristic(dev(X), mode).cpu().numpy()[0]
+        monkeypatch.delenv("NSVGD_MEDIAN_LARGE_KAPPA_SCALE")
+        assert np.float32(got).tobytes() == np.float32(want).tobytes(), (mode, got, want)
+
+
 def test_bandwidth_nan_and_zero():
     from nsvgd import engine
     X = np.random.default_rng(0).standard_normal((70, 3)).astype(np.float32)
