@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--no-offdiag", action="store_true", help="skip the secondary off-diagonal-median run")
     ap.add_argument("--no-secondary", action="store_true", help="skip the timings of the other BASELINE configs")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay the step as one CUDA graph (auto: when row-sharded, where host issue time limits the step)")
+                    help="replay the step as one CUDA graph (auto = on)")
     return ap.parse_args()
 
 
@@ -372,7 +372,9 @@ def main():
     S_loc = torch.tensor(Sh[r0:r1], device=dev)
     X_loc = X0.clone()
     flush = torch.empty(192 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    use_graph = args.graph == "on" or (args.graph == "auto" and world > 1)
+    # auto: the step is replayed as ONE CUDA graph at every N (round 2: also at N = 1, where it removes the launch gaps between
+    # the ~15 short kernels of the bandwidth selection: 6.28 -> 6.17 ms on the same box)
+    use_graph = args.graph in ("on", "auto")
     pk = peaks()
 
     def barrier():
@@ -654,7 +656,8 @@ def main():
         "arm": {"rows_per_gpu": m_local, "path": args.path,
                 "small_allreduces": ("peer memory over NVLink, fused into the consumer kernels (csrc/p2p.cuh)"
                                      if (sharded is not None and sharded.comm is not None) else ("nccl" if world > 1 else "none")),
-                "launch": "one CUDA graph replay per step (collectives captured)" if graphed is not None else "eager (C-ABI calls per op)"},
+                "launch": ("one CUDA graph replay per step" + (" (collectives captured)" if world > 1 else "")) if graphed is not None
+                          else "eager (C-ABI calls per op)"},
         "breakdown_ms_per_step": {"median_op": prof[3][0] / KP, "median_tc_filter_kernel": prof[6][0] / KP,
                                   "median_sample_kernel": prof[4][0] / KP, "median_exact_list_kernel": prof[5][0] / KP,
                                   "median_prepare": prof[12][0] / KP, "median_prep_kernels": prof[8][0] / KP,

@@ -51,7 +51,7 @@ struct LgSmem {
 
 struct LgParams {
   int epi;
-  int tiles_m, tiles_n, nsplit, group_m;   // tiles_m in units of 128 * CTAS rows
+  int tiles_m, tiles_n, nsplit, group_m, group_n;   // tiles_m in units of 128 * CTAS rows
   int total;                               // work units (tiles x splits) of the launch
   int kb_total, kb_per_split;              // 64-wide k-blocks: all of them / per accumulation run
   int m_rows;                              // valid rows of this launch
@@ -81,12 +81,19 @@ __device__ __forceinline__ void lg_decode(const LgParams& p, int u, int& mt, int
   const int per_split = p.tiles_m * p.tiles_n;
   s = u / per_split;
   int r = u - s * per_split;
-  const int band = p.group_m * p.tiles_n;      // bands of group_m row tiles: the tiles in flight share operands in L2
+  // super-tiles of group_m row tiles x group_n column tiles (~ one wave of CTAs), column-major inside; the super-tiles walk down
+  // the rows of one column group before moving to the next: consecutive waves share the column group's B operand in L2 and the
+  // tiles in flight share both operands
+  const int per_ngroup = p.tiles_m * p.group_n;
+  const int gn = min(r / per_ngroup, (p.tiles_n - 1) / p.group_n);
+  r -= gn * per_ngroup;
+  const int wn = min(p.group_n, p.tiles_n - gn * p.group_n);
+  const int band = p.group_m * wn;
   const int b = r / band;
   r -= b * band;
   const int gm = min(p.group_m, p.tiles_m - b * p.group_m);
-  nt = r / gm;
-  mt = b * p.group_m + (r - nt * gm);
+  nt = gn * p.group_n + r / gm;
+  mt = b * p.group_m + (r - (r / gm) * gm);
 }
 
 // symmetric launch: row tile mt (128 * ctas rows) takes the column tiles nt >= (mt * ctas) / 2; bands of group_m row tiles,
@@ -502,8 +509,11 @@ static int lg_launch(cudaStream_t st, int ctas, const __nv_bfloat16* A0, const _
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&mB0, B0, (uint64_t)kdim, (uint64_t)b_rows, (uint64_t)ldb * 2, LG_BK, (uint32_t)(LG_BN / ctas)));
   NSVGD_PROPAGATE(make_tmap_bf16_2d(&mB1, B1, (uint64_t)kdim, (uint64_t)b_rows, (uint64_t)ldb * 2, LG_BK, (uint32_t)(LG_BN / ctas)));
   prm.tiles_m = (int)ceil_div(prm.sym ? a_rows : prm.m_rows, LG_BM * ctas);
-  prm.group_m = ctas == 2 ? 4 : 8;
   prm.ctas = ctas;
+  // bands of 4 (pair) / 8 row tiles across ALL column tiles.  A 2-D super-tile raster (9 x 8 tiles ~ one wave, column groups
+  // outermost) was measured for the P.W launch at cfg5: DRAM reads 7.6 -> 9.9 GB, time unchanged (4.31 vs 4.34 ms) -- not kept.
+  prm.group_m = ctas == 2 ? 4 : 8;
+  prm.group_n = prm.tiles_n;
   const int64_t total = prm.sym ? lg_sym_tiles(prm.tiles_m, prm.tiles_n, ctas) : (int64_t)prm.tiles_m * prm.tiles_n * prm.nsplit;
   NSVGD_REQUIRE(total < (1ll << 31), NSVGD_ERR_INVALID, "phi_large: too many tiles");
   prm.total = (int)total;
