@@ -38,7 +38,9 @@ constexpr int ML_XSMEM = ML_XROWS_BYTES + 2 * (int)ML_TCAP * (int)sizeof(unsigne
 bool median_large_supported(int64_t n, int64_t dz) {
   const char* env = getenv("NSVGD_MEDIAN_LARGE");
   if (env && env[0] == '0') return false;
-  return dz > 128 && dz % 4 == 0 && n >= 2048 && n <= (1ll << 17);     // per-tile lists: 8 KB per 128 x 256 tile
+  return dz > 128 && n >= 2048 && n <= (1ll << 17);     // per-tile lists: 8 KB per 128 x 256 tile
+  // (rows must be 16-byte aligned with a leading dimension that is a multiple of 4 and ZERO columns in [dz, ceil4(dz)): true for
+  //  dz % 4 == 0, and for the literal-mode Z the driver pads itself -- e.g. the reference's BNN dimension 4594)
 }
 
 struct MlWs {
@@ -128,7 +130,8 @@ __device__ __forceinline__ uint64_t ml_mix(uint64_t x) {
 // Defined-order distances of 32 pairs by one warp (the slice-cooperative scheme of exact_list_coop_kernel, median_tc.cu): 8 lanes
 // load one 128-byte row slice, 4 rows per instruction; the loading lane holds both rows of its pair for its 4 coordinates and
 // parks the squared differences (the last coordinate already weighted) in the warp's tile; lane p then adds pair p's terms in
-// order.  d % 4 == 0, rows 16-byte aligned.
+// order.  Rows 16-byte aligned, ld % 4 == 0, columns [d, ceil4(d)) zero: the weighted coordinate d - 1 sits at position
+// (d - 1) & 3 of its float4 and the zero padding behind it adds exact +0.
 __device__ __forceinline__ float ml_warp_exact32(const float* __restrict__ P, int64_t ldp, int d, float w_last, uint32_t i, uint32_t j,
                                                  float* tA, int lane) {
   const int r = lane >> 3, q = lane & 7;
@@ -139,7 +142,8 @@ __device__ __forceinline__ float ml_warp_exact32(const float* __restrict__ P, in
     jb[u] = __shfl_sync(0xffffffffu, j, 4 * u + r);
   }
   const int nslices = (d + 31) >> 5;
-  const int last_group = (d >> 2) - 1;
+  const int last_group = (d - 1) >> 2, last_pos = (d - 1) & 3;
+  const int d4 = (d + 3) & ~3;
   float acc = 0.f;
   for (int sl = 0; sl < nslices; ++sl) {
     const int col = 32 * sl + 4 * q;
@@ -155,12 +159,17 @@ __device__ __forceinline__ float ml_warp_exact32(const float* __restrict__ P, in
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const float d0 = va[u].x - vb[u].x, d1 = va[u].y - vb[u].y, d2 = va[u].z - vb[u].z, d3 = va[u].w - vb[u].w;
-      float t3 = __fmul_rn(d3, d3);
-      if (wgt) t3 = __fmul_rn(w_last, t3);
-      *reinterpret_cast<float4*>(tA + (4 * u + r) * ML_XSTRIDE + 4 * q) = make_float4(__fmul_rn(d0, d0), __fmul_rn(d1, d1), __fmul_rn(d2, d2), t3);
+      float t0 = __fmul_rn(d0, d0), t1 = __fmul_rn(d1, d1), t2 = __fmul_rn(d2, d2), t3 = __fmul_rn(d3, d3);
+      if (wgt) {
+        if (last_pos == 0) t0 = __fmul_rn(w_last, t0);
+        else if (last_pos == 1) t1 = __fmul_rn(w_last, t1);
+        else if (last_pos == 2) t2 = __fmul_rn(w_last, t2);
+        else t3 = __fmul_rn(w_last, t3);
+      }
+      *reinterpret_cast<float4*>(tA + (4 * u + r) * ML_XSTRIDE + 4 * q) = make_float4(t0, t1, t2, t3);
     }
     __syncwarp();
-    const int kmax = min(8, (d - 32 * sl) >> 2);
+    const int kmax = min(8, (d4 - 32 * sl) >> 2);
     for (int k = 0; k < kmax; ++k) {
       const float4 t4 = *reinterpret_cast<const float4*>(tA + lane * ML_XSTRIDE + 4 * k);
       acc = __fadd_rn(acc, t4.x);
@@ -212,7 +221,8 @@ __global__ void __launch_bounds__(ML_XT, 2) ml_exact_tiles_kernel(const float* _
   const int seg = (int)((blockIdx.y * gridDim.x + blockIdx.x) % MF_NSEG);
   float* seg_cand = cand + (size_t)seg * cand_cap;
   const int nslices = (d + 31) >> 5;
-  const int last_group = (d >> 2) - 1;
+  const int last_group = (d - 1) >> 2, last_pos = (d - 1) & 3;  // the weighted coordinate; the zero padding behind it adds exact +0
+  const int d4 = (d + 3) & ~3;
   const int lrow = threadIdx.x >> 3, lq = threadIdx.x & 7;      // loads: 8 threads per row slice, 64 rows per pass
   // The filter appends the pairs of a tile in arbitrary order.  Counting sort by row (key = row << 8 | column, row in [0, 256)):
   // consecutive lanes then hold pairs of the SAME row, whose slice reads broadcast -- the kernel is bound by shared-memory
@@ -274,7 +284,7 @@ __global__ void __launch_bounds__(ML_XT, 2) ml_exact_tiles_kernel(const float* _
         *reinterpret_cast<float4*>(xs + lr * ML_XSTRIDE + 4 * lq) = v;
       }
       __syncthreads();
-      const int kmax = min(8, (d - 32 * sl) >> 2);
+      const int kmax = min(8, (d4 - 32 * sl) >> 2);
 #pragma unroll
       for (int k = 0; k < ML_XP; ++k) {
         const float* a = xs + ra[k] * ML_XSTRIDE;
@@ -283,11 +293,16 @@ __global__ void __launch_bounds__(ML_XT, 2) ml_exact_tiles_kernel(const float* _
         for (int g = 0; g < kmax; ++g) {
           const float4 av = *reinterpret_cast<const float4*>(a + 4 * g), bv = *reinterpret_cast<const float4*>(b + 4 * g);
           const float d0 = av.x - bv.x, d1 = av.y - bv.y, d2 = av.z - bv.z, d3 = av.w - bv.w;
-          s = __fadd_rn(s, __fmul_rn(d0, d0));
-          s = __fadd_rn(s, __fmul_rn(d1, d1));
-          s = __fadd_rn(s, __fmul_rn(d2, d2));
-          float t3 = __fmul_rn(d3, d3);
-          if (8 * sl + g == last_group) t3 = __fmul_rn(w_last, t3);
+          float t0 = __fmul_rn(d0, d0), t1 = __fmul_rn(d1, d1), t2 = __fmul_rn(d2, d2), t3 = __fmul_rn(d3, d3);
+          if (8 * sl + g == last_group) {
+            if (last_pos == 0) t0 = __fmul_rn(w_last, t0);
+            else if (last_pos == 1) t1 = __fmul_rn(w_last, t1);
+            else if (last_pos == 2) t2 = __fmul_rn(w_last, t2);
+            else t3 = __fmul_rn(w_last, t3);
+          }
+          s = __fadd_rn(s, t0);
+          s = __fadd_rn(s, t1);
+          s = __fadd_rn(s, t2);
           s = __fadd_rn(s, t3);
         }
         acc[k] = s;

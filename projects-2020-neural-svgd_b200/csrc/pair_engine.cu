@@ -376,11 +376,13 @@ __global__ void select_init_kernel(SelectState* s, long long r_lo, long long r_h
 
 // literal mode: Z[a] = [x_a without column a (a < d-1) | x_a[:d-1], x_a[d-1]]   (n > d)
 //               Z[a] = x_a[:n] without column a                                 (n <= d)
+// ldz >= dz: columns [dz, ldz) are written as zeros (the large-d select reads float4 groups)
 __global__ void literal_z_kernel(const float* __restrict__ X, int64_t n, int64_t d, int64_t ldx,
-                                 float* __restrict__ Z, int64_t dz) {
-  const int64_t total = n * dz;
+                                 float* __restrict__ Z, int64_t dz, int64_t ldz) {
+  const int64_t total = n * ldz;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t a = t / dz, c = t % dz;
+    const int64_t a = t / ldz, c = t % ldz;
+    if (c >= dz) { Z[t] = 0.f; continue; }
     int64_t src;
     if (n > d) {
       if (c == d - 1) src = d - 1;
@@ -520,8 +522,20 @@ void median_ranks_host(int64_t n, int mode, long long* r_lo, long long* r_hi) {
 
 using namespace nsvgd;
 
+// leading dimension of the literal-mode Z the single-GPU driver allocates: padded to a float4 multiple for the large-d select
+static int64_t literal_ldz(int64_t dz) { return dz > 128 ? round_up(dz, 4) : dz; }
+
+static int median_prepare_ld(void* stream, const float* X, int64_t n, int64_t d, int64_t ldx, int mode, float* Z, int64_t ldz_pad,
+                             int64_t* dz_out, float* w_last_out, void* state_dev);
+
 extern "C" int nsvgd_median_prepare(void* stream, const float* X, int64_t n, int64_t d, int64_t ldx, int mode,
                                     float* Z, int64_t* dz_out, float* w_last_out, void* state_dev) {
+  return median_prepare_ld(stream, X, n, d, ldx, mode, Z, 0, dz_out, w_last_out, state_dev);
+}
+
+// ldz_pad = 0: Z is dense (ld = dz, the public entry point); else its leading dimension
+static int median_prepare_ld(void* stream, const float* X, int64_t n, int64_t d, int64_t ldx, int mode, float* Z, int64_t ldz_pad,
+                             int64_t* dz_out, float* w_last_out, void* state_dev) {
   cudaStream_t st = (cudaStream_t)stream;
   NSVGD_REQUIRE(X && state_dev && dz_out && w_last_out, NSVGD_ERR_INVALID, "median_prepare: null pointer");
   NSVGD_REQUIRE(n >= 2 && d >= 1 && ldx >= d, NSVGD_ERR_INVALID, "median_prepare: need n >= 2, d >= 1, ldx >= d (n=%lld d=%lld)", (long long)n, (long long)d);
@@ -535,8 +549,9 @@ extern "C" int nsvgd_median_prepare(void* stream, const float* X, int64_t n, int
     const int64_t dz = n > d ? d : n - 1;
     *dz_out = dz;
     *w_last_out = n > d ? (float)(n - d) : 1.f;
-    const int64_t total = n * dz;
-    literal_z_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256), 4096), 256, 0, st>>>(X, n, d, ldx, Z, dz);
+    const int64_t ldz = ldz_pad ? ldz_pad : dz;
+    const int64_t total = n * ldz;
+    literal_z_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256), 4096), 256, 0, st>>>(X, n, d, ldx, Z, dz, ldz);
     NSVGD_LAUNCH_CHECK();
   } else {
     *dz_out = d;
@@ -599,7 +614,7 @@ static void median_ws_layout(int64_t n, int64_t d, int mode, WsCarver& w, void**
   *hist = w.take<uint64_t>(2 * NSVGD_SELECT_BINS);
   *Z = nullptr;
   const int64_t dz = mode == NSVGD_MEDIAN_LITERAL ? (n > d ? d : n - 1) : d;
-  if (mode == NSVGD_MEDIAN_LITERAL) *Z = w.take<float>((size_t)(n * dz));
+  if (mode == NSVGD_MEDIAN_LITERAL) *Z = w.take<float>((size_t)(n * literal_ldz(dz)));
   *fast = nullptr; *fast_bytes = 0;
   if (median_fast_supported(n, dz)) {
     *fast_bytes = median_fast_workspace(n, dz);
@@ -639,10 +654,11 @@ extern "C" int nsvgd_median_h_f32(void* stream, const float* X, int64_t n, int64
   int64_t dz; float w_last;
   prof_begin(3, st);
   prof_begin(12, st);
-  NSVGD_PROPAGATE(nsvgd_median_prepare(stream, X, n, d, ldx, mode, Z, &dz, &w_last, state));
+  const int64_t dz_lit = n > d ? d : n - 1;
+  NSVGD_PROPAGATE(median_prepare_ld(stream, X, n, d, ldx, mode, Z, mode == NSVGD_MEDIAN_LITERAL ? literal_ldz(dz_lit) : 0, &dz, &w_last, state));
   prof_end(12, st);
   const float* P = mode == NSVGD_MEDIAN_LITERAL ? Z : X;
-  const int64_t ldp = mode == NSVGD_MEDIAN_LITERAL ? dz : ldx;
+  const int64_t ldp = mode == NSVGD_MEDIAN_LITERAL ? literal_ldz(dz) : ldx;
   const char* env = getenv("NSVGD_MEDIAN_FAST");
   const bool want_fast = fast && !(env && env[0] == '0');
   if (want_fast) {
@@ -650,7 +666,8 @@ extern "C" int nsvgd_median_h_f32(void* stream, const float* X, int64_t n, int64
     // bracket misses (probability ~1e-9) or a candidate list overflows (massive ties)
     long long r_lo, r_hi;
     median_ranks_host(n, mode, &r_lo, &r_hi);
-    const bool aligned = ldp % 4 == 0 && (((uintptr_t)P) & 15) == 0;
+    // float4 rows; columns [dz, ceil4(dz)) must be zero: our own Z is padded that way, a caller's array only if dz % 4 == 0
+    const bool aligned = ldp % 4 == 0 && (((uintptr_t)P) & 15) == 0 && (dz % 4 == 0 || mode == NSVGD_MEDIAN_LITERAL);
     if (median_fast_supported(n, dz))
       NSVGD_PROPAGATE(median_fast(st, P, n, dz, ldp, w_last, r_lo, r_hi, 0, 1, (SelectState*)state, hist, fast, fast_bytes));
     else if (aligned)

@@ -348,8 +348,9 @@ class MedianSelect:
         self.P = self.Z if mode == "literal" else x
         self.fast_supported = bool(load().nsvgd_median_fast_supported(n, self.dz)) and os.environ.get("NSVGD_MEDIAN_FAST", "1") != "0"
         # d > 128: the single-GPU filtered select (csrc/median_large.cu) beats the row-sharded 3-pass SIMT select up to 16+ ranks
-        self.large_supported = bool(load().nsvgd_median_large_supported(n, self.dz)) and ld(self.P) % 4 == 0 \
-            and self.P.data_ptr() % 16 == 0
+        # (the single-GPU driver pads its own literal-mode Z to float4 rows; a caller's array must already be aligned)
+        self.large_supported = bool(load().nsvgd_median_large_supported(n, self.dz)) and (
+            mode == "literal" or (ld(x) % 4 == 0 and x.data_ptr() % 16 == 0 and self.dz % 4 == 0))
         self._fast_ws = None
         self.reduce = torch.zeros(4, dtype=torch.int64, device=x.device)
 

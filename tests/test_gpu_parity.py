@@ -77,7 +77,8 @@ def test_bandwidth_stored_distance_select(n, d, seed, mode, monkeypatch):
 
 
 @pytest.mark.parametrize("n,d,kind", [(2048, 132, "gauss"), (2500, 300, "gauss"), (3000, 1028, "gauss"), (2304, 512, "clusters"),
-                                      (2100, 256, "ties"), (2200, 640, "bnn")])
+                                      (2100, 256, "ties"), (2200, 640, "bnn"),
+                                      (2100, 1149, "bnn"), (2050, 4594, "bnn"), (2300, 202, "gauss")])     # d % 4 != 0 (4594: the reference's BNN)
 @pytest.mark.parametrize("mode", so.MEDIAN_MODES)
 def test_bandwidth_large_d_filtered_select(n, d, kind, mode, monkeypatch):
     """d > 128, n >= 2048: the tensor-core filtered select of csrc/median_large.cu (symmetric CTA-pair Gram with the classify
