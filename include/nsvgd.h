@@ -222,6 +222,13 @@ int nsvgd_ksd_f32(void* stream, const float* X, const float* Sx, int64_t n, int6
                   const float* Y, const float* Sy, int64_t m, int64_t ldy,
                   int64_t d, const float* h_dev, int variant, double* out_dev, void* ws, size_t ws_bytes);
 
+/* The U and V statistics through the fused phi* kernels (tensor cores for d > 32): stein_discrepancy(phi*) (stein.py:99-106)
+ * is the V-statistic (stein.py:327-349) and U = (n^2 V - sum_i(|s_i|^2 + d/h^2)) / (n(n-1)) (stein.py:299-323).  One phi* pass
+ * instead of n^2/2 fp32 SIMT pair evaluations: the route `stein.ksd_squared_u / _v` take for n >= 4096. */
+int nsvgd_ksd_tc_workspace_bytes(int64_t n, int64_t d, size_t* out_bytes);
+int nsvgd_ksd_tc_f32(void* stream, const float* X, const float* S, int64_t n, int64_t d, int64_t ldx, const float* h_dev,
+                     int variant, double* out_dev, void* ws, size_t ws_bytes);
+
 /* ---- A9: MMD^2  (metrics.py:88-127; funnel != 0 applies kernels.defunnelize, kernels.py:112-123)
  * out_dev: 1 double = mean offdiag Kxx + mean offdiag Kyy - 2 mean Kxy. */
 int nsvgd_mmd_f32(void* stream, const float* X, int64_t n, int64_t ldx,

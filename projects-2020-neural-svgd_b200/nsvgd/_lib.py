@@ -33,7 +33,7 @@ SYMBOLS = [
     "nsvgd_median_fast_cand_advance", "nsvgd_median_fast_commit", "nsvgd_median_fallback_hist",
     "nsvgd_median_fallback_advance", "nsvgd_phi_f32", "nsvgd_step_sgd_f32", "nsvgd_apply_update_f32",
     "nsvgd_ksd_f32", "nsvgd_mmd_f32", "nsvgd_ksum_f32", "nsvgd_adam_update_f32",
-    "nsvgd_loop_small_supported", "nsvgd_svgd_loop_small_f32", "nsvgd_median_large_supported",
+    "nsvgd_loop_small_supported", "nsvgd_svgd_loop_small_f32", "nsvgd_median_large_supported", "nsvgd_ksd_tc_workspace_bytes", "nsvgd_ksd_tc_f32",
     "nsvgd_scale_cols_f32", "nsvgd_matmul_f32", "nsvgd_ksd_ard_f32", "nsvgd_ksd_linear_f32", "nsvgd_ksd_dh_f32", "nsvgd_phi_vjp_workspace_bytes", "nsvgd_phi_vjp_f32",
     "nsvgd_score_funnel_f32", "nsvgd_score_gaussian_f32", "nsvgd_score_logreg_f32",
     "nsvgd_p2p_block_bytes", "nsvgd_p2p_alloc", "nsvgd_p2p_open", "nsvgd_p2p_close", "nsvgd_p2p_free",
@@ -89,6 +89,8 @@ def load():
     lib.nsvgd_ksum_f32.argtypes = [vp, vp, i64, i64, vp, i64, i64, i64, f32, i32, vp, vp, sz]
     lib.nsvgd_adam_update_f32.argtypes = [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, i64]
     lib.nsvgd_median_large_supported.argtypes = [i64, i64]
+    lib.nsvgd_ksd_tc_workspace_bytes.argtypes = [i64, i64, C.POINTER(sz)]
+    lib.nsvgd_ksd_tc_f32.argtypes = [vp, vp, vp, i64, i64, i64, vp, i32, vp, vp, sz]
     lib.nsvgd_loop_small_supported.argtypes = [i64, i64]
     lib.nsvgd_svgd_loop_small_f32.argtypes = [vp, vp, i64, i64, i32, vp, i32, f32, i32, f32, f32, i32, f32, i64, i64,
                                               vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, f32, vp, vp, vp]

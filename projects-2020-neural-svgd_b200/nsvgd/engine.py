@@ -196,6 +196,9 @@ class PeerComm:
         return t
 
 
+KSD_TC_MIN_N = 4096      # from here on the phi*-statistics route beats the fp32 SIMT pair tiles
+
+
 def ksd(X, Sx, h, variant="v", Y=None, Sy=None) -> torch.Tensor:
     """KSD^2 closed form (stein.py:273-349) -> 0-dim float64 device tensor."""
     X = require_cuda_f32(X, "X").contiguous(); Sx = require_cuda_f32(Sx, "Sx").contiguous()
@@ -206,6 +209,14 @@ def ksd(X, Sx, h, variant="v", Y=None, Sy=None) -> torch.Tensor:
         m = Y.shape[0]
     h_dev = as_h_dev(h, X.device)
     out = torch.empty(1, dtype=torch.float64, device=X.device)
+    if variant in ("u", "v") and n >= KSD_TC_MIN_N and os.environ.get("NSVGD_KSD_TC", "1") != "0":
+        # at scale the U / V statistics come out of the fused phi* kernels (tensor cores for d > 32): one phi* pass
+        need = C.c_size_t(0)
+        check(load().nsvgd_ksd_tc_workspace_bytes(n, d, C.byref(need)))
+        ws = workspace(int(need.value), X.device)
+        check(load().nsvgd_ksd_tc_f32(stream_ptr(X.device), ptr(X), ptr(Sx), n, d, d, ptr(h_dev), _lib.KSD_VARIANTS[variant],
+                                      ptr(out), ptr(ws), ws.numel()))
+        return out[0]
     ws = workspace(workspace_bytes("ksd", n, m, d), X.device)
     check(load().nsvgd_ksd_f32(stream_ptr(X.device), ptr(X), ptr(Sx), n, d, ptr(Y), ptr(Sy), m, d, d, ptr(h_dev),
                                _lib.KSD_VARIANTS[variant], ptr(out), ptr(ws), ws.numel()))

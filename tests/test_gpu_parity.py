@@ -132,6 +132,25 @@ def test_bandwidth_large_d_filter_radius_has_margin(n, d, kind, monkeypatch):
         assert np.float32(got).tobytes() == np.float32(want).tobytes(), (mode, got, want)
 
 
+@pytest.mark.parametrize("n,d,h", [(4096, 50, 5.0), (5000, 128, 8.0), (4100, 3, 1.3), (4200, 200, 12.0)])
+def test_ksd_u_v_through_phi_statistics(n, d, h, monkeypatch):
+    """n >= 4096: ksd_squared_u / _v come out of the fused phi* kernels (stein_discrepancy(phi*) == V-statistic,
+    U = (n^2 V - sum_i(|s_i|^2 + d/h^2)) / (n(n-1)); csrc/api.cu nsvgd_ksd_tc_f32) -- against the fp32 SIMT pair tiles
+    (nsvgd_ksd_f32) and, for the V statistic, the fp64 oracle."""
+    from nsvgd import engine
+    X, S = so.gaussian_diag_workload(n, d, seed=n + d, shift=0.5)
+    S = (S * 0.1).astype(np.float32)
+    Xd, Sd = dev(X), dev(S)
+    got = {v: engine.ksd(Xd, Sd, h, v).item() for v in ("u", "v")}
+    monkeypatch.setenv("NSVGD_KSD_TC", "0")
+    ref = {v: engine.ksd(Xd, Sd, h, v).item() for v in ("u", "v")}
+    monkeypatch.delenv("NSVGD_KSD_TC")
+    scale = abs(ref["v"])
+    for v in ("u", "v"):
+        assert got[v] == pytest.approx(ref[v], abs=TOL * scale), (v, got[v], ref[v])
+    assert got["v"] == pytest.approx(so.stein_discrepancy_phistar(X, S, h), rel=TOL)
+
+
 def test_bandwidth_nan_and_zero():
     from nsvgd import engine
     X = np.random.default_rng(0).standard_normal((70, 3)).astype(np.float32)
