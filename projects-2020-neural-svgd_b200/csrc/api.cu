@@ -99,7 +99,6 @@ static int choose_path(int path, int64_t n, int64_t m, int64_t d) {
 
 static int phi_dispatch(cudaStream_t st, const PhiArgs& a, int path, void* ws, size_t ws_bytes, bool dry, size_t* need) {
   int p = choose_path(path, a.n, a.m, a.d);
-  if (p == NSVGD_PATH_LARGE && a.aux && path == NSVGD_PATH_AUTO) p = NSVGD_PATH_GENERIC;   // aux split: generic path
   switch (p) {
     case NSVGD_PATH_SIMT: return phi_simt(st, a, ws, ws_bytes, dry, need);
     case NSVGD_PATH_TC: return phi_tc(st, a, ws, ws_bytes, dry, need);

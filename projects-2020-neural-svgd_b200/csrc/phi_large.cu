@@ -614,11 +614,49 @@ __global__ void __launch_bounds__(256) large_wt_kernel(const float* __restrict__
   }
 }
 
+// [S | Xc]^T pieces for the aux split (stein.phistar's [drift, repulsion], stein.py:206-222): rows [0, d) = S^T, rows
+// [dpad, dpad + d) = Xc^T; 64 particles x 32 coordinates per CTA, blockIdx.z selects the block
+__global__ void __launch_bounds__(256) large_vt_kernel(const float* __restrict__ X, const float* __restrict__ S, int64_t n,
+                                                       int64_t d, int64_t ldx, const float* __restrict__ mu, int64_t dpad,
+                                                       __nv_bfloat16* __restrict__ Vt0, __nv_bfloat16* __restrict__ Vt1, int64_t ldw) {
+  __shared__ float t[32][65];
+  const int64_t j0 = (int64_t)blockIdx.x * 64, c0 = (int64_t)blockIdx.y * 32;
+  const bool xblock = blockIdx.z == 1;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c = c0 + tx;
+  const float m = (xblock && c < d) ? mu[c] : 0.f;
+#pragma unroll
+  for (int jj = ty; jj < 64; jj += 8) {
+    const int64_t j = j0 + jj;
+    float w = 0.f;
+    if (j < n && c < d) w = xblock ? X[j * ldx + c] - m : S[j * ldx + c];
+    t[tx][jj] = w;
+  }
+  __syncthreads();
+  const int cc = threadIdx.x >> 3, jj0 = (threadIdx.x & 7) * 8;
+  if (c0 + cc < d) {
+    uint32_t w0[4], w1[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = t[cc][jj0 + 2 * e], b = t[cc][jj0 + 2 * e + 1];
+      w0[e] = pack_bf16x2(a, b);
+      w1[e] = pack_bf16x2(a - bf16lo_to_float(w0[e]), b - bf16hi_to_float(w0[e]));
+    }
+    const int64_t row = (xblock ? dpad : 0) + c0 + cc;
+    *reinterpret_cast<uint4*>(&Vt0[row * ldw + j0 + jj0]) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+    *reinterpret_cast<uint4*>(&Vt1[row * ldw + j0 + jj0]) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+  }
+}
+
 int phi_large(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool dry, size_t* need) {
   const int ctas = lg_ctas();
   const int64_t ldk = round_up(a.d, 8);
   const int64_t n_pad = round_up(a.n, LG_BN);
-  const int64_t ldo = round_up(a.d, 4);
+  // aux split requested: the second GEMM runs against [S | Xc] (2 d columns, GRAM form of the epilogue) instead of W
+  const bool want_aux = a.aux != nullptr;
+  const int64_t dpad = round_up(a.d, 4);
+  const int64_t v_rows = (want_aux || dry) ? dpad + a.d : a.d;       // rows of the K-major B operand of the second GEMM
+  const int64_t ldo = (want_aux || dry) ? 2 * dpad : dpad;
   const int nsplit = (int)ceil_div(n_pad, LG_NK);
   const int tiles_nx = (int)(n_pad / LG_BN);                 // 256-particle column tiles of the Gram
   // the queries are a row range of the particle array (the SVGD step: all of it; a row-sharded rank: its block of the
@@ -634,8 +672,8 @@ int phi_large(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool
   double* mpart = w.take<double>((size_t)colmean_partials(a.n, a.d));
   __nv_bfloat16* Xb0 = w.take<__nv_bfloat16>((size_t)(n_pad * ldk));
   __nv_bfloat16* Xb1 = w.take<__nv_bfloat16>((size_t)(n_pad * ldk));
-  __nv_bfloat16* Wt0 = w.take<__nv_bfloat16>((size_t)(a.d * n_pad));
-  __nv_bfloat16* Wt1 = w.take<__nv_bfloat16>((size_t)(a.d * n_pad));
+  __nv_bfloat16* Wt0 = w.take<__nv_bfloat16>((size_t)(v_rows * n_pad));
+  __nv_bfloat16* Wt1 = w.take<__nv_bfloat16>((size_t)(v_rows * n_pad));
   float* xn = w.take<float>((size_t)n_pad);
   float* cv = w.take<float>((size_t)n_pad);
   __nv_bfloat16 *Qb0 = Xb0, *Qb1 = Xb1;
@@ -657,15 +695,23 @@ int phi_large(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool
   if (need) *need = w.off;
   if (dry) return NSVGD_OK;
   NSVGD_REQUIRE(w.ok(), NSVGD_ERR_WORKSPACE, "phi_large: workspace too small (%zu < %zu)", ws_bytes, w.off);
-  NSVGD_REQUIRE(!a.aux, NSVGD_ERR_UNSUPPORTED, "phi_large: the [drift, repulsion] aux output is served by the generic path");
   NSVGD_REQUIRE(n_pad < (1ll << 31) && a.m < (1ll << 31) && ldk < (1ll << 31), NSVGD_ERR_INVALID, "phi_large: shape too large");
 
   NSVGD_CUDA(cudaMemsetAsync(err_flag, 0, 64 * sizeof(uint32_t), st));
   NSVGD_PROPAGATE(launch_colmean(st, a.X, a.n, a.d, a.ldx, mpart, mu));
   large_prep_kernel<<<(unsigned)ceil_div(n_pad * 32, 256), 256, 0, st>>>(a.X, a.S, a.n, n_pad, a.d, a.ldx, ldk, mu, Xb0, Xb1, xn, cv);
   NSVGD_LAUNCH_CHECK();
-  large_wt_kernel<<<dim3((unsigned)(n_pad / 64), (unsigned)ceil_div(a.d, 32)), 256, 0, st>>>(a.X, a.S, a.n, a.d, a.ldx, mu, a.h_dev,
-                                                                                          Wt0, Wt1, n_pad);
+  if (want_aux) {
+    if (dpad != a.d) {      // the (at most 3) rows between the two blocks
+      NSVGD_CUDA(cudaMemsetAsync(Wt0 + a.d * n_pad, 0, (size_t)((dpad - a.d) * n_pad) * sizeof(__nv_bfloat16), st));
+      NSVGD_CUDA(cudaMemsetAsync(Wt1 + a.d * n_pad, 0, (size_t)((dpad - a.d) * n_pad) * sizeof(__nv_bfloat16), st));
+    }
+    large_vt_kernel<<<dim3((unsigned)(n_pad / 64), (unsigned)ceil_div(a.d, 32), 2), 256, 0, st>>>(a.X, a.S, a.n, a.d, a.ldx, mu, dpad,
+                                                                                               Wt0, Wt1, n_pad);
+  } else {
+    large_wt_kernel<<<dim3((unsigned)(n_pad / 64), (unsigned)ceil_div(a.d, 32)), 256, 0, st>>>(a.X, a.S, a.n, a.d, a.ldx, mu, a.h_dev,
+                                                                                            Wt0, Wt1, n_pad);
+  }
   NSVGD_LAUNCH_CHECK();
   if (q_in_x) { Qb0 = Xb0 + diag_off * ldk; Qb1 = Xb1 + diag_off * ldk; qn = xn + diag_off; }
   else {
@@ -685,20 +731,20 @@ int phi_large(cudaStream_t st, const PhiArgs& a, void* ws, size_t ws_bytes, bool
     if (sym) NSVGD_CUDA(cudaMemsetAsync(scal, 0, (size_t)scal_parts * a.m * 4 * sizeof(float), st));   // slots no tile writes
     NSVGD_PROPAGATE(lg_launch(st, ctas, Qb0 + i0 * ldk, Qb1 + i0 * ldk, sym ? n_pad : mi, ldk, Xb0, Xb1, n_pad, ldk, ldk, g));
     LgParams o{};
-    o.epi = LG_EPI_STORE; o.tiles_n = (int)ceil_div(a.d, LG_BN); o.nsplit = nsplit;
+    o.epi = LG_EPI_STORE; o.tiles_n = (int)ceil_div(v_rows, LG_BN); o.nsplit = nsplit;
     o.kb_total = (int)(n_pad / LG_BK); o.kb_per_split = (int)(LG_NK / LG_BK);
     o.m_rows = (int)mi; o.row_off = i0;
     o.O = O + i0 * ldo; o.ldo = ldo; o.o_split_stride = a.m * ldo; o.n_cols = (int)ldo;
     o.err_flag = err_flag;
-    NSVGD_PROPAGATE(lg_launch(st, ctas, P0, P1, mi, n_pad, Wt0, Wt1, a.d, n_pad, n_pad, o));
+    NSVGD_PROPAGATE(lg_launch(st, ctas, P0, P1, mi, n_pad, Wt0, Wt1, v_rows, n_pad, n_pad, o));
   }
   prof_end(0, st);
 
   EpilogueArgs e{};
-  e.form = 2; e.err_flag = err_flag; e.O = O; e.scal = scal; e.nsplit = nsplit; e.scal_parts = scal_parts; e.m_pad = a.m; e.ldo = ldo;
-  e.dpad = 0; e.mu = mu;
+  e.form = want_aux ? 1 : 2; e.err_flag = err_flag; e.O = O; e.scal = scal; e.nsplit = nsplit; e.scal_parts = scal_parts; e.m_pad = a.m;
+  e.ldo = ldo; e.dpad = want_aux ? dpad : 0; e.mu = mu;
   e.Q = a.Q; e.ldq = a.ldq; e.Sq = a.Sq; e.m = a.m; e.n = a.n; e.d = a.d; e.h_dev = a.h_dev;
-  e.phi = a.phi; e.ldphi = a.ldphi; e.aux = nullptr; e.stats_dev = a.stats_dev; e.partials = partials;
+  e.phi = a.phi; e.ldphi = a.ldphi; e.aux = a.aux; e.stats_dev = a.stats_dev; e.partials = partials;
   return launch_epilogue(st, e);
 }
 

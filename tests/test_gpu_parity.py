@@ -266,13 +266,9 @@ def test_phi_paths_vs_oracle(path, n, d, h):
     Q = (np.random.default_rng(1).standard_normal((m, d)) * 0.9 + 0.4).astype(np.float32)
     Xd, Sd, Qd = dev(X), dev(S), dev(Q)
     ref, ref_aux = so.phistar(X, X, S, h, aux=True)
-    if path == "large":       # hand-written tcgen05 GEMM pair (csrc/phi_large.cu): COMBINED form only (the aux split of d > 128 is served by "generic")
-        with pytest.raises(NotImplementedError):
-            engine.phistar(Xd, Xd, Sd, h, Sq=Sd, aux=True, stats=True, path=path)
-        phi, stats = engine.phistar(Xd, Xd, Sd, h, Sq=Sd, stats=True, path=path)
-        _, aux = engine.phistar(Xd, Xd, Sd, h, aux=True)            # auto dispatch falls back to generic for aux
-    else:
-        phi, aux, stats = engine.phistar(Xd, Xd, Sd, h, Sq=Sd, aux=True, stats=True, path=path)
+    # every path serves the [drift, repulsion] aux split (d > 128: the second GEMM of csrc/phi_large.cu then runs against
+    # [S | Xc] instead of W = S - Xc/h^2)
+    phi, aux, stats = engine.phistar(Xd, Xd, Sd, h, Sq=Sd, aux=True, stats=True, path=path)
     assert rel_fro(phi.cpu(), ref) < TOL, rel_fro(phi.cpu(), ref)
     assert max_row_rel(phi.cpu(), ref) < ROW_TOL, max_row_rel(phi.cpu(), ref)
     assert rel_fro(aux.cpu(), ref_aux) < TOL
