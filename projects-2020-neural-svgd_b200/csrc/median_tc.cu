@@ -241,10 +241,10 @@ __global__ void __launch_bounds__(32 * WX_WARPS) sample_pairs_warp_kernel(const 
 // everything that can reach the result is recomputed in the defined order by exact_list_kernel.
 __global__ void __launch_bounds__(32 * WX_WARPS) sample_rows_kernel(const float* __restrict__ P, int64_t n, int d, int64_t ldp,
                                                                    float w_last, uint32_t s_begin, uint32_t ns,
-                                                                   float* __restrict__ Ds) {
+                                                                   float* __restrict__ Ds, uint32_t NB) {
+  // NB = warp-blocks of the whole sample set (MF_SAMPLES / 32, or the size of a REPLICATED reduced set / 32)
   __shared__ float part[WX_WARPS][32 * 33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  constexpr uint32_t NB = MF_SAMPLES / 32;
   float* mine = part[w];
   for (uint32_t s0 = s_begin + (blockIdx.x * WX_WARPS + w) * 32u; s0 < ns; s0 += gridDim.x * WX_WARPS * 32u) {
     const uint64_t i = ((uint64_t)(s0 >> 5) * (uint64_t)n) / NB;
@@ -1050,8 +1050,10 @@ static int launch_filter(cudaStream_t st, const CUtensorMap* maps, const MfParam
 }
 
 // stage 0: centred bf16 pieces, norms, thresholds, and this rank's slice of the sampled pair distances
+// replicated = true: every rank computes the SAME reduced sample set of MF_SAMPLES / nparts pairs (rows spread over all n),
+// so the bracket select needs no exchange at all (median_fast_run)
 int median_fast_sample(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, int64_t part,
-                       int64_t nparts, void* ws, size_t ws_bytes, size_t* samples_off, int64_t* samples_count) {
+                       int64_t nparts, void* ws, size_t ws_bytes, size_t* samples_off, int64_t* samples_count, bool replicated) {
   NSVGD_REQUIRE(median_fast_supported(n, dz), NSVGD_ERR_UNSUPPORTED, "median_fast: unsupported shape");
   NSVGD_REQUIRE(nparts >= 1 && part >= 0 && part < nparts && MF_SAMPLES % nparts == 0 && (MF_SAMPLES / nparts) % 32 == 0,
                 NSVGD_ERR_INVALID, "median_fast_sample: the sample count %u must split evenly over %lld parts", MF_SAMPLES,
@@ -1074,7 +1076,8 @@ int median_fast_sample(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   NSVGD_PROPAGATE(ensure_dyn_smem((const void*)sample_pairs_warp_kernel, WX_SMEM));
   NSVGD_PROPAGATE(ensure_dyn_smem((const void*)exact_list_warp_kernel, WX_SMEM));
   const uint32_t per = MF_SAMPLES / (uint32_t)nparts;
-  const uint32_t s_begin = per * (uint32_t)part, s_end = s_begin + per;
+  const uint32_t s_begin = replicated ? 0u : per * (uint32_t)part, s_end = s_begin + per;
+  const uint32_t nb_total = (replicated ? per : MF_SAMPLES) / 32u;
   prof_begin(4, st);
   const char* iid_env = getenv("NSVGD_MEDIAN_IID_SAMPLE");
   if (iid_env && iid_env[0] == '1') {     // A/B: the first version, i.i.d. pairs with defined-order arithmetic
@@ -1082,7 +1085,7 @@ int median_fast_sample(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
     sample_pairs_warp_kernel<<<blocks, 32 * WX_WARPS, WX_SMEM, st>>>(P, n, (int)dz, ldp, w_last, s_begin, s_end, f.Ds);
   } else {
     const unsigned blocks = (unsigned)std::min<int64_t>(sms * 8, ceil_div(per, 32 * WX_WARPS));
-    sample_rows_kernel<<<blocks, 32 * WX_WARPS, 0, st>>>(P, n, (int)dz, ldp, w_last, s_begin, s_end, f.Ds);
+    sample_rows_kernel<<<blocks, 32 * WX_WARPS, 0, st>>>(P, n, (int)dz, ldp, w_last, s_begin, s_end, f.Ds, nb_total);
   }
   prof_end(4, st);
   NSVGD_LAUNCH_CHECK();
@@ -1097,7 +1100,9 @@ int median_fast_sample(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
 int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, long long r_lo,
                        long long r_hi, int64_t block_row_start, int64_t block_row_stride, SelectState* main_state,
                        uint64_t* hist, void* ws, size_t ws_bytes, long long* red, const P2PComm* comm, uint32_t s_begin,
-                       uint32_t s_end) {
+                       uint32_t s_end, uint32_t ns_total = MF_SAMPLES, bool bracket_local = false) {
+  // ns_total: size of the sample set the bracket ranks refer to; bracket_local: the set [s_begin, s_end) = [0, ns_total) is
+  // replicated on every rank, so the bracket select runs without an exchange
   NSVGD_REQUIRE(median_fast_supported(n, dz), NSVGD_ERR_UNSUPPORTED, "median_fast: unsupported shape");
   NSVGD_REQUIRE(r_lo >= 0 && r_hi >= r_lo, NSVGD_ERR_UNSUPPORTED, "median_fast: needs genuine pair ranks");
   WsCarver w(ws, ws_bytes);
@@ -1111,21 +1116,21 @@ int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   // --- 1. bracket [L, U] from the sample quantiles: 6 sigma of the binomial rank error + slack
   //        (deterministic pseudo-random pairs: every rank computes the identical bracket)
   const double Ppairs = 0.5 * (double)n * (double)(n - 1);
-  const double ns = (double)MF_SAMPLES;
+  const double ns = (double)ns_total;
   const double p_lo = ((double)r_lo + 0.5) / Ppairs, p_hi = ((double)r_hi + 0.5) / Ppairs;
   const double sig_lo = sqrt(ns * p_lo * (1.0 - p_lo)), sig_hi = sqrt(ns * p_hi * (1.0 - p_hi));
   // 5 sigma + slack on either side: a miss (probability ~6e-7 per step) only costs the device-side fallback to the SIMT
   // select (still exact); the bracket is 17 % narrower than at 6 sigma and so is the list of pairs to re-evaluate
   long long a = (long long)floor(p_lo * ns - 5.0 * sig_lo - 16.0);
   long long b = (long long)ceil(p_hi * ns + 5.0 * sig_hi + 16.0);
-  const int l_is_zero = a < 0, u_is_inf = b >= (long long)MF_SAMPLES;
+  const int l_is_zero = a < 0, u_is_inf = b >= (long long)ns_total;
   if (a < 0) a = 0;
-  if (b >= (long long)MF_SAMPLES) b = (long long)MF_SAMPLES - 1;
+  if (b >= (long long)ns_total) b = (long long)ns_total - 1;
   (void)hist;
   prof_begin(9, st);
   NSVGD_PROPAGATE(launch_select_init(st, f.bracket, a, b, 1.f));
-  NSVGD_PROPAGATE(launch_fused_select(st, f.Ds, nullptr, 0, 1, 0, s_begin, s_end, f.bracket, &f.sel[0], comm, 1, f.fs, nullptr,
-                                      l_is_zero, u_is_inf));
+  NSVGD_PROPAGATE(launch_fused_select(st, f.Ds, nullptr, 0, 1, 0, s_begin, s_end, f.bracket, &f.sel[0], bracket_local ? nullptr : comm, 1,
+                                      f.fs, nullptr, l_is_zero, u_is_inf));
   prof_end(9, st);
 
   // --- 2. tensor-core filter over the upper triangle (128-row blocks strided across ranks)
@@ -1221,12 +1226,20 @@ int median_fast_run(cudaStream_t st, const float* P, int64_t n, int64_t dz, int6
   const int rank = comm ? comm->rank : 0, world = comm ? comm->world : 1;
   const bool slice = comm && MF_SAMPLES % (uint32_t)world == 0 && (MF_SAMPLES / (uint32_t)world) % 32 == 0;
   const uint32_t per = slice ? MF_SAMPLES / (uint32_t)world : MF_SAMPLES;
-  const uint32_t s_begin = slice ? per * (uint32_t)rank : 0u, s_end = s_begin + per;
-  NSVGD_PROPAGATE(median_fast_sample(st, P, n, dz, ldp, w_last, slice ? rank : 0, slice ? world : 1, ws, ws_bytes, nullptr, nullptr));
+  // NSVGD_MEDIAN_REPLICATED_SAMPLE=1 (row-sharded, off by default): every rank computes the SAME reduced sample set of
+  // 2^22 / world pairs and selects the bracket locally -- no exchange in the bracket phase (three grid-wide passes with a
+  // peer-memory all-reduce each).  The bracket is sqrt(world) x wider, so the exact list grows.  Measured at 2 ranks: bracket
+  // 0.153 -> 0.064 ms, exact list 0.225 -> 0.309 ms, step 3.415 -> 3.439 ms; extrapolated to 8 ranks: -0.20 + 0.15 ms.
+  // Bit-identical h either way (tests/test_sharded_gpu.py).
+  bool replicated = false;
+  if (const char* e = getenv("NSVGD_MEDIAN_REPLICATED_SAMPLE")) replicated = slice && e[0] == '1';
+  const uint32_t s_begin = (slice && !replicated) ? per * (uint32_t)rank : 0u, s_end = s_begin + per;
+  NSVGD_PROPAGATE(median_fast_sample(st, P, n, dz, ldp, w_last, slice ? rank : 0, slice ? world : 1, ws, ws_bytes, nullptr, nullptr,
+                                     replicated));
   // (an unsliceable world size: every rank samples everything and contributes 1/world-th... not needed: world | 2^22 in practice)
   NSVGD_REQUIRE(!comm || slice, NSVGD_ERR_UNSUPPORTED, "median_fast_run: world size %d does not divide the sample count", world);
   NSVGD_PROPAGATE(median_fast_stage1(st, P, n, dz, ldp, w_last, r_lo, r_hi, rank, world, main_state, hist, ws, ws_bytes, nullptr,
-                                     comm, s_begin, s_end));
+                                     comm, s_begin, s_end, replicated ? per : MF_SAMPLES, replicated));
   P2PComm c{};
   if (comm) c = *comm; else { c.rank = 0; c.world = 1; }
   prof_begin(10, st);
@@ -1273,7 +1286,7 @@ extern "C" int nsvgd_median_fast_sample(void* stream, const float* Z, int64_t n,
                                         int64_t* samples_count) {
   NSVGD_REQUIRE(Z && ws, NSVGD_ERR_INVALID, "median_fast_sample: null pointer");
   return median_fast_sample((cudaStream_t)stream, Z, n, dz, ldz, w_last, part, nparts, ws, ws_bytes, samples_offset_bytes,
-                            samples_count);
+                            samples_count, false);
 }
 
 extern "C" int nsvgd_median_fast_stage1(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last, int mode,
