@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-offdiag", action="store_true", help="skip the secondary off-diagonal-median run")
     ap.add_argument("--no-secondary", action="store_true", help="skip the timings of the other BASELINE configs")
+    ap.add_argument("--no-hint", action="store_true",
+                    help="do not warm-start the median bracket from the previous step (engine.median_heuristic(hint=))")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step as one CUDA graph (auto = on)")
     return ap.parse_args()
@@ -73,6 +75,7 @@ def config_of(args, world):
     """identical in both arms (ours / reference): the driver compares it"""
     return {"workload": f"svgd_step n={args.n} d={args.d} (BASELINE configs[3])", "n": args.n, "d": args.d,
             "bandwidth": (f"median heuristic ({args.median_mode}) every step" if args.bandwidth <= 0 else f"fixed {args.bandwidth}"),
+            "median_warm_start": bool(args.bandwidth <= 0 and not args.no_hint),
             "scaled": True, "optimizer": "sgd", "lr": LR, "lambda_reg": LAMBDA_REG,
             "parallelism": f"row-sharded x{world}", "l2_flush": "192 MiB fill between steps (GPU arm)"}
 
@@ -387,6 +390,12 @@ def main():
         sharded = ShardedSVGD(n, d, median_mode=mode) if world > 1 else None
         X_loc.copy_(X0)
         state = {"graphed": None}
+        # the SVGD loop keeps the warm-start state of the bandwidth selection between steps (bit-identical h; the sampling and
+        # bracket-select phases are skipped when the previous step's order statistics still bracket the target ranks)
+        if args.no_hint:
+            os.environ["NSVGD_MEDIAN_HINT"] = "0"
+        hint = None if (args.no_hint or world > 1) else engine.new_median_hint(dev)
+        state["hint"] = hint
 
         def one_step():
             if state["graphed"] is not None:
@@ -394,7 +403,7 @@ def main():
             if world > 1:
                 h, aux, _ = sharded.step(X_loc, S_loc, lr, scaled=True, lambda_reg=lam, bandwidth=fixed_h)
             else:
-                h = fixed_h if fixed_h else engine.median_heuristic(X_loc, mode)
+                h = fixed_h if fixed_h else engine.median_heuristic(X_loc, mode, hint=hint)
                 aux, _ = engine.svgd_step_sgd(X_loc, S_loc, h, lr, scaled=True, lambda_reg=lam, path=args.path)
             return h, aux
 
@@ -436,6 +445,8 @@ def main():
         step_ms = sum(a.elapsed_time(b) for a, b in ev)
         h_val = float(h) if not isinstance(h, torch.Tensor) else float(h.item())
         aux_host = aux.cpu().numpy()
+        hint_dev = hint if hint is not None else (getattr(sharded, "_hint", None) if sharded is not None else None)
+        hint_stats = engine.median_hint_stats(hint_dev) if hint_dev is not None else None     # after warm-up + the timed steps
         if graphed is not None:
             # per-kernel breakdown / roofline: a second, un-graphed pass of min(K, 5) steps with the library-side
             # CUDA events on (not part of `value`; says so in the notes)
@@ -456,7 +467,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
         return {"one_step": one_step, "state": state, "sharded": sharded, "total_ms": total_ms, "K": K, "KP": KP, "prof": prof,
-                "h": h_val, "aux": aux_host, "launches": int(launches), "clocks": clocks, "t_wall": t_wall, "graphed": graphed}
+                "h": h_val, "aux": aux_host, "launches": int(launches), "clocks": clocks, "t_wall": t_wall, "graphed": graphed,
+                "hint_stats": hint_stats}
 
     def kernel_roofline(res, mode):
         ms, cnt = res["prof"][0]
@@ -547,7 +559,7 @@ def main():
                 X_loc.copy_(Xp, non_blocking=True)
                 S_loc.copy_(Sp, non_blocking=True)
             if world == 1 and graphed is None and not fixed_h:
-                h_ = engine.median_heuristic(X_loc, args.median_mode)
+                h_ = engine.median_heuristic(X_loc, args.median_mode, hint=res["state"].get("hint"))
                 a, _ = engine.svgd_step_sgd(X_loc, S_loc, h_, lr, scaled=True, lambda_reg=lam, path=args.path)
             else:
                 _, a = one_step()
@@ -669,6 +681,8 @@ def main():
                                             f"a separate un-graphed pass of {KP} steps after the timed region")},
         "phi_only_value": (KP * float(m_local) * n * d / (prof[2][0] * 1e-3)) if prof[2][0] else None,
         "result": {"h": res["h"], "ksd": float(res["aux"][0]), "l2": float(res["aux"][1]), "alpha": float(res["aux"][2])},
+        "median_hint": (dict(res["hint_stats"], note="warm-started bracket of the exact bandwidth selection: hits / misses over warm-up + timed "
+                             "steps (a miss runs the exact fallback); h is bit-identical with --no-hint") if res.get("hint_stats") else None),
         "wall_s": res["t_wall"], "gpu_launches": res["launches"], "clocks": res["clocks"], "roofline": roofline,
         "roofline_step": step_roofline(res), "offdiag_mode": offdiag, "secondary": secondary, "cpu_baseline": cpu_baseline, "e2e": e2e,
     }

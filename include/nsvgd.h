@@ -90,6 +90,14 @@ int nsvgd_workspace_bytes(int op, int64_t n, int64_t m, int64_t d, int path, siz
 int nsvgd_median_h_f32(void* stream, const float* X, int64_t n, int64_t d, int64_t ldx,
                        int mode, float* h_dev, void* ws, size_t ws_bytes);
 
+/* The same with a warm start for SVGD loops (kernels.py:160-172 called every step, models.py:657): hint_dev = 32 bytes of
+ * caller-owned, zero-initialised device memory kept between calls.  On the tensor-core filtered path (d <= 128, n >= 8192) the
+ * bracket then comes from the previous call's order statistics (margin = 4 x the last relative change, 2^-13 .. 2^-7) and the
+ * sampling + bracket-select phases are skipped; exact counts verify the bracket, a miss runs the exact fallback and drops the
+ * hint.  Bit-identical result with or without it.  nsvgd_p2p_median_fast_run_hinted: the row-sharded form. */
+int nsvgd_median_h_hinted_f32(void* stream, const float* X, int64_t n, int64_t d, int64_t ldx, int mode, float* h_dev,
+                              void* hint_dev, void* ws, size_t ws_bytes);
+
 /* Building blocks of the same select for row-sharded multi-GPU runs: every rank
  * histograms the tile rows  tile_row_start, +tile_row_stride, ...  of the upper
  * triangle, the host all-reduces `hist` (NCCL sum over uint64[2*2048]) between
@@ -170,6 +178,9 @@ int nsvgd_p2p_median_advance(void* stream, int rank, int world, void* const* blo
 int nsvgd_p2p_median_fast_run(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last, int mode,
                               int rank, int world, void* const* blocks, void* state_dev, uint64_t* hist_dev, void* ws,
                               size_t ws_bytes);
+int nsvgd_p2p_median_fast_run_hinted(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last, int mode,
+                                     int rank, int world, void* const* blocks, void* state_dev, uint64_t* hist_dev,
+                                     void* hint_dev, void* ws, size_t ws_bytes);
 /* = all-reduce(reduce_dev[4]) + nsvgd_median_fast_resolve */
 int nsvgd_p2p_median_fast_resolve(void* stream, int rank, int world, void* const* blocks, void* state_dev, void* ws,
                                   size_t ws_bytes, int64_t n, int64_t dz, int64_t* reduce_dev);

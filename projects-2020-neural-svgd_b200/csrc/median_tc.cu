@@ -241,8 +241,9 @@ __global__ void __launch_bounds__(32 * WX_WARPS) sample_pairs_warp_kernel(const 
 // everything that can reach the result is recomputed in the defined order by exact_list_kernel.
 __global__ void __launch_bounds__(32 * WX_WARPS) sample_rows_kernel(const float* __restrict__ P, int64_t n, int d, int64_t ldp,
                                                                    float w_last, uint32_t s_begin, uint32_t ns,
-                                                                   float* __restrict__ Ds, uint32_t NB) {
+                                                                   float* __restrict__ Ds, uint32_t NB, const uint32_t* skip_flag) {
   // NB = warp-blocks of the whole sample set (MF_SAMPLES / 32, or the size of a REPLICATED reduced set / 32)
+  if (skip_flag && *skip_flag) return;      // the bracket comes from the caller's hint this time
   __shared__ float part[WX_WARPS][32 * 33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* mine = part[w];
@@ -909,7 +910,8 @@ __global__ void __launch_bounds__(256, 4) fused_select_kernel(const float* __res
                                                            int count_stride, int nseg, uint32_t seg_cap, uint32_t v_begin,
                                                            uint32_t v_end, SelectState* state, FusedSelScratch* sc, const P2PComm c,
                                                            int world, int final_mode, FastMedState* fs, SelectState* main_state,
-                                                           int l_is_zero, int u_is_inf) {
+                                                           int l_is_zero, int u_is_inf, const uint32_t* skip_flag) {
+  if (skip_flag && *skip_flag) return;      // (identical on every CTA and every rank: nobody enters the hand-shakes)
   __shared__ unsigned int hist_s[2 * NSVGD_SELECT_BINS];
   __shared__ uint32_t s_last;
   const int lane = threadIdx.x & 31;
@@ -1015,7 +1017,7 @@ __global__ void __launch_bounds__(256, 4) fused_select_kernel(const float* __res
 int launch_fused_select(cudaStream_t st, const float* vals, const uint32_t* counts_dev, int count_stride, int nseg,
                                uint32_t seg_cap, uint32_t v_begin, uint32_t v_end, SelectState* state, FusedSelScratch* sc,
                                const P2PComm* comm, int final_mode, FastMedState* fs, SelectState* main_state, int l_is_zero,
-                               int u_is_inf) {
+                               int u_is_inf, const uint32_t* skip_flag) {
   P2PComm c{};
   if (comm) c = *comm; else { c.rank = 0; c.world = 1; }
   // the grid MUST be co-resident (CTAs wait for each other): ask the occupancy calculator, at most four CTAs per SM
@@ -1028,7 +1030,7 @@ int launch_fused_select(cudaStream_t st, const float* vals, const uint32_t* coun
     per_sm_cached.store(per_sm);
   }
   fused_select_kernel<<<device_sm_count() * per_sm, 256, 0, st>>>(vals, counts_dev, count_stride, nseg, seg_cap, v_begin, v_end, state, sc,
-                                                         c, c.world, final_mode, fs, main_state, l_is_zero, u_is_inf);
+                                                         c, c.world, final_mode, fs, main_state, l_is_zero, u_is_inf, skip_flag);
   NSVGD_LAUNCH_CHECK();
   return NSVGD_OK;
 }
@@ -1050,10 +1052,45 @@ static int launch_filter(cudaStream_t st, const CUtensorMap* maps, const MfParam
 }
 
 // stage 0: centred bf16 pieces, norms, thresholds, and this rank's slice of the sampled pair distances
+// ---------------------------------------------------------------------------- warm-started bracket (MedianHint, select.cuh)
+// hint valid -> the bracket is [lo (1 - delta), hi (1 + delta)] around the previous call's order statistics, the sample and
+// the bracket select return at once (skip flag), and everything downstream is unchanged: the resolve step checks with exact
+// counts that the target ranks fall among the candidates and triggers the exact SIMT select otherwise.
+__global__ void hint_apply_kernel(const MedianHint* hint, FastMedState* fs, uint32_t* skip_flag) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const bool use = hint && hint->valid && hint->lo == hint->lo && hint->hi == hint->hi && hint->hi >= hint->lo && hint->lo >= 0.f;
+  *skip_flag = use ? 1u : 0u;
+  if (!use) return;
+  fs->below = 0ull; fs->list_count = 0u; fs->cand_count = 0u; fs->overflow = 0u; fs->fallback = 0u;
+  fs->L = hint->lo * (1.f - hint->delta);
+  fs->U = hint->hi * (1.f + hint->delta);
+  fs->u_is_inf = 0u; fs->pad = 0u;
+}
+// after the select: remember the order statistics; margin = 4 x the relative change between the last two calls, within
+// [2^-13, 2^-7]; a miss (the hinted bracket did not contain the target: the fallback ran) or a NaN drops the hint
+__global__ void hint_update_kernel(MedianHint* hint, const SelectState* main_state, const FastMedState* fs, const uint32_t* skip_flag) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const bool hinted = *skip_flag != 0u;
+  const float lo = main_state->value[0], hi = main_state->value[1];
+  const bool usable = !main_state->nan_flag && !main_state->is_zero[0] && !main_state->is_zero[1] && lo == lo && hi == hi && hi > 0.f;
+  if (hinted) { if (fs->fallback) ++hint->misses; else ++hint->hits; }
+  if (!usable || (hinted && fs->fallback)) { hint->valid = 0u; hint->seen = 0u; return; }
+  float delta = 4.8828125e-4f;                                     // 2^-11 until two consecutive values are known
+  if (hint->seen) {
+    const float mid_old = 0.5f * (hint->lo + hint->hi), mid_new = 0.5f * (lo + hi);
+    const float drift = fabsf(mid_new - mid_old) / mid_new;
+    delta = fminf(fmaxf(4.f * drift, 1.220703125e-4f), 7.8125e-3f);
+  }
+  hint->lo = lo; hint->hi = hi; hint->delta = delta;
+  hint->valid = hint->seen ? 1u : 0u;                               // the first call only observes
+  hint->seen = 1u;
+}
+
 // replicated = true: every rank computes the SAME reduced sample set of MF_SAMPLES / nparts pairs (rows spread over all n),
 // so the bracket select needs no exchange at all (median_fast_run)
 int median_fast_sample(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, int64_t part,
-                       int64_t nparts, void* ws, size_t ws_bytes, size_t* samples_off, int64_t* samples_count, bool replicated) {
+                       int64_t nparts, void* ws, size_t ws_bytes, size_t* samples_off, int64_t* samples_count, bool replicated,
+                       const MedianHint* hint = nullptr) {
   NSVGD_REQUIRE(median_fast_supported(n, dz), NSVGD_ERR_UNSUPPORTED, "median_fast: unsupported shape");
   NSVGD_REQUIRE(nparts >= 1 && part >= 0 && part < nparts && MF_SAMPLES % nparts == 0 && (MF_SAMPLES / nparts) % 32 == 0,
                 NSVGD_ERR_INVALID, "median_fast_sample: the sample count %u must split evenly over %lld parts", MF_SAMPLES,
@@ -1066,6 +1103,11 @@ int median_fast_sample(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   prof_begin(8, st);
   NSVGD_PROPAGATE(launch_colmean(st, P, n, dz, ldp, f.mpart, f.mu));
   NSVGD_CUDA(cudaMemsetAsync(f.zero_block, 0, f.zero_bytes, st));   // error flag, list / candidate counters, select scratch
+  uint32_t* skip_flag = f.err_flag + 2;                             // (inside the zero block: 0 unless a valid hint sets it)
+  if (hint) {
+    hint_apply_kernel<<<1, 32, 0, st>>>(hint, f.fs, skip_flag);
+    NSVGD_LAUNCH_CHECK();
+  }
   // weighted last coordinate scaled by sqrt(w) AFTER centring
   NSVGD_PROPAGATE(launch_tc_prep(st, P, nullptr, n, dz, ldp, f.n_pad, f.dp, f.mu, sqrtf(w_last), f.Zb0, f.Zb1, nullptr, nullptr,
                                  nullptr, 0, f.zn, nullptr, nullptr, nullptr));
@@ -1085,7 +1127,7 @@ int median_fast_sample(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
     sample_pairs_warp_kernel<<<blocks, 32 * WX_WARPS, WX_SMEM, st>>>(P, n, (int)dz, ldp, w_last, s_begin, s_end, f.Ds);
   } else {
     const unsigned blocks = (unsigned)std::min<int64_t>(sms * 8, ceil_div(per, 32 * WX_WARPS));
-    sample_rows_kernel<<<blocks, 32 * WX_WARPS, 0, st>>>(P, n, (int)dz, ldp, w_last, s_begin, s_end, f.Ds, nb_total);
+    sample_rows_kernel<<<blocks, 32 * WX_WARPS, 0, st>>>(P, n, (int)dz, ldp, w_last, s_begin, s_end, f.Ds, nb_total, skip_flag);
   }
   prof_end(4, st);
   NSVGD_LAUNCH_CHECK();
@@ -1130,7 +1172,7 @@ int median_fast_stage1(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   prof_begin(9, st);
   NSVGD_PROPAGATE(launch_select_init(st, f.bracket, a, b, 1.f));
   NSVGD_PROPAGATE(launch_fused_select(st, f.Ds, nullptr, 0, 1, 0, s_begin, s_end, f.bracket, &f.sel[0], bracket_local ? nullptr : comm, 1,
-                                      f.fs, nullptr, l_is_zero, u_is_inf));
+                                      f.fs, nullptr, l_is_zero, u_is_inf, f.err_flag + 2));
   prof_end(9, st);
 
   // --- 2. tensor-core filter over the upper triangle (128-row blocks strided across ranks)
@@ -1219,7 +1261,8 @@ const uint32_t* median_fast_fallback_flag(void* ws, size_t ws_bytes, int64_t n, 
 // rank, rank + world, ... of the filter; sample slice rank of world; every exchange fused into its consumer kernel).
 // 13 launches + 1 memset (+ 9 early-exit launches of the conditional SIMT fallback) instead of ~45.
 int median_fast_run(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, long long r_lo,
-                    long long r_hi, const P2PComm* comm, SelectState* main_state, uint64_t* hist, void* ws, size_t ws_bytes) {
+                    long long r_hi, const P2PComm* comm, SelectState* main_state, uint64_t* hist, void* ws, size_t ws_bytes,
+                    MedianHint* hint = nullptr) {
   FastWs f;
   NSVGD_PROPAGATE(fast_ws(n, dz, ws, ws_bytes, &f));
   long long* red = (long long*)(f.err_flag) + 8;      // err_flag block is 256 bytes, 16 used
@@ -1235,7 +1278,7 @@ int median_fast_run(cudaStream_t st, const float* P, int64_t n, int64_t dz, int6
   if (const char* e = getenv("NSVGD_MEDIAN_REPLICATED_SAMPLE")) replicated = slice && e[0] == '1';
   const uint32_t s_begin = (slice && !replicated) ? per * (uint32_t)rank : 0u, s_end = s_begin + per;
   NSVGD_PROPAGATE(median_fast_sample(st, P, n, dz, ldp, w_last, slice ? rank : 0, slice ? world : 1, ws, ws_bytes, nullptr, nullptr,
-                                     replicated));
+                                     replicated, hint));
   // (an unsliceable world size: every rank samples everything and contributes 1/world-th... not needed: world | 2^22 in practice)
   NSVGD_REQUIRE(!comm || slice, NSVGD_ERR_UNSUPPORTED, "median_fast_run: world size %d does not divide the sample count", world);
   NSVGD_PROPAGATE(median_fast_stage1(st, P, n, dz, ldp, w_last, r_lo, r_hi, rank, world, main_state, hist, ws, ws_bytes, nullptr,
@@ -1257,14 +1300,18 @@ int median_fast_run(cudaStream_t st, const float* P, int64_t n, int64_t dz, int6
     else NSVGD_PROPAGATE(launch_select_advance(st, main_state, hist, pass, &f.fs->fallback));
   }
   prof_end(11, st);
+  if (hint) {
+    hint_update_kernel<<<1, 32, 0, st>>>(hint, main_state, f.fs, f.err_flag + 2);
+    NSVGD_LAUNCH_CHECK();
+  }
   return NSVGD_OK;
 }
 
 int median_fast(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, long long r_lo,
                 long long r_hi, int64_t tile_row_start, int64_t tile_row_stride, SelectState* main_state, uint64_t* hist,
-                void* ws, size_t ws_bytes) {
+                void* ws, size_t ws_bytes, MedianHint* hint) {
   (void)tile_row_start; (void)tile_row_stride;
-  return median_fast_run(st, P, n, dz, ldp, w_last, r_lo, r_hi, nullptr, main_state, hist, ws, ws_bytes);
+  return median_fast_run(st, P, n, dz, ldp, w_last, r_lo, r_hi, nullptr, main_state, hist, ws, ws_bytes, hint);
 }
 
 }  // namespace nsvgd
@@ -1299,9 +1346,18 @@ extern "C" int nsvgd_median_fast_stage1(void* stream, const float* Z, int64_t n,
   return median_fast_stage1((cudaStream_t)stream, Z, n, dz, ldz, w_last, r_lo, r_hi, block_row_start, block_row_stride,
                             (SelectState*)state_dev, hist_dev, ws, ws_bytes, (long long*)reduce_dev, nullptr, 0u, MF_SAMPLES);
 }
+extern "C" int nsvgd_p2p_median_fast_run_hinted(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last, int mode,
+                                                int rank, int world, void* const* blocks, void* state_dev, uint64_t* hist_dev,
+                                                void* hint_dev, void* ws, size_t ws_bytes);
 extern "C" int nsvgd_p2p_median_fast_run(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last, int mode,
                                          int rank, int world, void* const* blocks, void* state_dev, uint64_t* hist_dev, void* ws,
                                          size_t ws_bytes) {
+  return nsvgd_p2p_median_fast_run_hinted(stream, Z, n, dz, ldz, w_last, mode, rank, world, blocks, state_dev, hist_dev, nullptr, ws,
+                                          ws_bytes);
+}
+extern "C" int nsvgd_p2p_median_fast_run_hinted(void* stream, const float* Z, int64_t n, int64_t dz, int64_t ldz, float w_last, int mode,
+                                                int rank, int world, void* const* blocks, void* state_dev, uint64_t* hist_dev,
+                                                void* hint_dev, void* ws, size_t ws_bytes) {
   NSVGD_REQUIRE(Z && state_dev && hist_dev && ws, NSVGD_ERR_INVALID, "p2p_median_fast_run: null pointer");
   NSVGD_REQUIRE(mode >= 0 && mode <= 2, NSVGD_ERR_INVALID, "p2p_median_fast_run: bad mode %d", mode);
   P2PComm c;
@@ -1309,7 +1365,7 @@ extern "C" int nsvgd_p2p_median_fast_run(void* stream, const float* Z, int64_t n
   long long r_lo, r_hi;
   median_ranks_host(n, mode, &r_lo, &r_hi);
   return median_fast_run((cudaStream_t)stream, Z, n, dz, ldz, w_last, r_lo, r_hi, world > 1 ? &c : nullptr, (SelectState*)state_dev,
-                         hist_dev, ws, ws_bytes);
+                         hist_dev, ws, ws_bytes, (MedianHint*)hint_dev);
 }
 
 extern "C" int nsvgd_median_fast_resolve(void* stream, void* state_dev, void* ws, size_t ws_bytes, int64_t n, int64_t dz,

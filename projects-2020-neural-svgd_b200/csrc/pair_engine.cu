@@ -641,8 +641,19 @@ size_t median_workspace(int64_t n, int64_t d) {
 }
 }  // namespace nsvgd
 
+extern "C" int nsvgd_median_h_hinted_f32(void* stream, const float* X, int64_t n, int64_t d, int64_t ldx, int mode, float* h_dev,
+                                         void* hint_dev, void* ws, size_t ws_bytes);
 extern "C" int nsvgd_median_h_f32(void* stream, const float* X, int64_t n, int64_t d, int64_t ldx, int mode,
                                   float* h_dev, void* ws, size_t ws_bytes) {
+  return nsvgd_median_h_hinted_f32(stream, X, n, d, ldx, mode, h_dev, nullptr, ws, ws_bytes);
+}
+
+// hint_dev (may be null): 32 bytes of caller-owned, zero-initialised device memory that persists between calls on particle
+// clouds that change slowly (an SVGD loop): the bracket of the tensor-core filtered select (d <= 128, n >= 8192) is then
+// warm-started from the previous call's order statistics and the sampling + bracket-select phases are skipped.  The result is
+// bit-identical with or without it (the select verifies the bracket with exact counts); shapes on other paths ignore it.
+extern "C" int nsvgd_median_h_hinted_f32(void* stream, const float* X, int64_t n, int64_t d, int64_t ldx, int mode, float* h_dev,
+                                         void* hint_dev, void* ws, size_t ws_bytes) {
   NSVGD_REQUIRE(X && h_dev && ws, NSVGD_ERR_INVALID, "median_h: null pointer");
   NSVGD_REQUIRE(n >= 2 && d >= 1 && ldx >= d, NSVGD_ERR_INVALID, "median_h: need n >= 2, d >= 1, ldx >= d (n=%lld d=%lld)", (long long)n, (long long)d);
   NSVGD_REQUIRE(mode >= 0 && mode <= 2, NSVGD_ERR_INVALID, "median_h: bad mode %d", mode);
@@ -669,7 +680,8 @@ extern "C" int nsvgd_median_h_f32(void* stream, const float* X, int64_t n, int64
     // float4 rows; columns [dz, ceil4(dz)) must be zero: our own Z is padded that way, a caller's array only if dz % 4 == 0
     const bool aligned = ldp % 4 == 0 && (((uintptr_t)P) & 15) == 0 && (dz % 4 == 0 || mode == NSVGD_MEDIAN_LITERAL);
     if (median_fast_supported(n, dz))
-      NSVGD_PROPAGATE(median_fast(st, P, n, dz, ldp, w_last, r_lo, r_hi, 0, 1, (SelectState*)state, hist, fast, fast_bytes));
+      NSVGD_PROPAGATE(median_fast(st, P, n, dz, ldp, w_last, r_lo, r_hi, 0, 1, (SelectState*)state, hist, fast, fast_bytes,
+                                  (MedianHint*)hint_dev));
     else if (aligned)
       NSVGD_PROPAGATE(median_large(st, P, n, dz, ldp, w_last, r_lo, r_hi, (SelectState*)state, hist, fast, fast_bytes));
     else

@@ -28,6 +28,19 @@ struct FastMedState {
   uint32_t u_is_inf, pad;
 };
 
+// Warm start of the bracket [L, U] of the filtered select (caller-owned, persistent, 32 bytes, zero-initialised): the two order
+// statistics of the previous call and the relative margin to put around them.  Only ever a HINT: the select verifies with exact
+// counts that the target ranks fall among the candidates inside the bracket and otherwise runs its exact fallback, so the
+// result is bit-identical with or without it.
+struct MedianHint {
+  float lo, hi;        // order statistics (squared distances) of the previous call
+  float delta;         // relative margin for the next bracket
+  uint32_t valid;      // 1: lo / hi / delta usable
+  uint32_t seen;       // a previous value exists (the drift is estimated from two consecutive calls)
+  uint32_t hits, misses, pad;
+};
+static_assert(sizeof(MedianHint) == 32, "hint layout");
+
 #ifdef __CUDACC__
 __device__ __forceinline__ int pass_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
 __device__ __forceinline__ int pass_bins(int pass) { return pass == 2 ? 1024 : 2048; }
@@ -145,7 +158,7 @@ bool median_fast_supported(int64_t n, int64_t dz);
 size_t median_fast_workspace(int64_t n, int64_t dz);
 int median_fast(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, long long r_lo,
                 long long r_hi, int64_t tile_row_start, int64_t tile_row_stride, SelectState* main_state, uint64_t* hist,
-                void* ws, size_t ws_bytes);
+                void* ws, size_t ws_bytes, MedianHint* hint = nullptr);
 
 // shared by the two filtered selects (median_tc.cu, median_large.cu)
 constexpr int MF_NSEG = 64;          // independent append segments (one atomic counter per 128-byte line)
@@ -160,7 +173,7 @@ struct FusedSelScratch {
 int launch_fused_select(cudaStream_t st, const float* vals, const uint32_t* counts_dev, int count_stride, int nseg,
                         uint32_t seg_cap, uint32_t v_begin, uint32_t v_end, SelectState* state, FusedSelScratch* sc,
                         const P2PComm* comm, int final_mode, FastMedState* fs, SelectState* main_state, int l_is_zero,
-                        int u_is_inf);
+                        int u_is_inf, const uint32_t* skip_flag = nullptr);
 int launch_fast_pack_resolve(cudaStream_t st, FastMedState* fs, const uint32_t* list_counts, uint32_t list_cap, uint32_t* cand_counts,
                              uint32_t cand_cap, const uint32_t* err_flag, SelectState* main_state, SelectState* cand_state,
                              long long* red);

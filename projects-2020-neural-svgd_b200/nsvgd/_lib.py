@@ -34,6 +34,7 @@ SYMBOLS = [
     "nsvgd_median_fallback_advance", "nsvgd_phi_f32", "nsvgd_step_sgd_f32", "nsvgd_apply_update_f32",
     "nsvgd_ksd_f32", "nsvgd_mmd_f32", "nsvgd_ksum_f32", "nsvgd_adam_update_f32",
     "nsvgd_loop_small_supported", "nsvgd_svgd_loop_small_f32", "nsvgd_median_large_supported", "nsvgd_ksd_tc_workspace_bytes", "nsvgd_ksd_tc_f32",
+    "nsvgd_median_h_hinted_f32", "nsvgd_p2p_median_fast_run_hinted",
     "nsvgd_scale_cols_f32", "nsvgd_matmul_f32", "nsvgd_ksd_ard_f32", "nsvgd_ksd_linear_f32", "nsvgd_ksd_dh_f32", "nsvgd_phi_vjp_workspace_bytes", "nsvgd_phi_vjp_f32",
     "nsvgd_score_funnel_f32", "nsvgd_score_gaussian_f32", "nsvgd_score_logreg_f32",
     "nsvgd_p2p_block_bytes", "nsvgd_p2p_alloc", "nsvgd_p2p_open", "nsvgd_p2p_close", "nsvgd_p2p_free",
@@ -115,6 +116,8 @@ def load():
     lib.nsvgd_p2p_median_fast_resolve.argtypes = [vp, i32, i32, pvp, vp, vp, sz, i64, i64, vp]
     lib.nsvgd_p2p_median_fast_advance2.argtypes = [vp, i32, i32, pvp, vp, vp, sz, i64, i64, vp, i32]
     lib.nsvgd_p2p_median_fast_run.argtypes = [vp, vp, i64, i64, i64, f32, i32, i32, i32, pvp, vp, vp, vp, sz]
+    lib.nsvgd_p2p_median_fast_run_hinted.argtypes = [vp, vp, i64, i64, i64, f32, i32, i32, i32, pvp, vp, vp, vp, vp, sz]
+    lib.nsvgd_median_h_hinted_f32.argtypes = [vp, vp, i64, i64, i64, i32, vp, vp, vp, sz]
     lib.nsvgd_p2p_apply_update_f32.argtypes = [vp, i32, i32, pvp, vp, vp, i64, i64, i64, i64, vp, f32, i32, f32, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)

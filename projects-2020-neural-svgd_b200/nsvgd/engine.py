@@ -25,10 +25,25 @@ def as_h_dev(h, device) -> torch.Tensor:
     return torch.full((1,), float(h), dtype=torch.float32, device=device)
 
 
-def median_heuristic(x: torch.Tensor, mode: str | None = None) -> torch.Tensor:
+def new_median_hint(device) -> torch.Tensor:
+    """32 bytes of persistent device state for `median_heuristic(..., hint=)` (struct MedianHint, csrc/select.cuh):
+    [lo, hi, delta (float32) | valid, seen, hits, misses, pad (uint32)] viewed as int32."""
+    return torch.zeros(8, dtype=torch.int32, device=device)
+
+
+def median_hint_stats(hint: torch.Tensor) -> dict:
+    v = hint.cpu()
+    f = v.view(torch.float32)
+    return {"lo": float(f[0]), "hi": float(f[1]), "delta": float(f[2]), "valid": int(v[3]), "seen": int(v[4]),
+            "hits": int(v[5]), "misses": int(v[6])}
+
+
+def median_heuristic(x: torch.Tensor, mode: str | None = None, hint: torch.Tensor | None = None) -> torch.Tensor:
     """kernels.median_heuristic (kernels.py:160-172) -> 1-element float32 device tensor.
 
-    mode: "literal" (what kernels.py:169 executes), "offdiag" (docstring intent), "full"."""
+    mode: "literal" (what kernels.py:169 executes), "offdiag" (docstring intent), "full".
+    hint: `new_median_hint(device)` kept by the caller across the steps of an SVGD loop: the tensor-core filtered select then
+    warm-starts its bracket from the previous call (bit-identical result; sampling + bracket select skipped on a hit)."""
     mode = mode or DEFAULT_MEDIAN_MODE
     if mode not in _lib.MEDIAN_MODES:
         raise ValueError(f"unknown median mode {mode!r}")
@@ -38,8 +53,12 @@ def median_heuristic(x: torch.Tensor, mode: str | None = None) -> torch.Tensor:
     n, d = x.shape
     h = torch.empty(1, dtype=torch.float32, device=x.device)
     ws = workspace(workspace_bytes("median", n, n, d), x.device)
-    check(load().nsvgd_median_h_f32(stream_ptr(x.device), ptr(x), n, d, ld(x), _lib.MEDIAN_MODES[mode],
-                                    ptr(h), ptr(ws), ws.numel()))
+    if hint is not None and os.environ.get("NSVGD_MEDIAN_HINT", "1") != "0":
+        check(load().nsvgd_median_h_hinted_f32(stream_ptr(x.device), ptr(x), n, d, ld(x), _lib.MEDIAN_MODES[mode],
+                                               ptr(h), ptr(hint), ptr(ws), ws.numel()))
+    else:
+        check(load().nsvgd_median_h_f32(stream_ptr(x.device), ptr(x), n, d, ld(x), _lib.MEDIAN_MODES[mode],
+                                        ptr(h), ptr(ws), ws.numel()))
     return h
 
 
@@ -431,12 +450,13 @@ class MedianSelect:
         check(load().nsvgd_p2p_median_fast_advance2(stream_ptr(self.x.device), comm.rank, comm.world, comm.blocks, ptr(self.state),
                                                     ptr(ws), ws.numel(), self.n, self.dz, ptr(self.hist_all), p))
 
-    def p2p_fast_run(self, comm):
-        """the whole filtered select of this rank in one C call (fused selects, every exchange inside its consumer kernel)"""
+    def p2p_fast_run(self, comm, hint=None):
+        """the whole filtered select of this rank in one C call (fused selects, every exchange inside its consumer kernel);
+        hint: see engine.median_heuristic (identical content on every rank by construction)"""
         ws = self._fws()
-        check(load().nsvgd_p2p_median_fast_run(stream_ptr(self.x.device), ptr(self.P), self.n, self.dz, ld(self.P), self.w_last,
-                                               _lib.MEDIAN_MODES[self.mode], comm.rank, comm.world, comm.blocks, ptr(self.state),
-                                               ptr(self.hist), ptr(ws), ws.numel()))
+        check(load().nsvgd_p2p_median_fast_run_hinted(stream_ptr(self.x.device), ptr(self.P), self.n, self.dz, ld(self.P),
+                                                      self.w_last, _lib.MEDIAN_MODES[self.mode], comm.rank, comm.world, comm.blocks,
+                                                      ptr(self.state), ptr(self.hist), ptr(hint), ptr(ws), ws.numel()))
 
     def p2p_advance(self, comm, p: int):
         check(load().nsvgd_p2p_median_advance(stream_ptr(self.x.device), comm.rank, comm.world, comm.blocks, ptr(self.state),

@@ -42,7 +42,16 @@ class KernelGradient:
         # truthiness test as in models.py:657/680: None or 0 -> median heuristic
         if isinstance(self.bandwidth, torch.Tensor) or self._ard():
             return self.bandwidth
-        return self.bandwidth if self.bandwidth else kernels.median_heuristic(inducing_particles)
+        if self.bandwidth:
+            return self.bandwidth
+        # the plug-in is called once per SVGD step on slowly moving particles: keep the warm-start state of the filtered
+        # select between calls (engine.median_heuristic; bit-identical bandwidth, sampling + bracket select skipped on a hit)
+        if inducing_particles.is_cuda:
+            key = (inducing_particles.device, tuple(inducing_particles.shape))
+            if getattr(self, "_median_hint_key", None) != key:
+                self._median_hint, self._median_hint_key = engine.new_median_hint(inducing_particles.device), key
+            return engine.median_heuristic(inducing_particles, None, hint=self._median_hint).reshape(())
+        return kernels.median_heuristic(inducing_particles)
 
     def _ard(self):
         """a (d,) bandwidth vector: served by stein.get_phistar (unscaled field); the fused scaled step needs a scalar"""

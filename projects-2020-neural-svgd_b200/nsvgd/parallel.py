@@ -12,6 +12,8 @@ with gloo and an oracle-backed stand-in (tests/test_parallel_gloo.py); the defau
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -42,6 +44,7 @@ class ShardedSVGD:
         self.max_rows = row_partition(n, self.world, 0)[1]
         self._buf = {}
         self._side = None
+        self._hint = None          # warm start of the median bracket (engine.new_median_hint), created on first use
         self.comm = None
         import os
         if p2p == "auto" and os.environ.get("NSVGD_P2P", "1") == "0":
@@ -92,7 +95,11 @@ class ShardedSVGD:
                 and (1 << 22) % self.world == 0 and ((1 << 22) // self.world) % 32 == 0:
             # one C call: sample slice, fused bracket select, filter, exact list, resolve, fused candidate select; every
             # exchange (4 histogram sums, the counts) happens inside its consumer kernel over NVLink peer memory
-            sel.p2p_fast_run(self.comm)
+            # warm-started bracket: the previous step's order statistics (identical on every rank) replace the sampling and
+            # bracket-select phases -- three of the serial exchange rounds of the step (NSVGD_MEDIAN_HINT=0 switches it off)
+            if self._hint is None and os.environ.get("NSVGD_MEDIAN_HINT", "1") != "0":
+                self._hint = self.engine.new_median_hint(X_all.device)
+            sel.p2p_fast_run(self.comm, self._hint)
             return sel.finish()
         if getattr(sel, "fast_supported", False):
             # tensor-core filtered select: the bracket is identical on every rank (deterministic sample of

@@ -151,6 +151,31 @@ def test_ksd_u_v_through_phi_statistics(n, d, h, monkeypatch):
     assert got["v"] == pytest.approx(so.stein_discrepancy_phistar(X, S, h), rel=TOL)
 
 
+@pytest.mark.parametrize("mode", so.MEDIAN_MODES)
+def test_bandwidth_warm_started_bracket_is_bit_identical(mode):
+    """engine.median_heuristic(hint=): over an SVGD-like sequence of slowly moving clouds the warm-started bracket gives the
+    same bits as the sampled one at every step and is actually used (hits); a jump of the cloud makes the hinted bracket miss
+    -- the exact fallback still returns the right bits and the hint is dropped, then rebuilt."""
+    from nsvgd import engine
+    rng = np.random.default_rng(21)
+    n, d = 8192, 64
+    X = (rng.standard_normal((n, d)) * 1.1 + 0.2).astype(np.float32)
+    V = (rng.standard_normal((n, d)) * 1e-4).astype(np.float32)
+    hint = engine.new_median_hint("cuda")
+    for step in range(8):
+        if step == 5:
+            X = (X * 1.5).astype(np.float32)            # the median of the squared distances moves by 2.25 x: a certain miss
+        Xd = dev(X)
+        want = engine.median_heuristic(Xd, mode).cpu().numpy()[0]
+        got = engine.median_heuristic(Xd, mode, hint=hint).cpu().numpy()[0]
+        assert np.float32(got).tobytes() == np.float32(want).tobytes(), (step, got, want)
+        X = (X + V).astype(np.float32)
+    st = engine.median_hint_stats(hint)
+    # steps 0, 1 observe; 2, 3, 4 hit; 5 misses (fallback) and drops the hint; 6, 7 observe again
+    assert st["hits"] == 3 and st["misses"] == 1, st
+    assert st["seen"] == 1 and st["valid"] == 1 and 0 < st["delta"] <= 2 ** -7, st
+
+
 def test_bandwidth_nan_and_zero():
     from nsvgd import engine
     X = np.random.default_rng(0).standard_normal((70, 3)).astype(np.float32)
