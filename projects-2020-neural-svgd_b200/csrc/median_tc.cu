@@ -912,9 +912,80 @@ __global__ void __launch_bounds__(256, 4) fused_select_kernel(const float* __res
                                                            int world, int final_mode, FastMedState* fs, SelectState* main_state,
                                                            int l_is_zero, int u_is_inf, const uint32_t* skip_flag) {
   if (skip_flag && *skip_flag) return;      // (identical on every CTA and every rank: nobody enters the hand-shakes)
-  __shared__ unsigned int hist_s[2 * NSVGD_SELECT_BINS];
+  constexpr uint32_t NARROW_BINS = 8192;    // <= the 3 x 4096 counters of sc->hist, <= 2 x the words of a peer-memory slot
+  __shared__ unsigned int hist_s[NARROW_BINS];
   __shared__ uint32_t s_last;
   const int lane = threadIdx.x & 31;
+  if (final_mode == 2) {
+    // NARROW BRACKET (a warm-started bracket is ~2^-12 wide): all candidates lie in [L, U] and the fp32 patterns of L and U are
+    // fewer than 8192 apart, so ONE histogram over key = bits(v) - bits(L) resolves both order statistics exactly -- one pass
+    // and one exchange instead of three.  L, U are identical on every rank, hence so is this decision.
+    const uint32_t bl = __float_as_uint(fs->L), bu = __float_as_uint(fs->U);
+    if (!fs->u_is_inf && !(bl >> 31) && bu >= bl && bu - bl < NARROW_BINS) {
+      unsigned int* gh = &sc->hist[0][0];
+      for (int t = threadIdx.x; t < (int)NARROW_BINS; t += 256) hist_s[t] = 0u;
+      __syncthreads();
+      const uint32_t G = min((uint32_t)nseg, gridDim.x);
+      const uint32_t peers_n = (gridDim.x - (blockIdx.x % G) + G - 1u) / G;
+      const uint32_t my_idx = blockIdx.x / G;
+      for (int sgm = (int)(blockIdx.x % G); sgm < nseg; sgm += (int)G) {
+        const uint32_t begin = counts_dev ? 0u : v_begin;
+        const uint32_t end = counts_dev ? min(counts_dev[sgm * count_stride], seg_cap) : v_end;
+        const float* v0 = vals + (size_t)sgm * seg_cap;
+        for (uint32_t t = begin + my_idx * 256u + threadIdx.x; t < end; t += peers_n * 256u) {
+          const uint32_t key = __float_as_uint(v0[t]) - bl;      // candidates are finite and inside [L, U]
+          if (key < NARROW_BINS) atomicAdd(&hist_s[key], 1u);
+        }
+      }
+      __syncthreads();
+      for (int t = threadIdx.x; t < (int)NARROW_BINS; t += 256) {
+        const unsigned int v = hist_s[t];
+        if (v) atomicAdd(&gh[t], v);
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) s_last = (atomicAdd(&sc->done[0], 1u) == gridDim.x - 1u) ? 1u : 0u;
+      __syncthreads();
+      if (!s_last) return;                                       // single pass: nobody waits for the decision
+      __threadfence();
+      if (world > 1 && !p2p_allreduce_cta(c, reinterpret_cast<unsigned long long*>(gh), NARROW_BINS / 2, false) && threadIdx.x == 0)
+        main_state->nan_flag = 1u;
+      __syncthreads();
+      for (int t = threadIdx.x; t < (int)NARROW_BINS; t += 256) hist_s[t] = gh[t];
+      __syncthreads();
+      // thread i owns bins [32 i, 32 i + 32): exclusive prefix over the 256 threads, then the owner walks its bins
+      __shared__ unsigned long long warp_tot[8];
+      unsigned long long mine = 0ull;
+      for (int b = 0; b < 32; ++b) mine += hist_s[threadIdx.x * 32 + b];
+      unsigned long long inc = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+      if (lane == 31) warp_tot[threadIdx.x >> 5] = inc;
+      __syncthreads();
+      unsigned long long excl = inc - mine;
+      for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) excl += warp_tot[w];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (state->is_zero[t]) continue;
+        const unsigned long long r = state->rank[t];
+        if (r >= excl && r < excl + mine) {
+          unsigned long long cum = excl;
+          for (int b = 0; b < 32; ++b) {
+            const unsigned long long cnt = hist_s[threadIdx.x * 32 + b];
+            if (r < cum + cnt) { state->value[t] = __uint_as_float(bl + (uint32_t)(threadIdx.x * 32 + b)); break; }
+            cum += cnt;
+          }
+        }
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0 && !fs->fallback) {                   // candidates resolved: commit (else the conditional SIMT passes do)
+        for (int t = 0; t < 2; ++t) main_state->value[t] = main_state->is_zero[t] ? 0.f : state->value[t];
+        main_state->done = 1;
+      }
+      return;
+    }
+  }
   for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {
     for (int t = threadIdx.x; t < 2 * NSVGD_SELECT_BINS; t += 256) hist_s[t] = 0u;
     __syncthreads();
