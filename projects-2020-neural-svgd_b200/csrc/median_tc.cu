@@ -16,6 +16,7 @@
 //                the conditional SIMT 3-pass kernels run instead — still enqueue-only, still exact.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -1127,9 +1128,9 @@ static int launch_filter(cudaStream_t st, const CUtensorMap* maps, const MfParam
 // hint valid -> the bracket is [lo (1 - delta), hi (1 + delta)] around the previous call's order statistics, the sample and
 // the bracket select return at once (skip flag), and everything downstream is unchanged: the resolve step checks with exact
 // counts that the target ranks fall among the candidates and triggers the exact SIMT select otherwise.
-__global__ void hint_apply_kernel(const MedianHint* hint, FastMedState* fs, uint32_t* skip_flag) {
+__global__ void hint_apply_kernel(const MedianHint* hint, FastMedState* fs, uint32_t* skip_flag, uint32_t key) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const bool use = hint && hint->valid && hint->lo == hint->lo && hint->hi == hint->hi && hint->hi >= hint->lo && hint->lo >= 0.f;
+  const bool use = hint && hint->valid && hint->key == key && hint->lo == hint->lo && hint->hi == hint->hi && hint->hi >= hint->lo && hint->lo >= 0.f;
   *skip_flag = use ? 1u : 0u;
   if (!use) return;
   fs->below = 0ull; fs->list_count = 0u; fs->cand_count = 0u; fs->overflow = 0u; fs->fallback = 0u;
@@ -1137,31 +1138,48 @@ __global__ void hint_apply_kernel(const MedianHint* hint, FastMedState* fs, uint
   fs->U = hint->hi * (1.f + hint->delta);
   fs->u_is_inf = 0u; fs->pad = 0u;
 }
-// after the select: remember the order statistics; margin = 4 x the relative change between the last two calls, within
-// [2^-13, 2^-7]; a miss (the hinted bracket did not contain the target: the fallback ran) or a NaN drops the hint
-__global__ void hint_update_kernel(MedianHint* hint, const SelectState* main_state, const FastMedState* fs, const uint32_t* skip_flag) {
+// after the select: remember the order statistics.  margin = 4 x the relative change between the last two calls (>= 2^-13); the
+// hint is only armed while that margin stays <= 2^-10 (about the width of the sampled bracket: a fast-moving cloud gains
+// nothing from a wide warm-started bracket and would overflow the candidate lists), and a miss (the hinted bracket did not
+// contain the target, so the exact SIMT fallback ran) disarms it for 16 << penalty calls, penalty growing with every further
+// miss (<= 6) and shrinking with every hit: the amortised cost of misses stays bounded on any dynamics.
+// `seen` packs: bit 0 = a previous value exists, bits 1-15 = remaining cool-down calls, bits 16-23 = penalty.
+__global__ void hint_update_kernel(MedianHint* hint, const SelectState* main_state, const FastMedState* fs, const uint32_t* skip_flag,
+                                   uint32_t key) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (hint->key != key) { hint->valid = 0u; hint->seen = 0u; hint->key = key; }      // another mode / shape wrote the old values
+  uint32_t seen = hint->seen & 1u, cool = (hint->seen >> 1) & 0x7FFFu, pen = (hint->seen >> 16) & 0xFFu;
   const bool hinted = *skip_flag != 0u;
+  const bool missed = hinted && fs->fallback;
   const float lo = main_state->value[0], hi = main_state->value[1];
   const bool usable = !main_state->nan_flag && !main_state->is_zero[0] && !main_state->is_zero[1] && lo == lo && hi == hi && hi > 0.f;
-  if (hinted) { if (fs->fallback) ++hint->misses; else ++hint->hits; }
-  if (!usable || (hinted && fs->fallback)) { hint->valid = 0u; hint->seen = 0u; return; }
-  float delta = 4.8828125e-4f;                                     // 2^-11 until two consecutive values are known
-  if (hint->seen) {
-    const float mid_old = 0.5f * (hint->lo + hint->hi), mid_new = 0.5f * (lo + hi);
-    const float drift = fabsf(mid_new - mid_old) / mid_new;
-    delta = fminf(fmaxf(4.f * drift, 1.220703125e-4f), 7.8125e-3f);
+  if (hinted) { if (missed) ++hint->misses; else { ++hint->hits; if (pen) --pen; } }
+  uint32_t valid = 0u;
+  if (!usable) {
+    seen = 0u;
+  } else {
+    float drift = 1.f;
+    if (seen) {
+      const float mid_old = 0.5f * (hint->lo + hint->hi), mid_new = 0.5f * (lo + hi);
+      drift = fabsf(mid_new - mid_old) / mid_new;
+    }
+    hint->lo = lo; hint->hi = hi;                                  // exact either way (the fallback is exact too)
+    if (missed) { pen = min(pen + 1u, 6u); cool = 16u << pen; }
+    else if (cool) --cool;
+    const float delta = fmaxf(4.f * drift, 1.220703125e-4f);       // >= 2^-13
+    hint->delta = delta;
+    valid = (seen && !cool && !missed && delta <= 9.765625e-4f) ? 1u : 0u;      // armed only while slow: margin <= 2^-10
+    seen = 1u;
   }
-  hint->lo = lo; hint->hi = hi; hint->delta = delta;
-  hint->valid = hint->seen ? 1u : 0u;                               // the first call only observes
-  hint->seen = 1u;
+  hint->valid = valid;
+  hint->seen = seen | (cool << 1) | (pen << 16);
 }
 
 // replicated = true: every rank computes the SAME reduced sample set of MF_SAMPLES / nparts pairs (rows spread over all n),
 // so the bracket select needs no exchange at all (median_fast_run)
 int median_fast_sample(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, int64_t part,
                        int64_t nparts, void* ws, size_t ws_bytes, size_t* samples_off, int64_t* samples_count, bool replicated,
-                       const MedianHint* hint = nullptr) {
+                       const MedianHint* hint = nullptr, uint32_t hint_key = 0u) {
   NSVGD_REQUIRE(median_fast_supported(n, dz), NSVGD_ERR_UNSUPPORTED, "median_fast: unsupported shape");
   NSVGD_REQUIRE(nparts >= 1 && part >= 0 && part < nparts && MF_SAMPLES % nparts == 0 && (MF_SAMPLES / nparts) % 32 == 0,
                 NSVGD_ERR_INVALID, "median_fast_sample: the sample count %u must split evenly over %lld parts", MF_SAMPLES,
@@ -1176,7 +1194,7 @@ int median_fast_sample(cudaStream_t st, const float* P, int64_t n, int64_t dz, i
   NSVGD_CUDA(cudaMemsetAsync(f.zero_block, 0, f.zero_bytes, st));   // error flag, list / candidate counters, select scratch
   uint32_t* skip_flag = f.err_flag + 2;                             // (inside the zero block: 0 unless a valid hint sets it)
   if (hint) {
-    hint_apply_kernel<<<1, 32, 0, st>>>(hint, f.fs, skip_flag);
+    hint_apply_kernel<<<1, 32, 0, st>>>(hint, f.fs, skip_flag, hint_key);
     NSVGD_LAUNCH_CHECK();
   }
   // weighted last coordinate scaled by sqrt(w) AFTER centring
@@ -1347,9 +1365,17 @@ int median_fast_run(cudaStream_t st, const float* P, int64_t n, int64_t dz, int6
   // Bit-identical h either way (tests/test_sharded_gpu.py).
   bool replicated = false;
   if (const char* e = getenv("NSVGD_MEDIAN_REPLICATED_SAMPLE")) replicated = slice && e[0] == '1';
+  // which problem a hint belongs to: shape, target rank (differs between the median modes), last-coordinate weight
+  uint32_t hint_key = 0x9E3779B9u;
+  {
+    uint32_t wb; memcpy(&wb, &w_last, 4);
+    const uint64_t parts[4] = {(uint64_t)n, (uint64_t)dz, (uint64_t)r_lo, (uint64_t)wb};
+    for (uint64_t v : parts) { hint_key ^= (uint32_t)(v ^ (v >> 32)) + 0x9E3779B9u + (hint_key << 6) + (hint_key >> 2); }
+    if (hint_key == 0u) hint_key = 1u;
+  }
   const uint32_t s_begin = (slice && !replicated) ? per * (uint32_t)rank : 0u, s_end = s_begin + per;
   NSVGD_PROPAGATE(median_fast_sample(st, P, n, dz, ldp, w_last, slice ? rank : 0, slice ? world : 1, ws, ws_bytes, nullptr, nullptr,
-                                     replicated, hint));
+                                     replicated, hint, hint_key));
   // (an unsliceable world size: every rank samples everything and contributes 1/world-th... not needed: world | 2^22 in practice)
   NSVGD_REQUIRE(!comm || slice, NSVGD_ERR_UNSUPPORTED, "median_fast_run: world size %d does not divide the sample count", world);
   NSVGD_PROPAGATE(median_fast_stage1(st, P, n, dz, ldp, w_last, r_lo, r_hi, rank, world, main_state, hist, ws, ws_bytes, nullptr,
@@ -1372,7 +1398,7 @@ int median_fast_run(cudaStream_t st, const float* P, int64_t n, int64_t dz, int6
   }
   prof_end(11, st);
   if (hint) {
-    hint_update_kernel<<<1, 32, 0, st>>>(hint, main_state, f.fs, f.err_flag + 2);
+    hint_update_kernel<<<1, 32, 0, st>>>(hint, main_state, f.fs, f.err_flag + 2, hint_key);
     NSVGD_LAUNCH_CHECK();
   }
   return NSVGD_OK;

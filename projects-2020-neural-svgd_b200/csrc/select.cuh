@@ -36,8 +36,10 @@ struct MedianHint {
   float lo, hi;        // order statistics (squared distances) of the previous call
   float delta;         // relative margin for the next bracket
   uint32_t valid;      // 1: lo / hi / delta usable
-  uint32_t seen;       // a previous value exists (the drift is estimated from two consecutive calls)
-  uint32_t hits, misses, pad;
+  uint32_t seen;       // bit 0: a previous value exists (drift = change between two consecutive calls); bits 1-15: cool-down calls
+                       // left after a miss; bits 16-23: penalty (the cool-down doubles with every further miss)
+  uint32_t hits, misses;
+  uint32_t key;        // (n, dz, target rank, last-coordinate weight) of the call that wrote lo / hi: a different problem -> no hint
 };
 static_assert(sizeof(MedianHint) == 32, "hint layout");
 

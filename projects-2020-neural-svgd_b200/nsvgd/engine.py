@@ -34,8 +34,8 @@ def new_median_hint(device) -> torch.Tensor:
 def median_hint_stats(hint: torch.Tensor) -> dict:
     v = hint.cpu()
     f = v.view(torch.float32)
-    return {"lo": float(f[0]), "hi": float(f[1]), "delta": float(f[2]), "valid": int(v[3]), "seen": int(v[4]),
-            "hits": int(v[5]), "misses": int(v[6])}
+    return {"lo": float(f[0]), "hi": float(f[1]), "delta": float(f[2]), "valid": int(v[3]), "seen": int(v[4]) & 1,
+            "cooldown": (int(v[4]) >> 1) & 0x7FFF, "penalty": (int(v[4]) >> 16) & 0xFF, "hits": int(v[5]), "misses": int(v[6])}
 
 
 def median_heuristic(x: torch.Tensor, mode: str | None = None, hint: torch.Tensor | None = None) -> torch.Tensor:

@@ -171,9 +171,18 @@ def test_bandwidth_warm_started_bracket_is_bit_identical(mode):
         assert np.float32(got).tobytes() == np.float32(want).tobytes(), (step, got, want)
         X = (X + V).astype(np.float32)
     st = engine.median_hint_stats(hint)
-    # steps 0, 1 observe; 2, 3, 4 hit; 5 misses (fallback) and drops the hint; 6, 7 observe again
+    # steps 0, 1 observe; 2, 3, 4 hit; 5 misses (exact fallback) and disarms the hint for 32 calls; 6, 7 observe under cool-down
     assert st["hits"] == 3 and st["misses"] == 1, st
-    assert st["seen"] == 1 and st["valid"] == 1 and 0 < st["delta"] <= 2 ** -7, st
+    assert st["seen"] == 1 and st["valid"] == 0 and st["cooldown"] == 30 and st["penalty"] == 1, st
+    # the same hint object handed to another problem (a different median mode / shape): keyed, so it is not used (no miss)
+    other = [m for m in so.MEDIAN_MODES if m != mode][0]
+    Xd = dev(X)
+    for m_, x_ in ((other, Xd), (other, Xd), (other, Xd), (mode, Xd[:8192 - 64].contiguous())):
+        want = engine.median_heuristic(x_, m_).cpu().numpy()[0]
+        got = engine.median_heuristic(x_, m_, hint=hint).cpu().numpy()[0]
+        assert np.float32(got).tobytes() == np.float32(want).tobytes(), (m_, got, want)
+    st2 = engine.median_hint_stats(hint)
+    assert st2["misses"] == 1 and st2["hits"] == 4, st2          # third call in the other mode hit; nothing missed
 
 
 def test_bandwidth_nan_and_zero():
