@@ -184,7 +184,8 @@ __device__ __forceinline__ float ml_warp_exact32(const float* __restrict__ P, in
 // sample s = 32 g + p: row i_g = floor(g n / G) (G = samples / 32 groups: the rows are visited evenly) against a pseudo-random
 // partner j != i_g; deterministic in (n, s)
 __global__ void __launch_bounds__(128) ml_sample_kernel(const float* __restrict__ P, int64_t n, int d, int64_t ldp, float w_last,
-                                                        float* __restrict__ Ds) {
+                                                        float* __restrict__ Ds, const uint32_t* skip_flag) {
+  if (skip_flag && *skip_flag) return;          // the bracket comes from the caller's hint this time (MedianHint, select.cuh)
   __shared__ __align__(16) float tiles[4][32 * ML_XSTRIDE];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t groups = ML_SAMPLES / 32u;
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(ML_XT, 2) ml_exact_tiles_kernel(const float* _
 }
 
 int median_large(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, long long r_lo, long long r_hi,
-                 SelectState* main_state, uint64_t* hist, void* ws, size_t ws_bytes) {
+                 SelectState* main_state, uint64_t* hist, void* ws, size_t ws_bytes, MedianHint* hint) {
   NSVGD_REQUIRE(median_large_supported(n, dz), NSVGD_ERR_UNSUPPORTED, "median_large: unsupported shape");
   NSVGD_REQUIRE(ldp % 4 == 0 && (((uintptr_t)P) & 15) == 0, NSVGD_ERR_UNSUPPORTED, "median_large: rows must be 16-byte aligned");
   NSVGD_REQUIRE(r_lo >= 0 && r_hi >= r_lo, NSVGD_ERR_UNSUPPORTED, "median_large: needs genuine pair ranks");
@@ -352,11 +353,14 @@ int median_large(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t
   prof_begin(8, st);
   NSVGD_PROPAGATE(launch_colmean(st, P, n, dz, ldp, f.mpart, f.mu));
   NSVGD_CUDA(cudaMemsetAsync(f.zero_block, 0, f.zero_bytes, st));
+  uint32_t* skip_flag = f.err_flag + 2;          // inside the zero block: 0 unless a valid hint arms the warm-started bracket
+  const uint32_t hint_key = median_hint_key(n, dz, r_lo, w_last);
+  if (hint) NSVGD_PROPAGATE(launch_hint_apply(st, hint, f.fs, skip_flag, hint_key));
   ml_prep_kernel<<<(unsigned)ceil_div(f.n_pad * 32, 256), 256, 0, st>>>(P, n, f.n_pad, dz, ldp, f.ldk, f.mu, sqrtf(w_last), f.Zb0, f.Zb1, f.zn);
   NSVGD_LAUNCH_CHECK();
   prof_end(8, st);
   prof_begin(4, st);
-  ml_sample_kernel<<<(unsigned)std::min<int64_t>(sms * 8, ML_SAMPLES / 128), 128, 0, st>>>(P, n, (int)dz, ldp, w_last, f.Ds);
+  ml_sample_kernel<<<(unsigned)std::min<int64_t>(sms * 8, ML_SAMPLES / 128), 128, 0, st>>>(P, n, (int)dz, ldp, w_last, f.Ds, skip_flag);
   NSVGD_LAUNCH_CHECK();
   prof_end(4, st);
 
@@ -373,7 +377,7 @@ int median_large(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t
   prof_begin(9, st);
   NSVGD_PROPAGATE(launch_select_init(st, f.bracket, a, b, 1.f));
   NSVGD_PROPAGATE(launch_fused_select(st, f.Ds, nullptr, 0, 1, 0, 0u, ML_SAMPLES, f.bracket, &f.sel[0], nullptr, 1, f.fs, nullptr,
-                                      l_is_zero, u_is_inf));
+                                      l_is_zero, u_is_inf, skip_flag));
   prof_end(9, st);
 
   // --- filter: symmetric Gram + classify
@@ -408,6 +412,7 @@ int median_large(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t
     NSVGD_PROPAGATE(launch_select_advance(st, main_state, hist, pass, &f.fs->fallback));
   }
   prof_end(11, st);
+  if (hint) NSVGD_PROPAGATE(launch_hint_update(st, hint, main_state, f.fs, skip_flag, hint_key));
   return NSVGD_OK;
 }
 

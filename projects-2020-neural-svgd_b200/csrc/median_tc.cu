@@ -1175,6 +1175,25 @@ __global__ void hint_update_kernel(MedianHint* hint, const SelectState* main_sta
   hint->seen = seen | (cool << 1) | (pen << 16);
 }
 
+uint32_t median_hint_key(int64_t n, int64_t dz, long long r_lo, float w_last) {
+  uint32_t key = 0x9E3779B9u, wb;
+  memcpy(&wb, &w_last, 4);
+  const uint64_t parts[4] = {(uint64_t)n, (uint64_t)dz, (uint64_t)r_lo, (uint64_t)wb};
+  for (uint64_t v : parts) key ^= (uint32_t)(v ^ (v >> 32)) + 0x9E3779B9u + (key << 6) + (key >> 2);
+  return key ? key : 1u;
+}
+int launch_hint_apply(cudaStream_t st, const MedianHint* hint, FastMedState* fs, uint32_t* skip_flag, uint32_t key) {
+  hint_apply_kernel<<<1, 32, 0, st>>>(hint, fs, skip_flag, key);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+int launch_hint_update(cudaStream_t st, MedianHint* hint, const SelectState* main_state, const FastMedState* fs,
+                       const uint32_t* skip_flag, uint32_t key) {
+  hint_update_kernel<<<1, 32, 0, st>>>(hint, main_state, fs, skip_flag, key);
+  NSVGD_LAUNCH_CHECK();
+  return NSVGD_OK;
+}
+
 // replicated = true: every rank computes the SAME reduced sample set of MF_SAMPLES / nparts pairs (rows spread over all n),
 // so the bracket select needs no exchange at all (median_fast_run)
 int median_fast_sample(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, int64_t part,
@@ -1366,13 +1385,7 @@ int median_fast_run(cudaStream_t st, const float* P, int64_t n, int64_t dz, int6
   bool replicated = false;
   if (const char* e = getenv("NSVGD_MEDIAN_REPLICATED_SAMPLE")) replicated = slice && e[0] == '1';
   // which problem a hint belongs to: shape, target rank (differs between the median modes), last-coordinate weight
-  uint32_t hint_key = 0x9E3779B9u;
-  {
-    uint32_t wb; memcpy(&wb, &w_last, 4);
-    const uint64_t parts[4] = {(uint64_t)n, (uint64_t)dz, (uint64_t)r_lo, (uint64_t)wb};
-    for (uint64_t v : parts) { hint_key ^= (uint32_t)(v ^ (v >> 32)) + 0x9E3779B9u + (hint_key << 6) + (hint_key >> 2); }
-    if (hint_key == 0u) hint_key = 1u;
-  }
+  const uint32_t hint_key = median_hint_key(n, dz, r_lo, w_last);
   const uint32_t s_begin = (slice && !replicated) ? per * (uint32_t)rank : 0u, s_end = s_begin + per;
   NSVGD_PROPAGATE(median_fast_sample(st, P, n, dz, ldp, w_last, slice ? rank : 0, slice ? world : 1, ws, ws_bytes, nullptr, nullptr,
                                      replicated, hint, hint_key));

@@ -683,7 +683,8 @@ extern "C" int nsvgd_median_h_hinted_f32(void* stream, const float* X, int64_t n
       NSVGD_PROPAGATE(median_fast(st, P, n, dz, ldp, w_last, r_lo, r_hi, 0, 1, (SelectState*)state, hist, fast, fast_bytes,
                                   (MedianHint*)hint_dev));
     else if (aligned)
-      NSVGD_PROPAGATE(median_large(st, P, n, dz, ldp, w_last, r_lo, r_hi, (SelectState*)state, hist, fast, fast_bytes));
+      NSVGD_PROPAGATE(median_large(st, P, n, dz, ldp, w_last, r_lo, r_hi, (SelectState*)state, hist, fast, fast_bytes,
+                                   (MedianHint*)hint_dev));
     else
       for (int pass = 0; pass < NSVGD_SELECT_PASSES; ++pass) {      // unaligned rows: the recomputing 3-pass select
         NSVGD_PROPAGATE(launch_pair_hist(st, P, n, dz, ldp, w_last, 0, 1, (const SelectState*)state, pass, hist, nullptr));

@@ -180,11 +180,17 @@ int launch_fast_pack_resolve(cudaStream_t st, FastMedState* fs, const uint32_t* 
                              uint32_t cand_cap, const uint32_t* err_flag, SelectState* main_state, SelectState* cand_state,
                              long long* red);
 
+// warm-started bracket (median_tc.cu): which problem a hint belongs to, arm (sets *skip_flag and the bracket in fs), update
+uint32_t median_hint_key(int64_t n, int64_t dz, long long r_lo, float w_last);
+int launch_hint_apply(cudaStream_t st, const MedianHint* hint, FastMedState* fs, uint32_t* skip_flag, uint32_t key);
+int launch_hint_update(cudaStream_t st, MedianHint* hint, const SelectState* main_state, const FastMedState* fs,
+                       const uint32_t* skip_flag, uint32_t key);
+
 // median_large.cu: the tensor-core filtered exact median for d > 128 (single GPU); phi_large.cu: its Gram + classify launch
 bool median_large_supported(int64_t n, int64_t dz);
 size_t median_large_workspace(int64_t n, int64_t dz);
 int median_large(cudaStream_t st, const float* P, int64_t n, int64_t dz, int64_t ldp, float w_last, long long r_lo, long long r_hi,
-                 SelectState* main_state, uint64_t* hist, void* ws, size_t ws_bytes);
+                 SelectState* main_state, uint64_t* hist, void* ws, size_t ws_bytes, MedianHint* hint = nullptr);
 int lg_launch_classify(cudaStream_t st, const void* Zb0, const void* Zb1, int64_t n, int64_t n_pad, int64_t ldk, const float* zn,
                        FastMedState* fs, unsigned short* tlist, uint32_t* tcount, uint32_t tcap, float kappa_g, float kappa_d,
                        uint32_t* err_flag);

@@ -185,6 +185,26 @@ def test_bandwidth_warm_started_bracket_is_bit_identical(mode):
     assert st2["misses"] == 1 and st2["hits"] == 4, st2          # third call in the other mode hit; nothing missed
 
 
+def test_bandwidth_warm_started_bracket_large_d():
+    """the same warm start on the d > 128 filter (csrc/median_large.cu): drifting BNN-regime cloud, literal and offdiag modes"""
+    from nsvgd import engine
+    rng = np.random.default_rng(31)
+    n, d = 2304, 512
+    X = (rng.standard_normal((n, d)) * 0.15).astype(np.float32)
+    V = (rng.standard_normal((n, d)) * 1e-5).astype(np.float32)
+    hints = {m: engine.new_median_hint("cuda") for m in ("literal", "offdiag")}
+    for step in range(6):
+        Xd = dev(X)
+        for m, hint in hints.items():
+            want = engine.median_heuristic(Xd, m).cpu().numpy()[0]
+            got = engine.median_heuristic(Xd, m, hint=hint).cpu().numpy()[0]
+            assert np.float32(got).tobytes() == np.float32(want).tobytes(), (step, m, got, want)
+        X = (X + V).astype(np.float32)
+    for m, hint in hints.items():
+        st = engine.median_hint_stats(hint)
+        assert st["hits"] == 4 and st["misses"] == 0, (m, st)
+
+
 def test_bandwidth_nan_and_zero():
     from nsvgd import engine
     X = np.random.default_rng(0).standard_normal((70, 3)).astype(np.float32)
